@@ -1,0 +1,28 @@
+#pragma once
+#include "host_util.h"
+
+namespace rsp {
+
+// out[row_map[m], n] = act(sum_k A[m,k] * W[n,k] + bias[n]) + residual[row_map[m] % res_mod, n]
+struct GemmArgs {
+  const void* A = nullptr;   // bf16 [M, K], row stride lda
+  const void* W = nullptr;   // bf16 [N, K] (nn.Linear layout), row stride ldw; or [K, N] if w_is_kn
+  void* out = nullptr;       // bf16 or fp32 [*, ldo]
+  const float* bias = nullptr;     // fp32 [N] or null
+  const void* residual = nullptr;  // fp32 or bf16 [*, ldr] or null (may alias out)
+  const int* row_map = nullptr;    // int32 [M] destination row (-1 = drop) or null = identity
+  int M = 0, N = 0, K = 0;
+  int lda = 0, ldw = 0, ldo = 0, ldr = 0;
+  int res_mod = 0;    // if > 0 the residual row is (destination row % res_mod)
+  int act = 0;        // 0 none, 1 GELU(erf), 2 ReLU   (applied before the residual add)
+  int out_fp32 = 0;
+  int res_fp32 = 1;
+  int w_is_kn = 0;    // W stored [K, N] (N contiguous): exercises the MN-major UMMA descriptor
+  int force_bn = 0;   // 0 = heuristic; else 32/64/128/256
+  int max_ctas = 0;   // 0 = one CTA per SM
+};
+
+int gemm_bf16(const GemmArgs& a, cudaStream_t stream);
+int gemm_bf16_simt(const GemmArgs& a, cudaStream_t stream);
+
+}  // namespace rsp
