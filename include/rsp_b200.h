@@ -1,0 +1,93 @@
+/* rsp_b200.h -- C ABI of librsp_b200.so: the B200 (sm_100a) kernels behind the RSPrompter
+ * inference hot path (SAM ViT encoder -> prompt-generator heads -> SAM mask decoder).
+ *
+ * The reference (KyanChen/RSPrompter) has no native code and no FFI: every operation below
+ * replaces a PyTorch / cuDNN / cuBLAS / mmcv.ops call made from Python.  Each entry point
+ * cites the reference call site it stands in for (paths relative to the reference tree;
+ * "HF:" = transformers/models/sam/modeling_sam.py, the un-vendored dependency that holds
+ * the encoder / decoder arithmetic, "VS:" = mmpretrain/models/backbones/vit_sam.py,
+ * "M:" = mmdet/rsprompter/models.py).
+ *
+ * Conventions
+ *   - plain C: pointers, ints, floats.  No torch types, no C++ exceptions cross the boundary.
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates); the
+ *     library allocates nothing and keeps no reference after the call returns.
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous, no hidden syncs.
+ *   - return value: 0 = ok, 1 = invalid argument, 2 = CUDA error, 3 = unsupported shape;
+ *     rsp_last_error() returns a thread-local message for the last non-zero return.
+ *   - bf16 = __nv_bfloat16 storage; matrices are row-major with an explicit leading
+ *     dimension counted in elements.
+ */
+#ifndef RSP_B200_H_
+#define RSP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSP_ABI_VERSION 1
+
+int rsp_abi_version(void);
+const char* rsp_last_error(void);
+
+/* Dense contraction with fused epilogue (tcgen05 + TMA):
+ *   out[row_map[m], n] = act(sum_k A[m,k] * W[n,k] + bias[n]) + residual[row_map[m] % res_mod, n]
+ * A bf16 [M,K]; W bf16 [N,K] (nn.Linear layout); out bf16 (out_fp32=0) or fp32.
+ * act: 0 none, 1 GELU(erf), 2 ReLU.  row_map NULL = identity, -1 entries drop the row
+ * (window_unpartition + crop, HF:925-952 / VS:47-75).  residual NULL or fp32/bf16 [*, ldr]
+ * (res_fp32 selects), may alias out.  res_mod > 0 broadcasts the residual over the batch
+ * (absolute position embedding, HF:1065-1066 / VS:576-588).
+ * Replaces: nn.Linear in SamVisionAttention.qkv/.proj (HF:717-718), SamMLPBlock (HF:132-143),
+ * mmcv FFN (VS:282-288), patch-embed / 1x1 / im2col'ed 3x3 convs (HF:116,975-992; M:1009-1057,
+ * 1296-1363; mmdet rpn_head.py:93-97), bbox-head FCs, and the SamAttention projections of the
+ * mask decoder (HF:231-270). */
+int rsp_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N,
+                  int K, const float* bias, const void* residual, int ldr, int res_fp32, int res_mod,
+                  const int32_t* row_map, int act, int out_fp32, void* stream);
+
+/* Same contract on CUDA cores (one thread per output); for contractions far below one
+ * 128-row tile and as the independent check of the tensor-core kernel in tests. */
+int rsp_gemm_bf16_simt(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M,
+                       int N, int K, const float* bias, const void* residual, int ldr, int res_fp32,
+                       int res_mod, const int32_t* row_map, int act, int out_fp32, void* stream);
+
+/* ViT-SAM attention core: out = softmax(hd^-0.5 * q k^T + rel_h + rel_w) v per (sequence, head).
+ * qkv bf16 [n_seq*T, 3*H*hd] (columns [q|k|v], heads contiguous inside each); rel_h / rel_w
+ * bf16 [2S-1, hd]; out bf16 [n_seq*T, H*hd].  T = S*S; S = 14 (windows) or 64 (global),
+ * hd = 64 or 80.  The T x T bias of get_decomposed_rel_pos is never materialised.
+ * Replaces: SamVisionAttention.forward after the qkv Linear and before proj (HF:803-831,
+ * HF:729-801) / Attention.forward + add_decomposed_rel_pos (VS:202-221, VS:117-157). */
+int rsp_vit_attention(const void* qkv, const void* rel_h, const void* rel_w, void* out, int n_seq,
+                      int T, int S, int H, int hd, void* stream);
+int rsp_vit_attention_simt(const void* qkv, const void* rel_h, const void* rel_w, void* out,
+                           int n_seq, int T, int S, int H, int hd, void* stream);
+
+/* LayerNorm over the last dim of [rows, C] (+ optional GELU), fp32 statistics.
+ * src_map (int32 [rows_out], NULL = identity): out row i is LN(in[src_map[i]]), or zeros when
+ * src_map[i] < 0 -- window_partition's zero padding after LN1 (HF:959-962, HF:900-922).
+ * Replaces nn.LayerNorm (HF:894-896), SamLayerNorm channels_first (HF:147-170), mmpretrain
+ * LayerNorm2d (norm.py:64-89) and LN2d (M:33-50) on channels-last data. */
+int rsp_layernorm(const void* in, int in_fp32, int ld_in, void* out, int out_fp32, int ld_out,
+                  const float* gamma, const float* beta, const int32_t* src_map, int rows_out, int C,
+                  float eps, int act, void* stream);
+
+/* fp32 NCHW image [B,3,H,W] -> bf16 [B*(H/16)*(W/16), 768] patch rows, k = c*256 + ky*16 + kx,
+ * so that patch embedding (HF:116,128; mmcv PatchEmbed VS:455) is one rsp_gemm_bf16. */
+int rsp_patchify16(const float* img, void* out, int B, int H, int W, void* stream);
+
+/* bf16 NHWC [B,H,W,C] -> [B*Ho*Wo, KH*KW*C] rows, k = (ky*KW + kx)*C + c, zero padding. */
+int rsp_im2col_nhwc(const void* in, void* out, int B, int H, int W, int C, int KH, int KW,
+                    int stride, int pad, void* stream);
+
+/* [B, HW, C] (bf16 or fp32) -> fp32 [B, C, HW]: hands NCHW tensors back at module boundaries. */
+int rsp_nhwc_to_nchw(const void* in, int in_fp32, float* out, int B, int HW, int C, void* stream);
+
+/* fp32 -> bf16 (n % 4 == 0): feeds fp32 hidden states to the bf16 tensor-core GEMMs. */
+int rsp_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSP_B200_H_ */

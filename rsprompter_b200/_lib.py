@@ -1,0 +1,246 @@
+"""ctypes binding of ``librsp_b200.so`` (C ABI declared in ``include/rsp_b200.h``).
+
+The product path has no CPU or eager-PyTorch fallback: if the shared library is missing the
+import fails loudly, and every wrapper raises ``RspError`` on a non-zero status.  Tensors are
+passed as raw device pointers; PyTorch is only the allocator and stream provider.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from pathlib import Path
+
+import torch
+
+_PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = _PKG_DIR / "librsp_b200.so"
+CSRC_DIR = _PKG_DIR / "csrc"
+
+
+class RspError(RuntimeError):
+    """Raised when an ``rsp_*`` entry point returns a non-zero status."""
+
+
+def build_library(verbose: bool = False) -> Path:
+    """Compile every CUDA source for sm_100a into ``librsp_b200.so`` (in-tree, via make)."""
+    cmd = ["make", "-C", str(CSRC_DIR), "-j", str(os.cpu_count() or 4), "all"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"building librsp_b200.so failed:\n{res.stdout[-4000:]}\n{res.stderr[-4000:]}")
+    if verbose:
+        print(res.stdout[-2000:])
+    return LIB_PATH
+
+
+def _load() -> ctypes.CDLL:
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension is mandatory (no fallback path). "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C rsprompter_b200/csrc`.")
+    return ctypes.CDLL(str(LIB_PATH))
+
+
+_lib = _load()
+
+_vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+
+_SIGNATURES = {
+    "rsp_abi_version": ([], _i),
+    "rsp_last_error": ([], ctypes.c_char_p),
+    "rsp_gemm_bf16": ([_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp], _i),
+    "rsp_gemm_bf16_simt": ([_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp], _i),
+    "rsp_vit_attention": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    "rsp_vit_attention_simt": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    "rsp_layernorm": ([_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _f, _i, _vp], _i),
+    "rsp_patchify16": ([_vp, _vp, _i, _i, _i, _vp], _i),
+    "rsp_im2col_nhwc": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
+    "rsp_nhwc_to_nchw": ([_vp, _i, _vp, _i, _i, _i, _vp], _i),
+    "rsp_cast_f32_bf16": ([_vp, _vp, ctypes.c_longlong, _vp], _i),
+}
+
+
+def declared_symbols() -> list[str]:
+    """Entry points this binding expects (kept in sync with include/rsp_b200.h by a test)."""
+    return sorted(_SIGNATURES)
+
+
+for _name, (_args, _ret) in _SIGNATURES.items():
+    _fn = getattr(_lib, _name)  # AttributeError here = the .so is stale: rebuild
+    _fn.argtypes = _args
+    _fn.restype = _ret
+
+ABI_VERSION = _lib.rsp_abi_version()
+
+# number of kernel launches issued through this binding (bench.py reports it)
+launch_count = 0
+
+
+def _check(status: int, what: str) -> None:
+    if status != 0:
+        msg = _lib.rsp_last_error()
+        raise RspError(f"{what} failed (status {status}): {msg.decode() if msg else ''}")
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*ts: torch.Tensor | None) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RspError("rsprompter_b200 kernels take CUDA tensors only (there is no CPU path)")
+
+
+ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2}
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *,
+         out: torch.Tensor | None = None, out_dtype: torch.dtype = torch.bfloat16,
+         act: str | None = None, residual: torch.Tensor | None = None, res_mod: int = 0,
+         row_map: torch.Tensor | None = None, out_rows: int | None = None,
+         simt: bool = False) -> torch.Tensor:
+    """``out[row_map[m]] = act(a @ w.T + bias) + residual`` (see rsp_gemm_bf16 in the header).
+
+    a: bf16 [M, K] (row stride may exceed K); w: bf16 [N, K]; bias fp32 [N]."""
+    global launch_count
+    _require_cuda(a, w, bias, out, residual, row_map)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16, "gemm operands must be bf16"
+    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N, K2 = w.shape
+    assert K == K2, f"gemm K mismatch {K} vs {K2}"
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
+    if out is None:
+        rows = out_rows if out_rows is not None else M
+        out = torch.empty((rows, N), device=a.device, dtype=out_dtype)
+    assert out.dim() == 2 and out.stride(1) == 1 and out.shape[1] >= N
+    assert out.dtype in (torch.bfloat16, torch.float32)
+    ldr = 0
+    res_fp32 = 1
+    if residual is not None:
+        assert residual.dim() == 2 and residual.stride(1) == 1
+        assert residual.dtype in (torch.bfloat16, torch.float32)
+        ldr = residual.stride(0)
+        res_fp32 = int(residual.dtype == torch.float32)
+    if row_map is not None:
+        assert row_map.dtype == torch.int32 and row_map.numel() == M and row_map.is_contiguous()
+    fn = _lib.rsp_gemm_bf16_simt if simt else _lib.rsp_gemm_bf16
+    st = fn(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K, _ptr(bias),
+            _ptr(residual), ldr, res_fp32, res_mod, _ptr(row_map), ACT[act],
+            int(out.dtype == torch.float32), _stream())
+    _check(st, "rsp_gemm_bf16")
+    launch_count += 1
+    return out
+
+
+def vit_attention(qkv: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor, n_seq: int, S: int,
+                  H: int, hd: int, *, out: torch.Tensor | None = None, simt: bool = False) -> torch.Tensor:
+    """softmax(q k^T / sqrt(hd) + decomposed rel-pos) v for n_seq sequences of S*S tokens."""
+    global launch_count
+    _require_cuda(qkv, rel_h, rel_w, out)
+    T = S * S
+    D = H * hd
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (n_seq * T, 3 * D)
+    assert rel_h.dtype == torch.bfloat16 and rel_h.is_contiguous() and rel_h.shape == (2 * S - 1, hd)
+    assert rel_w.dtype == torch.bfloat16 and rel_w.is_contiguous() and rel_w.shape == (2 * S - 1, hd)
+    if out is None:
+        out = torch.empty((n_seq * T, D), device=qkv.device, dtype=torch.bfloat16)
+    assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.shape == (n_seq * T, D)
+    fn = _lib.rsp_vit_attention_simt if simt else _lib.rsp_vit_attention
+    _check(fn(_ptr(qkv), _ptr(rel_h), _ptr(rel_w), _ptr(out), n_seq, T, S, H, hd, _stream()),
+           "rsp_vit_attention")
+    launch_count += 1
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *,
+              out: torch.Tensor | None = None, out_dtype: torch.dtype = torch.bfloat16,
+              src_map: torch.Tensor | None = None, gelu: bool = False) -> torch.Tensor:
+    """Row LayerNorm of x [rows, C] (fp32 or bf16); optional gather map (-1 -> zero row)."""
+    global launch_count
+    _require_cuda(x, gamma, beta, out, src_map)
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype in (torch.float32, torch.bfloat16)
+    C = x.shape[1]
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    assert gamma.numel() == C and beta.numel() == C and gamma.is_contiguous() and beta.is_contiguous()
+    rows_out = src_map.numel() if src_map is not None else x.shape[0]
+    if src_map is not None:
+        assert src_map.dtype == torch.int32 and src_map.is_contiguous()
+    if out is None:
+        out = torch.empty((rows_out, C), device=x.device, dtype=out_dtype)
+    assert out.shape == (rows_out, C) and out.stride(1) == 1
+    _check(_lib.rsp_layernorm(_ptr(x), int(x.dtype == torch.float32), x.stride(0), _ptr(out),
+                              int(out.dtype == torch.float32), out.stride(0), _ptr(gamma), _ptr(beta),
+                              _ptr(src_map), rows_out, C, float(eps), int(gelu), _stream()),
+           "rsp_layernorm")
+    launch_count += 1
+    return out
+
+
+def patchify16(img: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """fp32 NCHW [B,3,H,W] -> bf16 [B*(H/16)*(W/16), 768] patch rows."""
+    global launch_count
+    _require_cuda(img, out)
+    assert img.dtype == torch.float32 and img.is_contiguous() and img.dim() == 4 and img.shape[1] == 3
+    B, _, H, W = img.shape
+    rows = B * (H // 16) * (W // 16)
+    if out is None:
+        out = torch.empty((rows, 768), device=img.device, dtype=torch.bfloat16)
+    assert out.shape == (rows, 768) and out.is_contiguous() and out.dtype == torch.bfloat16
+    _check(_lib.rsp_patchify16(_ptr(img), _ptr(out), B, H, W, _stream()), "rsp_patchify16")
+    launch_count += 1
+    return out
+
+
+def im2col_nhwc(x: torch.Tensor, kh: int, kw: int, stride: int, pad: int,
+                out: torch.Tensor | None = None) -> torch.Tensor:
+    """bf16 NHWC [B,H,W,C] -> [B*Ho*Wo, kh*kw*C] (tap-major, channel-minor)."""
+    global launch_count
+    _require_cuda(x, out)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
+    B, H, W, C = x.shape
+    Ho = (H + 2 * pad - kh) // stride + 1
+    Wo = (W + 2 * pad - kw) // stride + 1
+    if out is None:
+        out = torch.empty((B * Ho * Wo, kh * kw * C), device=x.device, dtype=torch.bfloat16)
+    assert out.shape == (B * Ho * Wo, kh * kw * C) and out.is_contiguous()
+    _check(_lib.rsp_im2col_nhwc(_ptr(x), _ptr(out), B, H, W, C, kh, kw, stride, pad, _stream()),
+           "rsp_im2col_nhwc")
+    launch_count += 1
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """[B, H, W, C] (bf16 or fp32) -> fp32 [B, C, H, W]."""
+    global launch_count
+    _require_cuda(x, out)
+    assert x.is_contiguous() and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16)
+    B, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32)
+    assert out.shape == (B, C, H, W) and out.is_contiguous() and out.dtype == torch.float32
+    _check(_lib.rsp_nhwc_to_nchw(_ptr(x), int(x.dtype == torch.float32), _ptr(out), B, H * W, C, _stream()),
+           "rsp_nhwc_to_nchw")
+    launch_count += 1
+    return out
+
+
+def cast_bf16(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """fp32 -> bf16 copy (numel % 4 == 0)."""
+    global launch_count
+    _require_cuda(x, out)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    assert out.is_contiguous() and out.numel() == x.numel() and out.dtype == torch.bfloat16
+    _check(_lib.rsp_cast_f32_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "rsp_cast_f32_bf16")
+    launch_count += 1
+    return out

@@ -1,0 +1,89 @@
+// extern "C" surface of librsp_b200.so (declared in include/rsp_b200.h).
+#include "../../include/rsp_b200.h"
+
+#include "attention.h"
+#include "gemm.h"
+#include "rowops.h"
+
+namespace rsp { const char* last_error(); }
+using namespace rsp;
+
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int rsp_abi_version(void) { return RSP_ABI_VERSION; }
+const char* rsp_last_error(void) { return rsp::last_error(); }
+
+static GemmArgs make_gemm_args(const void* A, int lda, const void* W, int ldw, void* out, int ldo,
+                               int M, int N, int K, const float* bias, const void* residual, int ldr,
+                               int res_fp32, int res_mod, const int32_t* row_map, int act,
+                               int out_fp32) {
+  GemmArgs a;
+  a.A = A; a.lda = lda; a.W = W; a.ldw = ldw; a.out = out; a.ldo = ldo;
+  a.M = M; a.N = N; a.K = K; a.bias = bias; a.residual = residual; a.ldr = ldr;
+  a.res_fp32 = res_fp32; a.res_mod = res_mod; a.row_map = row_map; a.act = act;
+  a.out_fp32 = out_fp32;
+  return a;
+}
+
+int rsp_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N,
+                  int K, const float* bias, const void* residual, int ldr, int res_fp32, int res_mod,
+                  const int32_t* row_map, int act, int out_fp32, void* stream) {
+  return gemm_bf16(make_gemm_args(A, lda, W, ldw, out, ldo, M, N, K, bias, residual, ldr, res_fp32,
+                                  res_mod, row_map, act, out_fp32), S(stream));
+}
+
+int rsp_gemm_bf16_simt(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M,
+                       int N, int K, const float* bias, const void* residual, int ldr, int res_fp32,
+                       int res_mod, const int32_t* row_map, int act, int out_fp32, void* stream) {
+  return gemm_bf16_simt(make_gemm_args(A, lda, W, ldw, out, ldo, M, N, K, bias, residual, ldr,
+                                       res_fp32, res_mod, row_map, act, out_fp32), S(stream));
+}
+
+static AttentionArgs make_att_args(const void* qkv, const void* rel_h, const void* rel_w, void* out,
+                                   int n_seq, int T, int Sg, int H, int hd) {
+  AttentionArgs a;
+  a.qkv = qkv; a.rel_h = rel_h; a.rel_w = rel_w; a.out = out;
+  a.n_seq = n_seq; a.T = T; a.S = Sg; a.H = H; a.hd = hd;
+  return a;
+}
+
+int rsp_vit_attention(const void* qkv, const void* rel_h, const void* rel_w, void* out, int n_seq,
+                      int T, int Sg, int H, int hd, void* stream) {
+  return vit_attention(make_att_args(qkv, rel_h, rel_w, out, n_seq, T, Sg, H, hd), S(stream));
+}
+
+int rsp_vit_attention_simt(const void* qkv, const void* rel_h, const void* rel_w, void* out,
+                           int n_seq, int T, int Sg, int H, int hd, void* stream) {
+  return vit_attention_simt(make_att_args(qkv, rel_h, rel_w, out, n_seq, T, Sg, H, hd), S(stream));
+}
+
+int rsp_layernorm(const void* in, int in_fp32, int ld_in, void* out, int out_fp32, int ld_out,
+                  const float* gamma, const float* beta, const int32_t* src_map, int rows_out, int C,
+                  float eps, int act, void* stream) {
+  LayerNormArgs a;
+  a.in = in; a.in_fp32 = in_fp32; a.ld_in = ld_in; a.out = out; a.out_fp32 = out_fp32;
+  a.ld_out = ld_out; a.gamma = gamma; a.beta = beta; a.src_map = src_map; a.rows_out = rows_out;
+  a.C = C; a.eps = eps; a.act = act;
+  return layernorm_rows(a, S(stream));
+}
+
+int rsp_patchify16(const float* img, void* out, int B, int H, int W, void* stream) {
+  return patchify16(img, out, B, H, W, S(stream));
+}
+
+int rsp_im2col_nhwc(const void* in, void* out, int B, int H, int W, int C, int KH, int KW,
+                    int stride, int pad, void* stream) {
+  return im2col_nhwc(in, out, B, H, W, C, KH, KW, stride, pad, S(stream));
+}
+
+int rsp_nhwc_to_nchw(const void* in, int in_fp32, float* out, int B, int HW, int C, void* stream) {
+  return nhwc_to_nchw(in, in_fp32, out, B, HW, C, S(stream));
+}
+
+int rsp_cast_f32_bf16(const float* in, void* out, long long n, void* stream) {
+  return cast_f32_bf16(in, out, n, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,489 @@
+// ViT-SAM attention core for sm_100a: softmax(scale * q k^T + rel_h + rel_w) v per
+// (sequence, head), sequences being 14x14 windows (T = 196) or whole 64x64 images
+// (T = 4096).  Reference: transformers modeling_sam.py SamVisionAttention.forward
+// (:803-831), get_rel_pos / get_decomposed_rel_pos (:729-801); mmpretrain vit_sam.py
+// Attention.forward (:202-221), add_decomposed_rel_pos (:117-157).
+//
+// One CTA = 128 query rows of one (sequence, head); 192 threads:
+//   warps 0-3  softmax: thread r owns query row r (no cross-thread reductions); reads S
+//              from TMEM twice (max pass, exp pass), fp32 statistics, writes P (bf16) into
+//              128B-swizzled smem, rescales O in TMEM only when the running max grows by
+//              more than 2^8
+//   warp 4     TMA producer (Q once; K_j / V_j tiles; the two rel-pos tables) + TMEM alloc
+//   warp 5     tcgen05.mma issuer: S_j = Q K_j^T (128x128x hd), O += P_j V_j (128 x hd x128),
+//              V consumed straight from the qkv matrix as an MN-major operand
+// The decomposed relative-position bias is never materialised as a T x T tensor: a
+// prologue MMA computes Q (unscaled) x table^T for both tables (the reference's two
+// einsums), each thread gathers the <= 2S values its row needs, and the bias is added
+// inside the softmax FMA.  Scores stay fp32 until the exp (reference: softmax in fp32).
+#include "attention.h"
+#include "sm100.cuh"
+
+namespace rsp {
+
+constexpr int ATT_THREADS = 192;
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int HD>
+struct AttCfg {
+  static constexpr int NA = (HD + 63) / 64;           // 64-wide swizzle atoms per head
+  static constexpr int TILE_BYTES = NA * 16384;       // 128 rows x NA x 128 B
+  static constexpr int P_BYTES = 32768;               // 128 x 128 bf16
+  static constexpr int RELH_BYTES = 64 * 128 * 2;     // global: [kh][row] fp16
+  static constexpr int SMEM_BYTES = 3 * TILE_BYTES + P_BYTES + RELH_BYTES + 1024;
+  static constexpr int TMEM_COLS = 256;               // S: [0,128)  O: [128, 128 + HD)
+};
+
+struct AttDev {
+  __nv_bfloat16* out;  // [M_tok, D]
+  int T;               // tokens per sequence
+  int S;               // sqrt(T)
+  int H;
+  int D;
+  int n_qt;            // q tiles per sequence
+  int n_kt;            // key tiles per sequence
+  float scale2;        // hd^-0.5 * log2(e)
+};
+
+// bar indices
+enum { B_Q = 0, B_REL, B_RELC, B_KF, B_KE, B_VF, B_VE, B_SF, B_PF, B_PV, B_COUNT };
+
+template <int HD, bool GLOBAL>
+__global__ void __launch_bounds__(ATT_THREADS, (HD <= 64) ? 2 : 1)
+vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
+                     const __grid_constant__ CUtensorMap tm_relh,
+                     const __grid_constant__ CUtensorMap tm_relw, const AttDev p) {
+  using Cfg = AttCfg<HD>;
+  constexpr int NA = Cfg::NA;
+  constexpr int NREL = GLOBAL ? 128 : 32;  // padded table rows (2S-1 = 127 / 27)
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[B_COUNT];
+  __shared__ uint32_t tmem_base_s;
+
+  const uint32_t sQ = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = sQ + Cfg::TILE_BYTES;
+  const uint32_t sV = sK + Cfg::TILE_BYTES;
+  const uint32_t sP = sV + Cfg::TILE_BYTES;
+  const uint32_t sRH = sP + Cfg::P_BYTES;
+  uint8_t* gP = smem_raw + (sP - smem_u32(smem_raw));
+  uint8_t* gRH = smem_raw + (sRH - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  int bid = blockIdx.x;
+  const int qt = bid % p.n_qt; bid /= p.n_qt;
+  const int head = bid % p.H;
+  const int seq = bid / p.H;
+  const int row0 = seq * p.T;            // first token row of this sequence in qkv
+  const int q0 = qt * 128;               // first query of this tile inside the sequence
+  const int colq = head * HD;
+  const int colk = p.D + head * HD;
+  const int colv = 2 * p.D + head * HD;
+
+  auto bar = [&](int i) { return smem_u32(&bars[i]); };
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_relh);
+    tma_prefetch_desc(&tm_relw);
+    for (int i = 0; i < B_COUNT; ++i) mbar_init(bar(i), (i == B_RELC || i == B_PF) ? 128 : 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tS = tmem_base;
+  const uint32_t tO = tmem_base + 128;
+
+  if (warp == 4 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    mbar_expect_tx(bar(B_Q), Cfg::TILE_BYTES + 2 * NA * NREL * 128);
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      tma_load_2d(sQ + a * 16384, &tm_qkv, bar(B_Q), colq + a * 64, row0 + q0);
+      tma_load_2d(sK + a * 16384, &tm_relh, bar(B_Q), a * 64, 0);
+      tma_load_2d(sV + a * 16384, &tm_relw, bar(B_Q), a * 64, 0);
+    }
+    for (int j = 0; j < p.n_kt; ++j) {
+      const uint32_t par = j & 1;
+      mbar_wait(bar(B_KE), par);
+      mbar_expect_tx(bar(B_KF), Cfg::TILE_BYTES);
+#pragma unroll
+      for (int a = 0; a < NA; ++a)
+        tma_load_2d(sK + a * 16384, &tm_qkv, bar(B_KF), colk + a * 64, row0 + j * 128);
+      mbar_wait(bar(B_VE), par);
+      mbar_expect_tx(bar(B_VF), Cfg::TILE_BYTES);
+#pragma unroll
+      for (int a = 0; a < NA; ++a)
+        tma_load_2d(sV + a * 16384, &tm_qkv, bar(B_VF), colv + a * 64, row0 + j * 128);
+    }
+  } else if (warp == 5 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_rel = make_idesc_bf16(128, NREL, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, 0, 1);
+    mbar_wait(bar(B_Q), 0);
+    tc_fence_after();
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+      const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
+      umma_ss(tS, make_sdesc(sQ + off, 0, 1024), make_sdesc(sK + off, 0, 1024), idesc_rel, ks != 0);
+    }
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+      const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
+      umma_ss(tO, make_sdesc(sQ + off, 0, 1024), make_sdesc(sV + off, 0, 1024), idesc_rel, ks != 0);
+    }
+    umma_commit(bar(B_REL));
+    umma_commit(bar(B_KE));
+    umma_commit(bar(B_VE));
+    mbar_wait(bar(B_RELC), 0);
+    tc_fence_after();
+    for (int j = 0; j < p.n_kt; ++j) {
+      const uint32_t par = j & 1;
+      mbar_wait(bar(B_KF), par);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks) {
+        const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
+        umma_ss(tS, make_sdesc(sQ + off, 0, 1024), make_sdesc(sK + off, 0, 1024), idesc_s, ks != 0);
+      }
+      umma_commit(bar(B_SF));
+      umma_commit(bar(B_KE));
+      mbar_wait(bar(B_PF), par);
+      mbar_wait(bar(B_VF), par);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t adesc = make_sdesc(sP + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024);
+        const uint64_t bdesc = make_sdesc(sV + ks * 2048, 16384, 1024);
+        umma_ss(tO, adesc, bdesc, idesc_pv, (j | ks) != 0);
+      }
+      umma_commit(bar(B_PV));
+      umma_commit(bar(B_VE));
+    }
+  } else if (warp < 4) {
+    // ------------------------------------------------------------ softmax / correction / output
+    const int r = warp * 32 + lane;          // query row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const int tq = q0 + r;                    // query index inside the sequence
+    const int qh = tq / p.S;
+    const int qw = tq - qh * p.S;
+    constexpr int NW = GLOBAL ? 64 : 14;      // rel_w values kept in registers
+    constexpr int NH = GLOBAL ? 1 : 14;       // rel_h in registers (window) or smem (global)
+    float relw[NW];
+    float relh[NH];
+    (void)relh;
+
+    // ---- prologue: gather this row's rel-pos terms (pre-multiplied by log2 e)
+    mbar_wait(bar(B_REL), 0);
+    tc_fence_after();
+    float* scratch = reinterpret_cast<float*>(gP);  // aliases the P buffer (unused yet)
+    __half* relh_s = reinterpret_cast<__half*>(gRH);
+    if (GLOBAL) {
+      // table index t <-> key coordinate k: t = q - k + 63
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tS + lane_off + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int kh = qh + 63 - (c * 32 + i);
+          if (kh >= 0 && kh < 64) relh_s[kh * 128 + r] = __float2half_rn(__uint_as_float(v[i]) * LOG2E);
+        }
+      }
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tO + lane_off + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int kw = qw + 63 - (c * 32 + i);
+          if (kw >= 0 && kw < 64) scratch[kw * 128 + r] = __uint_as_float(v[i]) * LOG2E;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NW; ++i) relw[i] = scratch[i * 128 + r];
+    } else {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tS + lane_off, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 27; ++i) {
+        const int kh = qh + 13 - i;
+        if (kh >= 0 && kh < 14) scratch[kh * 128 + r] = __uint_as_float(v[i]) * LOG2E;
+      }
+      tmem_ld_32x32b_x32(tO + lane_off, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 27; ++i) {
+        const int kw = qw + 13 - i;
+        if (kw >= 0 && kw < 14) scratch[(14 + kw) * 128 + r] = __uint_as_float(v[i]) * LOG2E;
+      }
+      if (qh < 14) {
+#pragma unroll
+        for (int i = 0; i < 14; ++i) { relh[i] = scratch[i * 128 + r]; relw[i] = scratch[(14 + i) * 128 + r]; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 14; ++i) { relh[i] = 0.f; relw[i] = 0.f; }
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(bar(B_RELC));
+
+    float m_run = -INFINITY, l_run = 0.f;
+    const float scale2 = p.scale2;
+    const int T = GLOBAL ? p.T : 196;          // window: compile-time so key -> (kh, kw) folds
+    const int n_kt = GLOBAL ? p.n_kt : 2;
+    const uint32_t p_row = sP + r * 128;
+    const int sw = r & 7;
+
+#pragma unroll(GLOBAL ? 1 : 2)
+    for (int j = 0; j < n_kt; ++j) {
+      const uint32_t par = j & 1;
+      mbar_wait(bar(B_SF), par);
+      tc_fence_after();
+      float rh0 = 0.f, rh1 = 0.f;
+      if (GLOBAL) {
+        rh0 = __half2float(relh_s[(2 * j) * 128 + r]);
+        rh1 = __half2float(relh_s[(2 * j + 1) * 128 + r]);
+      }
+      const int key0 = j * 128;
+      // ---- pass 1: row max of the biased, log2-scaled scores
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (!GLOBAL && key0 + c * 32 >= T) break;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tS + lane_off + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float t;
+          if (GLOBAL) {
+            t = fmaf(__uint_as_float(v[i]), scale2, (c < 2 ? rh0 : rh1)) + relw[(c & 1) * 32 + i];
+          } else {
+            const int key = key0 + c * 32 + i;   // j in {0,1}: resolved after unrolling below
+            const int kh = key / 14, kw = key - kh * 14;
+            t = (key < T) ? fmaf(__uint_as_float(v[i]), scale2, relh[kh < 14 ? kh : 0]) + relw[kw]
+                            : -INFINITY;
+          }
+          mx = fmaxf(mx, t);
+        }
+      }
+      // ---- running max with lazy rescale (only when it grows by more than 2^8)
+      float m_new = m_run;
+      bool need = false;
+      if (j == 0) m_new = mx;
+      else if (mx > m_run + 8.0f) { need = true; m_new = mx; }
+      if (j > 0) {
+        mbar_wait(bar(B_PV), (j - 1) & 1);   // O and the P buffer are free again
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? fast_exp2(m_run - m_new) : 1.0f;
+          l_run *= alpha;
+#pragma unroll
+          for (int c = 0; c < HD / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(tO + lane_off + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x16(tO + lane_off + c * 16, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      m_run = m_new;
+      // ---- pass 2: P = exp2(t - m), row sum, bf16 P into swizzled smem
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+        if (!GLOBAL && key0 + c * 32 >= T) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+        } else {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tS + lane_off + c * 32, v);
+          tmem_ld_wait();
+          float e[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float t;
+            if (GLOBAL) {
+              t = fmaf(__uint_as_float(v[i]), scale2, (c < 2 ? rh0 : rh1)) + relw[(c & 1) * 32 + i];
+            } else {
+              const int key = key0 + c * 32 + i;
+              const int kh = key / 14, kw = key - kh * 14;
+              t = (key < T) ? fmaf(__uint_as_float(v[i]), scale2, relh[kh < 14 ? kh : 0]) + relw[kw]
+                              : -INFINITY;
+            }
+            e[i] = fast_exp2(t - m_run);
+            l_run += e[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+        }
+        // 32 keys = 64 B = 16-byte chunks (c&1)*4 .. +3 of atom (c>>1)
+        const uint32_t base = p_row + (c >> 1) * 16384;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t chunk = static_cast<uint32_t>(((c & 1) * 4 + q) ^ sw);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + chunk * 16),
+                       "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                       : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar(B_PF));
+    }
+
+    // ---- epilogue: O / l -> out[token, head*HD .. ]
+    mbar_wait(bar(B_PV), (n_kt - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.0f / l_run;
+    __nv_bfloat16* orow = p.out + static_cast<size_t>(row0 + tq) * p.D + colq;
+#pragma unroll
+    for (int c = 0; c < HD / 16; ++c) {
+      uint32_t o[16];
+      tmem_ld_32x32b_x16(tO + lane_off + c * 16, o);
+      tmem_ld_wait();
+      if (tq < T) {
+        uint4 w0 = make_uint4(pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv),
+                              pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv),
+                              pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv),
+                              pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv));
+        uint4 w1 = make_uint4(pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv),
+                              pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv),
+                              pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv),
+                              pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv));
+        reinterpret_cast<uint4*>(orow + c * 16)[0] = w0;
+        reinterpret_cast<uint4*>(orow + c * 16)[1] = w1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int HD, bool GLOBAL>
+static int launch_att(const AttentionArgs& a, cudaStream_t stream) {
+  using Cfg = AttCfg<HD>;
+  constexpr int NREL = GLOBAL ? 128 : 32;
+  const int D = a.H * HD;
+  const long long m_tok = static_cast<long long>(a.n_seq) * a.T;
+  CUtensorMap tq, th, tw;
+  RSP_TRY(make_tmap_bf16_2d(&tq, a.qkv, m_tok, 3 * D, static_cast<uint64_t>(3 * D) * 2, 128, 64));
+  RSP_TRY(make_tmap_bf16_2d(&th, a.rel_h, 2 * a.S - 1, HD, static_cast<uint64_t>(HD) * 2, NREL, 64));
+  RSP_TRY(make_tmap_bf16_2d(&tw, a.rel_w, 2 * a.S - 1, HD, static_cast<uint64_t>(HD) * 2, NREL, 64));
+  AttDev p;
+  p.out = static_cast<__nv_bfloat16*>(a.out);
+  p.T = a.T; p.S = a.S; p.H = a.H; p.D = D;
+  p.n_qt = (a.T + 127) / 128;
+  p.n_kt = (a.T + 127) / 128;
+  p.scale2 = (1.0f / sqrtf(static_cast<float>(HD))) * LOG2E;
+  auto kern = vit_attention_kernel<HD, GLOBAL>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RSP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const long long grid = static_cast<long long>(a.n_seq) * a.H * p.n_qt;
+  RSP_CHECK_ARG(grid > 0 && grid < (1ll << 31), "attention: grid %lld", grid);
+  kern<<<static_cast<unsigned>(grid), ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tq, th, tw, p);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
+int vit_attention(const AttentionArgs& a, cudaStream_t stream) {
+  RSP_CHECK_ARG(a.qkv && a.rel_h && a.rel_w && a.out, "attention: null pointer");
+  RSP_CHECK_ARG(a.T == a.S * a.S, "attention: T=%d is not S^2 (S=%d)", a.T, a.S);
+  RSP_CHECK_ARG(a.n_seq > 0 && a.H > 0, "attention: bad n_seq/H");
+  const bool global = (a.S == 64);
+  RSP_CHECK_ARG(global || a.S == 14, "attention: S=%d unsupported (14 = window, 64 = global)", a.S);
+  if (a.hd == 64) return global ? launch_att<64, true>(a, stream) : launch_att<64, false>(a, stream);
+  if (a.hd == 80) return global ? launch_att<80, true>(a, stream) : launch_att<80, false>(a, stream);
+  set_last_error("attention: head dim %d unsupported (64, 80)", a.hd);
+  return RSP_ERR_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------
+// SIMT restatement (one thread per query row, fp32 throughout): the device-side check of
+// the tcgen05 kernel in the native self-test, and the path for grid sizes the tensor-core
+// kernel does not specialise (S other than 14 / 64).
+__global__ void vit_attention_simt_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                          const __nv_bfloat16* __restrict__ rel_h,
+                                          const __nv_bfloat16* __restrict__ rel_w,
+                                          __nv_bfloat16* __restrict__ out, int T, int S, int H,
+                                          int hd, float scale) {
+  const int D = H * hd;
+  const int tq = blockIdx.x * blockDim.x + threadIdx.x;
+  const int head = blockIdx.y;
+  const int seq = blockIdx.z;
+  if (tq >= T) return;
+  const int qh = tq / S, qw = tq % S;
+  const __nv_bfloat16* qp = qkv + (static_cast<size_t>(seq) * T + tq) * 3 * D + head * hd;
+  float q[128];
+  for (int d = 0; d < hd; ++d) q[d] = __bfloat162float(qp[d]);
+  float rh[128], rw[128];  // S <= 128
+  for (int k = 0; k < S; ++k) {
+    float ah = 0.f, aw = 0.f;
+    const __nv_bfloat16* th = rel_h + static_cast<size_t>(qh - k + S - 1) * hd;
+    const __nv_bfloat16* tw = rel_w + static_cast<size_t>(qw - k + S - 1) * hd;
+    for (int d = 0; d < hd; ++d) {
+      ah += q[d] * __bfloat162float(th[d]);
+      aw += q[d] * __bfloat162float(tw[d]);
+    }
+    rh[k] = ah; rw[k] = aw;
+  }
+  float m = -INFINITY, l = 0.f;
+  float o[128];
+  for (int d = 0; d < hd; ++d) o[d] = 0.f;
+  for (int k = 0; k < T; ++k) {
+    const __nv_bfloat16* kp = qkv + (static_cast<size_t>(seq) * T + k) * 3 * D + D + head * hd;
+    const __nv_bfloat16* vp = kp + D;
+    float s = 0.f;
+    for (int d = 0; d < hd; ++d) s += q[d] * __bfloat162float(kp[d]);
+    s = s * scale + rh[k / S] + rw[k % S];
+    const float mn = fmaxf(m, s);
+    const float a = expf(m - mn), pe = expf(s - mn);
+    l = l * a + pe;
+    for (int d = 0; d < hd; ++d) o[d] = o[d] * a + pe * __bfloat162float(vp[d]);
+    m = mn;
+  }
+  __nv_bfloat16* op = out + (static_cast<size_t>(seq) * T + tq) * D + head * hd;
+  for (int d = 0; d < hd; ++d) op[d] = __float2bfloat16_rn(o[d] / l);
+}
+
+int vit_attention_simt(const AttentionArgs& a, cudaStream_t stream) {
+  RSP_CHECK_ARG(a.qkv && a.rel_h && a.rel_w && a.out, "attention_simt: null pointer");
+  RSP_CHECK_ARG(a.T == a.S * a.S && a.S <= 128 && a.hd <= 128, "attention_simt: bad T/S/hd");
+  dim3 block(64);
+  dim3 grid((a.T + 63) / 64, a.H, a.n_seq);
+  vit_attention_simt_kernel<<<grid, block, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(a.qkv), static_cast<const __nv_bfloat16*>(a.rel_h),
+      static_cast<const __nv_bfloat16*>(a.rel_w), static_cast<__nv_bfloat16*>(a.out), a.T, a.S, a.H,
+      a.hd, 1.0f / sqrtf(static_cast<float>(a.hd)));
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
+}  // namespace rsp
