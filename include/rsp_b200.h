@@ -84,6 +84,43 @@ int rsp_im2col_nhwc(const void* in, void* out, int B, int H, int W, int C, int K
 /* [B, HW, C] (bf16 or fp32) -> fp32 [B, C, HW]: hands NCHW tensors back at module boundaries. */
 int rsp_nhwc_to_nchw(const void* in, int in_fp32, float* out, int B, int HW, int C, void* stream);
 
+/* rsp_gemm_bf16 with the fused epilogues of the SAM mask decoder (HF:461-543):
+ *   epi_mode 0  standard (as rsp_gemm_bf16)
+ *   epi_mode 1  out = LayerNorm_N(acc + bias + residual) * ln_gamma + ln_beta, N % 32 == 0, N <= 256:
+ *               layer_norm1-4 / layer_norm_final_attn fused into the preceding out_proj / lin2
+ *               (HF:316-347, 398-404)
+ *   epi_mode 2  columns = (tap, 64 ch): out = GELU(LN_64(acc + bias)): upscale_conv1 as a GEMM over the
+ *               2x2 taps + upscale_layer_norm + GELU (HF:519-520); output rows are then (pixel, tap)
+ *   epi_mode 3  rows = (prompt, y, x, tap1), columns = (tap2, 32 ch): mask_out[prompt, 4y+.., 4x+..] =
+ *               sum_c GELU(acc + bias)[tap2, c] * hyper[prompt, c]: upscale_conv2 + GELU + the
+ *               hypernetwork product (HF:521-531); `out` is unused
+ * res_block_map (int32 [M / res_block_rows]) redirects the residual of row r to row
+ * map[r / res_block_rows] * res_block_rows + r % res_block_rows: prompts of one image share its
+ * embedding without the repeat_interleave copies of M:367-368 / M:1682-1683. */
+int rsp_gemm_bf16_ex(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N,
+                     int K, const float* bias, const void* residual, int ldr, int res_fp32, int res_mod,
+                     const int32_t* row_map, int act, int out_fp32, int epi_mode, const float* ln_gamma,
+                     const float* ln_beta, float ln_eps, const int32_t* res_block_map,
+                     int res_block_rows, const float* hyper, float* mask_out, int grid_h, int grid_w,
+                     void* stream);
+
+/* out = bf16(a + b[i % b_mod]) over n fp32 elements (b NULL = plain cast; n, b_mod % 4 == 0):
+ * "queries + query_point_embedding" before a projection (HF:318,325,338). */
+int rsp_add_cast_bf16(const float* a, const float* b, void* out, long long n, long long b_mod,
+                      void* stream);
+
+/* SamAttention core (HF:253-267) for the three shapes the two-way transformer uses; q/k/v are the
+ * already-projected bf16 matrices, softmax in fp32, scale = c^-0.5.
+ *   token self-attention: q,k,v [N, T, heads*c], T <= 16, c = 32 (or 16)
+ *   t2i: q [N, Tq, 128] (8 heads x 16) attends to K,V [*, 128] rows kv_block[n]*HW .. +HW (NULL: n)
+ *   i2t: Q [*, 128] rows q_block[n]*HW .. +HW attend to ktok,vtok [N, Tq, 128]; out [N*HW, 128] */
+int rsp_token_self_attention(const void* q, const void* k, const void* v, void* out, int N, int T,
+                             int heads, int c, void* stream);
+int rsp_t2i_attention(const void* q, const void* K, const void* V, const int32_t* kv_block, void* out,
+                      int N, int Tq, int HW, void* stream);
+int rsp_i2t_attention(const void* Q, const int32_t* q_block, const void* ktok, const void* vtok,
+                      void* out, int N, int Tq, int HW, void* stream);
+
 /* fp32 -> bf16 (n % 4 == 0): feeds fp32 hidden states to the bf16 tensor-core GEMMs. */
 int rsp_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
 

@@ -57,6 +57,12 @@ _SIGNATURES = {
     "rsp_im2col_nhwc": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
     "rsp_nhwc_to_nchw": ([_vp, _i, _vp, _i, _i, _i, _vp], _i),
     "rsp_cast_f32_bf16": ([_vp, _vp, ctypes.c_longlong, _vp], _i),
+    "rsp_gemm_bf16_ex": ([_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i,
+                          _i, _vp, _vp, _f, _vp, _i, _vp, _vp, _i, _i, _vp], _i),
+    "rsp_add_cast_bf16": ([_vp, _vp, _vp, ctypes.c_longlong, ctypes.c_longlong, _vp], _i),
+    "rsp_token_self_attention": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
+    "rsp_t2i_attention": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
+    "rsp_i2t_attention": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
 }
 
 
@@ -105,12 +111,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *,
          out: torch.Tensor | None = None, out_dtype: torch.dtype = torch.bfloat16,
          act: str | None = None, residual: torch.Tensor | None = None, res_mod: int = 0,
          row_map: torch.Tensor | None = None, out_rows: int | None = None,
-         simt: bool = False) -> torch.Tensor:
-    """``out[row_map[m]] = act(a @ w.T + bias) + residual`` (see rsp_gemm_bf16 in the header).
+         simt: bool = False, ln: tuple | None = None, ln64_gelu: tuple | None = None,
+         res_block_map: torch.Tensor | None = None, res_block_rows: int = 0) -> torch.Tensor:
+    """``out[row_map[m]] = act(a @ w.T + bias) + residual`` (see rsp_gemm_bf16 / _ex in the header).
 
-    a: bf16 [M, K] (row stride may exceed K); w: bf16 [N, K]; bias fp32 [N]."""
+    a: bf16 [M, K] (row stride may exceed K); w: bf16 [N, K]; bias fp32 [N].
+    ln=(gamma, beta, eps): LayerNorm over the whole output row after bias + residual (N <= 256).
+    ln64_gelu=(gamma, beta, eps): LayerNorm over each 64-column group, then GELU (bf16 out)."""
     global launch_count
-    _require_cuda(a, w, bias, out, residual, row_map)
+    _require_cuda(a, w, bias, out, residual, row_map, res_block_map)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16, "gemm operands must be bf16"
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
     M, K = a.shape
@@ -132,11 +141,122 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *,
         res_fp32 = int(residual.dtype == torch.float32)
     if row_map is not None:
         assert row_map.dtype == torch.int32 and row_map.numel() == M and row_map.is_contiguous()
-    fn = _lib.rsp_gemm_bf16_simt if simt else _lib.rsp_gemm_bf16
-    st = fn(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K, _ptr(bias),
-            _ptr(residual), ldr, res_fp32, res_mod, _ptr(row_map), ACT[act],
-            int(out.dtype == torch.float32), _stream())
+    if res_block_map is not None:
+        assert res_block_map.dtype == torch.int32 and res_block_map.is_contiguous() and res_block_rows > 0
+    epi, g, b, eps = 0, None, None, 1e-6
+    if ln is not None:
+        epi, (g, b, eps) = 1, ln
+    elif ln64_gelu is not None:
+        epi, (g, b, eps) = 2, ln64_gelu
+    if epi or res_block_map is not None:
+        assert not simt
+        if g is not None:
+            assert g.dtype == torch.float32 and b.dtype == torch.float32 and g.is_contiguous() and b.is_contiguous()
+        st = _lib.rsp_gemm_bf16_ex(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0),
+                                   M, N, K, _ptr(bias), _ptr(residual), ldr, res_fp32, res_mod,
+                                   _ptr(row_map), ACT[act], int(out.dtype == torch.float32), epi,
+                                   _ptr(g), _ptr(b), float(eps), _ptr(res_block_map), res_block_rows,
+                                   None, None, 0, 0, _stream())
+    else:
+        fn = _lib.rsp_gemm_bf16_simt if simt else _lib.rsp_gemm_bf16
+        st = fn(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K, _ptr(bias),
+                _ptr(residual), ldr, res_fp32, res_mod, _ptr(row_map), ACT[act],
+                int(out.dtype == torch.float32), _stream())
     _check(st, "rsp_gemm_bf16")
+    launch_count += 1
+    return out
+
+
+def gemm_upscale_mask(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, hyper: torch.Tensor,
+                      grid_h: int, grid_w: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Second mask upscale + GELU + hypernetwork product in one GEMM (epi_mode 3).
+
+    a: bf16 [P*4*h*w, 64] rows (prompt, y, x, tap1); w: bf16 [128, 64] rows (tap2, 32 ch);
+    hyper fp32 [P, 32] -> fp32 masks [P, 4h, 4w]."""
+    global launch_count
+    _require_cuda(a, w, bias, hyper, out)
+    M, K = a.shape
+    P = M // (4 * grid_h * grid_w)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape == (128, K)
+    assert hyper.dtype == torch.float32 and hyper.shape == (P, 32) and hyper.is_contiguous()
+    assert bias.dtype == torch.float32 and bias.numel() == 128
+    if out is None:
+        out = torch.empty((P, 4 * grid_h, 4 * grid_w), device=a.device, dtype=torch.float32)
+    assert out.is_contiguous() and out.dtype == torch.float32
+    st = _lib.rsp_gemm_bf16_ex(_ptr(a), a.stride(0), _ptr(w), w.stride(0), None, 0, M, 128, K, _ptr(bias),
+                               None, 0, 1, 0, None, 0, 0, 3, None, None, 0.0, None, 0, _ptr(hyper),
+                               _ptr(out), grid_h, grid_w, _stream())
+    _check(st, "rsp_gemm_bf16_ex(upscale_mask)")
+    launch_count += 1
+    return out
+
+
+def add_cast_bf16(a: torch.Tensor, b: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """bf16(a + b) for fp32 a; b is broadcast over leading dims when smaller (numel divides)."""
+    global launch_count
+    _require_cuda(a, b, out)
+    assert a.dtype == torch.float32 and a.is_contiguous()
+    b_mod = 0
+    if b is not None:
+        assert b.dtype == torch.float32 and b.is_contiguous() and a.numel() % b.numel() == 0
+        b_mod = b.numel() if b.numel() != a.numel() else 0
+    if out is None:
+        out = torch.empty(a.shape, device=a.device, dtype=torch.bfloat16)
+    _check(_lib.rsp_add_cast_bf16(_ptr(a), _ptr(b), _ptr(out), a.numel(), b_mod, _stream()), "rsp_add_cast_bf16")
+    launch_count += 1
+    return out
+
+
+def token_self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
+    """q, k, v bf16 [N, T, heads*c] -> bf16 [N, T, heads*c]."""
+    global launch_count
+    _require_cuda(q, k, v)
+    N, T, D = q.shape
+    for t in (q, k, v):
+        assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape == (N, T, D)
+    out = torch.empty_like(q)
+    _check(_lib.rsp_token_self_attention(_ptr(q), _ptr(k), _ptr(v), _ptr(out), N, T, heads, D // heads, _stream()),
+           "rsp_token_self_attention")
+    launch_count += 1
+    return out
+
+
+def t2i_attention(q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, hw: int,
+                  kv_block: torch.Tensor | None = None) -> torch.Tensor:
+    """q bf16 [N, Tq, 128]; K, V bf16 [blocks*hw, 128]; kv_block int32 [N] -> bf16 [N, Tq, 128]."""
+    global launch_count
+    _require_cuda(q, K, V, kv_block)
+    N, Tq, C = q.shape
+    assert C == 128 and q.dtype == torch.bfloat16 and q.is_contiguous()
+    assert K.dtype == torch.bfloat16 and V.dtype == torch.bfloat16 and K.is_contiguous() and V.is_contiguous()
+    assert K.shape[1] == 128 and V.shape == K.shape and K.shape[0] % hw == 0
+    if kv_block is not None:
+        assert kv_block.dtype == torch.int32 and kv_block.numel() == N and kv_block.is_contiguous()
+    else:
+        assert K.shape[0] == N * hw
+    out = torch.empty_like(q)
+    _check(_lib.rsp_t2i_attention(_ptr(q), _ptr(K), _ptr(V), _ptr(kv_block), _ptr(out), N, Tq, hw, _stream()),
+           "rsp_t2i_attention")
+    launch_count += 1
+    return out
+
+
+def i2t_attention(Q: torch.Tensor, ktok: torch.Tensor, vtok: torch.Tensor, hw: int,
+                  q_block: torch.Tensor | None = None) -> torch.Tensor:
+    """Q bf16 [blocks*hw, 128]; ktok, vtok bf16 [N, Tq, 128] -> bf16 [N*hw, 128]."""
+    global launch_count
+    _require_cuda(Q, ktok, vtok, q_block)
+    N, Tq, C = ktok.shape
+    assert C == 128 and Q.dtype == torch.bfloat16 and Q.is_contiguous() and Q.shape[1] == 128
+    assert ktok.dtype == torch.bfloat16 and vtok.dtype == torch.bfloat16
+    assert ktok.is_contiguous() and vtok.is_contiguous() and vtok.shape == ktok.shape
+    if q_block is not None:
+        assert q_block.dtype == torch.int32 and q_block.numel() == N and q_block.is_contiguous()
+    else:
+        assert Q.shape[0] == N * hw
+    out = torch.empty((N * hw, 128), device=Q.device, dtype=torch.bfloat16)
+    _check(_lib.rsp_i2t_attention(_ptr(Q), _ptr(q_block), _ptr(ktok), _ptr(vtok), _ptr(out), N, Tq, hw, _stream()),
+           "rsp_i2t_attention")
     launch_count += 1
     return out
 

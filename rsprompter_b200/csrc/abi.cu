@@ -87,3 +87,43 @@ int rsp_cast_f32_bf16(const float* in, void* out, long long n, void* stream) {
 }
 
 }  // extern "C"
+
+#include "decoder.h"
+
+extern "C" {
+
+int rsp_gemm_bf16_ex(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N,
+                     int K, const float* bias, const void* residual, int ldr, int res_fp32, int res_mod,
+                     const int32_t* row_map, int act, int out_fp32, int epi_mode, const float* ln_gamma,
+                     const float* ln_beta, float ln_eps, const int32_t* res_block_map,
+                     int res_block_rows, const float* hyper, float* mask_out, int grid_h, int grid_w,
+                     void* stream) {
+  GemmArgs a = make_gemm_args(A, lda, W, ldw, out, ldo, M, N, K, bias, residual, ldr, res_fp32,
+                              res_mod, row_map, act, out_fp32);
+  a.epi_mode = epi_mode; a.ln_gamma = ln_gamma; a.ln_beta = ln_beta; a.ln_eps = ln_eps;
+  a.res_block_map = res_block_map; a.res_block_rows = res_block_rows;
+  a.hyper = hyper; a.mask_out = mask_out; a.grid_h = grid_h; a.grid_w = grid_w;
+  return gemm_bf16(a, S(stream));
+}
+
+int rsp_add_cast_bf16(const float* a, const float* b, void* out, long long n, long long b_mod,
+                      void* stream) {
+  return add_cast_bf16(a, b, out, n, b_mod, S(stream));
+}
+
+int rsp_token_self_attention(const void* q, const void* k, const void* v, void* out, int N, int T,
+                             int heads, int c, void* stream) {
+  return token_self_attention(q, k, v, out, N, T, heads, c, S(stream));
+}
+
+int rsp_t2i_attention(const void* q, const void* K, const void* V, const int32_t* kv_block, void* out,
+                      int N, int Tq, int HW, void* stream) {
+  return t2i_attention(q, K, V, kv_block, out, N, Tq, HW, S(stream));
+}
+
+int rsp_i2t_attention(const void* Q, const int32_t* q_block, const void* ktok, const void* vtok,
+                      void* out, int N, int Tq, int HW, void* stream) {
+  return i2t_attention(Q, q_block, ktok, vtok, out, N, Tq, HW, S(stream));
+}
+
+}  // extern "C"

@@ -32,6 +32,8 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
 };
 
+enum { EPI_STD = 0, EPI_LN_ROW = 1, EPI_LN64_GELU = 2, EPI_GELU_HYPER = 3 };
+
 struct GemmDev {
   int M, N, K;
   const float* bias;
@@ -45,7 +47,200 @@ struct GemmDev {
   int res_fp32;
   int num_n_blocks;
   int num_tiles;
+  // --- epilogue variants (mask decoder) ---
+  int epi_mode;               // EPI_STD / EPI_LN_ROW / EPI_LN64_GELU / EPI_GELU_HYPER
+  const float* ln_gamma;      // [N] (row LN) or [64] (grouped LN)
+  const float* ln_beta;
+  float ln_eps;
+  const int* res_block_map;   // residual row = res_block_map[row / res_block_rows] * res_block_rows + row % res_block_rows
+  int res_block_rows;
+  const float* hyper;         // [n_prompts, 32]
+  float* mask_out;            // [n_prompts, 4*grid_h, 4*grid_w]
+  int grid_h, grid_w;
 };
+
+__device__ __forceinline__ int residual_row(const GemmDev& p, int orow) {
+  if (p.res_block_map) {
+    const int blk = orow / p.res_block_rows;
+    return p.res_block_map[blk] * p.res_block_rows + (orow - blk * p.res_block_rows);
+  }
+  return p.res_mod > 0 ? (orow % p.res_mod) : orow;
+}
+
+// v[0..31] += bias[col0..] ; v += residual[rrow, col0..]   (col0 + 32 <= N, 16-byte aligned)
+__device__ __forceinline__ void add_bias_residual32(const GemmDev& p, float (&v)[32], int rrow, int col0) {
+  if (p.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = __ldg(b4 + i);
+      v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
+  }
+  if (p.residual) {
+    if (p.res_fp32) {
+      const float4* r4 = reinterpret_cast<const float4*>(
+          static_cast<const float*>(p.residual) + static_cast<size_t>(rrow) * p.ldr + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 x = r4[i];
+        v[4 * i + 0] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+      }
+    } else {
+      const uint4* r4 = reinterpret_cast<const uint4*>(
+          static_cast<const __nv_bfloat16*>(p.residual) + static_cast<size_t>(rrow) * p.ldr + col0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 x = r4[i];
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+          v[8 * i + 2 * j + 0] += __bfloat162float(h.x);
+          v[8 * i + 2 * j + 1] += __bfloat162float(h.y);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void store32(const GemmDev& p, const float (&v)[32], int orow, int col0) {
+  if (p.out_fp32) {
+    float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(orow) * p.ldo + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(orow) * p.ldo + col0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      o4[i] = make_uint4(pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                         pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+  }
+}
+
+// EPI_LN_ROW: out = LayerNorm_N(acc + bias + residual) (N <= BN, one n-block: the thread owns the
+// whole row in TMEM; two passes over TMEM, statistics in fp32).  SamTwoWayAttentionBlock
+// layer_norm4 fused into cross_attn_image_to_token.out_proj (HF:341-347).
+template <int BN>
+__device__ __forceinline__ void epilogue_ln_row(const GemmDev& p, uint32_t t_row, int orow, int rrow) {
+  float sum = 0.f, sq = 0.f;
+  const int nch = p.N / 32;
+  for (int c = 0; c < nch; ++c) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_row + c * 32, r);
+    tmem_ld_wait();
+    if (orow < 0) continue;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    add_bias_residual32(p, v, rrow, c * 32);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { sum += v[i]; sq += v[i] * v[i]; }
+  }
+  const float mean = sum / p.N;
+  const float rstd = rsqrtf(fmaxf(sq / p.N - mean * mean, 0.f) + p.ln_eps);
+  for (int c = 0; c < nch; ++c) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_row + c * 32, r);
+    tmem_ld_wait();
+    if (orow < 0) continue;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    add_bias_residual32(p, v, rrow, c * 32);
+    const float4* g4 = reinterpret_cast<const float4*>(p.ln_gamma + c * 32);
+    const float4* b4 = reinterpret_cast<const float4*>(p.ln_beta + c * 32);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
+      v[4 * i + 0] = (v[4 * i + 0] - mean) * rstd * g.x + b.x;
+      v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * g.y + b.y;
+      v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * g.z + b.z;
+      v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * g.w + b.w;
+    }
+    store32(p, v, orow, c * 32);
+  }
+}
+
+// EPI_LN64_GELU: columns are (tap, 64 channels); out = GELU(LN_64(acc + bias)) per tap:
+// upscale_conv1 (ConvTranspose2d k2 s2 as a GEMM over taps) + upscale_layer_norm + GELU (HF:519-521).
+template <int BN>
+__device__ __forceinline__ void epilogue_ln64_gelu(const GemmDev& p, uint32_t t_row, int orow, int n_blk) {
+  for (int gi = 0; gi < BN / 64; ++gi) {
+    const int col0 = n_blk * BN + gi * 64;
+    uint32_t r0[32], r1[32];
+    tmem_ld_32x32b_x32(t_row + gi * 64, r0);
+    tmem_ld_32x32b_x32(t_row + gi * 64 + 32, r1);
+    tmem_ld_wait();
+    if (orow < 0 || col0 >= p.N) continue;
+    float v[64];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) { v[i] += __ldg(p.bias + col0 + i); sum += v[i]; }
+    const float mean = sum * (1.0f / 64.0f);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) { const float d = v[i] - mean; var += d * d; }
+    const float rstd = rsqrtf(var * (1.0f / 64.0f) + p.ln_eps);
+    uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(orow) * p.ldo + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = 8 * i + j;
+        y[j] = gelu_erf((v[c] - mean) * rstd * __ldg(p.ln_gamma + c) + __ldg(p.ln_beta + c));
+      }
+      o4[i] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
+                         pack_bf16x2(y[6], y[7]));
+    }
+  }
+}
+
+// EPI_GELU_HYPER: rows are (prompt, y, x, tap1) of the first upscale, columns (tap2, 32 channels) of
+// upscale_conv2; mask[prompt, 4y+2ty1+ty2, 4x+2tx1+tx2] = sum_c GELU(acc + bias)[tap2, c] * hyper[prompt, c]
+// (HF:521-531): the 32 x 4h x 4w upscaled embedding never leaves the SM.
+template <int BN>
+__device__ __forceinline__ void epilogue_gelu_hyper(const GemmDev& p, uint32_t t_row, int row) {
+  const bool valid = row < p.M;
+  const int rows_per_prompt = p.grid_h * p.grid_w * 4;
+  const int n = valid ? row / rows_per_prompt : 0;
+  const int rem = row - n * rows_per_prompt;
+  const int tap1 = rem & 3, pix = rem >> 2;
+  const int y = pix / p.grid_w, x = pix - y * p.grid_w;
+  float hyp[32];
+  if (valid) {
+    const float4* h4 = reinterpret_cast<const float4*>(p.hyper + static_cast<size_t>(n) * 32);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 h = __ldg(h4 + i);
+      hyp[4 * i] = h.x; hyp[4 * i + 1] = h.y; hyp[4 * i + 2] = h.z; hyp[4 * i + 3] = h.w;
+    }
+  }
+  float m[4];
+#pragma unroll
+  for (int t2 = 0; t2 < 4; ++t2) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_row + t2 * 32, r);
+    tmem_ld_wait();
+    float acc = 0.f;
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        acc += gelu_erf(__uint_as_float(r[i]) + __ldg(p.bias + t2 * 32 + i)) * hyp[i];
+    }
+    m[t2] = acc;
+  }
+  if (valid) {
+    const int W4 = 4 * p.grid_w;
+    const int Y = 4 * y + 2 * (tap1 >> 1), X = 4 * x + 2 * (tap1 & 1);
+    float* o = p.mask_out + (static_cast<size_t>(n) * 4 * p.grid_h + Y) * W4 + X;
+    *reinterpret_cast<float2*>(o) = make_float2(m[0], m[1]);
+    *reinterpret_cast<float2*>(o + W4) = make_float2(m[2], m[3]);
+  }
+}
 
 template <int BN, bool B_MN_MAJOR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -155,8 +350,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       const int row = m_blk * BM + ew * 32 + lane;
       int orow = -1;
       if (row < p.M) orow = p.row_map ? p.row_map[row] : row;
-      const int rrow = (orow >= 0 && p.res_mod > 0) ? (orow % p.res_mod) : orow;
+      const int rrow = (orow >= 0 && p.residual) ? residual_row(p, orow) : orow;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+      if (p.epi_mode == EPI_LN_ROW) {
+        epilogue_ln_row<BN>(p, t_row, orow, rrow);
+      } else if (p.epi_mode == EPI_LN64_GELU) {
+        if constexpr (BN >= 64) epilogue_ln64_gelu<BN>(p, t_row, orow, n_blk);
+      } else if (p.epi_mode == EPI_GELU_HYPER) {
+        if constexpr (BN == 128) epilogue_gelu_hyper<BN>(p, t_row, row);
+      } else
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -260,6 +462,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   }
 }
 
+static void fill_dev(GemmDev& p, const GemmArgs& a) {
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.row_map = a.row_map;
+  p.res_mod = a.res_mod; p.ldo = a.ldo; p.ldr = a.ldr; p.act = a.act;
+  p.out_fp32 = a.out_fp32; p.res_fp32 = a.res_fp32;
+  p.epi_mode = a.epi_mode; p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
+  p.res_block_map = a.res_block_map; p.res_block_rows = a.res_block_rows;
+  p.hyper = a.hyper; p.mask_out = a.mask_out; p.grid_h = a.grid_h; p.grid_w = a.grid_w;
+  p.num_n_blocks = 0; p.num_tiles = 0;
+}
+
 template <int BN, bool B_MN>
 static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -272,10 +485,7 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     RSP_TRY(make_tmap_bf16_2d(&tb, a.W, a.K, a.N, static_cast<uint64_t>(a.ldw) * 2, BK, 64));
   }
   GemmDev p;
-  p.M = a.M; p.N = a.N; p.K = a.K;
-  p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.row_map = a.row_map;
-  p.res_mod = a.res_mod; p.ldo = a.ldo; p.ldr = a.ldr; p.act = a.act;
-  p.out_fp32 = a.out_fp32; p.res_fp32 = a.res_fp32;
+  fill_dev(p, a);
   const int num_m_blocks = (a.M + BM - 1) / BM;
   p.num_n_blocks = (a.N + BN - 1) / BN;
   p.num_tiles = num_m_blocks * p.num_n_blocks;
@@ -294,10 +504,33 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
 }
 
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
-  RSP_CHECK_ARG(a.A && a.W && a.out, "gemm: null pointer");
+  RSP_CHECK_ARG(a.A && a.W && (a.out || a.mask_out), "gemm: null pointer");
   RSP_CHECK_ARG(a.M > 0 && a.N > 0 && a.K > 0, "gemm: bad shape %d %d %d", a.M, a.N, a.K);
   RSP_CHECK_ARG(a.lda % 8 == 0 && a.ldw % 8 == 0, "gemm: lda/ldw must be multiples of 8 bf16");
   RSP_CHECK_ARG(a.act >= 0 && a.act <= 2, "gemm: act %d", a.act);
+  if (a.res_block_map) RSP_CHECK_ARG(a.res_block_rows > 0, "gemm: res_block_rows");
+  if (a.epi_mode == EPI_LN_ROW) {
+    RSP_CHECK_ARG(a.N % 32 == 0 && a.N <= 256 && a.ln_gamma && a.ln_beta && !a.w_is_kn && !a.row_map,
+                  "gemm: row-LN epilogue needs N %% 32 == 0, N <= 256, gamma/beta");
+    RSP_CHECK_ARG(a.ldo % 8 == 0 && (!a.residual || a.ldr % 8 == 0), "gemm: row-LN epilogue alignment");
+    if (a.N > 128) return launch_gemm<256, false>(a, stream);
+    if (a.N > 64) return launch_gemm<128, false>(a, stream);
+    return launch_gemm<64, false>(a, stream);
+  }
+  if (a.epi_mode == EPI_LN64_GELU) {
+    RSP_CHECK_ARG(a.N % 64 == 0 && a.bias && a.ln_gamma && a.ln_beta && !a.out_fp32 && !a.w_is_kn &&
+                  !a.row_map && a.ldo % 8 == 0, "gemm: LN64+GELU epilogue needs N %% 64 == 0, bias, bf16 out");
+    if (a.N % 256 == 0) return launch_gemm<256, false>(a, stream);
+    if (a.N % 128 == 0) return launch_gemm<128, false>(a, stream);
+    return launch_gemm<64, false>(a, stream);
+  }
+  if (a.epi_mode == EPI_GELU_HYPER) {
+    RSP_CHECK_ARG(a.N == 128 && a.bias && a.hyper && a.mask_out && a.grid_h > 0 && a.grid_w > 0 &&
+                  a.M % (4 * a.grid_h * a.grid_w) == 0 && !a.w_is_kn,
+                  "gemm: GELU+hyper epilogue needs N == 128 and M = prompts * 4 * h * w");
+    return launch_gemm<128, false>(a, stream);
+  }
+  RSP_CHECK_ARG(a.epi_mode == EPI_STD, "gemm: epi_mode %d", a.epi_mode);
   if (a.w_is_kn) {
     RSP_CHECK_ARG(a.N % 64 == 0, "gemm: [K,N] weights need N %% 64 == 0");
     if (a.N % 128 == 0) return launch_gemm<128, true>(a, stream);
@@ -347,7 +580,7 @@ __global__ void gemm_bf16_simt_kernel(const __nv_bfloat16* __restrict__ A, int l
   }
   const int orow = p.row_map ? p.row_map[row] : row;
   if (orow < 0) return;
-  const int rrow = p.res_mod > 0 ? orow % p.res_mod : orow;
+  const int rrow = residual_row(p, orow);
   if (p.bias) acc += p.bias[col];
   if (p.act == 1) acc = gelu_erf(acc);
   else if (p.act == 2) acc = fmaxf(acc, 0.f);
@@ -364,12 +597,9 @@ __global__ void gemm_bf16_simt_kernel(const __nv_bfloat16* __restrict__ A, int l
 int gemm_bf16_simt(const GemmArgs& a, cudaStream_t stream) {
   RSP_CHECK_ARG(a.A && a.W && a.out, "gemm_simt: null pointer");
   RSP_CHECK_ARG(a.M > 0 && a.N > 0 && a.K > 0, "gemm_simt: bad shape");
+  RSP_CHECK_ARG(a.epi_mode == EPI_STD, "gemm_simt: only the standard epilogue");
   GemmDev p;
-  p.M = a.M; p.N = a.N; p.K = a.K;
-  p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.row_map = a.row_map;
-  p.res_mod = a.res_mod; p.ldo = a.ldo; p.ldr = a.ldr; p.act = a.act;
-  p.out_fp32 = a.out_fp32; p.res_fp32 = a.res_fp32;
-  p.num_n_blocks = 0; p.num_tiles = 0;
+  fill_dev(p, a);
   dim3 block(128);
   dim3 grid((a.N + 127) / 128, a.M);
   gemm_bf16_simt_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(a.A), a.lda,

@@ -20,6 +20,17 @@ struct GemmArgs {
   int w_is_kn = 0;    // W stored [K, N] (N contiguous): exercises the MN-major UMMA descriptor
   int force_bn = 0;   // 0 = heuristic; else 32/64/128/256
   int max_ctas = 0;   // 0 = one CTA per SM
+  // epilogue variants used by the mask decoder (see gemm.cu)
+  int epi_mode = 0;                   // 0 standard, 1 row LayerNorm, 2 LN over 64-column groups + GELU,
+                                      // 3 GELU + hypernetwork dot + 2x2 mask scatter
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  float ln_eps = 1e-6f;
+  const int* res_block_map = nullptr; // residual row = map[row / res_block_rows] * res_block_rows + row % res_block_rows
+  int res_block_rows = 0;
+  const float* hyper = nullptr;       // fp32 [prompts, 32]
+  float* mask_out = nullptr;          // fp32 [prompts, 4*grid_h, 4*grid_w]
+  int grid_h = 0, grid_w = 0;
 };
 
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream);

@@ -1,0 +1,66 @@
+"""SAM ViT encoder on the B200 kernels vs the CPU oracle (same seeded weights, same input)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(arch, B, seed):
+    from oracle import restate
+    from rsprompter_b200 import synthetic
+    from rsprompter_b200.sam_encoder import SamVisionEncoderB200
+    sd = synthetic.vision_encoder_state_dict(arch, seed=seed)
+    torch.manual_seed(seed)
+    x = torch.randn(B, 3, arch.image_size, arch.image_size)
+    emb_ref, hid_ref = restate.vit_encoder(sd, arch, x)
+    enc = SamVisionEncoderB200(arch)
+    enc.load_state_dict(sd)
+    enc = enc.cuda()
+    emb, hid, _ = enc.encode(x.cuda())
+    torch.cuda.synchronize()
+    return emb.cpu(), [h.cpu() for h in hid], emb_ref, hid_ref
+
+
+def _check(emb, hid, emb_ref, hid_ref, tol):
+    assert len(hid) == len(hid_ref)
+    for i, (a, b) in enumerate(zip(hid, hid_ref)):
+        assert a.shape == b.shape
+        err = (a - b).abs().max().item() / b.abs().max().item()
+        assert err < tol, f"hidden state {i}: rel err {err}"
+    err = (emb - emb_ref).abs().max().item()
+    assert emb.shape == emb_ref.shape
+    assert err < 2e-2 * max(1.0, emb_ref.abs().max().item()), f"embedding max abs err {err}"
+
+
+@pytest.mark.parametrize("heads,hd", [(2, 64), (2, 80)])
+def test_small_vit_matches_oracle(heads, hd):
+    from rsprompter_b200.sam_config import SamVisionArch
+    arch = SamVisionArch("tiny", hidden_size=heads * hd, num_layers=3, num_heads=heads, mlp_dim=512,
+                         global_attn_indexes=(1,), image_size=1024)
+    _check(*_run(arch, 2, 11), tol=2e-2)
+
+
+def test_vit_base_matches_oracle():
+    from rsprompter_b200.sam_config import VISION_ARCHS
+    _check(*_run(VISION_ARCHS["base"], 1, 12), tol=2e-2)
+
+
+def test_output_contract():
+    """forward() returns what extract_feat unpacks (M:97-106)."""
+    import dataclasses
+    from rsprompter_b200 import synthetic
+    from rsprompter_b200.registry import MODELS
+    from rsprompter_b200.sam_config import SamVisionArch
+    from rsprompter_b200.sam_encoder import SamVisionEncoderOutput
+    enc = MODELS.build(dict(type="RSSamVisionEncoder", hf_pretrain_name="facebook/sam-vit-base",
+                            extra_config=dict(output_hidden_states=True, num_layers=2,
+                                              global_attn_indexes=(1,))))
+    arch = enc.vision_encoder.arch
+    enc.vision_encoder.load_state_dict(synthetic.vision_encoder_state_dict(arch, seed=1))
+    enc = enc.cuda()
+    out = enc(torch.randn(1, 3, 1024, 1024, device="cuda"))
+    assert isinstance(out, SamVisionEncoderOutput)
+    assert out[0].shape == (1, 256, 64, 64)
+    assert len(out[1]) == 3 and out[1][0].shape == (1, 64, 64, 768)
+    with pytest.raises(ValueError):
+        enc(torch.randn(1, 3, 512, 512, device="cuda"))

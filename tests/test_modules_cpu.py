@@ -1,0 +1,80 @@
+"""Host-side contract of the registry modules, checked without a GPU: construction through
+MODELS.build, reference parameter names (state dicts load strictly), C-ABI symbol table."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import rsprompter_b200 as rb
+from rsprompter_b200 import _lib, synthetic
+from rsprompter_b200.registry import MODELS
+from rsprompter_b200.sam_config import SamDecoderArch, SamVisionArch, VISION_ARCHS, parse_arch_name
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_and_binding_export_the_same_symbols():
+    hdr = open(os.path.join(ROOT, "include", "rsp_b200.h")).read()
+    declared = set(re.findall(r"\b(rsp_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.declared_symbols())
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} missing from librsp_b200.so"
+    assert lib.rsp_abi_version() == 1
+
+
+def test_arch_name_parsing():
+    assert parse_arch_name("facebook/sam-vit-huge") == "huge"
+    assert parse_arch_name("work_dirs/sam_cache/sam_vit_base") == "base"
+    assert parse_arch_name("facebook/sam-vit-large") == "large"
+    with pytest.raises(ValueError):
+        parse_arch_name("resnet50")
+
+
+@pytest.mark.parametrize("name", ["base", "huge"])
+def test_encoder_state_dict_names_match_reference(name):
+    arch = VISION_ARCHS[name]
+    enc = MODELS.build(dict(type="RSSamVisionEncoder", hf_pretrain_name=f"facebook/sam-vit-{name}",
+                            extra_config=dict(output_hidden_states=True)))
+    sd = synthetic.vision_encoder_state_dict(arch, seed=0)
+    assert set(enc.vision_encoder.state_dict()) == set(sd)
+    enc.vision_encoder.load_state_dict(sd, strict=True)
+    assert enc.vision_encoder.arch.output_hidden_states
+    hd = arch.head_dim
+    assert enc.vision_encoder.layers[0].attn.rel_pos_h.shape == (27, hd)
+    g = arch.global_attn_indexes[0]
+    assert enc.vision_encoder.layers[g].attn.rel_pos_h.shape == (127, hd)
+
+
+def test_decoder_and_prompt_modules_load_reference_names():
+    dec = MODELS.build(dict(type="RSSamMaskDecoder", hf_pretrain_name="facebook/sam-vit-base"))
+    sd = synthetic.mask_decoder_state_dict(SamDecoderArch(), seed=1)
+    assert set(dec.mask_decoder.state_dict()) == set(sd)
+    dec.mask_decoder.load_state_dict(sd, strict=True)
+    pe = MODELS.build(dict(type="RSSamPromptEncoder", hf_pretrain_name="facebook/sam-vit-base"))
+    pe.prompt_encoder.load_state_dict(synthetic.prompt_encoder_state_dict(SamDecoderArch(), seed=2), strict=True)
+    assert pe.prompt_encoder.no_mask_embed.weight.shape == (1, 256)
+    pos = MODELS.build(dict(type="RSSamPositionalEmbedding", hf_pretrain_name="facebook/sam-vit-base"))
+    assert pos.shared_image_embedding.positional_embedding.shape == (2, 128)
+
+
+def test_no_cpu_fallback():
+    arch = SamVisionArch("tiny", 128, 1, 2, 256, (0,), image_size=1024)
+    from rsprompter_b200.sam_encoder import SamVisionEncoderB200
+    enc = SamVisionEncoderB200(arch)
+    enc.load_state_dict(synthetic.vision_encoder_state_dict(arch, seed=0))
+    with pytest.raises(_lib.RspError):
+        enc.encode(torch.zeros(1, 3, 1024, 1024))
+
+
+def test_window_map_matches_window_partition():
+    from oracle import restate
+    from rsprompter_b200.sam_encoder import window_maps
+    B, g, ws = 2, 64, 14
+    wmap, n_win = window_maps(B, g, ws, torch.device("cpu"))
+    tok = torch.arange(B * g * g, dtype=torch.float32).reshape(B, g, g, 1) + 1
+    ref, _ = restate.window_partition(tok, ws)
+    ref = ref.reshape(-1).long() - 1          # padding (0) -> -1
+    assert n_win == 25 and torch.equal(wmap.long(), ref)
