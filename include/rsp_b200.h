@@ -121,6 +121,66 @@ int rsp_t2i_attention(const void* q, const void* K, const void* V, const int32_t
 int rsp_i2t_attention(const void* Q, const int32_t* q_block, const void* ktok, const void* vtok,
                       void* out, int N, int Tq, int HW, void* stream);
 
+/* ---- detection side of the anchor variant: batched over B images with fixed-size padded
+ * candidate lists (score -1 = filtered / padding), so RPN -> RoI head -> mask head runs without
+ * host synchronisation.  All arithmetic that decides indices is fp32 without FMA contraction. ---- */
+
+/* RPN: for the K top anchors of one level (topk_idx int64 [B, K] into the (h, w, anchor) order of
+ * rpn_head.py:188-190) emit sigmoid scores and decoded, clipped boxes into boxes[B, out_ld, 4] /
+ * scores[B, out_ld] at column out_off.  head_out fp32 [B*H*W, ld]: columns [0,A) objectness logits,
+ * [A, 5A) deltas.  Anchors are generated analytically (AnchorGenerator, anchor_generator.py:161-301,
+ * base_anchors fp32 [A, 4]); boxes failing min_bbox_size get score -1 (rpn_head.py:267-271).
+ * Replaces RPNHead._predict_by_feat_single's per-level body + DeltaXYWHBBoxCoder.decode
+ * (rpn_head.py:188-226; delta_xywh_bbox_coder.py:325-359). */
+int rsp_rpn_decode(const float* head_out, int ld, const int64_t* topk_idx, int K, int B, int H, int W,
+                   int A, int stride, const float* base_anchors, float img_h, float img_w,
+                   float min_size, int out_off, int out_ld, float* boxes, float* scores, void* stream);
+
+/* RoI bbox head post-processing before NMS: softmax over C+1 logits, per-class delta2bbox with stds
+ * (.1,.1,.2,.2), score_thr filter; rois fp32 [n, 5], roi_valid uint8 [n] or NULL.  Outputs
+ * scores [n*C] (-1 = filtered), boxes [n*C, 4], labels int64 [n*C].
+ * Replaces BBoxHead._predict_by_feat_single up to multiclass_nms (bbox_head.py:520-555,
+ * bbox_nms.py:45-75). */
+int rsp_bbox_cls_decode(const float* cls, int ld_cls, const float* reg, int ld_reg, const float* rois,
+                        const uint8_t* roi_valid, int n, int C, float img_h, float img_w,
+                        float score_thr, float* scores, float* boxes, int64_t* labels, void* stream);
+
+/* mmcv.ops.batched_nms semantics on score-sorted candidates: boxes fp32 [B, n, 4], ids int64 [B, n]
+ * (level or class; boxes are offset by id * (max_coord + 1) exactly as mmcv does), nvalid int32 [B]
+ * = length of the valid sorted prefix; keep uint8 [B, n].  Suppression when IoU > thr.
+ * Workspaces: mask_ws uint64 [B, n, ceil(n/64)], max_coord_ws fp32 [B].
+ * Replaces mmcv.ops.batched_nms / nms (rpn_head.py:285, bbox_nms.py:95). */
+int rsp_nms_batched(const float* boxes, const int64_t* ids, const int32_t* nvalid, int B, int n, float thr,
+                    void* mask_ws, float* max_coord_ws, uint8_t* keep, void* stream);
+
+/* First K kept candidates per image, in order, zero padded; counts int32 [B].  labels / out_labels /
+ * out_index may be NULL.  Replaces results[keep][:max_per_img] (rpn_head.py:289, bbox_nms.py:97-99). */
+int rsp_compact_keep(const uint8_t* keep, const float* boxes, const float* scores, const int64_t* labels,
+                     int B, int n, int K, float* out_boxes, float* out_scores, int64_t* out_labels,
+                     int32_t* out_index, int32_t* counts, void* stream);
+
+/* SingleRoIExtractor + mmcv RoIAlign(output_size=P, sampling_ratio=0, aligned=True, avg)
+ * (single_level_roi_extractor.py:55-119, base_roi_extractor.py:58-67) on up to 4 channels-last bf16
+ * levels: feats[l] [B, Hs[l], Ws[l], C]; rois fp32 [n, 5] = (batch, x1, y1, x2, y2); level =
+ * clamp(floor(log2(sqrt(area) / finest_scale + 1e-6))).  pes (NULL or per-level fp32 [H, W, C]) is the
+ * batch-independent extra positional encoding of M:1566-1574, sampled and added on the fly.
+ * out bf16 [n, P*P*C] in (ph, pw, c) order.  feats / pes / Hs / Ws / scales are HOST arrays. */
+int rsp_roi_align_nhwc(const void* const* feats, const float* const* pes, const int32_t* Hs,
+                       const int32_t* Ws, const float* scales, int num_levels, const float* rois, int n,
+                       int C, int P, float finest_scale, void* out, void* stream);
+
+/* Mask post-processing: logits fp32 [n, hm, wm] -> uint8 [n, H, W] (W % 4 == 0), bilinear with
+ * align_corners=False.  mode 0: bilinear(sigmoid(x)) >= thr (M:1758-1780); mode 1: bilinear(x) > thr
+ * (M:652-656 + maskformer_fusion_head.py:169). */
+int rsp_mask_paste(const float* logits, uint8_t* out, int n, int hm, int wm, int H, int W, float thr,
+                   int mode, void* stream);
+
+/* bf16 NHWC pooling: mode 0 = MaxPool2d(2, 2) (M:1307), mode 1 = max_pool2d(k=1, stride=2) (M:1362). */
+int rsp_pool2_nhwc(const void* in, void* out, int B, int H, int W, int C, int mode, void* stream);
+
+/* out[i] = sin(in[2i]) + in[2i+1]: the sin/identity fold of the point embeddings (M:348, M:1672). */
+int rsp_sin_fold(const float* in, float* out, long long n_out, void* stream);
+
 /* fp32 -> bf16 (n % 4 == 0): feeds fp32 hidden states to the bf16 tensor-core GEMMs. */
 int rsp_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
 

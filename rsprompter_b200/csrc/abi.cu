@@ -127,3 +127,55 @@ int rsp_i2t_attention(const void* Q, const int32_t* q_block, const void* ktok, c
 }
 
 }  // extern "C"
+
+#include "detect.h"
+
+extern "C" {
+
+int rsp_rpn_decode(const float* head_out, int ld, const int64_t* topk_idx, int K, int B, int H, int W,
+                   int A, int stride, const float* base_anchors, float img_h, float img_w,
+                   float min_size, int out_off, int out_ld, float* boxes, float* scores, void* stream) {
+  return rpn_decode(head_out, ld, reinterpret_cast<const long long*>(topk_idx), K, B, H, W, A, stride,
+                    base_anchors, img_h, img_w, min_size, out_off, out_ld, boxes, scores, S(stream));
+}
+
+int rsp_bbox_cls_decode(const float* cls, int ld_cls, const float* reg, int ld_reg, const float* rois,
+                        const uint8_t* roi_valid, int n, int C, float img_h, float img_w,
+                        float score_thr, float* scores, float* boxes, int64_t* labels, void* stream) {
+  return bbox_cls_decode(cls, ld_cls, reg, ld_reg, rois, roi_valid, n, C, img_h, img_w, score_thr, scores,
+                         boxes, reinterpret_cast<long long*>(labels), S(stream));
+}
+
+int rsp_nms_batched(const float* boxes, const int64_t* ids, const int32_t* nvalid, int B, int n, float thr,
+                    void* mask_ws, float* max_coord_ws, uint8_t* keep, void* stream) {
+  return nms_batched(boxes, reinterpret_cast<const long long*>(ids), nvalid, B, n, thr,
+                     static_cast<unsigned long long*>(mask_ws), max_coord_ws, keep, S(stream));
+}
+
+int rsp_compact_keep(const uint8_t* keep, const float* boxes, const float* scores, const int64_t* labels,
+                     int B, int n, int K, float* out_boxes, float* out_scores, int64_t* out_labels,
+                     int32_t* out_index, int32_t* counts, void* stream) {
+  return compact_keep(keep, boxes, scores, reinterpret_cast<const long long*>(labels), B, n, K, out_boxes,
+                      out_scores, reinterpret_cast<long long*>(out_labels), out_index, counts, S(stream));
+}
+
+int rsp_roi_align_nhwc(const void* const* feats, const float* const* pes, const int32_t* Hs,
+                       const int32_t* Ws, const float* scales, int num_levels, const float* rois, int n,
+                       int C, int P, float finest_scale, void* out, void* stream) {
+  return roi_align_nhwc(feats, pes, Hs, Ws, scales, num_levels, rois, n, C, P, finest_scale, out, S(stream));
+}
+
+int rsp_mask_paste(const float* logits, uint8_t* out, int n, int hm, int wm, int H, int W, float thr,
+                   int mode, void* stream) {
+  return mask_paste(logits, out, n, hm, wm, H, W, thr, mode, S(stream));
+}
+
+int rsp_pool2_nhwc(const void* in, void* out, int B, int H, int W, int C, int mode, void* stream) {
+  return pool2_nhwc(in, out, B, H, W, C, mode, S(stream));
+}
+
+int rsp_sin_fold(const float* in, float* out, long long n_out, void* stream) {
+  return sin_fold(in, out, n_out, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,488 @@
+// Detection-side kernels of the RSPrompter-anchor path: all batched over images with fixed-size
+// padded candidate lists, so the whole RPN -> RoI -> mask pipeline runs without host syncs.
+//
+//   rpn_decode        top-k anchor indices -> sigmoid scores + delta2bbox boxes (rpn_head.py:188-226,
+//                     anchor_generator.py:161-301, delta_xywh_bbox_coder.py:325-359)
+//   bbox_cls_decode   softmax class scores + per-class delta2bbox (bbox_head.py:520-545)
+//   nms_batched       mmcv.ops.batched_nms semantics: boxes offset by id * (max + 1), greedy NMS,
+//                     suppress when IoU > thr (bbox_nms.py:95, rpn_head.py:285)
+//   compact_keep      first K kept candidates per image -> dense [B, K] outputs + counts
+//   roi_align_nhwc    mmcv RoIAlign(aligned=True, sampling_ratio=0, avg) over 4 FPN levels with the
+//                     level mapping of SingleRoIExtractor (single_level_roi_extractor.py:55-119); the
+//                     extra sine PE of M:1566-1574 is sampled from a per-level table and added
+//                     (RoIAlign is linear, so x + PE never has to be materialised)
+//   mask_paste        sigmoid + bilinear x4 + threshold (M:1758-1780) / bilinear + (> 0) (M:652-656)
+//   pool2_nhwc        MaxPool2d(2,2) and max_pool2d(k=1, s=2) on channels-last maps (M:1307,1362)
+//   sin_fold          x[..., ::2].sin() + x[..., 1::2]  (M:348, M:1672)
+#include "detect.h"
+#include "sm100.cuh"
+
+namespace rsp {
+
+// exact-rounding helpers: no FMA contraction, so IoU / box arithmetic matches the fp32 reference
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+
+__device__ __forceinline__ void delta2bbox_one(const float r[4], const float d[4], const float stds[4],
+                                               float max_h, float max_w, float out[4]) {
+  const float max_ratio = 4.135166556742356f;  // |log(16/1000)|
+  const float dx = fmul(d[0], stds[0]), dy = fmul(d[1], stds[1]);
+  float dw = fmul(d[2], stds[2]), dh = fmul(d[3], stds[3]);
+  const float px = fmul(fadd(r[0], r[2]), 0.5f), py = fmul(fadd(r[1], r[3]), 0.5f);
+  const float pw = fsub(r[2], r[0]), ph = fsub(r[3], r[1]);
+  dw = fminf(fmaxf(dw, -max_ratio), max_ratio);
+  dh = fminf(fmaxf(dh, -max_ratio), max_ratio);
+  const float gx = fadd(px, fmul(pw, dx)), gy = fadd(py, fmul(ph, dy));
+  const float gw = fmul(pw, expf(dw)), gh = fmul(ph, expf(dh));
+  out[0] = fminf(fmaxf(fsub(gx, fmul(gw, 0.5f)), 0.f), max_w);
+  out[1] = fminf(fmaxf(fsub(gy, fmul(gh, 0.5f)), 0.f), max_h);
+  out[2] = fminf(fmaxf(fadd(gx, fmul(gw, 0.5f)), 0.f), max_w);
+  out[3] = fminf(fmaxf(fadd(gy, fmul(gh, 0.5f)), 0.f), max_h);
+}
+
+// ---------------------------------------------------------------------------------------
+// head_out: fp32 [B*H*W, ld] rows = pixels, columns [0, A) cls logits, [A, 5A) box deltas (a*4 + k)
+__global__ void rpn_decode_kernel(const float* __restrict__ head_out, int ld,
+                                  const long long* __restrict__ topk_idx, int K, int B, int H, int W,
+                                  int A, int stride, const float* __restrict__ base_anchors,
+                                  float img_h, float img_w, float min_size, int out_off, int out_ld,
+                                  float* __restrict__ boxes, float* __restrict__ scores) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * K) return;
+  const int b = i / K, k = i - b * K;
+  const long long idx = topk_idx[i];
+  const int a = static_cast<int>(idx % A);
+  const long long pix = idx / A;
+  const int x = static_cast<int>(pix % W), y = static_cast<int>(pix / W);
+  const float* row = head_out + (static_cast<size_t>(b) * H * W + pix) * ld;
+  const float logit = row[a];
+  const float d[4] = {row[A + a * 4], row[A + a * 4 + 1], row[A + a * 4 + 2], row[A + a * 4 + 3]};
+  const float sx = static_cast<float>(x * stride), sy = static_cast<float>(y * stride);
+  const float r[4] = {base_anchors[a * 4] + sx, base_anchors[a * 4 + 1] + sy,
+                      base_anchors[a * 4 + 2] + sx, base_anchors[a * 4 + 3] + sy};
+  const float stds[4] = {1.f, 1.f, 1.f, 1.f};
+  float o[4];
+  delta2bbox_one(r, d, stds, img_h, img_w, o);
+  float s = 1.0f / (1.0f + expf(-logit));
+  if (!(fsub(o[2], o[0]) > min_size && fsub(o[3], o[1]) > min_size)) s = -1.0f;  // filtered (rpn_head.py:267-271)
+  const size_t oi = static_cast<size_t>(b) * out_ld + out_off + k;
+  boxes[oi * 4] = o[0]; boxes[oi * 4 + 1] = o[1]; boxes[oi * 4 + 2] = o[2]; boxes[oi * 4 + 3] = o[3];
+  scores[oi] = s;
+}
+
+int rpn_decode(const float* head_out, int ld, const long long* topk_idx, int K, int B, int H, int W,
+               int A, int stride, const float* base_anchors, float img_h, float img_w, float min_size,
+               int out_off, int out_ld, float* boxes, float* scores, cudaStream_t stream) {
+  RSP_CHECK_ARG(head_out && topk_idx && base_anchors && boxes && scores && B > 0 && K > 0, "rpn_decode: bad args");
+  const int n = B * K;
+  rpn_decode_kernel<<<(n + 127) / 128, 128, 0, stream>>>(head_out, ld, topk_idx, K, B, H, W, A, stride,
+                                                         base_anchors, img_h, img_w, min_size, out_off,
+                                                         out_ld, boxes, scores);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// cls fp32 [n, C+1], reg fp32 [n, 4C], rois fp32 [n, 5]; out scores [n*C] (-1 when <= thr or the
+// roi is padding), boxes [n*C, 4], labels int64 [n*C]
+__global__ void bbox_cls_decode_kernel(const float* __restrict__ cls, int ld_cls,
+                                       const float* __restrict__ reg, int ld_reg,
+                                       const float* __restrict__ rois, const unsigned char* __restrict__ roi_valid,
+                                       int n, int C, float img_h, float img_w, float score_thr,
+                                       float* __restrict__ scores, float* __restrict__ boxes,
+                                       long long* __restrict__ labels) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * C) return;
+  const int r = i / C, c = i - r * C;
+  const float* cr = cls + static_cast<size_t>(r) * ld_cls;
+  float mx = cr[0];
+  for (int j = 1; j <= C; ++j) mx = fmaxf(mx, cr[j]);
+  float sum = 0.f;
+  for (int j = 0; j <= C; ++j) sum += expf(cr[j] - mx);
+  float s = expf(cr[c] - mx) / sum;
+  const float* rr = rois + static_cast<size_t>(r) * 5;
+  const float roi[4] = {rr[1], rr[2], rr[3], rr[4]};
+  const float* dp = reg + static_cast<size_t>(r) * ld_reg + c * 4;
+  const float d[4] = {dp[0], dp[1], dp[2], dp[3]};
+  const float stds[4] = {0.1f, 0.1f, 0.2f, 0.2f};
+  float o[4];
+  delta2bbox_one(roi, d, stds, img_h, img_w, o);
+  if (!(s > score_thr) || (roi_valid && !roi_valid[r])) s = -1.0f;
+  scores[i] = s;
+  boxes[static_cast<size_t>(i) * 4] = o[0]; boxes[static_cast<size_t>(i) * 4 + 1] = o[1];
+  boxes[static_cast<size_t>(i) * 4 + 2] = o[2]; boxes[static_cast<size_t>(i) * 4 + 3] = o[3];
+  labels[i] = c;
+}
+
+int bbox_cls_decode(const float* cls, int ld_cls, const float* reg, int ld_reg, const float* rois,
+                    const unsigned char* roi_valid, int n, int C, float img_h, float img_w,
+                    float score_thr, float* scores, float* boxes, long long* labels, cudaStream_t stream) {
+  RSP_CHECK_ARG(cls && reg && rois && scores && boxes && labels && n > 0 && C > 0, "bbox_cls_decode: bad args");
+  const int t = n * C;
+  bbox_cls_decode_kernel<<<(t + 127) / 128, 128, 0, stream>>>(cls, ld_cls, reg, ld_reg, rois, roi_valid, n, C,
+                                                              img_h, img_w, score_thr, scores, boxes, labels);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// NMS over per-image candidate lists sorted by descending score.  boxes fp32 [B, n, 4]; ids
+// int64 [B, n] (level / class); nvalid int32 [B] (sorted prefix with score >= 0).  The offset
+// trick of mmcv.batched_nms is reproduced literally: box + id * (max_coord + 1), max over the
+// valid boxes of the image.
+__device__ __forceinline__ bool iou_gt(const float a[4], const float b[4], float thr) {
+  const float left = fmaxf(a[0], b[0]), right = fminf(a[2], b[2]);
+  const float top = fmaxf(a[1], b[1]), bottom = fminf(a[3], b[3]);
+  const float w = fmaxf(fsub(right, left), 0.f), h = fmaxf(fsub(bottom, top), 0.f);
+  const float inter = fmul(w, h);
+  const float sa = fmul(fsub(a[2], a[0]), fsub(a[3], a[1]));
+  const float sb = fmul(fsub(b[2], b[0]), fsub(b[3], b[1]));
+  return inter / fsub(fadd(sa, sb), inter) > thr;
+}
+
+__global__ void nms_max_coord_kernel(const float* __restrict__ boxes, const int* __restrict__ nvalid,
+                                     int n, float* __restrict__ max_coord) {
+  __shared__ float red[256];
+  const int b = blockIdx.x;
+  const int nv = nvalid[b];
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < nv * 4; i += blockDim.x) m = fmaxf(m, boxes[static_cast<size_t>(b) * n * 4 + i]);
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) max_coord[b] = red[0];
+}
+
+__global__ void nms_mask_kernel(const float* __restrict__ boxes, const long long* __restrict__ ids,
+                                const int* __restrict__ nvalid, const float* __restrict__ max_coord,
+                                int n, float thr, unsigned long long* __restrict__ mask) {
+  const int b = blockIdx.z;
+  const int nv = nvalid[b];
+  const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64;
+  if (row0 >= nv || col0 >= nv || blockIdx.x < blockIdx.y) return;
+  const float off1 = fadd(max_coord[b], 1.0f);
+  __shared__ float cb[64][4];
+  const int cn = min(64, nv - col0);
+  if (threadIdx.x < cn) {
+    const size_t j = static_cast<size_t>(b) * n + col0 + threadIdx.x;
+    const float off = fmul(static_cast<float>(ids[j]), off1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cb[threadIdx.x][k] = fadd(boxes[j * 4 + k], off);
+  }
+  __syncthreads();
+  const int i = row0 + threadIdx.x;
+  if (i >= nv) return;
+  const size_t gi = static_cast<size_t>(b) * n + i;
+  const float off = fmul(static_cast<float>(ids[gi]), off1);
+  float a[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a[k] = fadd(boxes[gi * 4 + k], off);
+  unsigned long long bits = 0;
+  const int start = (row0 == col0) ? threadIdx.x + 1 : 0;
+  for (int j = start; j < cn; ++j)
+    if (iou_gt(a, cb[j], thr)) bits |= 1ull << j;
+  const int words = (n + 63) / 64;
+  mask[(static_cast<size_t>(b) * n + i) * words + blockIdx.x] = bits;
+}
+
+// one warp per image: greedy scan in score order
+__global__ void nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ nvalid,
+                                int n, unsigned char* __restrict__ keep) {
+  extern __shared__ unsigned long long remv[];
+  const int b = blockIdx.x;
+  const int nv = nvalid[b];
+  const int words = (n + 63) / 64;
+  const int lane = threadIdx.x;
+  for (int w = lane; w < words; w += 32) remv[w] = 0ull;
+  __syncwarp();
+  for (int i = 0; i < n; ++i) {
+    unsigned char k = 0;
+    if (i < nv) {
+      const unsigned long long r = remv[i >> 6];
+      if (!((r >> (i & 63)) & 1ull)) {
+        k = 1;
+        const unsigned long long* mrow = mask + (static_cast<size_t>(b) * n + i) * words;
+        // only words >= i/64 were written by nms_mask_kernel (upper triangle)
+        for (int w = (i >> 6) + lane; w < (nv + 63) / 64; w += 32) remv[w] |= mrow[w];
+      }
+      __syncwarp();
+    }
+    if (lane == 0) keep[static_cast<size_t>(b) * n + i] = k;
+  }
+}
+
+int nms_batched(const float* boxes, const long long* ids, const int* nvalid, int B, int n, float thr,
+                unsigned long long* mask_ws, float* max_coord_ws, unsigned char* keep, cudaStream_t stream) {
+  RSP_CHECK_ARG(boxes && ids && nvalid && mask_ws && max_coord_ws && keep && B > 0 && n > 0, "nms: bad args");
+  const int words = (n + 63) / 64;
+  RSP_CHECK_ARG(words * 8 <= 48 * 1024, "nms: at most %d candidates per image", 48 * 1024 / 8 * 64);
+  nms_max_coord_kernel<<<B, 256, 0, stream>>>(boxes, nvalid, n, max_coord_ws);
+  RSP_CHECK_LAUNCH();
+  dim3 grid(words, words, B);
+  nms_mask_kernel<<<grid, 64, 0, stream>>>(boxes, ids, nvalid, max_coord_ws, n, thr, mask_ws);
+  RSP_CHECK_LAUNCH();
+  nms_scan_kernel<<<B, 32, words * 8, stream>>>(mask_ws, nvalid, n, keep);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// first K kept candidates of each image, in order.  One warp per image (ballot prefix).
+__global__ void compact_keep_kernel(const unsigned char* __restrict__ keep, const float* __restrict__ boxes,
+                                    const float* __restrict__ scores, const long long* __restrict__ labels,
+                                    int n, int K, float* __restrict__ out_boxes, float* __restrict__ out_scores,
+                                    long long* __restrict__ out_labels, int* __restrict__ out_index,
+                                    int* __restrict__ counts) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  int cnt = 0;
+  for (int base = 0; base < n && cnt < K; base += 32) {
+    const int i = base + lane;
+    const bool k = (i < n) && keep[static_cast<size_t>(b) * n + i];
+    const unsigned bal = __ballot_sync(0xffffffffu, k);
+    const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+    if (k && pos < K) {
+      const size_t src = static_cast<size_t>(b) * n + i, dst = static_cast<size_t>(b) * K + pos;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) out_boxes[dst * 4 + c] = boxes[src * 4 + c];
+      out_scores[dst] = scores[src];
+      if (labels) out_labels[dst] = labels[src];
+      if (out_index) out_index[dst] = i;
+    }
+    cnt += __popc(bal);
+  }
+  cnt = min(cnt, K);
+  for (int pos = cnt + lane; pos < K; pos += 32) {
+    const size_t dst = static_cast<size_t>(b) * K + pos;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out_boxes[dst * 4 + c] = 0.f;
+    out_scores[dst] = 0.f;
+    if (labels) out_labels[dst] = 0;
+    if (out_index) out_index[dst] = -1;
+  }
+  if (lane == 0) counts[b] = cnt;
+}
+
+int compact_keep(const unsigned char* keep, const float* boxes, const float* scores, const long long* labels,
+                 int B, int n, int K, float* out_boxes, float* out_scores, long long* out_labels,
+                 int* out_index, int* counts, cudaStream_t stream) {
+  RSP_CHECK_ARG(keep && boxes && scores && out_boxes && out_scores && counts && B > 0 && n > 0 && K > 0,
+                "compact_keep: bad args");
+  compact_keep_kernel<<<B, 32, 0, stream>>>(keep, boxes, scores, labels, n, K, out_boxes, out_scores,
+                                            out_labels, out_index, counts);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+struct RoiLevels {
+  const __nv_bfloat16* feat[4];
+  const float* pe[4];   // fp32 [H, W, C] per level or null
+  int H[4], W[4];
+  float scale[4];
+};
+
+__device__ __forceinline__ void bilinear_setup(float y, float x, int H, int W, int& y0, int& x0, int& y1,
+                                               int& x1, float& w00, float& w01, float& w10, float& w11,
+                                               bool& inside) {
+  inside = !(y < -1.0f || y > H || x < -1.0f || x > W);
+  if (y <= 0.f) y = 0.f;
+  if (x <= 0.f) x = 0.f;
+  y0 = static_cast<int>(y); x0 = static_cast<int>(x);
+  if (y0 >= H - 1) { y1 = y0 = H - 1; y = static_cast<float>(y0); } else { y1 = y0 + 1; }
+  if (x0 >= W - 1) { x1 = x0 = W - 1; x = static_cast<float>(x0); } else { x1 = x0 + 1; }
+  const float ly = y - y0, lx = x - x0, hy = 1.f - ly, hx = 1.f - lx;
+  w00 = hy * hx; w01 = hy * lx; w10 = ly * hx; w11 = ly * lx;
+}
+
+// thread = 8 channels of one (roi, bin); out bf16 [n, P*P*C] in (ph, pw, c) order
+__global__ void roi_align_nhwc_kernel(RoiLevels lv, const float* __restrict__ rois, int n, int C, int P,
+                                      int num_levels, float finest_scale, __nv_bfloat16* __restrict__ out) {
+  const int c8 = C / 8;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n) * P * P * c8;
+  if (idx >= total) return;
+  const int cc = static_cast<int>(idx % c8);
+  long long t = idx / c8;
+  const int pw = static_cast<int>(t % P); t /= P;
+  const int ph = static_cast<int>(t % P);
+  const int r = static_cast<int>(t / P);
+  const float* roi = rois + static_cast<size_t>(r) * 5;
+  const int b = static_cast<int>(roi[0]);
+  // map_roi_levels: floor(log2(sqrt(w*h) / finest + 1e-6)) clamped
+  const float sc = sqrtf((roi[3] - roi[1]) * (roi[4] - roi[2]));
+  int l = static_cast<int>(floorf(log2f(sc / finest_scale + 1e-6f)));
+  l = max(0, min(num_levels - 1, l));
+  const int H = lv.H[l], W = lv.W[l];
+  const float ss = lv.scale[l];
+  const float x1 = roi[1] * ss - 0.5f, y1 = roi[2] * ss - 0.5f;
+  const float rw = roi[3] * ss - 0.5f - x1, rh = roi[4] * ss - 0.5f - y1;
+  const float bw = rw / P, bh = rh / P;
+  const int gh = max(static_cast<int>(ceilf(rh / P)), 1), gw = max(static_cast<int>(ceilf(rw / P)), 1);
+  const float cnt = static_cast<float>(max(gh * gw, 1));
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  const __nv_bfloat16* fb = lv.feat[l] + static_cast<size_t>(b) * H * W * C + cc * 8;
+  const float* pb = lv.pe[l] ? lv.pe[l] + cc * 8 : nullptr;
+  for (int iy = 0; iy < gh; ++iy) {
+    const float y = y1 + ph * bh + (iy + 0.5f) * bh / gh;
+    for (int ix = 0; ix < gw; ++ix) {
+      const float x = x1 + pw * bw + (ix + 0.5f) * bw / gw;
+      int y0, x0, yy1, xx1;
+      float w00, w01, w10, w11;
+      bool inside;
+      bilinear_setup(y, x, H, W, y0, x0, yy1, xx1, w00, w01, w10, w11, inside);
+      if (!inside) continue;
+      const size_t o00 = (static_cast<size_t>(y0) * W + x0) * C, o01 = (static_cast<size_t>(y0) * W + xx1) * C;
+      const size_t o10 = (static_cast<size_t>(yy1) * W + x0) * C, o11 = (static_cast<size_t>(yy1) * W + xx1) * C;
+      const uint4 u00 = *reinterpret_cast<const uint4*>(fb + o00), u01 = *reinterpret_cast<const uint4*>(fb + o01);
+      const uint4 u10 = *reinterpret_cast<const uint4*>(fb + o10), u11 = *reinterpret_cast<const uint4*>(fb + o11);
+      const uint32_t a00[4] = {u00.x, u00.y, u00.z, u00.w}, a01[4] = {u01.x, u01.y, u01.z, u01.w};
+      const uint32_t a10[4] = {u10.x, u10.y, u10.z, u10.w}, a11[4] = {u11.x, u11.y, u11.z, u11.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 h00 = *reinterpret_cast<const __nv_bfloat162*>(&a00[j]);
+        const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&a01[j]);
+        const __nv_bfloat162 h10 = *reinterpret_cast<const __nv_bfloat162*>(&a10[j]);
+        const __nv_bfloat162 h11 = *reinterpret_cast<const __nv_bfloat162*>(&a11[j]);
+        acc[2 * j] += w00 * __bfloat162float(h00.x) + w01 * __bfloat162float(h01.x) +
+                      w10 * __bfloat162float(h10.x) + w11 * __bfloat162float(h11.x);
+        acc[2 * j + 1] += w00 * __bfloat162float(h00.y) + w01 * __bfloat162float(h01.y) +
+                          w10 * __bfloat162float(h10.y) + w11 * __bfloat162float(h11.y);
+      }
+      if (pb) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          acc[k] += w00 * pb[o00 + k] + w01 * pb[o01 + k] + w10 * pb[o10 + k] + w11 * pb[o11 + k];
+      }
+    }
+  }
+  const float inv = 1.0f / cnt;
+  __nv_bfloat16* o = out + (static_cast<size_t>(r) * P * P + ph * P + pw) * C + cc * 8;
+  *reinterpret_cast<uint4*>(o) =
+      make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
+                 pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
+}
+
+int roi_align_nhwc(const void* const* feats, const float* const* pes, const int* Hs, const int* Ws,
+                   const float* scales, int num_levels, const float* rois, int n, int C, int P,
+                   float finest_scale, void* out, cudaStream_t stream) {
+  RSP_CHECK_ARG(feats && Hs && Ws && scales && rois && out && n > 0 && C % 8 == 0 && num_levels >= 1 &&
+                num_levels <= 4, "roi_align: bad args");
+  RoiLevels lv;
+  for (int i = 0; i < 4; ++i) {
+    const int j = i < num_levels ? i : num_levels - 1;
+    lv.feat[i] = static_cast<const __nv_bfloat16*>(feats[j]);
+    lv.pe[i] = pes ? pes[j] : nullptr;
+    lv.H[i] = Hs[j]; lv.W[i] = Ws[j]; lv.scale[i] = scales[j];
+  }
+  const long long total = static_cast<long long>(n) * P * P * (C / 8);
+  roi_align_nhwc_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      lv, rois, n, C, P, num_levels, finest_scale, static_cast<__nv_bfloat16*>(out));
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// logits fp32 [n, hm, wm] -> uint8 [n, H, W].  mode 0: (bilinear(sigmoid(x)) >= thr);
+// mode 1: (bilinear(x) > thr).  PyTorch align_corners=False source index rule.
+__global__ void mask_paste_kernel(const float* __restrict__ logits, unsigned char* __restrict__ out, int n,
+                                  int hm, int wm, int H, int W, float thr, int mode) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n) * H * (W / 4);
+  if (idx >= total) return;
+  const int x4 = static_cast<int>(idx % (W / 4));
+  long long t = idx / (W / 4);
+  const int y = static_cast<int>(t % H);
+  const int m = static_cast<int>(t / H);
+  const float sy = fmaxf((y + 0.5f) * (static_cast<float>(hm) / H) - 0.5f, 0.f);
+  const int y0 = static_cast<int>(sy), y1 = min(y0 + 1, hm - 1);
+  const float ly = sy - y0;
+  const float* base = logits + static_cast<size_t>(m) * hm * wm;
+  unsigned char r[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = x4 * 4 + k;
+    const float sx = fmaxf((x + 0.5f) * (static_cast<float>(wm) / W) - 0.5f, 0.f);
+    const int x0 = static_cast<int>(sx), x1 = min(x0 + 1, wm - 1);
+    const float lx = sx - x0;
+    float v00 = base[y0 * wm + x0], v01 = base[y0 * wm + x1], v10 = base[y1 * wm + x0], v11 = base[y1 * wm + x1];
+    if (mode == 0) {
+      v00 = 1.f / (1.f + expf(-v00)); v01 = 1.f / (1.f + expf(-v01));
+      v10 = 1.f / (1.f + expf(-v10)); v11 = 1.f / (1.f + expf(-v11));
+    }
+    const float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+    r[k] = mode == 0 ? (v >= thr) : (v > thr);
+  }
+  *reinterpret_cast<uchar4*>(out + (static_cast<size_t>(m) * H + y) * W + x4 * 4) = make_uchar4(r[0], r[1], r[2], r[3]);
+}
+
+int mask_paste(const float* logits, unsigned char* out, int n, int hm, int wm, int H, int W, float thr,
+               int mode, cudaStream_t stream) {
+  RSP_CHECK_ARG(logits && out && n > 0 && W % 4 == 0, "mask_paste: bad args");
+  const long long total = static_cast<long long>(n) * H * (W / 4);
+  mask_paste_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(logits, out, n, hm, wm, H, W,
+                                                                                   thr, mode);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// mode 0: 2x2 max pool stride 2; mode 1: stride-2 subsample (max_pool2d(k=1, s=2)).  bf16 NHWC.
+__global__ void pool2_nhwc_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B,
+                                  int H, int W, int C, int mode) {
+  const int Ho = mode == 0 ? H / 2 : (H + 1) / 2, Wo = mode == 0 ? W / 2 : (W + 1) / 2;
+  const int c8 = C / 8;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * Ho * Wo * c8) return;
+  const int cc = static_cast<int>(idx % c8);
+  long long t = idx / c8;
+  const int x = static_cast<int>(t % Wo); t /= Wo;
+  const int y = static_cast<int>(t % Ho);
+  const int b = static_cast<int>(t / Ho);
+  const __nv_bfloat16* p = in + ((static_cast<size_t>(b) * H + 2 * y) * W + 2 * x) * C + cc * 8;
+  uint4 v = *reinterpret_cast<const uint4*>(p);
+  if (mode == 0) {
+    const uint4 o[3] = {*reinterpret_cast<const uint4*>(p + C), *reinterpret_cast<const uint4*>(p + static_cast<size_t>(W) * C),
+                        *reinterpret_cast<const uint4*>(p + static_cast<size_t>(W) * C + C)};
+    __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const __nv_bfloat162* bb = reinterpret_cast<const __nv_bfloat162*>(&o[k]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[j] = __hmax2(a[j], bb[j]);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * Ho + y) * Wo + x) * C + cc * 8) = v;
+}
+
+int pool2_nhwc(const void* in, void* out, int B, int H, int W, int C, int mode, cudaStream_t stream) {
+  RSP_CHECK_ARG(in && out && B > 0 && C % 8 == 0 && (mode == 0 || mode == 1), "pool2: bad args");
+  const int Ho = mode == 0 ? H / 2 : (H + 1) / 2, Wo = mode == 0 ? W / 2 : (W + 1) / 2;
+  const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
+  pool2_nhwc_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), B, H, W, C, mode);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void sin_fold_kernel(const float* __restrict__ in, float* __restrict__ out, long long n_out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const float2 v = *reinterpret_cast<const float2*>(in + 2 * i);
+  out[i] = sinf(v.x) + v.y;
+}
+
+int sin_fold(const float* in, float* out, long long n_out, cudaStream_t stream) {
+  RSP_CHECK_ARG(in && out && n_out > 0, "sin_fold: bad args");
+  sin_fold_kernel<<<static_cast<unsigned>((n_out + 255) / 256), 256, 0, stream>>>(in, out, n_out);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
+}  // namespace rsp
