@@ -63,6 +63,14 @@ _SIGNATURES = {
     "rsp_token_self_attention": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "rsp_t2i_attention": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
     "rsp_i2t_attention": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
+    "rsp_rpn_decode": ([_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _f, _f, _f, _i, _i, _vp, _vp, _vp], _i),
+    "rsp_bbox_cls_decode": ([_vp, _i, _vp, _i, _vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp], _i),
+    "rsp_nms_batched": ([_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp], _i),
+    "rsp_compact_keep": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "rsp_roi_align_nhwc": ([_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _f, _vp, _vp], _i),
+    "rsp_mask_paste": ([_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp], _i),
+    "rsp_pool2_nhwc": ([_vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    "rsp_sin_fold": ([_vp, _vp, ctypes.c_longlong, _vp], _i),
 }
 
 
@@ -362,5 +370,147 @@ def cast_bf16(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
     assert out.is_contiguous() and out.numel() == x.numel() and out.dtype == torch.bfloat16
     _check(_lib.rsp_cast_f32_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "rsp_cast_f32_bf16")
+    launch_count += 1
+    return out
+
+
+# ------------------------------------------------------------------------------ detection ops
+def rpn_decode(head_out: torch.Tensor, topk_idx: torch.Tensor, B: int, H: int, W: int, A: int, stride: int,
+               base_anchors: torch.Tensor, img_hw: tuple, min_size: float, boxes: torch.Tensor,
+               scores: torch.Tensor, out_off: int) -> None:
+    """Decode the K top anchors of one level into boxes[B, n, 4] / scores[B, n] at column out_off."""
+    global launch_count
+    _require_cuda(head_out, topk_idx, base_anchors, boxes, scores)
+    assert head_out.dtype == torch.float32 and head_out.dim() == 2 and head_out.stride(1) == 1
+    assert topk_idx.dtype == torch.int64 and topk_idx.is_contiguous() and topk_idx.shape[0] == B
+    assert boxes.is_contiguous() and scores.is_contiguous() and boxes.dtype == torch.float32
+    K = topk_idx.shape[1]
+    _check(_lib.rsp_rpn_decode(_ptr(head_out), head_out.stride(0), _ptr(topk_idx), K, B, H, W, A, stride,
+                               _ptr(base_anchors), float(img_hw[0]), float(img_hw[1]), float(min_size),
+                               out_off, scores.shape[1], _ptr(boxes), _ptr(scores), _stream()), "rsp_rpn_decode")
+    launch_count += 1
+
+
+def bbox_cls_decode(cls: torch.Tensor, reg: torch.Tensor, rois: torch.Tensor, roi_valid: torch.Tensor | None,
+                    C: int, img_hw: tuple, score_thr: float):
+    """-> scores fp32 [n*C] (-1 filtered), boxes fp32 [n*C, 4], labels int64 [n*C]."""
+    global launch_count
+    _require_cuda(cls, reg, rois, roi_valid)
+    n = rois.shape[0]
+    assert cls.dtype == torch.float32 and reg.dtype == torch.float32 and rois.dtype == torch.float32
+    assert cls.stride(1) == 1 and reg.stride(1) == 1 and rois.is_contiguous() and rois.shape[1] == 5
+    scores = torch.empty(n * C, device=cls.device, dtype=torch.float32)
+    boxes = torch.empty(n * C, 4, device=cls.device, dtype=torch.float32)
+    labels = torch.empty(n * C, device=cls.device, dtype=torch.int64)
+    if roi_valid is not None:
+        assert roi_valid.dtype == torch.uint8 and roi_valid.numel() == n
+    _check(_lib.rsp_bbox_cls_decode(_ptr(cls), cls.stride(0), _ptr(reg), reg.stride(0), _ptr(rois),
+                                    _ptr(roi_valid), n, C, float(img_hw[0]), float(img_hw[1]),
+                                    float(score_thr), _ptr(scores), _ptr(boxes), _ptr(labels), _stream()),
+           "rsp_bbox_cls_decode")
+    launch_count += 1
+    return scores, boxes, labels
+
+
+def nms_batched(boxes: torch.Tensor, ids: torch.Tensor, nvalid: torch.Tensor, iou_thr: float) -> torch.Tensor:
+    """boxes fp32 [B, n, 4] sorted by descending score, ids int64 [B, n], nvalid int32 [B] -> keep uint8 [B, n]."""
+    global launch_count
+    _require_cuda(boxes, ids, nvalid)
+    B, n, _ = boxes.shape
+    assert boxes.dtype == torch.float32 and boxes.is_contiguous()
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and ids.shape == (B, n)
+    assert nvalid.dtype == torch.int32 and nvalid.numel() == B
+    words = (n + 63) // 64
+    mask_ws = torch.empty(B * n * words, device=boxes.device, dtype=torch.int64)
+    mx = torch.empty(B, device=boxes.device, dtype=torch.float32)
+    keep = torch.empty(B, n, device=boxes.device, dtype=torch.uint8)
+    _check(_lib.rsp_nms_batched(_ptr(boxes), _ptr(ids), _ptr(nvalid), B, n, float(iou_thr), _ptr(mask_ws),
+                                _ptr(mx), _ptr(keep), _stream()), "rsp_nms_batched")
+    launch_count += 3
+    return keep
+
+
+def compact_keep(keep: torch.Tensor, boxes: torch.Tensor, scores: torch.Tensor, labels: torch.Tensor | None,
+                 K: int):
+    """-> boxes [B, K, 4], scores [B, K], labels [B, K] | None, index int32 [B, K], counts int32 [B]."""
+    global launch_count
+    _require_cuda(keep, boxes, scores, labels)
+    B, n = keep.shape
+    dev = keep.device
+    ob = torch.empty(B, K, 4, device=dev, dtype=torch.float32)
+    os_ = torch.empty(B, K, device=dev, dtype=torch.float32)
+    ol = torch.empty(B, K, device=dev, dtype=torch.int64) if labels is not None else None
+    oi = torch.empty(B, K, device=dev, dtype=torch.int32)
+    cnt = torch.empty(B, device=dev, dtype=torch.int32)
+    assert boxes.is_contiguous() and scores.is_contiguous() and keep.is_contiguous()
+    _check(_lib.rsp_compact_keep(_ptr(keep), _ptr(boxes), _ptr(scores), _ptr(labels), B, n, K, _ptr(ob),
+                                 _ptr(os_), _ptr(ol), _ptr(oi), _ptr(cnt), _stream()), "rsp_compact_keep")
+    launch_count += 1
+    return ob, os_, ol, oi, cnt
+
+
+def roi_align_nhwc(feats: list, rois: torch.Tensor, P: int, strides: list, pes: list | None = None,
+                   finest_scale: float = 56.0) -> torch.Tensor:
+    """feats: bf16 NHWC levels; rois fp32 [n, 5] -> bf16 [n, P*P*C] in (ph, pw, c) order."""
+    global launch_count
+    _require_cuda(rois, *feats)
+    L = len(feats)
+    C = feats[0].shape[3]
+    n = rois.shape[0]
+    for f in feats:
+        assert f.dtype == torch.bfloat16 and f.is_contiguous() and f.shape[3] == C
+    assert rois.dtype == torch.float32 and rois.is_contiguous() and rois.shape[1] == 5
+    fp = (ctypes.c_void_p * L)(*[f.data_ptr() for f in feats])
+    pp = None
+    if pes is not None:
+        for pe, f in zip(pes, feats):
+            assert pe.dtype == torch.float32 and pe.is_contiguous() and pe.shape == f.shape[1:]
+        pp = (ctypes.c_void_p * L)(*[pe.data_ptr() for pe in pes])
+    hs = (ctypes.c_int32 * L)(*[f.shape[1] for f in feats])
+    ws = (ctypes.c_int32 * L)(*[f.shape[2] for f in feats])
+    sc = (ctypes.c_float * L)(*[1.0 / s for s in strides])
+    out = torch.empty(n, P * P * C, device=rois.device, dtype=torch.bfloat16)
+    _check(_lib.rsp_roi_align_nhwc(ctypes.cast(fp, _vp), ctypes.cast(pp, _vp) if pp is not None else None,
+                                   ctypes.cast(hs, _vp), ctypes.cast(ws, _vp), ctypes.cast(sc, _vp), L,
+                                   _ptr(rois), n, C, P, float(finest_scale), _ptr(out), _stream()),
+           "rsp_roi_align_nhwc")
+    launch_count += 1
+    return out
+
+
+def mask_paste(logits: torch.Tensor, size: tuple, thr: float, mode: int) -> torch.Tensor:
+    """fp32 [n, hm, wm] -> bool [n, H, W]; mode 0 sigmoid+bilinear >= thr, mode 1 bilinear > thr."""
+    global launch_count
+    _require_cuda(logits)
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and logits.dim() == 3
+    n, hm, wm = logits.shape
+    out = torch.empty(n, size[0], size[1], device=logits.device, dtype=torch.uint8)
+    if n > 0:
+        _check(_lib.rsp_mask_paste(_ptr(logits), _ptr(out), n, hm, wm, size[0], size[1], float(thr), mode, _stream()),
+               "rsp_mask_paste")
+        launch_count += 1
+    return out.view(torch.bool)
+
+
+def pool2_nhwc(x: torch.Tensor, mode: int) -> torch.Tensor:
+    """bf16 NHWC: mode 0 = 2x2 max pool stride 2, mode 1 = stride-2 subsample."""
+    global launch_count
+    _require_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
+    B, H, W, C = x.shape
+    Ho, Wo = (H // 2, W // 2) if mode == 0 else ((H + 1) // 2, (W + 1) // 2)
+    out = torch.empty(B, Ho, Wo, C, device=x.device, dtype=torch.bfloat16)
+    _check(_lib.rsp_pool2_nhwc(_ptr(x), _ptr(out), B, H, W, C, mode, _stream()), "rsp_pool2_nhwc")
+    launch_count += 1
+    return out
+
+
+def sin_fold(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [..., 2k] -> fp32 [..., k]: sin(even) + odd."""
+    global launch_count
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] % 2 == 0
+    out = torch.empty(*x.shape[:-1], x.shape[-1] // 2, device=x.device, dtype=torch.float32)
+    _check(_lib.rsp_sin_fold(_ptr(x), _ptr(out), out.numel(), _stream()), "rsp_sin_fold")
     launch_count += 1
     return out

@@ -1,0 +1,122 @@
+"""RSPrompterAnchor / RSPrompterQuery detectors (M:53-272): orchestration of the B200 modules.
+
+``predict(batch_inputs, batch_data_samples, rescale=True)`` keeps the reference contract
+(mmdet BaseDetector.forward mode='predict', detectors/base.py:58-99): it returns the data samples
+with ``pred_instances`` holding ``bboxes``, ``scores``, ``labels`` and boolean ``masks``.
+Everything between the input tensor and the final per-image split runs on the device without
+host synchronisation; the one device->host read is the per-image detection count.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .necks import PseudoFeatureAggregator
+from .registry import MODELS, BaseModule, ConfigDict, DetDataSample, InstanceData, make_data_samples
+from .sam_encoder import MMPretrainSamVisionEncoder, SamVisionEncoderOutput
+
+
+def _cfg(d) -> ConfigDict:
+    return d if isinstance(d, ConfigDict) else ConfigDict(d or {})
+
+
+class _SamDetectorBase(BaseModule):
+    def _encode(self, batch_inputs: torch.Tensor):
+        """-> (emb_rows fp32 [B*g*g, C], pos_rows fp32 [g*g, C], (g, g), emb_nhwc_bf16 | None, hidden | None)."""
+        enc = self.backbone.vision_encoder
+        want_hidden = not isinstance(self.backbone, MMPretrainSamVisionEncoder)
+        emb, hidden, emb_nhwc = enc.encode(batch_inputs, want_hidden=want_hidden)
+        B, g = emb_nhwc.shape[0], emb_nhwc.shape[1]
+        pos_rows = self.shared_image_embedding.shared_image_embedding.image_wide_rows(g)
+        return emb_nhwc.reshape(B * g * g, -1), pos_rows, (g, g), emb_nhwc, hidden
+
+    def extract_feat(self, batch_inputs: torch.Tensor):
+        """Reference return convention (M:97-114): (x NCHW tuple, image_embeddings, image_positional_embeddings)."""
+        vision_outputs = self.backbone(batch_inputs)
+        if isinstance(vision_outputs, SamVisionEncoderOutput):
+            image_embeddings, hidden = vision_outputs[0], vision_outputs[1]
+        elif isinstance(vision_outputs, tuple):
+            image_embeddings, hidden = vision_outputs[0], vision_outputs
+        else:
+            raise NotImplementedError
+        size = image_embeddings.shape[-1]
+        pe = self.shared_image_embedding.shared_image_embedding.image_wide_rows(size)
+        pe = pe.view(size, size, -1).permute(2, 0, 1).unsqueeze(0).repeat(image_embeddings.shape[0], 1, 1, 1)
+        x = self.neck(hidden)
+        return x, image_embeddings, pe
+
+    @staticmethod
+    def _check_metas(batch_data_samples, batch_inputs):
+        hw = tuple(batch_inputs.shape[-2:])
+        for ds in batch_data_samples:
+            m = ds.metainfo
+            sf = tuple(float(s) for s in m.get("scale_factor", (1.0, 1.0)))
+            if tuple(m.get("ori_shape", hw))[:2] != hw or tuple(m.get("img_shape", hw))[:2] != hw or sf != (1.0, 1.0):
+                raise NotImplementedError(
+                    "rsprompter_b200 post-processing currently handles ori_shape == img_shape == batch shape "
+                    "with scale_factor 1 (the resize-to-original step of M:1763-1777 is listed as next work)")
+        return hw
+
+
+@MODELS.register_module(force=True)
+class RSPrompterAnchor(_SamDetectorBase):
+    """M:53-170 over mmdet MaskRCNN / TwoStageDetector (detectors/two_stage.py:15-107)."""
+
+    def __init__(self, shared_image_embedding, decoder_freeze=True, backbone=None, neck=None, rpn_head=None,
+                 roi_head=None, train_cfg=None, test_cfg=None, data_preprocessor=None, init_cfg=None, **kwargs):
+        BaseModule.__init__(self, init_cfg=None)
+        test_cfg = _cfg(test_cfg)
+        self.backbone = MODELS.build(backbone)
+        self.neck = MODELS.build(neck)
+        rpn = dict(rpn_head)
+        rpn.update(train_cfg=None, test_cfg=test_cfg.get("rpn"))
+        rpn.setdefault("num_classes", 1)
+        self.rpn_head = MODELS.build(rpn)
+        roi = dict(roi_head)
+        roi.update(train_cfg=None, test_cfg=test_cfg.get("rcnn"))
+        self.roi_head = MODELS.build(roi)
+        self.shared_image_embedding = MODELS.build(shared_image_embedding)
+        self.decoder_freeze = decoder_freeze
+        self.test_cfg = test_cfg
+        self.data_preprocessor_cfg = data_preprocessor
+        self.eval()
+
+    @torch.no_grad()
+    def predict_raw(self, batch_inputs: torch.Tensor):
+        """Device-resident results: dict(bboxes [B,M,4], scores, labels, counts, mask_logits [B*M,1,4g,4g])."""
+        img_hw = tuple(batch_inputs.shape[-2:])
+        emb_rows, pos_rows, ghw, emb_nhwc, hidden = self._encode(batch_inputs)
+        if isinstance(getattr(self.neck, "feature_aggregator", None), PseudoFeatureAggregator):
+            feats = self.neck.forward_nhwc(None, _lib.cast_bf16(emb_nhwc.contiguous()))
+        else:
+            feats = self.neck.forward_nhwc(hidden)
+        props, _, pcnt = self.rpn_head.predict_nhwc(feats, img_hw)
+        return self.roi_head.predict_nhwc(feats, props, pcnt, img_hw, emb_rows, pos_rows, ghw)
+
+    @torch.no_grad()
+    def predict(self, batch_inputs: torch.Tensor, batch_data_samples=None, rescale: bool = True):
+        if batch_data_samples is None:
+            batch_data_samples = make_data_samples(batch_inputs.shape[0], tuple(batch_inputs.shape[-2:]))
+        hw = self._check_metas(batch_data_samples, batch_inputs)
+        r = self.predict_raw(batch_inputs)
+        thr = float(self.test_cfg.rcnn.get("mask_thr_binary", 0.5))
+        B, M = r["scores"].shape
+        logits = r["mask_logits"][:, 0].contiguous()
+        masks = _lib.mask_paste(logits, hw, thr, 0).view(B, M, hw[0], hw[1])
+        counts = r["counts"].cpu().tolist()          # the only device->host read
+        for b, ds in enumerate(batch_data_samples):
+            n = counts[b]
+            ds.pred_instances = InstanceData(bboxes=r["bboxes"][b, :n], scores=r["scores"][b, :n],
+                                             labels=r["labels"][b, :n], masks=masks[b, :n])
+        return batch_data_samples
+
+    def forward(self, inputs, data_samples=None, mode: str = "predict"):
+        if mode == "predict":
+            return self.predict(inputs, data_samples)
+        raise NotImplementedError("rsprompter_b200 implements the inference path only (mode='predict')")
+
+    def test_step(self, data):
+        return self.predict(data["inputs"], data.get("data_samples"))
+
+
+__all__ = ["RSPrompterAnchor"]

@@ -128,3 +128,128 @@ def positional_embedding_state_dict(arch: SamVisionArch, seed: int = 3) -> dict[
     numerical test (HF's default 384 for ViT-B turns sin/cos of 2*pi*x into noise)."""
     gen = torch.Generator().manual_seed(seed)
     return {"positional_embedding": _randn(gen, 2, arch.num_pos_feats, std=1.0)}
+
+
+# ================================================================================================
+# RSPrompter-anchor heads (reference module tree, M:53-170 + configs/rsprompter/_base_/rsprompter_anchor.py)
+# ================================================================================================
+def _conv_sd(sd: dict, gen: torch.Generator, prefix: str, cout: int, cin: int, k: int, bias: bool = True,
+             gain: float = 1.0) -> None:
+    sd[prefix + ".weight"] = _randn(gen, cout, cin, k, k, std=gain / math.sqrt(cin * k * k))
+    if bias:
+        sd[prefix + ".bias"] = _randn(gen, cout, std=0.05)
+
+
+def _bn_sd(sd: dict, gen: torch.Generator, prefix: str, c: int) -> None:
+    sd[prefix + ".weight"] = 1.0 + _randn(gen, c, std=0.1)
+    sd[prefix + ".bias"] = _randn(gen, c, std=0.1)
+    sd[prefix + ".running_mean"] = _randn(gen, c, std=0.1)
+    sd[prefix + ".running_var"] = 1.0 + _randn(gen, c, std=0.1).abs()
+    sd[prefix + ".num_batches_tracked"] = torch.tensor(100, dtype=torch.long)
+
+
+def feature_aggregator_state_dict(in_channels: int, n_select: int, hidden: int = 32, out: int = 256,
+                                  seed: int = 10) -> dict[str, torch.Tensor]:
+    gen = torch.Generator().manual_seed(seed)
+    sd: dict[str, torch.Tensor] = {}
+    for i in range(n_select):
+        _conv_sd(sd, gen, f"downconvs.{i}.0", hidden, in_channels, 1, gain=1.4)
+        _bn_sd(sd, gen, f"downconvs.{i}.1", hidden)
+        _conv_sd(sd, gen, f"downconvs.{i}.3", hidden, hidden, 3, gain=1.4)
+        _bn_sd(sd, gen, f"downconvs.{i}.4", hidden)
+        _conv_sd(sd, gen, f"hidden_convs.{i}.0", hidden, hidden, 3, gain=1.0)
+        _bn_sd(sd, gen, f"hidden_convs.{i}.1", hidden)
+    _conv_sd(sd, gen, "fusion_conv.0", out, hidden, 1, gain=1.4)
+    _bn_sd(sd, gen, "fusion_conv.1", out)
+    _conv_sd(sd, gen, "fusion_conv.3", out, out, 3, gain=1.4)
+    _bn_sd(sd, gen, "fusion_conv.4", out)
+    _conv_sd(sd, gen, "fusion_conv.6", out, out, 3)
+    return sd
+
+
+def pseudo_aggregator_state_dict(in_channels: int = 256, hidden: int = 512, out: int = 256, seed: int = 11):
+    gen = torch.Generator().manual_seed(seed)
+    sd: dict[str, torch.Tensor] = {}
+    _conv_sd(sd, gen, "channel_fusion.0", hidden, in_channels, 1, bias=False)
+    _norm(sd, gen, "channel_fusion.1", hidden)
+    _conv_sd(sd, gen, "channel_fusion.2", hidden, hidden, 3, bias=False)
+    _norm(sd, gen, "channel_fusion.3", hidden)
+    _conv_sd(sd, gen, "channel_fusion.4", out, hidden, 3, bias=False)
+    _norm(sd, gen, "channel_fusion.5", out)
+    return sd
+
+
+def simple_fpn_state_dict(bc: int = 256, in_channels=(64, 128, 256, 256), out: int = 256, seed: int = 12):
+    gen = torch.Generator().manual_seed(seed)
+    sd: dict[str, torch.Tensor] = {}
+
+    def convT(prefix, cin, cout):
+        sd[prefix + ".weight"] = _randn(gen, cin, cout, 2, 2, std=1.0 / math.sqrt(cin))
+        sd[prefix + ".bias"] = _randn(gen, cout, std=0.05)
+
+    convT("fpn1.0", bc, bc // 2)
+    _norm(sd, gen, "fpn1.1", bc // 2)
+    convT("fpn1.3", bc // 2, bc // 4)
+    convT("fpn2.0", bc, bc // 2)
+    for i, c in enumerate(in_channels):
+        _conv_sd(sd, gen, f"lateral_convs.{i}.conv", out, c, 1, bias=False)
+        _norm(sd, gen, f"lateral_convs.{i}.ln", out)
+        _conv_sd(sd, gen, f"fpn_convs.{i}.conv", out, out, 3, bias=False)
+        _norm(sd, gen, f"fpn_convs.{i}.ln", out)
+    return sd
+
+
+def rpn_head_state_dict(c: int = 256, num_anchors: int = 6, seed: int = 13):
+    gen = torch.Generator().manual_seed(seed)
+    sd: dict[str, torch.Tensor] = {}
+    _conv_sd(sd, gen, "rpn_conv", c, c, 3, gain=1.4)
+    _conv_sd(sd, gen, "rpn_cls", num_anchors, c, 1, gain=2.0)
+    _conv_sd(sd, gen, "rpn_reg", num_anchors * 4, c, 1, gain=0.5)
+    return sd
+
+
+def bbox_head_state_dict(num_classes: int, c: int = 256, roi: int = 7, fc: int = 1024, seed: int = 14):
+    gen = torch.Generator().manual_seed(seed)
+    sd: dict[str, torch.Tensor] = {}
+    _linear(sd, gen, "shared_fcs.0", fc, c * roi * roi, std=1.4 / math.sqrt(c * roi * roi))
+    _linear(sd, gen, "shared_fcs.1", fc, fc, std=1.4 / math.sqrt(fc))
+    _linear(sd, gen, "fc_cls", num_classes + 1, fc, std=3.0 / math.sqrt(fc))
+    _linear(sd, gen, "fc_reg", 4 * num_classes, fc, std=1.0 / math.sqrt(fc))
+    return sd
+
+
+def mask_head_state_dict(c: int = 256, roi: int = 14, points: int = 5, seed: int = 15):
+    """point_emb.* of RSPrompterAnchorMaskHead (M:1641-1651); decoder / no_mask_embed come from the SAM dicts."""
+    gen = torch.Generator().manual_seed(seed)
+    sd: dict[str, torch.Tensor] = {}
+    _conv_sd(sd, gen, "point_emb.0", c, c, 3, gain=1.4)
+    _bn_sd(sd, gen, "point_emb.1", c)
+    _linear(sd, gen, "point_emb.4", c, c * roi * roi // 4, std=1.4 / math.sqrt(c * roi * roi // 4))
+    _linear(sd, gen, "point_emb.6", c, c, std=1.4 / math.sqrt(c))
+    _linear(sd, gen, "point_emb.8", c * 2 * points, c, std=1.0 / math.sqrt(c))
+    return sd
+
+
+def _prefixed(prefix: str, sd: dict) -> dict:
+    return {prefix + k: v for k, v in sd.items()}
+
+
+def anchor_detector_state_dict(arch: SamVisionArch, num_classes: int, n_select: int, seed: int = 0,
+                               pseudo_neck: bool = False) -> dict[str, torch.Tensor]:
+    """Full RSPrompterAnchor state dict with the reference's key names."""
+    sd: dict[str, torch.Tensor] = {}
+    sd.update(_prefixed("backbone.vision_encoder.", vision_encoder_state_dict(arch, seed)))
+    if pseudo_neck:
+        sd.update(_prefixed("neck.feature_aggregator.", pseudo_aggregator_state_dict(seed=seed + 11)))
+    else:
+        sd.update(_prefixed("neck.feature_aggregator.",
+                            feature_aggregator_state_dict(arch.hidden_size, n_select, seed=seed + 10)))
+    sd.update(_prefixed("neck.feature_spliter.", simple_fpn_state_dict(seed=seed + 12)))
+    sd.update(_prefixed("rpn_head.", rpn_head_state_dict(seed=seed + 13)))
+    sd.update(_prefixed("roi_head.bbox_head.", bbox_head_state_dict(num_classes, seed=seed + 14)))
+    sd.update(_prefixed("roi_head.mask_head.", mask_head_state_dict(seed=seed + 15)))
+    sd.update(_prefixed("roi_head.mask_head.mask_decoder.mask_decoder.", mask_decoder_state_dict(seed=seed + 1)))
+    sd["roi_head.mask_head.no_mask_embed.weight"] = prompt_encoder_state_dict(seed=seed + 2)["no_mask_embed.weight"]
+    sd.update(_prefixed("shared_image_embedding.shared_image_embedding.",
+                        positional_embedding_state_dict(arch, seed + 3)))
+    return sd

@@ -1,0 +1,167 @@
+"""RSPrompter-anchor head path on the GPU vs the CPU oracle, stage by stage.  Continuous stages are
+compared with a bf16 tolerance on the same inputs; index-producing stages (top-k / decode / NMS /
+compaction) are checked EXACTLY by running the oracle's post-processing on the tensors the GPU
+stage produced."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+NUM_CLASSES = 10
+
+
+def _relerr(a, b):
+    return (a.float().cpu() - b.float().cpu()).abs().max().item() / max(b.abs().max().item(), 1e-6)
+
+
+@pytest.fixture(scope="module")
+def model_and_sd():
+    from rsprompter_b200 import model_configs, synthetic
+    from rsprompter_b200.registry import MODELS
+    from rsprompter_b200.sam_config import VISION_ARCHS
+    cfg = model_configs.anchor_model_cfg("base", NUM_CLASSES)
+    m = MODELS.build(cfg)
+    sd = synthetic.anchor_detector_state_dict(VISION_ARCHS["base"], NUM_CLASSES, 6, seed=3)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda(), sd
+
+
+def _sub(sd, prefix):
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def _nhwc_bf16(x):
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+
+
+def test_neck_matches_oracle(model_and_sd):
+    from oracle import restate_anchor as ra
+    m, sd = model_and_sd
+    g = torch.Generator().manual_seed(5)
+    hidden = [torch.randn(1, 64, 64, 768, generator=g) for _ in range(13)]
+    agg_sd, fpn_sd = _sub(sd, "neck.feature_aggregator."), _sub(sd, "neck.feature_spliter.")
+    ref_agg = ra.feature_aggregator(agg_sd, hidden, list(range(1, 13, 2)))
+    ref = ra.simple_fpn(fpn_sd, ref_agg)
+    agg = m.neck.feature_aggregator.forward_nhwc([h.cuda() for h in hidden])
+    assert _relerr(agg.permute(0, 3, 1, 2), ref_agg) < 3e-2
+    outs = m.neck.forward_nhwc([h.cuda() for h in hidden])
+    torch.cuda.synchronize()
+    assert len(outs) == 5
+    for o, r in zip(outs, ref):
+        assert tuple(o.shape) == (r.shape[0], r.shape[2], r.shape[3], r.shape[1])
+        assert _relerr(o.permute(0, 3, 1, 2), r) < 4e-2
+
+
+def test_rpn_head_and_proposals(model_and_sd):
+    from oracle import restate_anchor as ra
+    m, sd = model_and_sd
+    g = torch.Generator().manual_seed(6)
+    B = 2
+    sizes = [256, 128, 64, 32, 16]
+    feats = [torch.randn(B, 256, s, s, generator=g).to(torch.bfloat16).float() for s in sizes]
+    cap = {}
+    props, scores, cnt = m.rpn_head.predict_nhwc([_nhwc_bf16(f) for f in feats], (1024, 1024), capture=cap)
+    torch.cuda.synchronize()
+    ref = ra.rpn_forward(_sub(sd, "rpn_head."), feats, prefix="")
+    strides = [4, 8, 16, 32, 64]
+    A = 6
+    for lvl, (c_ref, r_ref) in enumerate(ref):
+        out = cap["head_out"][lvl].cpu()
+        assert _relerr(out[..., :A].permute(0, 3, 1, 2), c_ref) < 2e-2
+        assert _relerr(out[..., A:5 * A].permute(0, 3, 1, 2), r_ref) < 2e-2
+    # exact post-processing on the GPU head outputs
+    for b in range(B):
+        cls_l, reg_l, pri_l = [], [], []
+        for lvl, s in enumerate(sizes):
+            out = cap["head_out"][lvl][b].cpu()
+            cls_l.append(out[..., :A].permute(2, 0, 1))
+            reg_l.append(out[..., A:5 * A].permute(2, 0, 1))
+            pri_l.append(ra.grid_anchors((s, s), strides[lvl], ra.base_anchors(strides[lvl], [4, 8], [0.5, 1.0, 2.0])))
+        pb, ps = ra.rpn_predict_single(cls_l, reg_l, pri_l, (1024, 1024))
+        n = cnt[b].item()
+        assert n == pb.shape[0], f"proposal count {n} vs oracle {pb.shape[0]}"
+        torch.testing.assert_close(props[b, :n].cpu(), pb, rtol=0, atol=2e-3)
+        torch.testing.assert_close(scores[b, :n].cpu(), ps, rtol=0, atol=1e-5)
+        assert (props[b, n:] == 0).all()
+
+
+def test_roi_head_stages(model_and_sd):
+    from oracle import restate_anchor as ra
+    m, sd = model_and_sd
+    g = torch.Generator().manual_seed(7)
+    B, K = 2, 200
+    sizes = [256, 128, 64, 32, 16]
+    feats = [torch.randn(B, 256, s, s, generator=g).to(torch.bfloat16).float() for s in sizes]
+    # plausible proposals: random boxes of assorted sizes
+    ctr = torch.rand(B, K, 2, generator=g) * 1024
+    wh = torch.exp(torch.rand(B, K, 2, generator=g) * 5.0 + 1.5)
+    props = torch.cat([(ctr - wh / 2).clamp(0, 1024), (ctr + wh / 2).clamp(0, 1024)], dim=2)
+    pcnt = torch.tensor([K, K - 37], dtype=torch.int32)
+    props[1, K - 37:] = 0
+    emb_rows = torch.randn(B * 4096, 256, generator=g).cuda()
+    pos_rows = torch.randn(4096, 256, generator=g).cuda()
+    cap = {}
+    r = m.roi_head.predict_nhwc([_nhwc_bf16(f) for f in feats], props.cuda(), pcnt.cuda(), (1024, 1024),
+                                emb_rows, pos_rows, (64, 64), capture=cap)
+    torch.cuda.synchronize()
+    # RoIAlign(7x7) with the extra PE + bbox FCs vs oracle
+    feats_pe = ra.add_extra_pe(feats)
+    rois = cap["rois"].cpu()
+    ref7 = ra.roi_extract(feats_pe[:4], rois, 7)
+    got7 = cap["roi_feats7"].float().cpu().view(-1, 7, 7, 256).permute(0, 3, 1, 2)
+    assert _relerr(got7, ref7) < 2e-2
+    bsd = _sub(sd, "roi_head.bbox_head.")
+    cls_ref, reg_ref = ra.bbox_head_forward(bsd, ref7, prefix="")
+    assert _relerr(cap["cls"], cls_ref) < 3e-2 and _relerr(cap["reg"], reg_ref) < 3e-2
+    # exact detection post-processing on the GPU logits
+    for b in range(B):
+        n_roi = pcnt[b].item()
+        sl = slice(b * K, b * K + n_roi)
+        db, ds, dl = ra.bbox_predict_single(rois[sl], cap["cls"][sl].cpu(), cap["reg"][sl].cpu(), (1024, 1024),
+                                            NUM_CLASSES)
+        n = r["counts"][b].item()
+        assert n == db.shape[0]
+        torch.testing.assert_close(r["bboxes"][b, :n].cpu(), db, rtol=0, atol=2e-3)
+        torch.testing.assert_close(r["scores"][b, :n].cpu(), ds, rtol=0, atol=1e-5)
+        assert torch.equal(r["labels"][b, :n].cpu(), dl)
+    # mask branch: RoIAlign(14x14) + prompt generator
+    mrois = cap["mask_rois"].cpu()
+    ref14 = ra.roi_extract(feats_pe[:4], mrois, 14)
+    got14 = cap["roi_feats14"].float().cpu().view(-1, 14, 14, 256).permute(0, 3, 1, 2)
+    assert _relerr(got14, ref14) < 2e-2
+    sparse_ref = ra.mask_head_prompts(_sub(sd, "roi_head.mask_head."), ref14, 5, prefix="")
+    sparse = m.roi_head.mask_head.prompts_from_roi_feats(cap["roi_feats14"])
+    assert sparse.shape == sparse_ref.shape == (B * 100, 5, 256)
+    assert _relerr(sparse, sparse_ref) < 3e-2
+    assert r["mask_logits"].shape == (B * 100, 1, 256, 256)
+
+
+def test_mask_paste_matches_oracle():
+    from oracle import restate_anchor as ra
+    from rsprompter_b200 import _lib
+    g = torch.Generator().manual_seed(8)
+    logits = torch.randn(5, 1, 256, 256, generator=g) * 3
+    ref = ra.mask_postprocess(logits, (1024, 1024), 0.5)
+    got = _lib.mask_paste(logits[:, 0].contiguous().cuda(), (1024, 1024), 0.5, 0)
+    torch.cuda.synchronize()
+    assert got.dtype == torch.bool and got.shape == ref.shape
+    assert (got.cpu() != ref).float().mean().item() < 1e-5
+
+
+def test_end_to_end_predict_contract(model_and_sd):
+    m, _ = model_and_sd
+    from rsprompter_b200.registry import make_data_samples
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 1024, 1024, device="cuda")
+    out = m.predict(x, make_data_samples(2, 1024))
+    assert len(out) == 2
+    for ds in out:
+        p = ds.pred_instances
+        n = len(p)
+        assert 0 <= n <= 100
+        assert p.bboxes.shape == (n, 4) and p.scores.shape == (n,) and p.labels.shape == (n,)
+        assert p.masks.shape == (n, 1024, 1024) and p.masks.dtype == torch.bool
+        assert p.labels.dtype == torch.int64 and (p.labels >= 0).all() and (p.labels < NUM_CLASSES).all()
+        assert (p.scores[:-1] >= p.scores[1:]).all()
+    out2 = m.predict(x, make_data_samples(2, 1024))
+    assert torch.equal(out[0].pred_instances.bboxes, out2[0].pred_instances.bboxes)
