@@ -292,3 +292,67 @@ def mask_postprocess(mask_logits: torch.Tensor, size, thr: float = 0.5) -> torch
     m = F.interpolate(mask_logits.sigmoid(), size=size, mode="bilinear", align_corners=False).squeeze(1)
     m = F.interpolate(m.unsqueeze(1), size=size, mode="bilinear", align_corners=False).squeeze(1)
     return m >= thr
+
+
+# --------------------------------------------------------------------------------------------
+# whole detector
+# --------------------------------------------------------------------------------------------
+def _sub(sd: dict, prefix: str) -> dict:
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def anchor_predict(sd: dict, vision_arch, decoder_arch, images: torch.Tensor, num_classes: int,
+                   select_layers, strides=(4, 8, 16, 32, 64), scales=(4, 8), ratios=(0.5, 1.0, 2.0),
+                   points: int = 5, timings: dict | None = None):
+    """RSPrompterAnchor.predict (M:148-170) for metainfo img_shape == ori_shape == batch shape,
+    scale_factor 1: returns a list of per-image dicts(bboxes, scores, labels, masks, mask_logits)."""
+    import time
+    t0 = time.perf_counter()
+    B, _, H, W = images.shape
+    emb, hidden = restate.vit_encoder(_sub(sd, "backbone.vision_encoder."), vision_arch, images)
+    t1 = time.perf_counter()
+    agg = feature_aggregator(_sub(sd, "neck.feature_aggregator."), hidden, list(select_layers))
+    feats = simple_fpn(_sub(sd, "neck.feature_spliter."), agg)
+    pe = restate.image_wide_positional_embedding(
+        sd["shared_image_embedding.shared_image_embedding.positional_embedding"], emb.shape[-1])
+    t2 = time.perf_counter()
+    heads = rpn_forward(_sub(sd, "rpn_head."), feats, prefix="")
+    priors = [grid_anchors(f.shape[-2:], s, base_anchors(s, scales, ratios)) for f, s in zip(feats, strides)]
+    props = []
+    for b in range(B):
+        pb, _ = rpn_predict_single([c[b] for c, _ in heads], [r[b] for _, r in heads], priors, (H, W))
+        props.append(pb)
+    t3 = time.perf_counter()
+    feats_pe = add_extra_pe(feats)
+    rois = torch.cat([torch.cat([pb.new_full((pb.shape[0], 1), b), pb], dim=1) for b, pb in enumerate(props)])
+    roi_feats = roi_extract(feats_pe[:4], rois, 7)
+    cls, reg = bbox_head_forward(_sub(sd, "roi_head.bbox_head."), roi_feats, prefix="")
+    results, off = [], 0
+    for b, pb in enumerate(props):
+        n = pb.shape[0]
+        db, ds, dl = bbox_predict_single(rois[off:off + n], cls[off:off + n], reg[off:off + n], (H, W), num_classes)
+        off += n
+        results.append(dict(bboxes=db, scores=ds, labels=dl))
+    t4 = time.perf_counter()
+    mrois = torch.cat([torch.cat([r["bboxes"].new_full((r["bboxes"].shape[0], 1), b), r["bboxes"]], dim=1)
+                       for b, r in enumerate(results)])
+    if mrois.shape[0] > 0:
+        mfeats = roi_extract(feats_pe[:4], mrois, 14)
+        msd = _sub(sd, "roi_head.mask_head.")
+        sparse = mask_head_prompts(msd, mfeats, points, prefix="")
+        ids = mrois[:, 0].long()
+        dense = sd["roi_head.mask_head.no_mask_embed.weight"].reshape(1, -1, 1, 1).expand(
+            ids.numel(), -1, emb.shape[-2], emb.shape[-1])
+        logits, _ = restate.mask_decoder(_sub(msd, "mask_decoder.mask_decoder."), decoder_arch, emb[ids],
+                                         pe.expand(ids.numel(), -1, -1, -1), sparse[:, None], dense, False)
+        logits = logits[:, 0]
+        off = 0
+        for r in results:
+            n = r["bboxes"].shape[0]
+            r["mask_logits"] = logits[off:off + n]
+            r["masks"] = mask_postprocess(logits[off:off + n], (H, W))
+            off += n
+    t5 = time.perf_counter()
+    if timings is not None:
+        timings.update(encoder=t1 - t0, neck=t2 - t1, rpn=t3 - t2, roi=t4 - t3, mask=t5 - t4)
+    return results

@@ -321,7 +321,7 @@ __global__ void roi_align_nhwc_kernel(RoiLevels lv, const float* __restrict__ ro
   const float x1 = roi[1] * ss - 0.5f, y1 = roi[2] * ss - 0.5f;
   const float rw = roi[3] * ss - 0.5f - x1, rh = roi[4] * ss - 0.5f - y1;
   const float bw = rw / P, bh = rh / P;
-  const int gh = max(static_cast<int>(ceilf(rh / P)), 1), gw = max(static_cast<int>(ceilf(rw / P)), 1);
+  const int gh = static_cast<int>(ceilf(rh / P)), gw = static_cast<int>(ceilf(rw / P));  // may be 0 (degenerate roi)
   const float cnt = static_cast<float>(max(gh * gw, 1));
   float acc[8];
 #pragma unroll

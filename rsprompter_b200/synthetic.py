@@ -203,7 +203,7 @@ def rpn_head_state_dict(c: int = 256, num_anchors: int = 6, seed: int = 13):
     gen = torch.Generator().manual_seed(seed)
     sd: dict[str, torch.Tensor] = {}
     _conv_sd(sd, gen, "rpn_conv", c, c, 3, gain=1.4)
-    _conv_sd(sd, gen, "rpn_cls", num_anchors, c, 1, gain=2.0)
+    _conv_sd(sd, gen, "rpn_cls", num_anchors, c, 1, gain=0.3)
     _conv_sd(sd, gen, "rpn_reg", num_anchors * 4, c, 1, gain=0.5)
     return sd
 

@@ -1,0 +1,57 @@
+"""The reference's own config files load unchanged through the registry surface and build the B200
+modules (skipped where /root/reference is not mounted, e.g. on the GPU box)."""
+import os
+
+import pytest
+import torch
+
+REF_CFG = "/root/reference/configs/rsprompter"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF_CFG), reason="reference tree not mounted")
+
+
+def _strip_init(cfg):
+    """Pretrained checkpoints do not exist offline: drop init_cfg (random init is loaded instead)."""
+    if isinstance(cfg, dict):
+        cfg.pop("init_cfg", None)
+        for v in cfg.values():
+            _strip_init(v)
+    elif isinstance(cfg, (list, tuple)):
+        for v in cfg:
+            _strip_init(v)
+    return cfg
+
+
+def test_base_config_inheritance_and_delete():
+    from rsprompter_b200.registry import Config
+    cfg = Config.fromfile(os.path.join(REF_CFG, "rsprompter_anchor-nwpu-peft-512.py"))
+    m = cfg.model
+    assert m.type == "RSPrompterAnchor"                                   # from _base_
+    assert m.backbone.type == "MMPretrainSamVisionEncoder" and "extra_config" not in m.backbone  # _delete_
+    assert m.neck.feature_aggregator.type == "PseudoFeatureAggregator"
+    assert m.neck.feature_spliter.type == "RSSimpleFPN"                   # merged, not replaced
+    assert m.roi_head.bbox_head.num_classes == 10
+    assert m.test_cfg.rcnn.max_per_img == 100
+    assert cfg.custom_imports["imports"] == ["mmdet.rsprompter"]
+
+
+@pytest.mark.parametrize("name,enc_cls", [("rsprompter_anchor-nwpu.py", "RSSamVisionEncoder"),
+                                          ("rsprompter_anchor-nwpu-peft-512.py", "MMPretrainSamVisionEncoder")])
+def test_reference_anchor_configs_build(name, enc_cls):
+    from rsprompter_b200 import synthetic
+    from rsprompter_b200.registry import MODELS, Config
+    cfg = Config.fromfile(os.path.join(REF_CFG, name))
+    model_cfg = _strip_init(cfg.to_dict()["model"])
+    model = MODELS.build(model_cfg)
+    assert type(model).__name__ == "RSPrompterAnchor"
+    assert type(model.backbone).__name__ == enc_cls
+    arch = model.backbone.vision_encoder.arch
+    assert arch.name == "base" and arch.hidden_size == 768
+    if enc_cls == "MMPretrainSamVisionEncoder":
+        assert arch.image_size == 512 and arch.grid == 32
+        assert model.backbone.vision_encoder.layers[2].attn.rel_pos_h.shape == (63, 64)
+        sd = synthetic.anchor_detector_state_dict(arch, 10, 0, seed=0, pseudo_neck=True)
+    else:
+        sd = synthetic.anchor_detector_state_dict(arch, 10, 6, seed=0)
+    assert set(model.state_dict()) == set(sd)
+    model.load_state_dict(sd, strict=True)
+    assert model.roi_head.test_cfg.score_thr == 0.05 and model.rpn_head.test_cfg.nms_pre == 1000
