@@ -176,6 +176,7 @@ def run_ours(args) -> None:
     from rsprompter_b200 import _lib, model_configs, synthetic
     from rsprompter_b200.model_configs import SELECT_LAYERS
     from rsprompter_b200.registry import MODELS, make_data_samples
+    from rsprompter_b200.results import gather_records, pack_records
     from rsprompter_b200.sam_config import VISION_ARCHS
 
     rank = int(os.environ.get("RANK", "0"))
@@ -202,22 +203,16 @@ def run_ours(args) -> None:
     def step_resident(i):
         r = model.predict_raw(resident[i % N_INPUT_SETS])
         masks = _lib.mask_paste(r["mask_logits"][:, 0].contiguous(), (SIZE, SIZE), thr, 0)
-        rec = torch.cat([r["bboxes"], r["scores"][..., None], r["labels"][..., None].float()], dim=2)  # [B, M, 6]
-        if world > 1:
-            out = torch.empty(world * BATCH, M, 6, device=dev)
-            dist.all_gather_into_tensor(out, rec.contiguous())
-            cnt = torch.empty(world * BATCH, dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(cnt, r["counts"])
-        return masks, rec, r["counts"]
+        rec = pack_records(r["bboxes"], r["scores"], r["labels"])      # [B, M, 6]
+        rec, cnt = gather_records(rec, r["counts"])                    # the one collective of the path
+        return masks, rec, cnt
 
     def step_e2e(i):
         x = host[i % N_INPUT_SETS].to(dev, non_blocking=True)
         r = model.predict_raw(x)
         masks = _lib.mask_paste(r["mask_logits"][:, 0].contiguous(), (SIZE, SIZE), thr, 0)
-        rec = torch.cat([r["bboxes"], r["scores"][..., None], r["labels"][..., None].float()], dim=2)
-        if world > 1:
-            out = torch.empty(world * BATCH, M, 6, device=dev)
-            dist.all_gather_into_tensor(out, rec.contiguous())
+        rec = pack_records(r["bboxes"], r["scores"], r["labels"])
+        gather_records(rec, r["counts"])
         rec_h = rec.cpu()
         cnt_h = r["counts"].cpu()
         return masks, rec_h, cnt_h

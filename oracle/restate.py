@@ -38,14 +38,21 @@ def vit_attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, rel_h:
     N, T, hd = q.shape
     scale = hd ** -0.5
     attn = (q * scale) @ k.transpose(-2, -1)
+    bias = decomposed_rel_pos_bias(q, rel_h, rel_w, S)
+    attn = torch.softmax((attn + bias).float(), dim=-1).to(q.dtype)
+    return attn @ v
+
+
+def decomposed_rel_pos_bias(q: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor, S: int) -> torch.Tensor:
+    """bias[n, (qh,qw), (kh,kw)] = q . Rh[qh-kh+S-1] + q . Rw[qw-kw+S-1] with the UNscaled q
+    (HF:760-801 get_decomposed_rel_pos, VS:117-157 add_decomposed_rel_pos).  q [N, S*S, hd]."""
+    N, T, hd = q.shape
     Rh = rel_pos_gather(rel_h, S, S)  # [qh, kh, hd]
     Rw = rel_pos_gather(rel_w, S, S)
     q4 = q.reshape(N, S, S, hd)
     bh = torch.einsum("bhwc,hkc->bhwk", q4, Rh)  # [N, qh, qw, kh]
     bw = torch.einsum("bhwc,wkc->bhwk", q4, Rw)  # [N, qh, qw, kw]
-    bias = (bh[:, :, :, :, None] + bw[:, :, :, None, :]).reshape(N, T, T)
-    attn = torch.softmax((attn + bias).float(), dim=-1).to(q.dtype)
-    return attn @ v
+    return (bh[:, :, :, :, None] + bw[:, :, :, None, :]).reshape(N, T, T)
 
 
 def window_partition(x: torch.Tensor, ws: int):

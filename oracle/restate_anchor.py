@@ -356,3 +356,15 @@ def anchor_predict(sd: dict, vision_arch, decoder_arch, images: torch.Tensor, nu
     if timings is not None:
         timings.update(encoder=t1 - t0, neck=t2 - t1, rpn=t3 - t2, roi=t4 - t3, mask=t5 - t4)
     return results
+
+
+def mask2bbox(masks: torch.Tensor) -> torch.Tensor:
+    """Tight boxes of boolean masks (mmdet/structures/mask/utils.py:56-77)."""
+    n = masks.shape[0]
+    out = masks.new_zeros((n, 4), dtype=torch.float32)
+    xa, ya = torch.any(masks, dim=1), torch.any(masks, dim=2)
+    for i in range(n):
+        x, y = torch.where(xa[i])[0], torch.where(ya[i])[0]
+        if len(x) > 0 and len(y) > 0:
+            out[i] = out.new_tensor([x[0], y[0], x[-1] + 1, y[-1] + 1])
+    return out

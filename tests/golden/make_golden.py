@@ -1,0 +1,121 @@
+"""Generates tests/golden/reference_functions.pt by EXECUTING the reference's own in-tree source
+(read from /root/reference at generation time; nothing is copied into this repo).
+
+The reference package cannot be imported here (mmcv / mmengine / peft are absent), so the pure
+tensor functions / methods on the hot path are pulled out of their files with `ast` and executed
+in a namespace that only provides torch / numpy / math; methods get a SimpleNamespace `self`.
+Run in the build container:   python tests/golden/make_golden.py
+The fixtures pin oracle/restate*.py in tests/test_golden_cpu.py (no /root/reference at test time).
+"""
+import ast
+import math
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_functions.pt")
+
+
+def load_defs(relpath, names, cls=None):
+    """Compile the named top-level functions (or methods of class `cls`) of a reference file."""
+    src = open(os.path.join(REF, relpath)).read()
+    tree = ast.parse(src)
+    body = tree.body
+    if cls is not None:
+        body = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls).body
+    ns = dict(torch=torch, F=F, np=np, math=math, Tensor=torch.Tensor, Tuple=tuple, Optional=None,
+              Sequence=None, Union=None, List=list)
+    for node in body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            node.decorator_list = []
+            node.returns = None
+            for a in node.args.args + node.args.kwonlyargs:
+                a.annotation = None
+            mod = ast.Module(body=[node], type_ignores=[])
+            exec(compile(ast.fix_missing_locations(mod), relpath, "exec"), ns)
+    missing = [n for n in names if n not in ns]
+    assert not missing, f"{relpath}: {missing} not found"
+    return ns
+
+
+def main():
+    g = torch.Generator().manual_seed(1234)
+    fx = {}
+
+    # ---- mmpretrain/models/backbones/vit_sam.py:17-157
+    vs = load_defs("mmpretrain/models/backbones/vit_sam.py",
+                   ["window_partition", "window_unpartition", "get_rel_pos", "add_decomposed_rel_pos"])
+    x = torch.randn(2, 20, 23, 8, generator=g)
+    win, pad_hw = vs["window_partition"](x, 14)
+    fx["window_partition"] = dict(x=x, ws=14, windows=win, pad_hw=tuple(pad_hw),
+                                  back=vs["window_unpartition"](win, 14, pad_hw, (20, 23)))
+    table = torch.randn(27, 16, generator=g)
+    fx["get_rel_pos_same"] = dict(q=14, k=14, table=table, out=vs["get_rel_pos"](14, 14, table))
+    table2 = torch.randn(127, 16, generator=g)
+    fx["get_rel_pos_resized"] = dict(q=32, k=32, table=table2, out=vs["get_rel_pos"](32, 32, table2))
+    S, hd, nb = 6, 16, 3
+    q = torch.randn(nb, S * S, hd, generator=g)
+    rh, rw = torch.randn(2 * S - 1, hd, generator=g), torch.randn(2 * S - 1, hd, generator=g)
+    attn = torch.zeros(nb, S * S, S * S)
+    fx["decomposed_rel_pos"] = dict(q=q, rel_h=rh, rel_w=rw, S=S,
+                                    bias=vs["add_decomposed_rel_pos"](attn, q, rh, rw, (S, S), (S, S)))
+
+    # ---- mmdet/models/task_modules/coders/delta_xywh_bbox_coder.py:262-359
+    dc = load_defs("mmdet/models/task_modules/coders/delta_xywh_bbox_coder.py", ["delta2bbox"])
+    rois = torch.rand(40, 4, generator=g) * 200
+    rois[:, 2:] = rois[:, :2] + torch.rand(40, 2, generator=g) * 300 + 1
+    deltas = torch.randn(40, 12, generator=g) * 2
+    fx["delta2bbox"] = dict(rois=rois, deltas=deltas, stds=(0.1, 0.1, 0.2, 0.2), max_shape=(256, 320),
+                            out=dc["delta2bbox"](rois, deltas, (0., 0., 0., 0.), (0.1, 0.1, 0.2, 0.2), (256, 320)))
+    d1 = torch.randn(40, 4, generator=g)
+    fx["delta2bbox_rpn"] = dict(rois=rois, deltas=d1, stds=(1., 1., 1., 1.), max_shape=(256, 320),
+                                out=dc["delta2bbox"](rois, d1, (0., 0., 0., 0.), (1., 1., 1., 1.), (256, 320)))
+
+    # ---- mmdet/models/task_modules/prior_generators/anchor_generator.py:161-301
+    ag = load_defs("mmdet/models/task_modules/prior_generators/anchor_generator.py",
+                   ["gen_single_level_base_anchors", "_meshgrid", "single_level_grid_priors"], cls="AnchorGenerator")
+    self_ = SimpleNamespace(center_offset=0.0, scale_major=True, strides=[(8, 8)], use_box_type=False)
+    self_._meshgrid = lambda x, y, row_major=True: ag["_meshgrid"](self_, x, y, row_major)
+    base = ag["gen_single_level_base_anchors"](self_, 8, torch.tensor([4., 8.]), torch.tensor([0.5, 1.0, 2.0]))
+    self_.base_anchors = [base]
+    fx["anchors"] = dict(base_size=8, scales=[4, 8], ratios=[0.5, 1.0, 2.0], base=base, featmap=(3, 5), stride=8,
+                         grid=ag["single_level_grid_priors"](self_, (3, 5), 0, torch.float32, "cpu"))
+
+    # ---- mmdet/models/layers/positional_encoding.py:60-110
+    pe = load_defs("mmdet/models/layers/positional_encoding.py", ["forward"], cls="SinePositionalEncoding")
+    self_ = SimpleNamespace(num_feats=8, temperature=10000, normalize=True, scale=2 * math.pi, eps=1e-6, offset=0.0)
+    fx["sine_pe"] = dict(B=2, H=5, W=7, num_feats=8, out=pe["forward"](self_, torch.zeros(2, 5, 7, dtype=torch.bool)))
+
+    # ---- mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py:40-62
+    re_ = load_defs("mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py", ["map_roi_levels"],
+                    cls="SingleRoIExtractor")
+    r5 = torch.cat([torch.zeros(40, 1), rois * torch.rand(40, 1, generator=g) * 4], dim=1)
+    fx["map_roi_levels"] = dict(rois=r5, num_levels=4,
+                                out=re_["map_roi_levels"](SimpleNamespace(finest_scale=56), r5, 4))
+
+    # ---- mmdet/structures/mask/utils.py:56-77
+    mu = load_defs("mmdet/structures/mask/utils.py", ["mask2bbox"])
+    masks = torch.rand(6, 20, 30, generator=g) > 0.9
+    masks[2] = False
+    fx["mask2bbox"] = dict(masks=masks, out=mu["mask2bbox"](masks))
+
+    # ---- mmdet/rsprompter/models.py:45-50 LN2d.forward
+    ln = load_defs("mmdet/rsprompter/models.py", ["forward"], cls="LN2d")
+    w, b = torch.randn(8, generator=g), torch.randn(8, generator=g)
+    xx = torch.randn(2, 8, 4, 5, generator=g)
+    fx["ln2d"] = dict(x=xx, weight=w, bias=b, eps=1e-6,
+                      out=ln["forward"](SimpleNamespace(weight=w, bias=b, eps=1e-6), xx))
+
+    torch.save(fx, OUT)
+    print("wrote", OUT, {k: list(v.keys()) for k, v in fx.items()})
+
+
+if __name__ == "__main__":
+    if not os.path.isdir(REF):
+        sys.exit("/root/reference not mounted")
+    main()

@@ -1,0 +1,53 @@
+"""N > 1 path on CPU: world_size-2 gloo run of the result-record gather that bench.py performs once per
+step over NCCL (batch-sharded images, no data-path collective)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rsprompter_b200.results import gather_records, pack_records, unpack_records
+    B, M = 3, 5
+    g = torch.Generator().manual_seed(rank)
+    boxes = torch.rand(B, M, 4, generator=g)
+    scores = torch.rand(B, M, generator=g)
+    labels = torch.randint(0, 10, (B, M), generator=g)
+    counts = torch.tensor([M, 2, 0], dtype=torch.int32) + rank
+    counts = counts.clamp(max=M)
+    rec = pack_records(boxes, scores, labels)
+    all_rec, all_cnt = gather_records(rec, counts)
+    assert all_rec.shape == (world * B, M, 6) and all_cnt.shape == (world * B,)
+    mine = unpack_records(all_rec[rank * B:(rank + 1) * B], all_cnt[rank * B:(rank + 1) * B])
+    ok = all(torch.equal(mine[i]["bboxes"], boxes[i, :counts[i]]) and
+             torch.equal(mine[i]["labels"], labels[i, :counts[i]]) for i in range(B))
+    q.put((rank, ok, all_cnt.tolist()))
+    dist.destroy_process_group()
+
+
+def test_record_gather_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)
+    assert res[0][2] == res[1][2]          # every rank sees the same global counts

@@ -1,0 +1,76 @@
+"""Pins oracle/restate*.py against fixtures produced by EXECUTING the reference's own in-tree
+functions (tests/golden/make_golden.py; generated in the build container from /root/reference)."""
+import os
+
+import pytest
+import torch
+
+from oracle import restate, restate_anchor as ra
+
+FX = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_functions.pt"), weights_only=False)
+
+
+def test_window_partition_roundtrip():
+    f = FX["window_partition"]
+    win, pad = restate.window_partition(f["x"], f["ws"])
+    assert tuple(pad) == f["pad_hw"]
+    assert torch.equal(win, f["windows"])
+    back = restate.window_unpartition(win, f["ws"], pad, f["x"].shape[1:3])
+    assert torch.equal(back, f["back"]) and torch.equal(back, f["x"])
+
+
+@pytest.mark.parametrize("key", ["get_rel_pos_same", "get_rel_pos_resized"])
+def test_rel_pos_gather(key):
+    f = FX[key]
+    torch.testing.assert_close(restate.rel_pos_gather(f["table"], f["q"], f["k"]), f["out"], rtol=0, atol=1e-6)
+
+
+def test_decomposed_rel_pos_bias():
+    f = FX["decomposed_rel_pos"]
+    got = restate.decomposed_rel_pos_bias(f["q"], f["rel_h"], f["rel_w"], f["S"])
+    torch.testing.assert_close(got, f["bias"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("key", ["delta2bbox", "delta2bbox_rpn"])
+def test_delta2bbox(key):
+    f = FX[key]
+    got = ra.delta2bbox(f["rois"], f["deltas"], f["stds"], f["max_shape"])
+    torch.testing.assert_close(got, f["out"], rtol=0, atol=1e-4)
+
+
+def test_anchor_generation():
+    f = FX["anchors"]
+    base = ra.base_anchors(f["base_size"], f["scales"], f["ratios"])
+    torch.testing.assert_close(base, f["base"], rtol=0, atol=1e-5)
+    torch.testing.assert_close(ra.grid_anchors(f["featmap"], f["stride"], base), f["grid"], rtol=0, atol=1e-5)
+
+
+def test_anchor_generator_module_matches_reference():
+    from rsprompter_b200.anchor_heads import AnchorGenerator
+    f = FX["anchors"]
+    gen = AnchorGenerator(strides=[8], ratios=f["ratios"], scales=f["scales"])
+    torch.testing.assert_close(gen.base_anchors(0), f["base"], rtol=0, atol=1e-5)
+
+
+def test_sine_positional_encoding():
+    f = FX["sine_pe"]
+    got = ra.sine_positional_encoding(f["B"], f["H"], f["W"], f["num_feats"])
+    torch.testing.assert_close(got, f["out"], rtol=1e-5, atol=1e-6)
+    from rsprompter_b200.anchor_heads import sine_pe_rows
+    torch.testing.assert_close(sine_pe_rows(f["H"], f["W"], f["num_feats"], "cpu"), f["out"][:1], rtol=1e-5, atol=1e-6)
+
+
+def test_map_roi_levels():
+    f = FX["map_roi_levels"]
+    assert torch.equal(ra.map_roi_levels(f["rois"], f["num_levels"]), f["out"])
+
+
+def test_ln2d():
+    f = FX["ln2d"]
+    got = restate.layer_norm_channels_first(f["x"], f["weight"], f["bias"], f["eps"])
+    torch.testing.assert_close(got, f["out"], rtol=1e-5, atol=1e-5)
+
+
+def test_mask2bbox():
+    f = FX["mask2bbox"]
+    assert torch.equal(ra.mask2bbox(f["masks"]), f["out"])
