@@ -171,9 +171,13 @@ int rsp_roi_align_nhwc(const void* const* feats, const float* const* pes, const 
 
 /* Mask post-processing: logits fp32 [n, hm, wm] -> uint8 [n, H, W] (W % 4 == 0), bilinear with
  * align_corners=False.  mode 0: bilinear(sigmoid(x)) >= thr (M:1758-1780); mode 1: bilinear(x) > thr
- * (M:652-656 + maskformer_fusion_head.py:169). */
+ * (M:652-656 + maskformer_fusion_head.py:169); mode 2: as mode 0 on input that rsp_sigmoid_f32 has
+ * already activated (one exp per low-resolution pixel instead of four per output pixel). */
 int rsp_mask_paste(const float* logits, uint8_t* out, int n, int hm, int wm, int H, int W, float thr,
                    int mode, void* stream);
+
+/* out = 1 / (1 + exp(-in)) over n fp32 values (n % 4 == 0): mask_preds.sigmoid() (M:1758). */
+int rsp_sigmoid_f32(const float* in, float* out, long long n, void* stream);
 
 /* bf16 NHWC pooling: mode 0 = MaxPool2d(2, 2) (M:1307), mode 1 = max_pool2d(k=1, stride=2) (M:1362). */
 int rsp_pool2_nhwc(const void* in, void* out, int B, int H, int W, int C, int mode, void* stream);

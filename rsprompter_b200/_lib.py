@@ -70,6 +70,7 @@ _SIGNATURES = {
     "rsp_roi_align_nhwc": ([_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _f, _vp, _vp], _i),
     "rsp_mask_paste": ([_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp], _i),
     "rsp_pool2_nhwc": ([_vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    "rsp_sigmoid_f32": ([_vp, _vp, ctypes.c_longlong, _vp], _i),
     "rsp_sin_fold": ([_vp, _vp, ctypes.c_longlong, _vp], _i),
 }
 
@@ -486,7 +487,13 @@ def mask_paste(logits: torch.Tensor, size: tuple, thr: float, mode: int) -> torc
     n, hm, wm = logits.shape
     out = torch.empty(n, size[0], size[1], device=logits.device, dtype=torch.uint8)
     if n > 0:
-        _check(_lib.rsp_mask_paste(_ptr(logits), _ptr(out), n, hm, wm, size[0], size[1], float(thr), mode, _stream()),
+        src = logits
+        if mode == 0 and logits.numel() % 4 == 0:   # activate once per low-res pixel, then paste
+            src = torch.empty_like(logits)
+            _check(_lib.rsp_sigmoid_f32(_ptr(logits), _ptr(src), logits.numel(), _stream()), "rsp_sigmoid_f32")
+            launch_count += 1
+            mode = 2
+        _check(_lib.rsp_mask_paste(_ptr(src), _ptr(out), n, hm, wm, size[0], size[1], float(thr), mode, _stream()),
                "rsp_mask_paste")
         launch_count += 1
     return out.view(torch.bool)

@@ -170,6 +170,10 @@ int rsp_mask_paste(const float* logits, uint8_t* out, int n, int hm, int wm, int
   return mask_paste(logits, out, n, hm, wm, H, W, thr, mode, S(stream));
 }
 
+int rsp_sigmoid_f32(const float* in, float* out, long long n, void* stream) {
+  return sigmoid_f32(in, out, n, S(stream));
+}
+
 int rsp_pool2_nhwc(const void* in, void* out, int B, int H, int W, int C, int mode, void* stream) {
   return pool2_nhwc(in, out, B, H, W, C, mode, S(stream));
 }

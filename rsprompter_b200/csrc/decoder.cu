@@ -268,9 +268,13 @@ __global__ void i2t_attention_kernel(const __nv_bfloat16* __restrict__ Q,      /
   __shared__ __align__(16) float sk[16 * 128];
   __shared__ __align__(16) float sv[16 * 128];
   const int n = blockIdx.y;
+  // smem layout [token][d/4][head][4]: the 8 heads read by one warp instruction are 128 contiguous
+  // bytes (conflict-free); the natural [token][head][16] layout is 4-way bank conflicted
   for (int i = threadIdx.x; i < Tq * 128; i += blockDim.x) {
-    sk[i] = __bfloat162float(ktok[static_cast<size_t>(n) * Tq * 128 + i]) * scale;
-    sv[i] = __bfloat162float(vtok[static_cast<size_t>(n) * Tq * 128 + i]);
+    const int j = i >> 7, hh = (i >> 4) & 7, d = i & 15;
+    const int o = ((j * 4 + (d >> 2)) * 8 + hh) * 4 + (d & 3);
+    sk[o] = __bfloat162float(ktok[static_cast<size_t>(n) * Tq * 128 + i]) * scale;
+    sv[o] = __bfloat162float(vtok[static_cast<size_t>(n) * Tq * 128 + i]);
   }
   __syncthreads();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (pixel, head)
@@ -288,11 +292,11 @@ __global__ void i2t_attention_kernel(const __nv_bfloat16* __restrict__ Q,      /
   float s[16];
   float mx = -INFINITY;
   for (int j = 0; j < Tq; ++j) {
-    const float4* kp = reinterpret_cast<const float4*>(sk + j * 128 + h * 16);
+    const float4* kp = reinterpret_cast<const float4*>(sk + j * 128) + h;
     float acc = 0.f;
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
-      const float4 kk = kp[d];
+      const float4 kk = kp[d * 8];
       acc += qf[4 * d] * kk.x + qf[4 * d + 1] * kk.y + qf[4 * d + 2] * kk.z + qf[4 * d + 3] * kk.w;
     }
     s[j] = acc;
@@ -305,10 +309,10 @@ __global__ void i2t_attention_kernel(const __nv_bfloat16* __restrict__ Q,      /
   for (int j = 0; j < Tq; ++j) {
     const float pj = __expf(s[j] - mx);
     l += pj;
-    const float4* vp = reinterpret_cast<const float4*>(sv + j * 128 + h * 16);
+    const float4* vp = reinterpret_cast<const float4*>(sv + j * 128) + h;
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
-      const float4 vv = vp[d];
+      const float4 vv = vp[d * 8];
       o[4 * d] += pj * vv.x; o[4 * d + 1] += pj * vv.y; o[4 * d + 2] += pj * vv.z; o[4 * d + 3] += pj * vv.w;
     }
   }

@@ -416,9 +416,25 @@ __global__ void mask_paste_kernel(const float* __restrict__ logits, unsigned cha
       v10 = 1.f / (1.f + expf(-v10)); v11 = 1.f / (1.f + expf(-v11));
     }
     const float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
-    r[k] = mode == 0 ? (v >= thr) : (v > thr);
+    r[k] = mode == 1 ? (v > thr) : (v >= thr);   // mode 2: input already sigmoid-activated
   }
   *reinterpret_cast<uchar4*>(out + (static_cast<size_t>(m) * H + y) * W + x4 * 4) = make_uchar4(r[0], r[1], r[2], r[3]);
+}
+
+__global__ void sigmoid_f32_kernel(const float4* __restrict__ in, float4* __restrict__ out, long long n4) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 x = in[i];
+  out[i] = make_float4(1.f / (1.f + expf(-x.x)), 1.f / (1.f + expf(-x.y)), 1.f / (1.f + expf(-x.z)),
+                       1.f / (1.f + expf(-x.w)));
+}
+
+int sigmoid_f32(const float* in, float* out, long long n, cudaStream_t stream) {
+  RSP_CHECK_ARG(in && out && n > 0 && n % 4 == 0, "sigmoid: n must be a positive multiple of 4");
+  sigmoid_f32_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), n / 4);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
 }
 
 int mask_paste(const float* logits, unsigned char* out, int n, int hm, int wm, int H, int W, float thr,

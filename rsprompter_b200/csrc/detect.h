@@ -19,6 +19,7 @@ int roi_align_nhwc(const void* const* feats, const float* const* pes, const int*
                    float finest_scale, void* out, cudaStream_t stream);
 int mask_paste(const float* logits, unsigned char* out, int n, int hm, int wm, int H, int W, float thr,
                int mode, cudaStream_t stream);
+int sigmoid_f32(const float* in, float* out, long long n, cudaStream_t stream);
 int pool2_nhwc(const void* in, void* out, int B, int H, int W, int C, int mode, cudaStream_t stream);
 int sin_fold(const float* in, float* out, long long n_out, cudaStream_t stream);
 

@@ -16,6 +16,8 @@
 #include "gemm.h"
 #include "sm100.cuh"
 
+#include <stdlib.h>
+
 namespace rsp {
 
 constexpr int BM = 128;
@@ -548,6 +550,10 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
       const int t256 = mt * ((a.N + 255) / 256);
       if ((a.N % 256 != 0 && a.N % 256 <= 128) || t256 < num_sms()) bn = 128;
     }
+  }
+  {
+    static const bool force_v1 = getenv("RSP_GEMM_V1") != nullptr;
+    if (!force_v1 && gemm_v2_eligible(a)) return gemm_bf16_v2(a, bn, stream);
   }
   switch (bn) {
     case 256: return launch_gemm<256, false>(a, stream);

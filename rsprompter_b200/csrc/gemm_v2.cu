@@ -1,0 +1,349 @@
+// Second-generation epilogue for the persistent tcgen05 GEMM (standard epilogue only: bias,
+// GELU / ReLU, residual, row scatter, bf16 / fp32 out).  Same mainloop as gemm.cu; what changes is
+// how the accumulator leaves the SM:
+//   * 8 epilogue warps (2 per TMEM lane quarter, each owning half of the tile's columns) instead
+//     of 4, so the GELU / conversion work and the TMEM drain are spread over twice the issue slots;
+//   * every warp transposes its 32-row x 128-byte slab through a private, bank-conflict-free smem
+//     staging buffer, so global traffic is fully coalesced: each half-warp reads (residual) and
+//     writes one whole 128-byte line per instruction instead of 32 lanes touching 32 different
+//     lines (the thread-per-row pattern of the first version, which left K = 768 GEMMs
+//     epilogue-bound at ~35-55 % of the large-K rate).
+// All shared memory is dynamic (1024-byte aligned by declaration), barriers live at its end:
+//   [ STAGES x (A 16 KB + B BN*128 B) | 8 x 32 x 136 B staging | barriers ]
+#include "gemm.h"
+#include "sm100.cuh"
+
+namespace rsp {
+
+namespace v2 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int THREADS = 384;          // 4 control warps + 8 epilogue warps
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int STG_ROW = 136;          // 128-byte payload + 8 pad: conflict-free 8-byte accesses
+constexpr int STG_WARP = 32 * STG_ROW;
+constexpr int STG_BYTES = 8 * STG_WARP;
+constexpr int BAR_BYTES = 256;
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES;
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int NHALF = (BN >= 128) ? 2 : 1;   // epilogue warps per lane quarter that have work
+  static constexpr int COLS_PER_WARP = BN / NHALF;
+};
+
+struct Dev {
+  int M, N, K;
+  const float* bias;
+  const void* residual;
+  void* out;
+  const int* row_map;
+  const int* res_block_map;
+  int res_block_rows;
+  int res_mod;
+  int ldo, ldr;
+  int act;
+  int out_fp32;
+  int res_fp32;
+  int num_n_blocks;
+  int num_tiles;
+};
+
+__device__ __forceinline__ int residual_row(const Dev& p, int orow) {
+  if (p.res_block_map) {
+    const int blk = orow / p.res_block_rows;
+    return p.res_block_map[blk] * p.res_block_rows + (orow - blk * p.res_block_rows);
+  }
+  return p.res_mod > 0 ? (orow % p.res_mod) : orow;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a,
+                            const __grid_constant__ CUtensorMap tma_b, const Dev p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  uint8_t* stg_all = smem + STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + STG_BYTES);
+  uint64_t* bar_full = bars;
+  uint64_t* bar_empty = bars + STAGES;
+  uint64_t* bar_tmem_full = bars + 2 * STAGES;
+  uint64_t* bar_tmem_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_tmem_full[s]), 1);
+      mbar_init(smem_u32(&bar_tmem_empty[s]), 4 * C::NHALF);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_base_s), C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_s;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.num_n_blocks;
+      const int n_blk = tile % p.num_n_blocks;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+        const uint32_t full = smem_u32(&bar_full[stage]);
+        const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+        mbar_expect_tx(full, C::STAGE_BYTES);
+        tma_load_2d(sa, &tma_a, full, kb * BK, m_blk * BM);
+        tma_load_2d(sa + A_BYTES, &tma_b, full, kb * BK, n_blk * BN);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(smem_u32(&bar_tmem_empty[as]), ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_ss(d_tmem, make_sdesc(sa + k * 32, 0, 1024), make_sdesc(sb + k * 32, 0, 1024), idesc,
+                  (kb | k) != 0);
+        umma_commit(smem_u32(&bar_empty[stage]));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(smem_u32(&bar_tmem_full[as]));
+    }
+  } else if (warp >= 4 && ((warp - 4) >> 2) < C::NHALF) {
+    // ------------------------------------------------------------ epilogue (8 warps)
+    const int e = warp - 4;
+    const int q = e & 3, hf = e >> 2;
+    uint8_t* stg = stg_all + e * STG_WARP;
+    const uint32_t stg_s = smem_u32(stg);
+    const bool stage_f32 = p.out_fp32 || (p.residual != nullptr);
+    const int W = stage_f32 ? 32 : (C::COLS_PER_WARP < 64 ? C::COLS_PER_WARP : 64);   // columns per pass
+    const int n_pass = C::COLS_PER_WARP / W;
+    const int lpr = stage_f32 ? 16 : (W * 2) / 8;     // lanes per row at 8 bytes each
+    const int rpi = 32 / lpr;                          // rows per write-out iteration
+    const int epl = stage_f32 ? 2 : 4;                 // elements per lane (8 bytes)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / p.num_n_blocks;
+      const int n_blk = tile % p.num_n_blocks;
+      const int as = it & 1;
+      const int my_row = m_blk * BM + q * 32 + lane;
+      int my_orow = -1;
+      if (my_row < p.M) my_orow = p.row_map ? p.row_map[my_row] : my_row;
+      const int my_rrow = (my_orow >= 0 && p.residual) ? residual_row(p, my_orow) : 0;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + hf * C::COLS_PER_WARP;
+      const int col_warp = n_blk * BN + hf * C::COLS_PER_WARP;
+      const int sub = lane / lpr, cl = lane - sub * lpr;
+      // residual prefetch (fp32-staged path: 16 lanes x 8 B per row, 2 rows per instruction): the 16
+      // loads of a pass are issued back to back before the accumulator is touched, so ~4 KB per warp
+      // is in flight while the TMEM drain / activation of the same pass runs
+      float2 resv[16];
+      auto load_residual = [&](int col_pass) {
+        const int col = col_pass + cl * 2;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int rr = 2 * k + sub;
+          const int orow = __shfl_sync(0xffffffffu, my_orow, rr);
+          const int rrow = __shfl_sync(0xffffffffu, my_rrow, rr);
+          resv[k] = make_float2(0.f, 0.f);
+          if (orow >= 0 && col < p.N) {
+            if (p.res_fp32) {
+              resv[k] = *reinterpret_cast<const float2*>(static_cast<const float*>(p.residual) +
+                                                         static_cast<size_t>(rrow) * p.ldr + col);
+            } else {
+              const __nv_bfloat162 rv = *reinterpret_cast<const __nv_bfloat162*>(
+                  static_cast<const __nv_bfloat16*>(p.residual) + static_cast<size_t>(rrow) * p.ldr + col);
+              resv[k] = make_float2(__bfloat162float(rv.x), __bfloat162float(rv.y));
+            }
+          }
+        }
+      };
+      if (p.residual && col_warp < p.N) load_residual(col_warp);
+      mbar_wait(smem_u32(&bar_tmem_full[as]), (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ps = 0; ps < n_pass; ++ps) {
+        const int col_pass = col_warp + ps * W;
+        if (col_pass < p.N) {
+          if (p.residual && ps > 0) load_residual(col_pass);
+          // ---- phase 1: TMEM -> registers -> bias / activation -> staging row `lane`
+#pragma unroll 1
+          for (int c = 0; c < W / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + ps * W + c * 32, r);
+            tmem_ld_wait();
+            const int col0 = col_pass + c * 32;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            if (p.bias) {
+              if (col0 + 32 <= p.N) {
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 b = __ldg(b4 + i);
+                  v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += (col0 + i < p.N) ? __ldg(p.bias + col0 + i) : 0.f;
+              }
+            }
+            if (p.act == 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            } else if (p.act == 2) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (stage_f32) {
+              const uint32_t a = stg_s + lane * STG_ROW;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a + i * 8), "f"(v[2 * i]), "f"(v[2 * i + 1])
+                             : "memory");
+            } else {
+              const uint32_t a = stg_s + lane * STG_ROW + c * 64;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a + i * 8),
+                             "r"(pack_bf16x2(v[4 * i], v[4 * i + 1])), "r"(pack_bf16x2(v[4 * i + 2], v[4 * i + 3]))
+                             : "memory");
+            }
+          }
+          __syncwarp();
+          // ---- phase 2: coalesced write-out, 8 bytes per lane, whole 128-byte lines per half-warp
+          const int col = col_pass + cl * epl;
+          if (stage_f32) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const int rr = 2 * k + sub;
+              const int orow = __shfl_sync(0xffffffffu, my_orow, rr);
+              if (orow < 0 || col >= p.N) continue;
+              float x0, x1;
+              asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1) : "r"(stg_s + rr * STG_ROW + cl * 8));
+              if (p.residual) { x0 += resv[k].x; x1 += resv[k].y; }
+              if (p.out_fp32)
+                *reinterpret_cast<float2*>(static_cast<float*>(p.out) + static_cast<size_t>(orow) * p.ldo + col) =
+                    make_float2(x0, x1);
+              else
+                *reinterpret_cast<uint32_t*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(orow) * p.ldo +
+                                             col) = pack_bf16x2(x0, x1);
+            }
+          } else {
+#pragma unroll 4
+            for (int r0 = 0; r0 < 32; r0 += rpi) {
+              const int rr = r0 + sub;
+              const int orow = __shfl_sync(0xffffffffu, my_orow, rr);
+              if (orow < 0 || col >= p.N) continue;
+              uint32_t w0, w1;
+              asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(stg_s + rr * STG_ROW + cl * 8));
+              *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(orow) * p.ldo + col) =
+                  make_uint2(w0, w1);
+            }
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[as]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch(const GemmArgs& a, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  CUtensorMap ta, tb;
+  RSP_TRY(make_tmap_bf16_2d(&ta, a.A, a.M, a.K, static_cast<uint64_t>(a.lda) * 2, BM, BK));
+  RSP_TRY(make_tmap_bf16_2d(&tb, a.W, a.N, a.K, static_cast<uint64_t>(a.ldw) * 2, BN, BK));
+  Dev p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.row_map = a.row_map;
+  p.res_block_map = a.res_block_map; p.res_block_rows = a.res_block_rows;
+  p.res_mod = a.res_mod; p.ldo = a.ldo; p.ldr = a.ldr; p.act = a.act;
+  p.out_fp32 = a.out_fp32; p.res_fp32 = a.res_fp32;
+  p.num_n_blocks = (a.N + BN - 1) / BN;
+  p.num_tiles = ((a.M + BM - 1) / BM) * p.num_n_blocks;
+  auto kern = gemm_bf16_tcgen05_v2_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RSP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
+  kern<<<grid, THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
+}  // namespace v2
+
+// Eligibility: standard epilogue, [N,K] weights, 8-byte alignable rows.
+bool gemm_v2_eligible(const GemmArgs& a) {
+  if (a.epi_mode != 0 || a.w_is_kn || !a.out) return false;
+  const bool stage_f32 = a.out_fp32 || a.residual;
+  const uintptr_t po = reinterpret_cast<uintptr_t>(a.out), pr = reinterpret_cast<uintptr_t>(a.residual);
+  if (stage_f32) {
+    if (a.N % 2 != 0 || a.ldo % 2 != 0 || (po & (a.out_fp32 ? 7 : 3)) != 0) return false;
+  } else {
+    if (a.N % 4 != 0 || a.ldo % 4 != 0 || (po & 7) != 0) return false;
+  }
+  if (a.residual && (a.ldr % 2 != 0 || (pr & (a.res_fp32 ? 7 : 3)) != 0)) return false;
+  if (a.bias && (reinterpret_cast<uintptr_t>(a.bias) & 15) != 0) return false;
+  return true;
+}
+
+int gemm_bf16_v2(const GemmArgs& a, int bn, cudaStream_t stream) {
+  switch (bn) {
+    case 256: return v2::launch<256>(a, stream);
+    case 128: return v2::launch<128>(a, stream);
+    case 64: return v2::launch<64>(a, stream);
+    case 32: return v2::launch<32>(a, stream);
+    default: set_last_error("gemm_v2: unsupported BN %d", bn); return RSP_ERR_INVALID;
+  }
+}
+
+}  // namespace rsp
