@@ -522,6 +522,9 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   if (a.epi_mode == EPI_LN64_GELU) {
     RSP_CHECK_ARG(a.N % 64 == 0 && a.bias && a.ln_gamma && a.ln_beta && !a.out_fp32 && !a.w_is_kn &&
                   !a.row_map && a.ldo % 8 == 0, "gemm: LN64+GELU epilogue needs N %% 64 == 0, bias, bf16 out");
+    static const bool v1 = getenv("RSP_GEMM_V1") != nullptr;
+    if (!v1 && a.N % 128 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 7) == 0 && a.ldo % 4 == 0)
+      return gemm_bf16_v2_ln64_gelu(a, stream);
     if (a.N % 256 == 0) return launch_gemm<256, false>(a, stream);
     if (a.N % 128 == 0) return launch_gemm<128, false>(a, stream);
     return launch_gemm<64, false>(a, stream);
@@ -530,6 +533,8 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
     RSP_CHECK_ARG(a.N == 128 && a.bias && a.hyper && a.mask_out && a.grid_h > 0 && a.grid_w > 0 &&
                   a.M % (4 * a.grid_h * a.grid_w) == 0 && !a.w_is_kn,
                   "gemm: GELU+hyper epilogue needs N == 128 and M = prompts * 4 * h * w");
+    static const bool v1h = getenv("RSP_GEMM_V1") != nullptr;
+    if (!v1h && a.grid_w % 2 == 0) return gemm_bf16_v2_gelu_hyper(a, stream);
     return launch_gemm<128, false>(a, stream);
   }
   RSP_CHECK_ARG(a.epi_mode == EPI_STD, "gemm: epi_mode %d", a.epi_mode);

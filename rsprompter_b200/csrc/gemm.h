@@ -38,5 +38,7 @@ int gemm_bf16_simt(const GemmArgs& a, cudaStream_t stream);
 // coalesced-epilogue kernel (gemm_v2.cu); gemm_bf16 dispatches to it when eligible
 bool gemm_v2_eligible(const GemmArgs& a);
 int gemm_bf16_v2(const GemmArgs& a, int bn, cudaStream_t stream);
+int gemm_bf16_v2_ln64_gelu(const GemmArgs& a, cudaStream_t stream);     // N % 128 == 0
+int gemm_bf16_v2_gelu_hyper(const GemmArgs& a, cudaStream_t stream);    // N == 128
 
 }  // namespace rsp

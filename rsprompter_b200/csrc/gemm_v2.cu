@@ -52,7 +52,16 @@ struct Dev {
   int res_fp32;
   int num_n_blocks;
   int num_tiles;
+  // EPI 2 / 3 (mask-decoder upscaler, see gemm.cu for the maths)
+  const float* ln_gamma;
+  const float* ln_beta;
+  float ln_eps;
+  const float* hyper;
+  float* mask_out;
+  int grid_h, grid_w;
 };
+
+enum { EPI_STD = 0, EPI_LN64_GELU = 2, EPI_GELU_HYPER = 3 };
 
 __device__ __forceinline__ int residual_row(const Dev& p, int orow) {
   if (p.res_block_map) {
@@ -62,7 +71,7 @@ __device__ __forceinline__ int residual_row(const Dev& p, int orow) {
   return p.res_mod > 0 ? (orow % p.res_mod) : orow;
 }
 
-template <int BN>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a,
                             const __grid_constant__ CUtensorMap tma_b, const Dev p) {
@@ -160,6 +169,115 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a,
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile % p.num_n_blocks;
       const int as = it & 1;
+      if constexpr (EPI == EPI_GELU_HYPER) {
+        // rows = (prompt, y, x, tap1); this warp owns tap2 in {2hf, 2hf+1} = output row 4y + 2ty1 + hf.
+        // 16 consecutive lanes (4 x-positions... 8 with both tx1) write one contiguous 128-byte run.
+        mbar_wait(smem_u32(&bar_tmem_full[as]), (it >> 1) & 1);
+        tc_fence_after();
+        const int row = m_blk * BM + q * 32 + lane;
+        const bool valid = row < p.M;
+        const int rows_per_prompt = p.grid_h * p.grid_w * 4;
+        const int n = valid ? row / rows_per_prompt : 0;
+        const int rem = row - n * rows_per_prompt;
+        const int tap1 = rem & 3, pix = rem >> 2;
+        const int y = pix / p.grid_w, x = pix - y * p.grid_w;
+        float hyp[32];
+        {
+          const float4* h4 = reinterpret_cast<const float4*>(p.hyper + static_cast<size_t>(n) * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 h = __ldg(h4 + i);
+            hyp[4 * i] = h.x; hyp[4 * i + 1] = h.y; hyp[4 * i + 2] = h.z; hyp[4 * i + 3] = h.w;
+          }
+        }
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + hf * 64;
+        float m2[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + t * 32, r);
+          tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + hf * 64 + t * 32);
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(b4 + i);
+            acc += gelu_fast(__uint_as_float(r[4 * i]) + b.x) * hyp[4 * i];
+            acc += gelu_fast(__uint_as_float(r[4 * i + 1]) + b.y) * hyp[4 * i + 1];
+            acc += gelu_fast(__uint_as_float(r[4 * i + 2]) + b.z) * hyp[4 * i + 2];
+            acc += gelu_fast(__uint_as_float(r[4 * i + 3]) + b.w) * hyp[4 * i + 3];
+          }
+          m2[t] = acc;
+        }
+        if (valid) {
+          const int W4 = 4 * p.grid_w;
+          const int Y = 4 * y + 2 * (tap1 >> 1) + hf, X = 4 * x + 2 * (tap1 & 1);
+          *reinterpret_cast<float2*>(p.mask_out + (static_cast<size_t>(n) * 4 * p.grid_h + Y) * W4 + X) =
+              make_float2(m2[0], m2[1]);
+        }
+      } else if constexpr (EPI == EPI_LN64_GELU) {
+        // this warp owns two 64-column groups (taps); per group: bias, LayerNorm over the 64
+        // channels, GELU, bf16 -> staging -> coalesced 128-byte rows
+        mbar_wait(smem_u32(&bar_tmem_full[as]), (it >> 1) & 1);
+        tc_fence_after();
+        const int my_row = m_blk * BM + q * 32 + lane;
+        const int my_orow = my_row < p.M ? my_row : -1;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + hf * C::COLS_PER_WARP;
+        const int col_warp = n_blk * BN + hf * C::COLS_PER_WARP;
+        const int sub = lane >> 4, cl = lane & 15;
+#pragma unroll 1
+        for (int gi = 0; gi < C::COLS_PER_WARP / 64; ++gi) {
+          const int col0 = col_warp + gi * 64;
+          if (col0 >= p.N) break;
+          float v[64];
+          {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32b_x32(t_row + gi * 64, r0);
+            tmem_ld_32x32b_x32(t_row + gi * 64 + 32, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
+          }
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
+            v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            sum += v[4 * i] + v[4 * i + 1] + v[4 * i + 2] + v[4 * i + 3];
+          }
+          const float mean = sum * (1.0f / 64.0f);
+          float var = 0.f;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) { const float d = v[i] - mean; var += d * d; }
+          const float rstd = rsqrtf(var * (1.0f / 64.0f) + p.ln_eps);
+          const uint32_t a = stg_s + lane * STG_ROW;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma) + i);
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_beta) + i);
+            const float y0 = gelu_fast((v[4 * i] - mean) * rstd * g.x + bt.x);
+            const float y1 = gelu_fast((v[4 * i + 1] - mean) * rstd * g.y + bt.y);
+            const float y2 = gelu_fast((v[4 * i + 2] - mean) * rstd * g.z + bt.z);
+            const float y3 = gelu_fast((v[4 * i + 3] - mean) * rstd * g.w + bt.w);
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a + i * 8), "r"(pack_bf16x2(y0, y1)),
+                         "r"(pack_bf16x2(y2, y3))
+                         : "memory");
+          }
+          __syncwarp();
+          const int col = col0 + cl * 4;
+#pragma unroll 4
+          for (int k = 0; k < 16; ++k) {
+            const int rr = 2 * k + sub;
+            const int orow = __shfl_sync(0xffffffffu, my_orow, rr);
+            if (orow < 0) continue;
+            uint32_t w0, w1;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(stg_s + rr * STG_ROW + cl * 8));
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(orow) * p.ldo + col) =
+                make_uint2(w0, w1);
+          }
+          __syncwarp();
+        }
+      } else {
       const int my_row = m_blk * BM + q * 32 + lane;
       int my_orow = -1;
       if (my_row < p.M) my_orow = p.row_map ? p.row_map[my_row] : my_row;
@@ -224,7 +342,7 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a,
             }
             if (p.act == 1) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+              for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
             } else if (p.act == 2) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -278,6 +396,7 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a,
           __syncwarp();
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[as]));
@@ -292,7 +411,7 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a,
   }
 }
 
-template <int BN>
+template <int BN, int EPI>
 static int launch(const GemmArgs& a, cudaStream_t stream) {
   using C = Cfg<BN>;
   CUtensorMap ta, tb;
@@ -306,7 +425,9 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
   p.out_fp32 = a.out_fp32; p.res_fp32 = a.res_fp32;
   p.num_n_blocks = (a.N + BN - 1) / BN;
   p.num_tiles = ((a.M + BM - 1) / BM) * p.num_n_blocks;
-  auto kern = gemm_bf16_tcgen05_v2_kernel<BN>;
+  p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
+  p.hyper = a.hyper; p.mask_out = a.mask_out; p.grid_h = a.grid_h; p.grid_w = a.grid_w;
+  auto kern = gemm_bf16_tcgen05_v2_kernel<BN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     RSP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -338,12 +459,22 @@ bool gemm_v2_eligible(const GemmArgs& a) {
 
 int gemm_bf16_v2(const GemmArgs& a, int bn, cudaStream_t stream) {
   switch (bn) {
-    case 256: return v2::launch<256>(a, stream);
-    case 128: return v2::launch<128>(a, stream);
-    case 64: return v2::launch<64>(a, stream);
-    case 32: return v2::launch<32>(a, stream);
+    case 256: return v2::launch<256, v2::EPI_STD>(a, stream);
+    case 128: return v2::launch<128, v2::EPI_STD>(a, stream);
+    case 64: return v2::launch<64, v2::EPI_STD>(a, stream);
+    case 32: return v2::launch<32, v2::EPI_STD>(a, stream);
     default: set_last_error("gemm_v2: unsupported BN %d", bn); return RSP_ERR_INVALID;
   }
+}
+
+// mask-decoder upscaler epilogues on the 8-warp kernel (called from gemm_bf16 for epi_mode 2 / 3)
+int gemm_bf16_v2_ln64_gelu(const GemmArgs& a, cudaStream_t stream) {
+  if (a.N % 256 == 0) return v2::launch<256, v2::EPI_LN64_GELU>(a, stream);
+  return v2::launch<128, v2::EPI_LN64_GELU>(a, stream);
+}
+
+int gemm_bf16_v2_gelu_hyper(const GemmArgs& a, cudaStream_t stream) {
+  return v2::launch<128, v2::EPI_GELU_HYPER>(a, stream);
 }
 
 }  // namespace rsp

@@ -252,4 +252,18 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// GELU(erf) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. at fp32 resolution of
+// erf's range): 2 MUFU + ~12 FMA instead of libdevice erff's ~25-instruction polynomial chain.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float ax = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float erf_abs = 1.0f - poly * __expf(-ax * ax);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
 }  // namespace rsp
