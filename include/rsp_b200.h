@@ -169,7 +169,7 @@ int rsp_roi_align_nhwc(const void* const* feats, const float* const* pes, const 
                        const int32_t* Ws, const float* scales, int num_levels, const float* rois, int n,
                        int C, int P, float finest_scale, void* out, void* stream);
 
-/* Mask post-processing: logits fp32 [n, hm, wm] -> uint8 [n, H, W] (W % 4 == 0), bilinear with
+/* Mask post-processing: logits fp32 [n, hm, wm] -> uint8 [n, H, W] (W % 16 == 0), bilinear with
  * align_corners=False.  mode 0: bilinear(sigmoid(x)) >= thr (M:1758-1780); mode 1: bilinear(x) > thr
  * (M:652-656 + maskformer_fusion_head.py:169); mode 2: as mode 0 on input that rsp_sigmoid_f32 has
  * already activated (one exp per low-resolution pixel instead of four per output pixel). */

@@ -130,126 +130,174 @@ int token_self_attention(const void* q, const void* k, const void* v, void* out,
 }
 
 // ---------------------------------------------------------------------------------------
-// t2i: CTA = one prompt.  K / V tiles of 64 image tokens x 128 channels are staged in smem
-// (coalesced 16-byte loads, rows padded to 272 B), thread = (head, query, key-lane of 4).
+// t2i: CTA = one prompt, warp = one head.  K / V tiles of 64 image tokens x 128 channels are staged
+// in smem with cp.async (double buffered, rows padded to 272 B so the fragment loads are
+// conflict-free); S = Q K^T and O += P V run on mma.sync m16n8k16 (bf16 -> fp32): the 10 prompt
+// tokens are the M dimension padded to 16, far too few rows for a tcgen05 tile, but enough to keep
+// this kernel on the K / V byte stream (2 MB per prompt) instead of on CUDA-core FMAs.
 constexpr int T2I_TILE = 64;
 constexpr int T2I_ROWB = 272;  // bytes per staged row (256 + 16 pad)
+constexpr int T2I_STAGE = 2 * T2I_TILE * T2I_ROWB;   // K + V of one tile
 
-__global__ void t2i_attention_kernel(const __nv_bfloat16* __restrict__ q,   // [N, Tq, 128]
-                                     const __nv_bfloat16* __restrict__ K,   // [blocks*HW, 128]
-                                     const __nv_bfloat16* __restrict__ V,
-                                     const int* __restrict__ kv_block,      // [N] or null
-                                     __nv_bfloat16* __restrict__ out,       // [N, Tq, 128]
-                                     int Tq, int HW, float scale) {
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+t2i_attention_kernel(const __nv_bfloat16* __restrict__ q,   // [N, Tq, 128]
+                     const __nv_bfloat16* __restrict__ K,   // [blocks*HW, 128]
+                     const __nv_bfloat16* __restrict__ V,
+                     const int* __restrict__ kv_block,      // [N] or null
+                     __nv_bfloat16* __restrict__ out,       // [N, Tq, 128]
+                     int Tq, int HW, float scale) {
   extern __shared__ __align__(16) uint8_t t2i_smem[];
-  uint8_t* sK = t2i_smem;
-  uint8_t* sV = t2i_smem + T2I_TILE * T2I_ROWB;
+  const uint32_t s_base = smem_u32(t2i_smem);
   const int n = blockIdx.x;
   const int blk = kv_block ? kv_block[n] : n;
   const __nv_bfloat16* Kb = K + static_cast<size_t>(blk) * HW * 128;
   const __nv_bfloat16* Vb = V + static_cast<size_t>(blk) * HW * 128;
-  const int tid = threadIdx.x;
-  const int nthreads = blockDim.x;
-  // compute-thread mapping
-  const int kl = tid & 3;
-  const int pair = tid >> 2;             // head * Tq + query
-  const bool active = pair < 8 * Tq;
-  const int h = active ? pair / Tq : 0;
-  const int tq = active ? pair % Tq : 0;
-  float qf[16];
-  {
-    const __nv_bfloat16* qp = q + (static_cast<size_t>(n) * Tq + tq) * 128 + h * 16;
-    float t[8];
-    unpack8(*reinterpret_cast<const uint4*>(qp), t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) qf[j] = t[j] * scale;
-    unpack8(*reinterpret_cast<const uint4*>(qp + 8), t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) qf[8 + j] = t[j] * scale;
-  }
-  float m = -INFINITY, l = 0.f;
-  float o[16];
-#pragma unroll
-  for (int d = 0; d < 16; ++d) o[d] = 0.f;
+  const int tid = threadIdx.x, lane = tid & 31, h = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int n_tiles = (HW + T2I_TILE - 1) / T2I_TILE;
 
-  for (int t0 = 0; t0 < HW; t0 += T2I_TILE) {
-    __syncthreads();
-    // stage: 64 rows x 16 chunks of 16 B, for K and V
-    for (int i = tid; i < T2I_TILE * 16 * 2; i += nthreads) {
-      const int which = i / (T2I_TILE * 16);
-      const int j = i - which * (T2I_TILE * 16);
+  auto issue_tile = [&](int tile, int stage) {
+    // 64 rows x 16 chunks of 16 B for K and for V: 2048 chunks / 256 threads = 8 each
+    const int t0 = tile * T2I_TILE;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + i * 256;
+      const int which = idx >> 10, j = idx & 1023;
       const int row = j >> 4, ch = j & 15;
-      uint4 val = make_uint4(0, 0, 0, 0);
-      if (t0 + row < HW)
-        val = *reinterpret_cast<const uint4*>((which ? Vb : Kb) + static_cast<size_t>(t0 + row) * 128 + ch * 8);
-      *reinterpret_cast<uint4*>((which ? sV : sK) + row * T2I_ROWB + ch * 16) = val;
+      const int grow = min(t0 + row, HW - 1);   // rows past the end are masked in the softmax
+      const __nv_bfloat16* src = (which ? Vb : Kb) + static_cast<size_t>(grow) * 128 + ch * 8;
+      cp_async16(s_base + stage * T2I_STAGE + which * (T2I_TILE * T2I_ROWB) + row * T2I_ROWB + ch * 16, src);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // Q fragment (A operand, rows = prompt tokens padded to 16, k = the head's 16 channels), pre-scaled
+  uint32_t qa[4];
+  {
+    auto ldq = [&](int row, int col) -> uint32_t {
+      if (row >= Tq) return 0u;
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(
+          q + (static_cast<size_t>(n) * Tq + row) * 128 + h * 16 + col);
+      return pack_bf16x2(__bfloat162float(v.x) * scale, __bfloat162float(v.y) * scale);
+    };
+    qa[0] = ldq(g, 2 * t); qa[1] = ldq(g + 8, 2 * t); qa[2] = ldq(g, 2 * t + 8); qa[3] = ldq(g + 8, 2 * t + 8);
+  }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+
+  issue_tile(0, 0);
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int stage = tile & 1;
+    if (tile + 1 < n_tiles) {
+      issue_tile(tile + 1, stage ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    if (active) {
-      const int lim = min(T2I_TILE, HW - t0);
-      for (int key = kl; key < lim; key += 4) {
-        float kf[16], t[8];
-        const uint8_t* kp = sK + key * T2I_ROWB + h * 32;
-        unpack8(*reinterpret_cast<const uint4*>(kp), t);
+    const uint32_t sK = s_base + stage * T2I_STAGE + h * 32;
+    const uint32_t sV = sK + T2I_TILE * T2I_ROWB;
+    const int valid = min(T2I_TILE, HW - tile * T2I_TILE);
+    // ---- S = Q K^T for the 64 keys of the tile (8 n-tiles of 8 keys)
+    float s[8][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) kf[j] = t[j];
-        unpack8(*reinterpret_cast<const uint4*>(kp + 16), t);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) kf[8 + j] = t[j];
-        float s = 0.f;
-#pragma unroll
-        for (int d = 0; d < 16; ++d) s += qf[d] * kf[d];
-        const float mn = fmaxf(m, s);
-        const float a = __expf(m - mn), pe = __expf(s - mn);
-        l = l * a + pe;
-        const uint8_t* vp = sV + key * T2I_ROWB + h * 32;
-        float vf[16];
-        unpack8(*reinterpret_cast<const uint4*>(vp), t);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) vf[j] = t[j];
-        unpack8(*reinterpret_cast<const uint4*>(vp + 16), t);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) vf[8 + j] = t[j];
-#pragma unroll
-        for (int d = 0; d < 16; ++d) o[d] = o[d] * a + pe * vf[d];
-        m = mn;
+    for (int j = 0; j < 8; ++j) {
+      uint32_t b0, b1;
+      const uint32_t addr = sK + (j * 8 + g) * T2I_ROWB + t * 4;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b0) : "r"(addr));
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b1) : "r"(addr + 16));
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      mma_bf16_16816(s[j], qa, b0, b1);
+      if (valid < T2I_TILE) {
+        const int key = j * 8 + 2 * t;
+        if (key >= valid) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+        if (key + 1 >= valid) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
       }
     }
-  }
-  // merge the 4 key-lanes of each (head, query) -- they are adjacent lanes of one warp
+    // ---- online softmax: rows g and g + 8; the 4 lanes of a quad hold the 64 keys of a row
+    float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-  for (int off = 1; off < 4; off <<= 1) {
-    const float m2 = __shfl_xor_sync(0xffffffffu, m, off);
-    const float l2 = __shfl_xor_sync(0xffffffffu, l, off);
-    const float mn = fmaxf(m, m2);
-    const float a1 = (m == -INFINITY) ? 0.f : __expf(m - mn);
-    const float a2 = (m2 == -INFINITY) ? 0.f : __expf(m2 - mn);
-    l = l * a1 + l2 * a2;
-#pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      const float o2 = __shfl_xor_sync(0xffffffffu, o[d], off);
-      o[d] = o[d] * a1 + o2 * a2;
+    for (int j = 0; j < 8; ++j) {
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
     }
-    m = mn;
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float a0 = __expf(m0 - mn0), a1 = __expf(m1 - mn1);
+    m0 = mn0; m1 = mn1;
+    float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = __expf(s[j][0] - mn0); s[j][1] = __expf(s[j][1] - mn0);
+      s[j][2] = __expf(s[j][2] - mn1); s[j][3] = __expf(s[j][3] - mn1);
+      ps0 += s[j][0] + s[j][1];
+      ps1 += s[j][2] + s[j][3];
+    }
+    l0 = l0 * a0 + ps0; l1 = l1 * a1 + ps1;
+#pragma unroll
+    for (int d = 0; d < 2; ++d) { o[d][0] *= a0; o[d][1] *= a0; o[d][2] *= a1; o[d][3] *= a1; }
+    // ---- O += P V: 4 k-chunks of 16 keys, 2 n-tiles of 8 channels
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(s[2 * c][0], s[2 * c][1]);
+      pa[1] = pack_bf16x2(s[2 * c][2], s[2 * c][3]);
+      pa[2] = pack_bf16x2(s[2 * c + 1][0], s[2 * c + 1][1]);
+      pa[3] = pack_bf16x2(s[2 * c + 1][2], s[2 * c + 1][3]);
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        // B[k = key][n = channel]: {V[key0][ch], V[key0+1][ch]} and keys + 8
+        const uint32_t addr = sV + (c * 16 + 2 * t) * T2I_ROWB + (d * 8 + g) * 2;
+        uint16_t v00, v01, v10, v11;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v00) : "r"(addr));
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v01) : "r"(addr + T2I_ROWB));
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v10) : "r"(addr + 8 * T2I_ROWB));
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v11) : "r"(addr + 9 * T2I_ROWB));
+        const uint32_t b0 = static_cast<uint32_t>(v00) | (static_cast<uint32_t>(v01) << 16);
+        const uint32_t b1 = static_cast<uint32_t>(v10) | (static_cast<uint32_t>(v11) << 16);
+        mma_bf16_16816(o[d], pa, b0, b1);
+      }
+    }
+    __syncthreads();   // everyone is done with this stage before it is refilled
   }
-  if (active && kl == 0) {
-    const float inv = 1.0f / l;
-    __nv_bfloat16* op = out + (static_cast<size_t>(n) * Tq + tq) * 128 + h * 16;
-    reinterpret_cast<uint4*>(op)[0] =
-        make_uint4(pack_bf16x2(o[0] * inv, o[1] * inv), pack_bf16x2(o[2] * inv, o[3] * inv),
-                   pack_bf16x2(o[4] * inv, o[5] * inv), pack_bf16x2(o[6] * inv, o[7] * inv));
-    reinterpret_cast<uint4*>(op)[1] =
-        make_uint4(pack_bf16x2(o[8] * inv, o[9] * inv), pack_bf16x2(o[10] * inv, o[11] * inv),
-                   pack_bf16x2(o[12] * inv, o[13] * inv), pack_bf16x2(o[14] * inv, o[15] * inv));
+  // row sums live per lane: reduce across the quad
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    if (g < Tq)
+      *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(n) * Tq + g) * 128 + h * 16 + d * 8 + 2 * t) =
+          pack_bf16x2(o[d][0] * i0, o[d][1] * i0);
+    if (g + 8 < Tq)
+      *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(n) * Tq + g + 8) * 128 + h * 16 + d * 8 + 2 * t) =
+          pack_bf16x2(o[d][2] * i1, o[d][3] * i1);
   }
 }
 
 int t2i_attention(const void* q, const void* K, const void* V, const int* kv_block, void* out, int N,
                   int Tq, int HW, cudaStream_t stream) {
   RSP_CHECK_ARG(q && K && V && out && N > 0 && Tq > 0 && Tq <= 16 && HW > 0, "t2i_attention: bad args");
-  const int threads = ((8 * Tq * 4 + 31) / 32) * 32;
-  const int smem = 2 * T2I_TILE * T2I_ROWB;
-  t2i_attention_kernel<<<N, threads, smem, stream>>>(
+  const int smem = 2 * T2I_STAGE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RSP_CHECK_CUDA(cudaFuncSetAttribute(t2i_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  t2i_attention_kernel<<<N, 256, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(K),
       static_cast<const __nv_bfloat16*>(V), kv_block, static_cast<__nv_bfloat16*>(out), Tq, HW, 0.25f);
   RSP_CHECK_LAUNCH();

@@ -189,29 +189,52 @@ __global__ void nms_mask_kernel(const float* __restrict__ boxes, const long long
   mask[(static_cast<size_t>(b) * n + i) * words + blockIdx.x] = bits;
 }
 
-// one warp per image: greedy scan in score order
+// one warp per image: greedy scan in score order, 64 candidates at a time.  For block b the 64
+// diagonal mask words are held two per lane; the serial part is a 64-step register loop
+// (shuffle-broadcast of one word per step), then the rows that were kept OR their remaining words
+// into the suppression bitmap with the 32 lanes striding over the words.
 __global__ void nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ nvalid,
                                 int n, unsigned char* __restrict__ keep) {
   extern __shared__ unsigned long long remv[];
   const int b = blockIdx.x;
   const int nv = nvalid[b];
   const int words = (n + 63) / 64;
+  const int nvw = (nv + 63) / 64;
   const int lane = threadIdx.x;
   for (int w = lane; w < words; w += 32) remv[w] = 0ull;
   __syncwarp();
-  for (int i = 0; i < n; ++i) {
-    unsigned char k = 0;
-    if (i < nv) {
-      const unsigned long long r = remv[i >> 6];
-      if (!((r >> (i & 63)) & 1ull)) {
-        k = 1;
-        const unsigned long long* mrow = mask + (static_cast<size_t>(b) * n + i) * words;
-        // only words >= i/64 were written by nms_mask_kernel (upper triangle)
-        for (int w = (i >> 6) + lane; w < (nv + 63) / 64; w += 32) remv[w] |= mrow[w];
+  const unsigned long long* mbase = mask + static_cast<size_t>(b) * n * words;
+  for (int blk = 0; blk < words; ++blk) {
+    const int i0 = blk * 64;
+    unsigned long long keptbits = 0ull;
+    if (blk < nvw) {
+      // diagonal words of rows i0 + lane and i0 + 32 + lane
+      const int r0 = i0 + lane, r1 = i0 + 32 + lane;
+      const unsigned long long d0 = (r0 < nv) ? mbase[static_cast<size_t>(r0) * words + blk] : 0ull;
+      const unsigned long long d1 = (r1 < nv) ? mbase[static_cast<size_t>(r1) * words + blk] : 0ull;
+      unsigned long long cur = remv[blk];
+      for (int tbit = 0; tbit < 64; ++tbit) {
+        const unsigned long long dw = __shfl_sync(0xffffffffu, tbit < 32 ? d0 : d1, tbit & 31);
+        if (i0 + tbit < nv && !((cur >> tbit) & 1ull)) {
+          keptbits |= 1ull << tbit;
+          cur |= dw;
+        }
+      }
+      // spread the kept rows' remaining words
+      for (int w = blk + 1 + lane; w < nvw; w += 32) {
+        unsigned long long acc = remv[w];
+        unsigned long long kb = keptbits;
+        while (kb) {
+          const int tbit = __ffsll(static_cast<long long>(kb)) - 1;
+          kb &= kb - 1;
+          acc |= mbase[static_cast<size_t>(i0 + tbit) * words + w];
+        }
+        remv[w] = acc;
       }
       __syncwarp();
     }
-    if (lane == 0) keep[static_cast<size_t>(b) * n + i] = k;
+    for (int tbit = lane; tbit < 64; tbit += 32)
+      if (i0 + tbit < n) keep[static_cast<size_t>(b) * n + i0 + tbit] = (keptbits >> tbit) & 1ull;
   }
 }
 
@@ -392,33 +415,39 @@ int roi_align_nhwc(const void* const* feats, const float* const* pes, const int*
 // mode 1: (bilinear(x) > thr).  PyTorch align_corners=False source index rule.
 __global__ void mask_paste_kernel(const float* __restrict__ logits, unsigned char* __restrict__ out, int n,
                                   int hm, int wm, int H, int W, float thr, int mode) {
+  // thread = 16 consecutive output pixels of one row (one 16-byte store)
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(n) * H * (W / 4);
+  const int w16 = W / 16;
+  const long long total = static_cast<long long>(n) * H * w16;
   if (idx >= total) return;
-  const int x4 = static_cast<int>(idx % (W / 4));
-  long long t = idx / (W / 4);
+  const int xb = static_cast<int>(idx % w16);
+  long long t = idx / w16;
   const int y = static_cast<int>(t % H);
   const int m = static_cast<int>(t / H);
   const float sy = fmaxf((y + 0.5f) * (static_cast<float>(hm) / H) - 0.5f, 0.f);
   const int y0 = static_cast<int>(sy), y1 = min(y0 + 1, hm - 1);
   const float ly = sy - y0;
-  const float* base = logits + static_cast<size_t>(m) * hm * wm;
-  unsigned char r[4];
+  const float* r0 = logits + (static_cast<size_t>(m) * hm + y0) * wm;
+  const float* r1 = logits + (static_cast<size_t>(m) * hm + y1) * wm;
+  const float sxs = static_cast<float>(wm) / W;
+  uint32_t packed[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int x = x4 * 4 + k;
-    const float sx = fmaxf((x + 0.5f) * (static_cast<float>(wm) / W) - 0.5f, 0.f);
+  for (int k = 0; k < 16; ++k) {
+    const int x = xb * 16 + k;
+    const float sx = fmaxf((x + 0.5f) * sxs - 0.5f, 0.f);
     const int x0 = static_cast<int>(sx), x1 = min(x0 + 1, wm - 1);
     const float lx = sx - x0;
-    float v00 = base[y0 * wm + x0], v01 = base[y0 * wm + x1], v10 = base[y1 * wm + x0], v11 = base[y1 * wm + x1];
+    float v00 = __ldg(r0 + x0), v01 = __ldg(r0 + x1), v10 = __ldg(r1 + x0), v11 = __ldg(r1 + x1);
     if (mode == 0) {
       v00 = 1.f / (1.f + expf(-v00)); v01 = 1.f / (1.f + expf(-v01));
       v10 = 1.f / (1.f + expf(-v10)); v11 = 1.f / (1.f + expf(-v11));
     }
     const float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
-    r[k] = mode == 1 ? (v > thr) : (v >= thr);   // mode 2: input already sigmoid-activated
+    const uint32_t bit = (mode == 1 ? (v > thr) : (v >= thr)) ? 1u : 0u;   // mode 2: input already activated
+    packed[k >> 2] |= bit << ((k & 3) * 8);
   }
-  *reinterpret_cast<uchar4*>(out + (static_cast<size_t>(m) * H + y) * W + x4 * 4) = make_uchar4(r[0], r[1], r[2], r[3]);
+  *reinterpret_cast<uint4*>(out + (static_cast<size_t>(m) * H + y) * W + xb * 16) =
+      make_uint4(packed[0], packed[1], packed[2], packed[3]);
 }
 
 __global__ void sigmoid_f32_kernel(const float4* __restrict__ in, float4* __restrict__ out, long long n4) {
@@ -439,8 +468,8 @@ int sigmoid_f32(const float* in, float* out, long long n, cudaStream_t stream) {
 
 int mask_paste(const float* logits, unsigned char* out, int n, int hm, int wm, int H, int W, float thr,
                int mode, cudaStream_t stream) {
-  RSP_CHECK_ARG(logits && out && n > 0 && W % 4 == 0, "mask_paste: bad args");
-  const long long total = static_cast<long long>(n) * H * (W / 4);
+  RSP_CHECK_ARG(logits && out && n > 0 && W % 16 == 0, "mask_paste: W must be a multiple of 16");
+  const long long total = static_cast<long long>(n) * H * (W / 16);
   mask_paste_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(logits, out, n, hm, wm, H, W,
                                                                                    thr, mode);
   RSP_CHECK_LAUNCH();

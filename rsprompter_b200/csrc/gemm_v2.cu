@@ -302,9 +302,10 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a,
               resv[k] = *reinterpret_cast<const float2*>(static_cast<const float*>(p.residual) +
                                                          static_cast<size_t>(rrow) * p.ldr + col);
             } else {
-              const __nv_bfloat162 rv = *reinterpret_cast<const __nv_bfloat162*>(
-                  static_cast<const __nv_bfloat16*>(p.residual) + static_cast<size_t>(rrow) * p.ldr + col);
-              resv[k] = make_float2(__bfloat162float(rv.x), __bfloat162float(rv.y));
+              // keep the raw bits: converting here would make every load wait for its own data
+              // before the next one can issue (in-order issue) and serialise the 16 latencies
+              resv[k].x = __uint_as_float(*reinterpret_cast<const uint32_t*>(
+                  static_cast<const __nv_bfloat16*>(p.residual) + static_cast<size_t>(rrow) * p.ldr + col));
             }
           }
         }
@@ -373,7 +374,14 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a,
               if (orow < 0 || col >= p.N) continue;
               float x0, x1;
               asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1) : "r"(stg_s + rr * STG_ROW + cl * 8));
-              if (p.residual) { x0 += resv[k].x; x1 += resv[k].y; }
+              if (p.residual) {
+                if (p.res_fp32) {
+                  x0 += resv[k].x; x1 += resv[k].y;
+                } else {
+                  const uint32_t raw = __float_as_uint(resv[k].x);
+                  x0 += __uint_as_float(raw << 16); x1 += __uint_as_float(raw & 0xffff0000u);
+                }
+              }
               if (p.out_fp32)
                 *reinterpret_cast<float2*>(static_cast<float*>(p.out) + static_cast<size_t>(orow) * p.ldo + col) =
                     make_float2(x0, x1);

@@ -141,7 +141,7 @@ static int run_case(const Case& c) {
   return nbad ? 1 : 0;
 }
 
-static void bench_gemm(int M, int N, int K, int bn, int act, int out_fp32, int residual) {
+static void bench_gemm(int M, int N, int K, int bn, int act, int out_fp32, int residual, int res_bf16 = 0, int iters = 20) {
   void *dA, *dW, *dO, *dR = nullptr;
   float* db;
   CK(cudaMalloc(&dA, (size_t)M * K * 2));
@@ -152,15 +152,15 @@ static void bench_gemm(int M, int N, int K, int bn, int act, int out_fp32, int r
   CK(cudaMemset(dW, 0x11, (size_t)N * K * 2));
   CK(cudaMemset(db, 0, N * 4));
   if (residual) { CK(cudaMalloc(&dR, (size_t)M * N * 4)); CK(cudaMemset(dR, 0, (size_t)M * N * 4)); }
+  (void)res_bf16;
   GemmArgs a;
   a.A = dA; a.W = dW; a.out = dO; a.bias = db; a.M = M; a.N = N; a.K = K;
   a.lda = K; a.ldw = K; a.ldo = N; a.ldr = N; a.act = act; a.out_fp32 = out_fp32; a.force_bn = bn;
-  a.residual = dR; a.res_fp32 = 1;
+  a.residual = dR; a.res_fp32 = res_bf16 ? 0 : 1;
   for (int i = 0; i < 3; ++i) gemm_bf16(a, 0);
   CK(cudaDeviceSynchronize());
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  const int iters = 20;
   cudaEventRecord(e0);
   for (int i = 0; i < iters; ++i) gemm_bf16(a, 0);
   cudaEventRecord(e1);
@@ -168,8 +168,10 @@ static void bench_gemm(int M, int N, int K, int bn, int act, int out_fp32, int r
   float ms;
   cudaEventElapsedTime(&ms, e0, e1);
   ms /= iters;
-  printf("bench gemm M=%d N=%d K=%d bn=%d act=%d outf32=%d res=%d: %.3f ms  %.1f TFLOP/s\n", M, N, K,
-         bn, act, out_fp32, residual, ms, 2.0 * M * N * K / ms * 1e-9);
+  const double bytes = (double)M * K * 2 + (double)N * K * 2 + (double)M * N * (out_fp32 ? 4 : 2) +
+                       (residual ? (double)M * N * (res_bf16 ? 2 : 4) : 0.0);
+  printf("bench gemm M=%d N=%d K=%d bn=%d act=%d outf32=%d res=%d%s: %.3f ms  %.1f TFLOP/s  %.0f GB/s\n", M, N, K,
+         bn, act, out_fp32, residual, res_bf16 ? "(bf16)" : "", ms, 2.0 * M * N * K / ms * 1e-9, bytes / ms * 1e-6);
   cudaFree(dA); cudaFree(dW); cudaFree(dO); cudaFree(db);
   if (dR) cudaFree(dR);
 }
@@ -212,6 +214,12 @@ int main(int argc, char** argv) {
       bench_gemm(8192, 8192, 8192, 256, 0, 0, 0);
       bench_gemm(8192, 8192, 8192, 128, 0, 0, 0);
     }
+  }
+  if (!strcmp(what, "gemmprof")) {
+    // mask-decoder shapes (N prompts * 4096 image tokens rows)
+    bench_gemm(1 << 20, 256, 128, 0, 0, 1, 1, 1, 3);   // i2t out_proj + bf16 residual -> fp32
+    bench_gemm(1 << 20, 128, 256, 0, 0, 0, 0, 0, 3);   // k / v / q projections
+    bench_gemm(1 << 20, 256, 128, 0, 0, 0, 0, 0, 3);
   }
   if (!strcmp(what, "attn") || !strcmp(what, "all")) fails += selftest_attention(bench);
   printf("selftest: %d failing case(s)\n", fails);
