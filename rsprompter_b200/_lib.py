@@ -54,6 +54,7 @@ _SIGNATURES = {
     "rsp_vit_attention_simt": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "rsp_layernorm": ([_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _f, _i, _vp], _i),
     "rsp_patchify16": ([_vp, _vp, _i, _i, _i, _vp], _i),
+    "rsp_layernorm_add": ([_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, ctypes.c_longlong, _i, _f, _vp], _i),
     "rsp_im2col_nhwc": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
     "rsp_nhwc_to_nchw": ([_vp, _i, _vp, _i, _i, _i, _vp], _i),
     "rsp_cast_f32_bf16": ([_vp, _vp, ctypes.c_longlong, _vp], _i),
@@ -519,5 +520,26 @@ def sin_fold(x: torch.Tensor) -> torch.Tensor:
     assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] % 2 == 0
     out = torch.empty(*x.shape[:-1], x.shape[-1] // 2, device=x.device, dtype=torch.float32)
     _check(_lib.rsp_sin_fold(_ptr(x), _ptr(out), out.numel(), _stream()), "rsp_sin_fold")
+    launch_count += 1
+    return out
+
+
+def layernorm_add(x: torch.Tensor, residual: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+                  res_block_map: torch.Tensor | None = None, res_block_rows: int = 0) -> torch.Tensor:
+    """bf16 LayerNorm(x + residual) for bf16 x [rows, C <= 256]; residual fp32 / bf16, optionally block-mapped."""
+    global launch_count
+    _require_cuda(x, residual, gamma, beta, res_block_map)
+    rows, C = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    assert residual.is_contiguous() and residual.shape[1] == C and residual.dtype in (torch.float32, torch.bfloat16)
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == C
+    if res_block_map is not None:
+        assert res_block_map.dtype == torch.int32 and res_block_map.is_contiguous() and res_block_rows > 0
+    else:
+        assert residual.shape[0] == rows
+    out = torch.empty_like(x)
+    _check(_lib.rsp_layernorm_add(_ptr(x), _ptr(residual), int(residual.dtype == torch.float32), _ptr(res_block_map),
+                                  res_block_rows, _ptr(gamma), _ptr(beta), _ptr(out), rows, C, float(eps), _stream()),
+           "rsp_layernorm_add")
     launch_count += 1
     return out

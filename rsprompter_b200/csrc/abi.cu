@@ -69,6 +69,12 @@ int rsp_layernorm(const void* in, int in_fp32, int ld_in, void* out, int out_fp3
   return layernorm_rows(a, S(stream));
 }
 
+int rsp_layernorm_add(const void* x, const void* res, int res_fp32, const int32_t* res_block_map,
+                      int res_block_rows, const float* gamma, const float* beta, void* out, long long rows, int C,
+                      float eps, void* stream) {
+  return layernorm_add(x, res, res_fp32, res_block_map, res_block_rows, gamma, beta, out, rows, C, eps, S(stream));
+}
+
 int rsp_patchify16(const float* img, void* out, int B, int H, int W, void* stream) {
   return patchify16(img, out, B, H, W, S(stream));
 }

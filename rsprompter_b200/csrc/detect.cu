@@ -189,52 +189,68 @@ __global__ void nms_mask_kernel(const float* __restrict__ boxes, const long long
   mask[(static_cast<size_t>(b) * n + i) * words + blockIdx.x] = bits;
 }
 
-// one warp per image: greedy scan in score order, 64 candidates at a time.  For block b the 64
-// diagonal mask words are held two per lane; the serial part is a 64-step register loop
-// (shuffle-broadcast of one word per step), then the rows that were kept OR their remaining words
-// into the suppression bitmap with the 32 lanes striding over the words.
-__global__ void nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ nvalid,
-                                int n, unsigned char* __restrict__ keep) {
+// one CTA (4 warps) per image: greedy scan in score order, 64 candidates at a time.  Warp 0 resolves a
+// block serially in registers (the 64 diagonal mask words are held two per lane and broadcast by
+// shuffle); then all 128 threads OR the kept rows' remaining words into the suppression bitmap,
+// eight independent loads in flight per thread (the mask is L2-resident).
+__global__ void __launch_bounds__(128)
+nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ nvalid, int n,
+                unsigned char* __restrict__ keep) {
   extern __shared__ unsigned long long remv[];
+  __shared__ unsigned long long kept_s;
   const int b = blockIdx.x;
   const int nv = nvalid[b];
   const int words = (n + 63) / 64;
   const int nvw = (nv + 63) / 64;
-  const int lane = threadIdx.x;
-  for (int w = lane; w < words; w += 32) remv[w] = 0ull;
-  __syncwarp();
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int w = tid; w < words; w += blockDim.x) remv[w] = 0ull;
+  __syncthreads();
   const unsigned long long* mbase = mask + static_cast<size_t>(b) * n * words;
   for (int blk = 0; blk < words; ++blk) {
     const int i0 = blk * 64;
-    unsigned long long keptbits = 0ull;
     if (blk < nvw) {
-      // diagonal words of rows i0 + lane and i0 + 32 + lane
-      const int r0 = i0 + lane, r1 = i0 + 32 + lane;
-      const unsigned long long d0 = (r0 < nv) ? mbase[static_cast<size_t>(r0) * words + blk] : 0ull;
-      const unsigned long long d1 = (r1 < nv) ? mbase[static_cast<size_t>(r1) * words + blk] : 0ull;
-      unsigned long long cur = remv[blk];
-      for (int tbit = 0; tbit < 64; ++tbit) {
-        const unsigned long long dw = __shfl_sync(0xffffffffu, tbit < 32 ? d0 : d1, tbit & 31);
-        if (i0 + tbit < nv && !((cur >> tbit) & 1ull)) {
-          keptbits |= 1ull << tbit;
-          cur |= dw;
+      if (tid < 32) {
+        const int r0 = i0 + lane, r1 = i0 + 32 + lane;
+        const unsigned long long d0 = (r0 < nv) ? mbase[static_cast<size_t>(r0) * words + blk] : 0ull;
+        const unsigned long long d1 = (r1 < nv) ? mbase[static_cast<size_t>(r1) * words + blk] : 0ull;
+        unsigned long long cur = remv[blk], keptbits = 0ull;
+        for (int tbit = 0; tbit < 64; ++tbit) {
+          const unsigned long long dw = __shfl_sync(0xffffffffu, tbit < 32 ? d0 : d1, tbit & 31);
+          if (i0 + tbit < nv && !((cur >> tbit) & 1ull)) {
+            keptbits |= 1ull << tbit;
+            cur |= dw;
+          }
         }
+        if (lane == 0) kept_s = keptbits;
       }
-      // spread the kept rows' remaining words
-      for (int w = blk + 1 + lane; w < nvw; w += 32) {
+      __syncthreads();
+      const unsigned long long keptbits = kept_s;
+      for (int w = blk + 1 + tid; w < nvw; w += blockDim.x) {
         unsigned long long acc = remv[w];
         unsigned long long kb = keptbits;
         while (kb) {
-          const int tbit = __ffsll(static_cast<long long>(kb)) - 1;
-          kb &= kb - 1;
-          acc |= mbase[static_cast<size_t>(i0 + tbit) * words + w];
+          unsigned long long v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            v[u] = 0ull;
+            if (kb) {
+              const int tbit = __ffsll(static_cast<long long>(kb)) - 1;
+              kb &= kb - 1;
+              v[u] = mbase[static_cast<size_t>(i0 + tbit) * words + w];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc |= v[u];
         }
         remv[w] = acc;
       }
-      __syncwarp();
+      for (int tbit = tid; tbit < 64; tbit += blockDim.x)
+        if (i0 + tbit < n) keep[static_cast<size_t>(b) * n + i0 + tbit] = (keptbits >> tbit) & 1ull;
+      __syncthreads();
+    } else {
+      for (int tbit = tid; tbit < 64; tbit += blockDim.x)
+        if (i0 + tbit < n) keep[static_cast<size_t>(b) * n + i0 + tbit] = 0;
     }
-    for (int tbit = lane; tbit < 64; tbit += 32)
-      if (i0 + tbit < n) keep[static_cast<size_t>(b) * n + i0 + tbit] = (keptbits >> tbit) & 1ull;
   }
 }
 
@@ -248,7 +264,7 @@ int nms_batched(const float* boxes, const long long* ids, const int* nvalid, int
   dim3 grid(words, words, B);
   nms_mask_kernel<<<grid, 64, 0, stream>>>(boxes, ids, nvalid, max_coord_ws, n, thr, mask_ws);
   RSP_CHECK_LAUNCH();
-  nms_scan_kernel<<<B, 32, words * 8, stream>>>(mask_ws, nvalid, n, keep);
+  nms_scan_kernel<<<B, 128, words * 8, stream>>>(mask_ws, nvalid, n, keep);
   RSP_CHECK_LAUNCH();
   return RSP_OK;
 }

@@ -285,6 +285,19 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a,
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + hf * C::COLS_PER_WARP;
       const int col_warp = n_blk * BN + hf * C::COLS_PER_WARP;
       const int sub = lane / lpr, cl = lane - sub * lpr;
+      // destination / residual row of tile-local row rr: plain arithmetic when there is no scatter map
+      // (warp-uniform choice), otherwise a shuffle from the lane that owns the row
+      const bool simple_rows = (p.row_map == nullptr) && (p.res_block_map == nullptr) && (p.res_mod % 32 == 0);
+      const int tile_row0 = m_blk * BM + q * 32;
+      const int res_row0 = p.res_mod > 0 ? tile_row0 % p.res_mod : tile_row0;   // tiles never straddle res_mod
+      auto get_orow = [&](int rr) -> int {
+        if (simple_rows) return (tile_row0 + rr < p.M) ? tile_row0 + rr : -1;
+        return __shfl_sync(0xffffffffu, my_orow, rr);
+      };
+      auto get_rrow = [&](int rr) -> int {
+        if (simple_rows) return res_row0 + rr;
+        return __shfl_sync(0xffffffffu, my_rrow, rr);
+      };
       // residual prefetch (fp32-staged path: 16 lanes x 8 B per row, 2 rows per instruction): the 16
       // loads of a pass are issued back to back before the accumulator is touched, so ~4 KB per warp
       // is in flight while the TMEM drain / activation of the same pass runs
@@ -294,8 +307,8 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a,
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
           const int rr = 2 * k + sub;
-          const int orow = __shfl_sync(0xffffffffu, my_orow, rr);
-          const int rrow = __shfl_sync(0xffffffffu, my_rrow, rr);
+          const int orow = get_orow(rr);
+          const int rrow = get_rrow(rr);
           resv[k] = make_float2(0.f, 0.f);
           if (orow >= 0 && col < p.N) {
             if (p.res_fp32) {
@@ -370,7 +383,7 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a,
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
               const int rr = 2 * k + sub;
-              const int orow = __shfl_sync(0xffffffffu, my_orow, rr);
+              const int orow = get_orow(rr);
               if (orow < 0 || col >= p.N) continue;
               float x0, x1;
               asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1) : "r"(stg_s + rr * STG_ROW + cl * 8));
@@ -393,7 +406,7 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a,
 #pragma unroll 4
             for (int r0 = 0; r0 < 32; r0 += rpi) {
               const int rr = r0 + sub;
-              const int orow = __shfl_sync(0xffffffffu, my_orow, rr);
+              const int orow = get_orow(rr);
               if (orow < 0 || col >= p.N) continue;
               uint32_t w0, w1;
               asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(stg_s + rr * STG_ROW + cl * 8));

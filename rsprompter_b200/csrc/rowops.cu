@@ -261,4 +261,96 @@ int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t stream) 
   return RSP_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// out = LayerNorm(x + residual) over rows of C <= 256 channels (warp per row, 8 channels per lane):
+// the "keys = layer_norm4(keys + attn_out)" step of SamTwoWayAttentionBlock (HF:345-347) after a
+// plain bf16 out_proj GEMM.  The residual row can be block-mapped (prompts sharing an image).
+template <typename TRes>
+__global__ void layernorm_add_kernel(const __nv_bfloat16* __restrict__ x, const TRes* __restrict__ res,
+                                     const int* __restrict__ res_block_map, int res_block_rows,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     __nv_bfloat16* __restrict__ out, long long rows, int C, float eps) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  long long rrow = row;
+  if (res_block_map) {
+    const long long blk = row / res_block_rows;
+    rrow = static_cast<long long>(res_block_map[blk]) * res_block_rows + (row - blk * res_block_rows);
+  }
+  const int c = lane * 8;
+  float v[8];
+  const bool on = c < C;
+  if (on) {
+    const uint4 u = *reinterpret_cast<const uint4*>(x + row * C + c);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[2 * j] = __uint_as_float(w[j] << 16);
+      v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+    }
+    if (sizeof(TRes) == 4) {
+      const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(res) + rrow * C + c);
+      const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(res) + rrow * C + c + 4);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    } else {
+      const uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(res) + rrow * C + c);
+      const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[2 * j] += __uint_as_float(rw[j] << 16);
+        v[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sum += v[j];
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+  const float mean = sum / C;
+  float var = 0.f;
+  if (on) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; var += d * d; }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) var += __shfl_xor_sync(0xffffffffu, var, s);
+  const float rstd = rsqrtf(var / C + eps);
+  if (on) {
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = (v[j] - mean) * rstd * g[j] + bb[j];
+    *reinterpret_cast<uint4*>(out + row * C + c) =
+        make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+  }
+}
+
+int layernorm_add(const void* x, const void* res, int res_fp32, const int* res_block_map, int res_block_rows,
+                  const float* gamma, const float* beta, void* out, long long rows, int C, float eps,
+                  cudaStream_t stream) {
+  RSP_CHECK_ARG(x && res && gamma && beta && out && rows > 0, "layernorm_add: null pointer");
+  RSP_CHECK_ARG(C % 8 == 0 && C <= 256, "layernorm_add: C=%d (multiple of 8, <= 256)", C);
+  RSP_CHECK_ARG(!res_block_map || res_block_rows > 0, "layernorm_add: res_block_rows");
+  const int warps = 8;
+  const unsigned blocks = static_cast<unsigned>((rows + warps - 1) / warps);
+  if (res_fp32)
+    layernorm_add_kernel<float><<<blocks, warps * 32, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const float*>(res), res_block_map, res_block_rows, gamma,
+        beta, static_cast<__nv_bfloat16*>(out), rows, C, eps);
+  else
+    layernorm_add_kernel<__nv_bfloat16><<<blocks, warps * 32, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(res), res_block_map, res_block_rows,
+        gamma, beta, static_cast<__nv_bfloat16*>(out), rows, C, eps);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
 }  // namespace rsp

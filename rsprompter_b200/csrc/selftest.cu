@@ -141,7 +141,7 @@ static int run_case(const Case& c) {
   return nbad ? 1 : 0;
 }
 
-static void bench_gemm(int M, int N, int K, int bn, int act, int out_fp32, int residual, int res_bf16 = 0, int iters = 20) {
+static void bench_gemm(int M, int N, int K, int bn, int act, int out_fp32, int residual, int res_bf16 = 0, int iters = 20, int res_mod = 0) {
   void *dA, *dW, *dO, *dR = nullptr;
   float* db;
   CK(cudaMalloc(&dA, (size_t)M * K * 2));
@@ -156,7 +156,7 @@ static void bench_gemm(int M, int N, int K, int bn, int act, int out_fp32, int r
   GemmArgs a;
   a.A = dA; a.W = dW; a.out = dO; a.bias = db; a.M = M; a.N = N; a.K = K;
   a.lda = K; a.ldw = K; a.ldo = N; a.ldr = N; a.act = act; a.out_fp32 = out_fp32; a.force_bn = bn;
-  a.residual = dR; a.res_fp32 = res_bf16 ? 0 : 1;
+  a.residual = dR; a.res_fp32 = res_bf16 ? 0 : 1; a.res_mod = res_mod;
   for (int i = 0; i < 3; ++i) gemm_bf16(a, 0);
   CK(cudaDeviceSynchronize());
   cudaEvent_t e0, e1;
@@ -220,6 +220,7 @@ int main(int argc, char** argv) {
     bench_gemm(1 << 20, 256, 128, 0, 0, 1, 1, 1, 3);   // i2t out_proj + bf16 residual -> fp32
     bench_gemm(1 << 20, 128, 256, 0, 0, 0, 0, 0, 3);   // k / v / q projections
     bench_gemm(1 << 20, 256, 128, 0, 0, 0, 0, 0, 3);
+    bench_gemm(1 << 20, 128, 256, 0, 0, 0, 1, 0, 3, 4096);   // k-proj + broadcast fp32 residual (k_proj(pe))
   }
   if (!strcmp(what, "attn") || !strcmp(what, "all")) fails += selftest_attention(bench);
   printf("selftest: %d failing case(s)\n", fails);

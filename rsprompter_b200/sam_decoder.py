@@ -246,11 +246,11 @@ class SamMaskDecoderB200(nn.Module):
             pq = _lib.gemm(pos_b, i2t["qw"], None, out_dtype=torch.float32)
             Qimg = _lib.gemm(keys_b, i2t["qw"], i2t["qb"], residual=pq, res_mod=HW)
             att = _lib.i2t_attention(Qimg, ktok.view(N, Tt, -1), vtok.view(N, Tt, -1), HW, q_block=kblk)
-            # out_proj + residual on the coalesced-epilogue GEMM, then layer_norm4 as a row kernel
-            # (the fused row-LN epilogue is thread-per-row and slower at N*HW = 3.3 M rows)
-            pre = _lib.gemm(att, i2t["ow"], i2t["ob"], residual=keys_res, res_block_map=kblk,
-                            res_block_rows=HW if kblk is not None else 0, out_dtype=torch.float32)
-            keys_b = _lib.layernorm(pre, *L["ln4"], a.layer_norm_eps)
+            # out_proj as a plain bf16 GEMM (HBM-roofline epilogue), then keys = LN4(keys + attn_out) in
+            # one row kernel that also applies the prompt -> image block map of the residual
+            proj = _lib.gemm(att, i2t["ow"], i2t["ob"])
+            keys_b = _lib.layernorm_add(proj, keys_res, *L["ln4"], a.layer_norm_eps, res_block_map=kblk,
+                                        res_block_rows=HW if kblk is not None else 0)
             keys_res, kblk = keys_b, None
         queries = t2i(p["final"], queries, keys_b, None, (*p["lnf"], 1e-5))
         qv = queries.view(N, Tt, C)
