@@ -75,10 +75,12 @@ int rsp_layernorm(const void* in, int in_fp32, int ld_in, void* out, int out_fp3
 
 /* out = LayerNorm(x + residual) over bf16 rows of C <= 256 channels (fp32 statistics): x bf16 [rows, C];
  * residual fp32 or bf16 [*, C], optionally block-mapped as in rsp_gemm_bf16_ex.  The
- * keys = layer_norm4(keys + attn_out) step of SamTwoWayAttentionBlock (HF:345-347). */
+ * keys = layer_norm4(keys + attn_out) step of SamTwoWayAttentionBlock (HF:345-347).  If out_pe is not
+ * NULL it also receives bf16(out + pos[row % pos_mod]) (pos fp32 [pos_mod, C]): "key = keys +
+ * key_point_embedding" (HF:326,339), the operand of the following k / q projections. */
 int rsp_layernorm_add(const void* x, const void* res, int res_fp32, const int32_t* res_block_map,
-                      int res_block_rows, const float* gamma, const float* beta, void* out, long long rows, int C,
-                      float eps, void* stream);
+                      int res_block_rows, const float* gamma, const float* beta, void* out, const float* pos,
+                      int pos_mod, void* out_pe, long long rows, int C, float eps, void* stream);
 
 /* fp32 NCHW image [B,3,H,W] -> bf16 [B*(H/16)*(W/16), 768] patch rows, k = c*256 + ky*16 + kx,
  * so that patch embedding (HF:116,128; mmcv PatchEmbed VS:455) is one rsp_gemm_bf16. */

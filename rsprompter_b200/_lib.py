@@ -54,7 +54,7 @@ _SIGNATURES = {
     "rsp_vit_attention_simt": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "rsp_layernorm": ([_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _f, _i, _vp], _i),
     "rsp_patchify16": ([_vp, _vp, _i, _i, _i, _vp], _i),
-    "rsp_layernorm_add": ([_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, ctypes.c_longlong, _i, _f, _vp], _i),
+    "rsp_layernorm_add": ([_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, ctypes.c_longlong, _i, _f, _vp], _i),
     "rsp_im2col_nhwc": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
     "rsp_nhwc_to_nchw": ([_vp, _i, _vp, _i, _i, _i, _vp], _i),
     "rsp_cast_f32_bf16": ([_vp, _vp, ctypes.c_longlong, _vp], _i),
@@ -525,8 +525,10 @@ def sin_fold(x: torch.Tensor) -> torch.Tensor:
 
 
 def layernorm_add(x: torch.Tensor, residual: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
-                  res_block_map: torch.Tensor | None = None, res_block_rows: int = 0) -> torch.Tensor:
-    """bf16 LayerNorm(x + residual) for bf16 x [rows, C <= 256]; residual fp32 / bf16, optionally block-mapped."""
+                  res_block_map: torch.Tensor | None = None, res_block_rows: int = 0,
+                  pos: torch.Tensor | None = None):
+    """bf16 LayerNorm(x + residual) for bf16 x [rows, C <= 256]; residual fp32 / bf16, optionally block-mapped.
+    With pos (fp32 [P, C]) also returns bf16(out + pos[row % P])."""
     global launch_count
     _require_cuda(x, residual, gamma, beta, res_block_map)
     rows, C = x.shape
@@ -538,8 +540,12 @@ def layernorm_add(x: torch.Tensor, residual: torch.Tensor, gamma: torch.Tensor, 
     else:
         assert residual.shape[0] == rows
     out = torch.empty_like(x)
+    out_pe, pos_mod = None, 0
+    if pos is not None:
+        assert pos.dtype == torch.float32 and pos.is_contiguous() and pos.shape[1] == C
+        out_pe, pos_mod = torch.empty_like(x), pos.shape[0]
     _check(_lib.rsp_layernorm_add(_ptr(x), _ptr(residual), int(residual.dtype == torch.float32), _ptr(res_block_map),
-                                  res_block_rows, _ptr(gamma), _ptr(beta), _ptr(out), rows, C, float(eps), _stream()),
-           "rsp_layernorm_add")
+                                  res_block_rows, _ptr(gamma), _ptr(beta), _ptr(out), _ptr(pos), pos_mod,
+                                  _ptr(out_pe), rows, C, float(eps), _stream()), "rsp_layernorm_add")
     launch_count += 1
-    return out
+    return out if pos is None else (out, out_pe)

@@ -70,9 +70,10 @@ int rsp_layernorm(const void* in, int in_fp32, int ld_in, void* out, int out_fp3
 }
 
 int rsp_layernorm_add(const void* x, const void* res, int res_fp32, const int32_t* res_block_map,
-                      int res_block_rows, const float* gamma, const float* beta, void* out, long long rows, int C,
-                      float eps, void* stream) {
-  return layernorm_add(x, res, res_fp32, res_block_map, res_block_rows, gamma, beta, out, rows, C, eps, S(stream));
+                      int res_block_rows, const float* gamma, const float* beta, void* out, const float* pos,
+                      int pos_mod, void* out_pe, long long rows, int C, float eps, void* stream) {
+  return layernorm_add(x, res, res_fp32, res_block_map, res_block_rows, gamma, beta, out, pos, pos_mod, out_pe, rows,
+                       C, eps, S(stream));
 }
 
 int rsp_patchify16(const float* img, void* out, int B, int H, int W, void* stream) {

@@ -305,81 +305,119 @@ int t2i_attention(const void* q, const void* K, const void* V, const int* kv_blo
 }
 
 // ---------------------------------------------------------------------------------------
-// i2t: thread = (image token, head).  The prompt's Tq token keys / values (Tq x 128 each) sit
-// in smem; Q rows stream from HBM once, coalesced (8 heads x 32 B = one 256-byte row).
-__global__ void i2t_attention_kernel(const __nv_bfloat16* __restrict__ Q,      // [blocks*HW, 128]
-                                     const int* __restrict__ q_block,          // [N] or null
-                                     const __nv_bfloat16* __restrict__ ktok,   // [N, Tq, 128]
-                                     const __nv_bfloat16* __restrict__ vtok,
-                                     __nv_bfloat16* __restrict__ out,          // [N*HW, 128]
-                                     int Tq, int HW, float scale) {
-  __shared__ __align__(16) float sk[16 * 128];
-  __shared__ __align__(16) float sv[16 * 128];
+// i2t: CTA = (prompt, 128 image tokens), warp = head.  The Q tile (128 x 256 B) is staged with
+// cp.async, S = Q K_tok^T and O = P V_tok run on mma.sync m16n8k16 with the prompt's 10 token keys /
+// values (padded to 16) held in registers as B fragments for the whole tile; the result overwrites
+// the warp's own 32-byte column slice of the staged tile, which is then written out coalesced.
+// HBM traffic = Q in + O out, 2 MB per prompt: the kernel's roofline.
+constexpr int I2T_PIX = 128;
+constexpr int I2T_ROWB = 272;
+
+__global__ void __launch_bounds__(256)
+i2t_attention_kernel(const __nv_bfloat16* __restrict__ Q,      // [blocks*HW, 128]
+                     const int* __restrict__ q_block,          // [N] or null
+                     const __nv_bfloat16* __restrict__ ktok,   // [N, Tq, 128]
+                     const __nv_bfloat16* __restrict__ vtok,
+                     __nv_bfloat16* __restrict__ out,          // [N*HW, 128]
+                     int Tq, int HW, float scale) {
+  __shared__ __align__(16) uint8_t tile[I2T_PIX * I2T_ROWB];
+  const uint32_t s_tile = smem_u32(tile);
   const int n = blockIdx.y;
-  // smem layout [token][d/4][head][4]: the 8 heads read by one warp instruction are 128 contiguous
-  // bytes (conflict-free); the natural [token][head][16] layout is 4-way bank conflicted
-  for (int i = threadIdx.x; i < Tq * 128; i += blockDim.x) {
-    const int j = i >> 7, hh = (i >> 4) & 7, d = i & 15;
-    const int o = ((j * 4 + (d >> 2)) * 8 + hh) * 4 + (d & 3);
-    sk[o] = __bfloat162float(ktok[static_cast<size_t>(n) * Tq * 128 + i]) * scale;
-    sv[o] = __bfloat162float(vtok[static_cast<size_t>(n) * Tq * 128 + i]);
+  const int p0 = blockIdx.x * I2T_PIX;
+  const int tid = threadIdx.x, lane = tid & 31, h = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int blk = q_block ? q_block[n] : n;
+  const __nv_bfloat16* Qb = Q + (static_cast<size_t>(blk) * HW + p0) * 128;
+  const int npix = min(I2T_PIX, HW - p0);
+  // stage Q: 128 rows x 16 chunks of 16 B = 2048 chunks / 256 threads
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = tid + i * 256;
+    const int row = idx >> 4, ch = idx & 15;
+    const int srow = min(row, npix - 1);
+    cp_async16(s_tile + row * I2T_ROWB + ch * 16, Qb + static_cast<size_t>(srow) * 128 + ch * 8);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // token K / V fragments of this (prompt, head): constant for the tile
+  uint32_t kb[2][2], vb[2][2];
+  {
+    const __nv_bfloat16* kp = ktok + static_cast<size_t>(n) * Tq * 128 + h * 16;
+    const __nv_bfloat16* vp = vtok + static_cast<size_t>(n) * Tq * 128 + h * 16;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int tok = j * 8 + g;                       // B[k = dim][n = token]
+      kb[j][0] = kb[j][1] = 0u;
+      if (tok < Tq) {
+        const __nv_bfloat162 k0 = *reinterpret_cast<const __nv_bfloat162*>(kp + tok * 128 + 2 * t);
+        const __nv_bfloat162 k1 = *reinterpret_cast<const __nv_bfloat162*>(kp + tok * 128 + 2 * t + 8);
+        kb[j][0] = pack_bf16x2(__bfloat162float(k0.x) * scale, __bfloat162float(k0.y) * scale);
+        kb[j][1] = pack_bf16x2(__bfloat162float(k1.x) * scale, __bfloat162float(k1.y) * scale);
+      }
+      // B[k = token][n = dim]: dims j*8 + g, tokens (2t, 2t+1) and (2t+8, 2t+9)
+      auto ldv = [&](int tok2) -> uint32_t {
+        return tok2 < Tq ? static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(vp + tok2 * 128 + j * 8 + g)) : 0u;
+      };
+      vb[j][0] = ldv(2 * t) | (ldv(2 * t + 1) << 16);
+      vb[j][1] = ldv(2 * t + 8) | (ldv(2 * t + 9) << 16);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const uint32_t sq = s_tile + h * 32;
+#pragma unroll 2
+  for (int c = 0; c < I2T_PIX / 16; ++c) {
+    uint32_t qa[4];
+    const uint32_t a0 = sq + (c * 16 + g) * I2T_ROWB + t * 4;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(qa[0]) : "r"(a0));
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(qa[1]) : "r"(a0 + 8 * I2T_ROWB));
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(qa[2]) : "r"(a0 + 16));
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(qa[3]) : "r"(a0 + 8 * I2T_ROWB + 16));
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_bf16_16816(s0, qa, kb[0][0], kb[0][1]);
+    mma_bf16_16816(s1, qa, kb[1][0], kb[1][1]);
+    // mask padded tokens (columns 2t, 2t+1 of tile 0 and 8 + 2t, 9 + 2t of tile 1)
+    if (2 * t >= Tq) { s0[0] = -INFINITY; s0[2] = -INFINITY; }
+    if (2 * t + 1 >= Tq) { s0[1] = -INFINITY; s0[3] = -INFINITY; }
+    if (8 + 2 * t >= Tq) { s1[0] = -INFINITY; s1[2] = -INFINITY; }
+    if (9 + 2 * t >= Tq) { s1[1] = -INFINITY; s1[3] = -INFINITY; }
+    float m0 = fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1]));
+    float m1 = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    s0[0] = __expf(s0[0] - m0); s0[1] = __expf(s0[1] - m0); s1[0] = __expf(s1[0] - m0); s1[1] = __expf(s1[1] - m0);
+    s0[2] = __expf(s0[2] - m1); s0[3] = __expf(s0[3] - m1); s1[2] = __expf(s1[2] - m1); s1[3] = __expf(s1[3] - m1);
+    float l0 = s0[0] + s0[1] + s1[0] + s1[1], l1 = s0[2] + s0[3] + s1[2] + s1[3];
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    uint32_t pa[4] = {pack_bf16x2(s0[0], s0[1]), pack_bf16x2(s0[2], s0[3]), pack_bf16x2(s1[0], s1[1]),
+                      pack_bf16x2(s1[2], s1[3])};
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_bf16_16816(o0, pa, vb[0][0], vb[0][1]);
+    mma_bf16_16816(o1, pa, vb[1][0], vb[1][1]);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    __syncwarp();   // all lanes have read this chunk's Q fragments before the slice is overwritten
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a0), "r"(pack_bf16x2(o0[0] * i0, o0[1] * i0)) : "memory");
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a0 + 8 * I2T_ROWB), "r"(pack_bf16x2(o0[2] * i1, o0[3] * i1)) : "memory");
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a0 + 16), "r"(pack_bf16x2(o1[0] * i0, o1[1] * i0)) : "memory");
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a0 + 8 * I2T_ROWB + 16), "r"(pack_bf16x2(o1[2] * i1, o1[3] * i1)) : "memory");
   }
   __syncthreads();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (pixel, head)
-  const int pix = idx >> 3, h = idx & 7;
-  if (pix >= HW) return;
-  const int blk = q_block ? q_block[n] : n;
-  const __nv_bfloat16* qp = Q + (static_cast<size_t>(blk) * HW + pix) * 128 + h * 16;
-  float qf[16], t[8];
-  unpack8(*reinterpret_cast<const uint4*>(qp), t);
+  __nv_bfloat16* Ob = out + (static_cast<size_t>(n) * HW + p0) * 128;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) qf[j] = t[j];
-  unpack8(*reinterpret_cast<const uint4*>(qp + 8), t);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) qf[8 + j] = t[j];
-  float s[16];
-  float mx = -INFINITY;
-  for (int j = 0; j < Tq; ++j) {
-    const float4* kp = reinterpret_cast<const float4*>(sk + j * 128) + h;
-    float acc = 0.f;
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      const float4 kk = kp[d * 8];
-      acc += qf[4 * d] * kk.x + qf[4 * d + 1] * kk.y + qf[4 * d + 2] * kk.z + qf[4 * d + 3] * kk.w;
-    }
-    s[j] = acc;
-    mx = fmaxf(mx, acc);
+  for (int i = 0; i < 8; ++i) {
+    const int idx = tid + i * 256;
+    const int row = idx >> 4, ch = idx & 15;
+    if (row < npix)
+      *reinterpret_cast<uint4*>(Ob + static_cast<size_t>(row) * 128 + ch * 8) =
+          *reinterpret_cast<const uint4*>(tile + row * I2T_ROWB + ch * 16);
   }
-  float l = 0.f;
-  float o[16];
-#pragma unroll
-  for (int d = 0; d < 16; ++d) o[d] = 0.f;
-  for (int j = 0; j < Tq; ++j) {
-    const float pj = __expf(s[j] - mx);
-    l += pj;
-    const float4* vp = reinterpret_cast<const float4*>(sv + j * 128) + h;
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      const float4 vv = vp[d * 8];
-      o[4 * d] += pj * vv.x; o[4 * d + 1] += pj * vv.y; o[4 * d + 2] += pj * vv.z; o[4 * d + 3] += pj * vv.w;
-    }
-  }
-  const float inv = 1.0f / l;
-  __nv_bfloat16* op = out + (static_cast<size_t>(n) * HW + pix) * 128 + h * 16;
-  reinterpret_cast<uint4*>(op)[0] =
-      make_uint4(pack_bf16x2(o[0] * inv, o[1] * inv), pack_bf16x2(o[2] * inv, o[3] * inv),
-                 pack_bf16x2(o[4] * inv, o[5] * inv), pack_bf16x2(o[6] * inv, o[7] * inv));
-  reinterpret_cast<uint4*>(op)[1] =
-      make_uint4(pack_bf16x2(o[8] * inv, o[9] * inv), pack_bf16x2(o[10] * inv, o[11] * inv),
-                 pack_bf16x2(o[12] * inv, o[13] * inv), pack_bf16x2(o[14] * inv, o[15] * inv));
 }
 
 int i2t_attention(const void* Q, const int* q_block, const void* ktok, const void* vtok, void* out,
                   int N, int Tq, int HW, cudaStream_t stream) {
   RSP_CHECK_ARG(Q && ktok && vtok && out && N > 0 && Tq > 0 && Tq <= 16 && HW > 0, "i2t_attention: bad args");
-  const int threads = 256;
-  dim3 grid((HW * 8 + threads - 1) / threads, N);
-  i2t_attention_kernel<<<grid, threads, 0, stream>>>(
+  dim3 grid((HW + I2T_PIX - 1) / I2T_PIX, N);
+  i2t_attention_kernel<<<grid, 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(Q), q_block, static_cast<const __nv_bfloat16*>(ktok),
       static_cast<const __nv_bfloat16*>(vtok), static_cast<__nv_bfloat16*>(out), Tq, HW, 0.25f);
   RSP_CHECK_LAUNCH();

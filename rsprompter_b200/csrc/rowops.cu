@@ -269,7 +269,8 @@ template <typename TRes>
 __global__ void layernorm_add_kernel(const __nv_bfloat16* __restrict__ x, const TRes* __restrict__ res,
                                      const int* __restrict__ res_block_map, int res_block_rows,
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                                     __nv_bfloat16* __restrict__ out, long long rows, int C, float eps) {
+                                     __nv_bfloat16* __restrict__ out, const float* __restrict__ pos, int pos_mod,
+                                     __nv_bfloat16* __restrict__ out_pe, long long rows, int C, float eps) {
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -330,13 +331,21 @@ __global__ void layernorm_add_kernel(const __nv_bfloat16* __restrict__ x, const 
     for (int j = 0; j < 8; ++j) y[j] = (v[j] - mean) * rstd * g[j] + bb[j];
     *reinterpret_cast<uint4*>(out + row * C + c) =
         make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+    if (out_pe) {   // second output: keys + positional embedding, the A operand of the next k / q projections
+      const float* pp = pos + (row % pos_mod) * C + c;
+      const float4 p0 = *reinterpret_cast<const float4*>(pp), p1 = *reinterpret_cast<const float4*>(pp + 4);
+      *reinterpret_cast<uint4*>(out_pe + row * C + c) =
+          make_uint4(pack_bf16x2(y[0] + p0.x, y[1] + p0.y), pack_bf16x2(y[2] + p0.z, y[3] + p0.w),
+                     pack_bf16x2(y[4] + p1.x, y[5] + p1.y), pack_bf16x2(y[6] + p1.z, y[7] + p1.w));
+    }
   }
 }
 
 int layernorm_add(const void* x, const void* res, int res_fp32, const int* res_block_map, int res_block_rows,
-                  const float* gamma, const float* beta, void* out, long long rows, int C, float eps,
-                  cudaStream_t stream) {
+                  const float* gamma, const float* beta, void* out, const float* pos, int pos_mod, void* out_pe,
+                  long long rows, int C, float eps, cudaStream_t stream) {
   RSP_CHECK_ARG(x && res && gamma && beta && out && rows > 0, "layernorm_add: null pointer");
+  RSP_CHECK_ARG(!out_pe || (pos && pos_mod > 0), "layernorm_add: out_pe needs pos / pos_mod");
   RSP_CHECK_ARG(C % 8 == 0 && C <= 256, "layernorm_add: C=%d (multiple of 8, <= 256)", C);
   RSP_CHECK_ARG(!res_block_map || res_block_rows > 0, "layernorm_add: res_block_rows");
   const int warps = 8;
@@ -344,11 +353,11 @@ int layernorm_add(const void* x, const void* res, int res_fp32, const int* res_b
   if (res_fp32)
     layernorm_add_kernel<float><<<blocks, warps * 32, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(x), static_cast<const float*>(res), res_block_map, res_block_rows, gamma,
-        beta, static_cast<__nv_bfloat16*>(out), rows, C, eps);
+        beta, static_cast<__nv_bfloat16*>(out), pos, pos_mod, static_cast<__nv_bfloat16*>(out_pe), rows, C, eps);
   else
     layernorm_add_kernel<__nv_bfloat16><<<blocks, warps * 32, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(res), res_block_map, res_block_rows,
-        gamma, beta, static_cast<__nv_bfloat16*>(out), rows, C, eps);
+        gamma, beta, static_cast<__nv_bfloat16*>(out), pos, pos_mod, static_cast<__nv_bfloat16*>(out_pe), rows, C, eps);
   RSP_CHECK_LAUNCH();
   return RSP_OK;
 }

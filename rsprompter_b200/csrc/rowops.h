@@ -22,8 +22,8 @@ int im2col_nhwc(const void* in, void* out, int B, int H, int W, int C, int KH, i
 int nhwc_to_nchw(const void* in, int in_fp32, float* out, int B, int HW, int C, cudaStream_t stream);
 
 int layernorm_add(const void* x, const void* res, int res_fp32, const int* res_block_map, int res_block_rows,
-                  const float* gamma, const float* beta, void* out, long long rows, int C, float eps,
-                  cudaStream_t stream);
+                  const float* gamma, const float* beta, void* out, const float* pos, int pos_mod, void* out_pe,
+                  long long rows, int C, float eps, cudaStream_t stream);
 int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t stream);
 
 }  // namespace rsp

@@ -198,21 +198,23 @@ class SamMaskDecoderB200(nn.Module):
             blk = prompt_img if shared else None
         src32 = src32.contiguous()
         src_b = _lib.cast_bf16(src32)
-        pos_b = _lib.cast_bf16(pos_rows.contiguous())
+        pos_rows = pos_rows.contiguous()
+        # "keys + key_point_embedding" (HF:326,339) is kept as a second bf16 tensor next to the keys, so
+        # the k / q projections are plain GEMMs; later layers get it from the LayerNorm kernel for free
+        src_pe_b = _lib.add_cast_bf16(src32, pos_rows)
         tokens = torch.cat([p["out_tokens"].unsqueeze(0).expand(N, -1, -1), sparse.to(torch.float32)], dim=1)
         tokens = tokens.reshape(N * Tt, C).contiguous()
 
-        def t2i(layer: dict, queries: torch.Tensor, keys_b: torch.Tensor, kv_blk, ln):
+        def t2i(layer: dict, queries: torch.Tensor, keys_b: torch.Tensor, keys_pe_b: torch.Tensor, kv_blk, ln):
             qin = _lib.add_cast_bf16(queries, tokens)
             q = _lib.gemm(qin, layer["qw"], layer["qb"])
-            pk = _lib.gemm(pos_b, layer["kw"], None, out_dtype=torch.float32)      # k_proj(pe), no bias
-            K = _lib.gemm(keys_b, layer["kw"], layer["kb"], residual=pk, res_mod=HW)
+            K = _lib.gemm(keys_pe_b, layer["kw"], layer["kb"])
             V = _lib.gemm(keys_b, layer["vw"], layer["vb"])
             att = _lib.t2i_attention(q.view(N, Tt, -1), K, V, HW, kv_block=kv_blk)
             return _lib.gemm(att.view(N * Tt, -1), layer["ow"], layer["ob"], residual=queries,
                              out_dtype=torch.float32, ln=ln)
 
-        keys_b, keys_res, kblk = src_b, src32, blk
+        keys_b, keys_pe_b, keys_res, kblk = src_b, src_pe_b, src32, blk
         queries = None
         for li, L in enumerate(p["layers"]):
             sa = L["sa"]
@@ -233,7 +235,7 @@ class SamMaskDecoderB200(nn.Module):
                 queries = _lib.gemm(att.view(N * Tt, C), sa["ow"], sa["ob"], residual=queries,
                                     out_dtype=torch.float32, ln=(*L["ln1"], a.layer_norm_eps))
             # tokens -> image cross attention (HF:323-333)
-            queries = t2i(L["t2i"], queries, keys_b, kblk, (*L["ln2"], a.layer_norm_eps))
+            queries = t2i(L["t2i"], queries, keys_b, keys_pe_b, kblk, (*L["ln2"], a.layer_norm_eps))
             # MLP (HF:335-338)
             hdn = _lib.gemm(_lib.cast_bf16(queries), L["w1"], L["b1"], act="relu")
             queries = _lib.gemm(hdn, L["w2"], L["b2"], residual=queries, out_dtype=torch.float32,
@@ -243,16 +245,15 @@ class SamMaskDecoderB200(nn.Module):
             qin = _lib.add_cast_bf16(queries, tokens)
             ktok = _lib.gemm(qin, i2t["kw"], i2t["kb"])
             vtok = _lib.gemm(_lib.cast_bf16(queries), i2t["vw"], i2t["vb"])
-            pq = _lib.gemm(pos_b, i2t["qw"], None, out_dtype=torch.float32)
-            Qimg = _lib.gemm(keys_b, i2t["qw"], i2t["qb"], residual=pq, res_mod=HW)
+            Qimg = _lib.gemm(keys_pe_b, i2t["qw"], i2t["qb"])
             att = _lib.i2t_attention(Qimg, ktok.view(N, Tt, -1), vtok.view(N, Tt, -1), HW, q_block=kblk)
             # out_proj as a plain bf16 GEMM (HBM-roofline epilogue), then keys = LN4(keys + attn_out) in
             # one row kernel that also applies the prompt -> image block map of the residual
             proj = _lib.gemm(att, i2t["ow"], i2t["ob"])
-            keys_b = _lib.layernorm_add(proj, keys_res, *L["ln4"], a.layer_norm_eps, res_block_map=kblk,
-                                        res_block_rows=HW if kblk is not None else 0)
+            keys_b, keys_pe_b = _lib.layernorm_add(proj, keys_res, *L["ln4"], a.layer_norm_eps, res_block_map=kblk,
+                                                   res_block_rows=HW if kblk is not None else 0, pos=pos_rows)
             keys_res, kblk = keys_b, None
-        queries = t2i(p["final"], queries, keys_b, None, (*p["lnf"], 1e-5))
+        queries = t2i(p["final"], queries, keys_b, keys_pe_b, None, (*p["lnf"], 1e-5))
         qv = queries.view(N, Tt, C)
         iou_tok = _lib.cast_bf16(qv[:, 0].contiguous())
         iou = self._ff(iou_tok, p["iou"])                                   # [N, num_mask_tokens]
