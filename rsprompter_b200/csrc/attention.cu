@@ -54,14 +54,15 @@ struct AttDev {
 // bar indices
 enum { B_Q = 0, B_REL, B_RELC, B_KF, B_KE, B_VF, B_VE, B_SF, B_PF, B_PV, B_COUNT };
 
-template <int HD, bool GLOBAL>
+template <int HD, int GS>   // GS = 0: 14x14 windows; GS = 64 / 32: global attention over a GS x GS grid
 __global__ void __launch_bounds__(ATT_THREADS, (HD <= 64) ? 2 : 1)
 vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
                      const __grid_constant__ CUtensorMap tm_relh,
                      const __grid_constant__ CUtensorMap tm_relw, const AttDev p) {
   using Cfg = AttCfg<HD>;
   constexpr int NA = Cfg::NA;
-  constexpr int NREL = GLOBAL ? 128 : 32;  // padded table rows (2S-1 = 127 / 27)
+  constexpr bool GLOBAL = GS > 0;
+  constexpr int NREL = GLOBAL ? 2 * GS : 32;  // padded table rows (2S-1 = 127 / 63 / 27)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[B_COUNT];
   __shared__ uint32_t tmem_base_s;
@@ -178,7 +179,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
     const int tq = q0 + r;                    // query index inside the sequence
     const int qh = tq / p.S;
     const int qw = tq - qh * p.S;
-    constexpr int NW = GLOBAL ? 64 : 14;      // rel_w values kept in registers
+    constexpr int NW = GLOBAL ? GS : 14;      // rel_w values kept in registers
     constexpr int NH = GLOBAL ? 1 : 14;       // rel_h in registers (window) or smem (global)
     float relw[NW];
     float relh[NH];
@@ -190,27 +191,27 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
     float* scratch = reinterpret_cast<float*>(gP);  // aliases the P buffer (unused yet)
     __half* relh_s = reinterpret_cast<__half*>(gRH);
     if (GLOBAL) {
-      // table index t <-> key coordinate k: t = q - k + 63
+      // table index t <-> key coordinate k: t = q - k + (GS - 1)
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NREL / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tS + lane_off + c * 32, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int kh = qh + 63 - (c * 32 + i);
-          if (kh >= 0 && kh < 64) relh_s[kh * 128 + r] = __float2half_rn(__uint_as_float(v[i]) * LOG2E);
+          const int kh = qh + (GS - 1) - (c * 32 + i);
+          if (kh >= 0 && kh < GS) relh_s[kh * 128 + r] = __float2half_rn(__uint_as_float(v[i]) * LOG2E);
         }
       }
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NREL / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tO + lane_off + c * 32, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int kw = qw + 63 - (c * 32 + i);
-          if (kw >= 0 && kw < 64) scratch[kw * 128 + r] = __uint_as_float(v[i]) * LOG2E;
+          const int kw = qw + (GS - 1) - (c * 32 + i);
+          if (kw >= 0 && kw < GS) scratch[kw * 128 + r] = __uint_as_float(v[i]) * LOG2E;
         }
       }
 #pragma unroll
@@ -254,10 +255,11 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
       const uint32_t par = j & 1;
       mbar_wait(bar(B_SF), par);
       tc_fence_after();
-      float rh0 = 0.f, rh1 = 0.f;
+      constexpr int RPT = GLOBAL ? 128 / GS : 1;   // image rows of keys per 128-key tile
+      float rh[RPT];
       if (GLOBAL) {
-        rh0 = __half2float(relh_s[(2 * j) * 128 + r]);
-        rh1 = __half2float(relh_s[(2 * j + 1) * 128 + r]);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) rh[k] = __half2float(relh_s[(RPT * j + k) * 128 + r]);
       }
       const int key0 = j * 128;
       // ---- pass 1: row max of the biased, log2-scaled scores
@@ -272,7 +274,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
         for (int i = 0; i < 32; ++i) {
           float t;
           if (GLOBAL) {
-            t = fmaf(__uint_as_float(v[i]), scale2, (c < 2 ? rh0 : rh1)) + relw[(c & 1) * 32 + i];
+            t = fmaf(__uint_as_float(v[i]), scale2, rh[(c * 32) / (GLOBAL ? GS : 32)]) + relw[(c * 32) % (GLOBAL ? GS : 32) + i];
           } else {
             const int key = key0 + c * 32 + i;   // j in {0,1}: resolved after unrolling below
             const int kh = key / 14, kw = key - kh * 14;
@@ -322,7 +324,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
           for (int i = 0; i < 32; ++i) {
             float t;
             if (GLOBAL) {
-              t = fmaf(__uint_as_float(v[i]), scale2, (c < 2 ? rh0 : rh1)) + relw[(c & 1) * 32 + i];
+              t = fmaf(__uint_as_float(v[i]), scale2, rh[(c * 32) / (GLOBAL ? GS : 32)]) + relw[(c * 32) % (GLOBAL ? GS : 32) + i];
             } else {
               const int key = key0 + c * 32 + i;
               const int kh = key / 14, kw = key - kh * 14;
@@ -383,10 +385,10 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
   }
 }
 
-template <int HD, bool GLOBAL>
+template <int HD, int GS>
 static int launch_att(const AttentionArgs& a, cudaStream_t stream) {
   using Cfg = AttCfg<HD>;
-  constexpr int NREL = GLOBAL ? 128 : 32;
+  constexpr int NREL = GS > 0 ? 2 * GS : 32;
   const int D = a.H * HD;
   const long long m_tok = static_cast<long long>(a.n_seq) * a.T;
   CUtensorMap tq, th, tw;
@@ -399,7 +401,7 @@ static int launch_att(const AttentionArgs& a, cudaStream_t stream) {
   p.n_qt = (a.T + 127) / 128;
   p.n_kt = (a.T + 127) / 128;
   p.scale2 = (1.0f / sqrtf(static_cast<float>(HD))) * LOG2E;
-  auto kern = vit_attention_kernel<HD, GLOBAL>;
+  auto kern = vit_attention_kernel<HD, GS>;
   static bool attr_set = false;
   if (!attr_set) {
     RSP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -417,10 +419,18 @@ int vit_attention(const AttentionArgs& a, cudaStream_t stream) {
   RSP_CHECK_ARG(a.qkv && a.rel_h && a.rel_w && a.out, "attention: null pointer");
   RSP_CHECK_ARG(a.T == a.S * a.S, "attention: T=%d is not S^2 (S=%d)", a.T, a.S);
   RSP_CHECK_ARG(a.n_seq > 0 && a.H > 0, "attention: bad n_seq/H");
-  const bool global = (a.S == 64);
-  RSP_CHECK_ARG(global || a.S == 14, "attention: S=%d unsupported (14 = window, 64 = global)", a.S);
-  if (a.hd == 64) return global ? launch_att<64, true>(a, stream) : launch_att<64, false>(a, stream);
-  if (a.hd == 80) return global ? launch_att<80, true>(a, stream) : launch_att<80, false>(a, stream);
+  if (a.S != 14 && a.S != 32 && a.S != 64)   // other grids (768^2 / 1280^2 inputs): CUDA-core kernel
+    return vit_attention_simt(a, stream);
+  if (a.hd == 64) {
+    if (a.S == 64) return launch_att<64, 64>(a, stream);
+    if (a.S == 32) return launch_att<64, 32>(a, stream);
+    return launch_att<64, 0>(a, stream);
+  }
+  if (a.hd == 80) {
+    if (a.S == 64) return launch_att<80, 64>(a, stream);
+    if (a.S == 32) return launch_att<80, 32>(a, stream);
+    return launch_att<80, 0>(a, stream);
+  }
   set_last_error("attention: head dim %d unsupported (64, 80)", a.hd);
   return RSP_ERR_UNSUPPORTED;
 }
