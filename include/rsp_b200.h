@@ -194,6 +194,45 @@ int rsp_pool2_nhwc(const void* in, void* out, int B, int H, int W, int C, int mo
 /* out[i] = sin(in[2i]) + in[2i+1]: the sin/identity fold of the point embeddings (M:348, M:1672). */
 int rsp_sin_fold(const float* in, float* out, long long n_out, void* stream);
 
+/* ---- RSPrompter-query head (M:274-715) ---- */
+
+/* GroupNorm(G) over channels-last bf16 [B,H,W,C] (C/G = 4), fp32 statistics in stats_ws (fp32 [B,G,2], zeroed by
+ * the call); optional `up` bf16 [B,H/2,W/2,C] is bilinearly x2-upsampled (align_corners=False) and added after the
+ * affine, optional ReLU last: the ConvModule(norm=GN) tails and the FPN top-down add of MSDeformAttnPixelDecoder
+ * (msdeformattn_pixel_decoder.py:94-109, 230-240). */
+int rsp_groupnorm_nhwc(const void* x, float* stats_ws, const float* gamma, const float* beta, const void* up,
+                       void* out, int B, int H, int W, int C, int G, float eps, int relu, void* stream);
+
+/* mmcv MultiScaleDeformableAttention core (deformable_detr_layers.py:237-249): value bf16 [B,NQ,128] (8 heads x 16,
+ * already value_proj'ed), ow fp32 [B*NQ, ld_ow] = [sampling_offsets (8*L*P*2) | attention logits (8*L*P)] from one
+ * GEMM, levels hs/ws (HOST int arrays, low -> high resolution, sum h*w = NQ).  Softmax over L*P, reference point =
+ * the query's own cell centre, bilinear zero-padded sampling as grid_sample(align_corners=False).  out bf16. */
+int rsp_ms_deform_attn_sample(const void* value, const float* ow, int ld_ow, const int32_t* hs, const int32_t* ws,
+                              int L, int P, int B, int NQ, void* out, void* stream);
+
+/* nn.MultiheadAttention core, 8 heads x 16: Q bf16 [B,nq,ldq], K / V bf16 [B,nk,ld*], mask uint8 [B,nq,nk]
+ * (1 = masked, shared by the heads) or NULL; out bf16 [B,nq,128].  Masked cross-attention / self-attention of
+ * Mask2FormerTransformerDecoderLayer (mask2former_layers.py:113-135). */
+int rsp_mha_small(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const uint8_t* mask, int B,
+                  int nq, int nk, void* out, void* stream);
+
+/* attn_mask = sigmoid(bilinear(mask_pred_plus -> (h, w))) < 0.5 per (image, query) map, and a map that is entirely
+ * masked is cleared (M:386-392, M:439-442).  mpp fp32 [n_maps, hm, wm] -> uint8 [n_maps, h*w]. */
+int rsp_attn_mask_build(const float* mpp, int n_maps, int hm, int wm, int h, int w, uint8_t* mask, void* stream);
+
+/* SamMaskEmbedding (HF:569-593) on mask_pred_plus + image embedding + key PE: for prompt n (image n / n_per_img)
+ * src = emb[img] + mask_embed(mpp[n]) and src_pe = src + pos, both bf16 [N*h*w, 256] -- the mask decoder's two
+ * source tensors (M:359-368, HF:499).  wts = HOST array of 10 device pointers (conv1 w,b, ln1 g,b, conv2 w,b,
+ * ln2 g,b, conv3 w,b).  emb fp32 [imgs*h*w, 256], pos fp32 [h*w, 256], mpp fp32 [N, 4h, 4w]. */
+int rsp_mask_embed_src(const float* mpp, const float* const* wts, const float* emb, const float* pos, int N,
+                       int n_per_img, int hm, int wm, int h, int w, float eps, void* src, void* src_pe, void* stream);
+
+/* Instance post-processing of the query variant (M:652-656; maskformer_fusion_head.py:149-182; mask/utils.py:56-77):
+ * for instance i (map sel[i] of logits fp32 [*, hm, wm]): bilinear to H x W, mask = > 0, score = cls_scores[i] *
+ * mean sigmoid over the positive pixels, tight box.  part_ws fp32 [n_inst, ceil(H/16), 6]. */
+int rsp_query_postprocess(const float* logits, const int32_t* sel, const float* cls_scores, int n_inst, int hm, int wm,
+                          int H, int W, uint8_t* masks, float* part_ws, float* scores, float* boxes, void* stream);
+
 /* fp32 -> bf16 (n % 4 == 0): feeds fp32 hidden states to the bf16 tensor-core GEMMs. */
 int rsp_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
 

@@ -72,6 +72,12 @@ _SIGNATURES = {
     "rsp_mask_paste": ([_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp], _i),
     "rsp_pool2_nhwc": ([_vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "rsp_sigmoid_f32": ([_vp, _vp, ctypes.c_longlong, _vp], _i),
+    "rsp_groupnorm_nhwc": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp], _i),
+    "rsp_ms_deform_attn_sample": ([_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "rsp_mha_small": ([_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp], _i),
+    "rsp_attn_mask_build": ([_vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
+    "rsp_mask_embed_src": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp], _i),
+    "rsp_query_postprocess": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "rsp_sin_fold": ([_vp, _vp, ctypes.c_longlong, _vp], _i),
 }
 
@@ -549,3 +555,104 @@ def layernorm_add(x: torch.Tensor, residual: torch.Tensor, gamma: torch.Tensor, 
                                   _ptr(out_pe), rows, C, float(eps), _stream()), "rsp_layernorm_add")
     launch_count += 1
     return out if pos is None else (out, out_pe)
+
+
+# ------------------------------------------------------------------------------ query-head ops
+def groupnorm_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int = 32, eps: float = 1e-5,
+                   up: torch.Tensor | None = None, relu: bool = False) -> torch.Tensor:
+    """GroupNorm on bf16 NHWC (+ bilinear x2 of `up` added after the affine, + ReLU)."""
+    global launch_count
+    _require_cuda(x, gamma, beta, up)
+    B, H, W, C = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    if up is not None:
+        assert up.dtype == torch.bfloat16 and up.is_contiguous() and up.shape == (B, H // 2, W // 2, C)
+    stats = torch.empty(B * groups * 2, device=x.device, dtype=torch.float32)
+    out = torch.empty_like(x)
+    _check(_lib.rsp_groupnorm_nhwc(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(up), _ptr(out), B, H, W, C,
+                                   groups, float(eps), int(relu), _stream()), "rsp_groupnorm_nhwc")
+    launch_count += 2
+    return out
+
+
+def ms_deform_attn_sample(value: torch.Tensor, ow: torch.Tensor, shapes: list, points: int) -> torch.Tensor:
+    """value bf16 [B, NQ, 128]; ow fp32 [B*NQ, >= 8*L*P*3]; shapes [(h, w)] low -> high res -> bf16 [B*NQ, 128]."""
+    global launch_count
+    _require_cuda(value, ow)
+    B, NQ, E = value.shape
+    L = len(shapes)
+    assert E == 128 and value.dtype == torch.bfloat16 and value.is_contiguous()
+    assert ow.dtype == torch.float32 and ow.stride(1) == 1 and ow.shape[0] == B * NQ and ow.shape[1] >= 8 * L * points * 3
+    hs = (ctypes.c_int32 * L)(*[s[0] for s in shapes])
+    ws = (ctypes.c_int32 * L)(*[s[1] for s in shapes])
+    out = torch.empty(B * NQ, 128, device=value.device, dtype=torch.bfloat16)
+    _check(_lib.rsp_ms_deform_attn_sample(_ptr(value), _ptr(ow), ow.stride(0), ctypes.cast(hs, _vp), ctypes.cast(ws, _vp),
+                                          L, points, B, NQ, _ptr(out), _stream()), "rsp_ms_deform_attn_sample")
+    launch_count += 1
+    return out
+
+
+def mha_small(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, nq: int, nk: int,
+              mask: torch.Tensor | None = None) -> torch.Tensor:
+    """q [B*nq, >=128], k / v [B*nk, >=128] bf16 row views (row stride = leading dim) -> bf16 [B*nq, 128]."""
+    global launch_count
+    _require_cuda(q, k, v, mask)
+    for t in (q, k, v):
+        assert t.dtype == torch.bfloat16 and t.stride(1) == 1
+    if mask is not None:
+        assert mask.dtype == torch.uint8 and mask.is_contiguous() and mask.numel() == B * nq * nk
+    out = torch.empty(B * nq, 128, device=q.device, dtype=torch.bfloat16)
+    _check(_lib.rsp_mha_small(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(mask), B, nq, nk,
+                              _ptr(out), _stream()), "rsp_mha_small")
+    launch_count += 1
+    return out
+
+
+def attn_mask_build(mpp: torch.Tensor, hw: tuple) -> torch.Tensor:
+    """fp32 [n_maps, hm, wm] -> uint8 [n_maps, h*w] (1 = masked)."""
+    global launch_count
+    _require_cuda(mpp)
+    assert mpp.dtype == torch.float32 and mpp.is_contiguous() and mpp.dim() == 3
+    n, hm, wm = mpp.shape
+    out = torch.empty(n, hw[0] * hw[1], device=mpp.device, dtype=torch.uint8)
+    _check(_lib.rsp_attn_mask_build(_ptr(mpp), n, hm, wm, hw[0], hw[1], _ptr(out), _stream()), "rsp_attn_mask_build")
+    launch_count += 1
+    return out
+
+
+def mask_embed_src(mpp: torch.Tensor, weights: list, emb_rows: torch.Tensor, pos_rows: torch.Tensor, n_per_img: int,
+                   hw: tuple, eps: float = 1e-6):
+    """-> (src, src_pe) bf16 [N*h*w, 256]; weights = 10 fp32 tensors (conv1 w,b, ln1 g,b, conv2 w,b, ln2 g,b, conv3 w,b)."""
+    global launch_count
+    _require_cuda(mpp, emb_rows, pos_rows, *weights)
+    N, hm, wm = mpp.shape
+    h, w = hw
+    assert mpp.dtype == torch.float32 and mpp.is_contiguous() and len(weights) == 10
+    for t in weights:
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    assert emb_rows.dtype == torch.float32 and emb_rows.is_contiguous() and pos_rows.dtype == torch.float32
+    wp = (ctypes.c_void_p * 10)(*[t.data_ptr() for t in weights])
+    src = torch.empty(N * h * w, 256, device=mpp.device, dtype=torch.bfloat16)
+    src_pe = torch.empty_like(src)
+    _check(_lib.rsp_mask_embed_src(_ptr(mpp), ctypes.cast(wp, _vp), _ptr(emb_rows), _ptr(pos_rows), N, n_per_img, hm, wm,
+                                   h, w, float(eps), _ptr(src), _ptr(src_pe), _stream()), "rsp_mask_embed_src")
+    launch_count += 1
+    return src, src_pe
+
+
+def query_postprocess(logits: torch.Tensor, sel: torch.Tensor, cls_scores: torch.Tensor, size: tuple):
+    """logits fp32 [n_maps, hm, wm]; sel int32 [n]; cls_scores fp32 [n] -> (masks bool [n,H,W], scores [n], boxes [n,4])."""
+    global launch_count
+    _require_cuda(logits, sel, cls_scores)
+    n = sel.numel()
+    _, hm, wm = logits.shape
+    H, W = size
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and sel.dtype == torch.int32 and cls_scores.dtype == torch.float32
+    masks = torch.empty(n, H, W, device=logits.device, dtype=torch.uint8)
+    part = torch.empty(n * ((H + 15) // 16) * 6, device=logits.device, dtype=torch.float32)
+    scores = torch.empty(n, device=logits.device, dtype=torch.float32)
+    boxes = torch.empty(n, 4, device=logits.device, dtype=torch.float32)
+    _check(_lib.rsp_query_postprocess(_ptr(logits), _ptr(sel), _ptr(cls_scores), n, hm, wm, H, W, _ptr(masks), _ptr(part),
+                                      _ptr(scores), _ptr(boxes), _stream()), "rsp_query_postprocess")
+    launch_count += 2
+    return masks.view(torch.bool), scores, boxes

@@ -190,3 +190,38 @@ int rsp_sin_fold(const float* in, float* out, long long n_out, void* stream) {
 }
 
 }  // extern "C"
+
+#include "query.h"
+
+extern "C" {
+
+int rsp_groupnorm_nhwc(const void* x, float* stats_ws, const float* gamma, const float* beta, const void* up,
+                       void* out, int B, int H, int W, int C, int G, float eps, int relu, void* stream) {
+  return groupnorm_nhwc(x, stats_ws, gamma, beta, up, out, B, H, W, C, G, eps, relu, S(stream));
+}
+
+int rsp_ms_deform_attn_sample(const void* value, const float* ow, int ld_ow, const int32_t* hs, const int32_t* ws,
+                              int L, int P, int B, int NQ, void* out, void* stream) {
+  return ms_deform_attn_sample(value, ow, ld_ow, hs, ws, L, P, B, NQ, out, S(stream));
+}
+
+int rsp_mha_small(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const uint8_t* mask, int B,
+                  int nq, int nk, void* out, void* stream) {
+  return mha_small(Q, ldq, K, ldk, V, ldv, mask, B, nq, nk, out, S(stream));
+}
+
+int rsp_attn_mask_build(const float* mpp, int n_maps, int hm, int wm, int h, int w, uint8_t* mask, void* stream) {
+  return attn_mask_build(mpp, n_maps, hm, wm, h, w, mask, S(stream));
+}
+
+int rsp_mask_embed_src(const float* mpp, const float* const* wts, const float* emb, const float* pos, int N,
+                       int n_per_img, int hm, int wm, int h, int w, float eps, void* src, void* src_pe, void* stream) {
+  return mask_embed_src(mpp, wts, emb, pos, N, n_per_img, hm, wm, h, w, eps, src, src_pe, S(stream));
+}
+
+int rsp_query_postprocess(const float* logits, const int32_t* sel, const float* cls_scores, int n_inst, int hm, int wm,
+                          int H, int W, uint8_t* masks, float* part_ws, float* scores, float* boxes, void* stream) {
+  return query_postprocess(logits, sel, cls_scores, n_inst, hm, wm, H, W, masks, part_ws, scores, boxes, S(stream));
+}
+
+}  // extern "C"

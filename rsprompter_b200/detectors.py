@@ -119,4 +119,65 @@ class RSPrompterAnchor(_SamDetectorBase):
         return self.predict(data["inputs"], data.get("data_samples"))
 
 
-__all__ = ["RSPrompterAnchor"]
+@MODELS.register_module(force=True)
+class RSPrompterQuery(_SamDetectorBase):
+    """M:172-272 over mmdet Mask2Former / MaskFormer (detectors/maskformer.py:14-170)."""
+
+    def __init__(self, shared_image_embedding, decoder_freeze=True, backbone=None, neck=None, panoptic_head=None,
+                 panoptic_fusion_head=None, train_cfg=None, test_cfg=None, data_preprocessor=None, init_cfg=None,
+                 **kwargs):
+        BaseModule.__init__(self, init_cfg=None)
+        test_cfg = _cfg(test_cfg)
+        self.backbone = MODELS.build(backbone)
+        self.neck = MODELS.build(neck)
+        ph = dict(panoptic_head)
+        ph.update(train_cfg=None, test_cfg=test_cfg)
+        self.panoptic_head = MODELS.build(ph)
+        pf = dict(panoptic_fusion_head)
+        pf.update(test_cfg=test_cfg)
+        self.panoptic_fusion_head = MODELS.build(pf)
+        self.shared_image_embedding = MODELS.build(shared_image_embedding)
+        self.decoder_freeze = decoder_freeze
+        self.test_cfg = test_cfg
+        self.data_preprocessor_cfg = data_preprocessor
+        self.eval()
+
+    @torch.no_grad()
+    def predict_raw(self, batch_inputs: torch.Tensor, capture: dict | None = None):
+        """-> dict(cls fp32 [B, nq, C+1], mask_logits fp32 [B*nq, 4g, 4g], mask_pred_plus fp32 [B, nq, H/4, W/4])."""
+        emb_rows, pos_rows, ghw, emb_nhwc, hidden = self._encode(batch_inputs)
+        if isinstance(getattr(self.neck, "feature_aggregator", None), PseudoFeatureAggregator):
+            feats = self.neck.forward_nhwc(None, _lib.cast_bf16(emb_nhwc.contiguous()))
+        else:
+            feats = self.neck.forward_nhwc(hidden)
+        cls, masks, mpp = self.panoptic_head.forward_nhwc(feats, emb_rows.contiguous(), pos_rows, ghw, capture=capture)
+        return dict(cls=cls, mask_logits=masks, mask_pred_plus=mpp)
+
+    @torch.no_grad()
+    def predict(self, batch_inputs: torch.Tensor, batch_data_samples=None, rescale: bool = True):
+        if batch_data_samples is None:
+            batch_data_samples = make_data_samples(batch_inputs.shape[0], tuple(batch_inputs.shape[-2:]))
+        hw = self._check_metas(batch_data_samples, batch_inputs)
+        if self.test_cfg.get("panoptic_on", True) or self.test_cfg.get("semantic_on", False):
+            raise NotImplementedError("rsprompter_b200 implements instance_on post-processing (every RSPrompter config)")
+        r = self.predict_raw(batch_inputs)
+        out = self.panoptic_fusion_head.instance_postprocess_batched(r["cls"], r["mask_logits"], hw)
+        stuff = self.panoptic_fusion_head.num_stuff_classes > 0
+        for b, ds in enumerate(batch_data_samples):
+            inst = dict(bboxes=out["bboxes"][b], scores=out["scores"][b], labels=out["labels"][b], masks=out["masks"][b])
+            if stuff:                                   # maskformer_fusion_head.py:160-164 (data-dependent size)
+                k = out["is_thing"][b]
+                inst = {n: v[k] for n, v in inst.items()}
+            ds.pred_instances = InstanceData(**inst)
+        return batch_data_samples
+
+    def forward(self, inputs, data_samples=None, mode: str = "predict"):
+        if mode == "predict":
+            return self.predict(inputs, data_samples)
+        raise NotImplementedError("rsprompter_b200 implements the inference path only (mode='predict')")
+
+    def test_step(self, data):
+        return self.predict(data["inputs"], data.get("data_samples"))
+
+
+__all__ = ["RSPrompterAnchor", "RSPrompterQuery"]

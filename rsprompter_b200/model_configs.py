@@ -51,3 +51,56 @@ def anchor_model_cfg(arch: str = "base", num_classes: int = 10, points: int = 5,
                                min_bbox_size=0),
                       rcnn=dict(score_thr=0.05, nms=dict(type="nms", iou_threshold=0.5), max_per_img=100,
                                 mask_thr_binary=0.5)))
+
+
+def _backbone_neck(arch: str, mmpretrain_img_size: int | None):
+    name = f"facebook/sam-vit-{arch}"
+    if mmpretrain_img_size is None:
+        backbone = dict(type="RSSamVisionEncoder", hf_pretrain_name=name,
+                        extra_config=dict(output_hidden_states=True))
+        aggregator = dict(type="RSFeatureAggregator", in_channels=name, out_channels=256, hidden_channels=32,
+                          select_layers=SELECT_LAYERS[arch])
+    else:
+        backbone = dict(type="MMPretrainSamVisionEncoder", hf_pretrain_name=name, img_size=mmpretrain_img_size)
+        aggregator = dict(type="PseudoFeatureAggregator", in_channels=256, hidden_channels=512, out_channels=256)
+    neck = dict(type="RSFPN", feature_aggregator=aggregator,
+                feature_spliter=dict(type="RSSimpleFPN", backbone_channel=256, in_channels=[64, 128, 256, 256],
+                                     out_channels=256, num_outs=5, norm_cfg=dict(type="LN2d", requires_grad=True)))
+    return name, backbone, neck
+
+
+def query_model_cfg(arch: str = "base", num_classes: int = 10, prompt_shape: tuple = (100, 5),
+                    mmpretrain_img_size: int | None = None) -> dict:
+    """configs/rsprompter/_base_/rsprompter_query.py:57-190 + rsprompter_query-nwpu.py overrides."""
+    name, backbone, neck = _backbone_neck(arch, mmpretrain_img_size)
+    attn = dict(embed_dims=128, num_heads=8, dropout=0.0, batch_first=True)
+    ffn = dict(embed_dims=128, feedforward_channels=512, num_fcs=2, ffn_drop=0.0, act_cfg=dict(type="ReLU", inplace=True))
+    return dict(
+        type="RSPrompterQuery",
+        decoder_freeze=False,
+        shared_image_embedding=dict(type="RSSamPositionalEmbedding", hf_pretrain_name=name),
+        backbone=backbone,
+        neck=neck,
+        panoptic_head=dict(
+            type="RSMask2FormerHead", decoder_plus=True,
+            mask_decoder=dict(type="RSSamMaskDecoder", hf_pretrain_name=name),
+            per_pointset_point=prompt_shape[1], with_sincos=True, multimask_output=False,
+            in_channels=[256, 256, 256, 256, 256], feat_channels=128, out_channels=256,
+            num_things_classes=num_classes, num_stuff_classes=0, num_queries=prompt_shape[0],
+            num_transformer_feat_level=3,
+            pixel_decoder=dict(
+                type="MSDeformAttnPixelDecoder", strides=[4, 8, 16, 32, 64], num_outs=3,
+                norm_cfg=dict(type="GN", num_groups=32), act_cfg=dict(type="ReLU"),
+                encoder=dict(num_layers=3, layer_cfg=dict(
+                    self_attn_cfg=dict(embed_dims=128, num_heads=8, num_levels=3, num_points=4, dropout=0.0,
+                                       batch_first=True), ffn_cfg=ffn)),
+                positional_encoding=dict(num_feats=64, normalize=True)),
+            enforce_decoder_input_project=False,
+            positional_encoding=dict(num_feats=64, normalize=True),
+            transformer_decoder=dict(return_intermediate=True, num_layers=6,
+                                     layer_cfg=dict(self_attn_cfg=attn, cross_attn_cfg=attn, ffn_cfg=ffn),
+                                     init_cfg=None)),
+        panoptic_fusion_head=dict(type="RSMaskFormerFusionHead", num_things_classes=num_classes,
+                                  num_stuff_classes=0, loss_panoptic=None, init_cfg=None),
+        test_cfg=dict(panoptic_on=False, semantic_on=False, instance_on=True, max_per_image=prompt_shape[0],
+                      iou_thr=0.8, filter_low_score=True))

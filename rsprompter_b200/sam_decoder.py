@@ -171,7 +171,7 @@ class SamMaskDecoderB200(nn.Module):
     def decode(self, emb_rows: torch.Tensor, pos_rows: torch.Tensor, sparse: torch.Tensor,
                hw: tuple[int, int], prompt_img: torch.Tensor | None = None,
                dense_vec: torch.Tensor | None = None, dense_rows: torch.Tensor | None = None,
-               multimask_output: bool = False):
+               multimask_output: bool = False, src_pair: tuple | None = None):
         """emb_rows fp32 [Bi*HW, C] channels-last image embeddings (Bi images, or N when
         prompt_img is None); pos_rows fp32 [HW, C]; sparse fp32 [N, P, C]; prompt_img int32 [N]
         image of each prompt; dense_vec fp32 [C] (no_mask_embed broadcast, M:1680) or dense_rows
@@ -185,10 +185,15 @@ class SamMaskDecoderB200(nn.Module):
         N, P, _ = sparse.shape
         Tt = 1 + self.num_mask_tokens + P
         dev = sparse.device
-        assert pos_rows.shape == (HW, C) and emb_rows.shape[1] == C
+        assert pos_rows.shape == (HW, C) and (emb_rows is None or emb_rows.shape[1] == C)
         shared = prompt_img is not None and dense_rows is None
+        pos_rows = pos_rows.contiguous()
         # ---- src = image_embeddings + dense (HF:499)
-        if dense_rows is not None:
+        if src_pair is not None:
+            # per-prompt sources already built on the device (rsp_mask_embed_src): bf16 src and src + pe
+            src_b, src_pe_b = src_pair
+            src32, blk = src_b, None
+        elif dense_rows is not None:
             if prompt_img is not None:  # per-prompt dense on per-image embeddings: expand once
                 emb_rows = emb_rows.view(-1, HW, C)[prompt_img.long()].reshape(N * HW, C)
             src32 = emb_rows + dense_rows
@@ -196,12 +201,12 @@ class SamMaskDecoderB200(nn.Module):
         else:
             src32 = emb_rows if dense_vec is None else emb_rows + dense_vec.view(1, C)
             blk = prompt_img if shared else None
-        src32 = src32.contiguous()
-        src_b = _lib.cast_bf16(src32)
-        pos_rows = pos_rows.contiguous()
-        # "keys + key_point_embedding" (HF:326,339) is kept as a second bf16 tensor next to the keys, so
-        # the k / q projections are plain GEMMs; later layers get it from the LayerNorm kernel for free
-        src_pe_b = _lib.add_cast_bf16(src32, pos_rows)
+        if src_pair is None:
+            src32 = src32.contiguous()
+            src_b = _lib.cast_bf16(src32)
+            # "keys + key_point_embedding" (HF:326,339) is kept as a second bf16 tensor next to the keys, so
+            # the k / q projections are plain GEMMs; later layers get it from the LayerNorm kernel for free
+            src_pe_b = _lib.add_cast_bf16(src32, pos_rows)
         tokens = torch.cat([p["out_tokens"].unsqueeze(0).expand(N, -1, -1), sparse.to(torch.float32)], dim=1)
         tokens = tokens.reshape(N * Tt, C).contiguous()
 

@@ -253,3 +253,84 @@ def anchor_detector_state_dict(arch: SamVisionArch, num_classes: int, n_select: 
     sd.update(_prefixed("shared_image_embedding.shared_image_embedding.",
                         positional_embedding_state_dict(arch, seed + 3)))
     return sd
+
+
+# ================================================================================================
+# RSPrompter-query head (reference module tree, M:274-330 + configs/rsprompter/_base_/rsprompter_query.py)
+# ================================================================================================
+def _gn_conv_sd(sd: dict, gen: torch.Generator, prefix: str, cout: int, cin: int, k: int, bias: bool) -> None:
+    _conv_sd(sd, gen, prefix + ".conv", cout, cin, k, bias=bias, gain=1.2)
+    _norm(sd, gen, prefix + ".gn", cout)
+
+
+def _ffn_sd(sd: dict, gen: torch.Generator, prefix: str, E: int, F: int) -> None:
+    _linear(sd, gen, prefix + ".layers.0.0", F, E, std=1.2 / math.sqrt(E))
+    _linear(sd, gen, prefix + ".layers.1", E, F, std=1.0 / math.sqrt(F))
+
+
+def query_head_state_dict(num_classes: int, nq: int = 100, points: int = 5, E: int = 128, C: int = 256, F: int = 512,
+                          in_levels: int = 5, enc_levels: int = 3, enc_layers: int = 3, enc_points: int = 4,
+                          dec_layers: int = 6, heads: int = 8, seed: int = 20) -> dict[str, torch.Tensor]:
+    """RSMask2FormerHead parameters except the SAM decoder / sam_mask_embed (added by the caller)."""
+    gen = torch.Generator().manual_seed(seed)
+    sd: dict[str, torch.Tensor] = {}
+    pd = "pixel_decoder."
+    for i in range(enc_levels):
+        _gn_conv_sd(sd, gen, f"{pd}input_convs.{i}", E, C, 1, True)
+    for l in range(enc_layers):
+        p = f"{pd}encoder.layers.{l}."
+        _linear(sd, gen, p + "self_attn.sampling_offsets", heads * enc_levels * enc_points * 2, E, std=0.3 / math.sqrt(E))
+        sd[p + "self_attn.sampling_offsets.bias"] = _randn(gen, heads * enc_levels * enc_points * 2, std=1.5)
+        _linear(sd, gen, p + "self_attn.attention_weights", heads * enc_levels * enc_points, E, std=1.0 / math.sqrt(E))
+        _linear(sd, gen, p + "self_attn.value_proj", E, E)
+        _linear(sd, gen, p + "self_attn.output_proj", E, E)
+        _ffn_sd(sd, gen, p + "ffn", E, F)
+        _norm(sd, gen, p + "norms.0", E)
+        _norm(sd, gen, p + "norms.1", E)
+    sd[pd + "level_encoding.weight"] = _randn(gen, enc_levels, E, std=0.5)
+    for i in range(in_levels - enc_levels):
+        _gn_conv_sd(sd, gen, f"{pd}lateral_convs.{i}", E, C, 1, False)
+        _gn_conv_sd(sd, gen, f"{pd}output_convs.{i}", E, E, 3, False)
+    _conv_sd(sd, gen, pd + "mask_feature", C, E, 1, gain=0.5)
+    for i in range(dec_layers):
+        p = f"transformer_decoder.layers.{i}."
+        for a in ("cross_attn", "self_attn"):
+            sd[f"{p}{a}.attn.in_proj_weight"] = _randn(gen, 3 * E, E, std=1.3 / math.sqrt(E))
+            sd[f"{p}{a}.attn.in_proj_bias"] = _randn(gen, 3 * E, std=0.02)
+            _linear(sd, gen, f"{p}{a}.attn.out_proj", E, E)
+        _ffn_sd(sd, gen, p + "ffn", E, F)
+        for n in range(3):
+            _norm(sd, gen, f"{p}norms.{n}", E)
+    _norm(sd, gen, "transformer_decoder.post_norm", E)
+    sd["query_embed.weight"] = _randn(gen, nq, E, std=1.0)
+    sd["query_feat.weight"] = _randn(gen, nq, E, std=1.0)
+    sd["level_embed.weight"] = _randn(gen, enc_levels, E, std=0.5)
+    _linear(sd, gen, "cls_embed.0", E, E, std=1.4 / math.sqrt(E))
+    _linear(sd, gen, "cls_embed.2", num_classes + 1, E, std=2.0 / math.sqrt(E))
+    _linear(sd, gen, "mask_embed.0", E, E, std=1.4 / math.sqrt(E))
+    _linear(sd, gen, "mask_embed.2", E, E, std=1.4 / math.sqrt(E))
+    _linear(sd, gen, "mask_embed.4", C, E, std=1.0 / math.sqrt(E))
+    _linear(sd, gen, "point_emb.0", E // 2, E, std=1.4 / math.sqrt(E))
+    _linear(sd, gen, "point_emb.2", E // 2, E // 2, std=1.4 / math.sqrt(E // 2))
+    _linear(sd, gen, "point_emb.4", C * 2 * points, E // 2, std=1.0 / math.sqrt(E // 2))
+    return sd
+
+
+def query_detector_state_dict(arch: SamVisionArch, num_classes: int, n_select: int, nq: int = 100, points: int = 5,
+                              seed: int = 0, pseudo_neck: bool = False) -> dict[str, torch.Tensor]:
+    """Full RSPrompterQuery state dict with the reference's key names."""
+    sd: dict[str, torch.Tensor] = {}
+    sd.update(_prefixed("backbone.vision_encoder.", vision_encoder_state_dict(arch, seed)))
+    if pseudo_neck:
+        sd.update(_prefixed("neck.feature_aggregator.", pseudo_aggregator_state_dict(seed=seed + 11)))
+    else:
+        sd.update(_prefixed("neck.feature_aggregator.",
+                            feature_aggregator_state_dict(arch.hidden_size, n_select, seed=seed + 10)))
+    sd.update(_prefixed("neck.feature_spliter.", simple_fpn_state_dict(seed=seed + 12)))
+    sd.update(_prefixed("panoptic_head.", query_head_state_dict(num_classes, nq, points, seed=seed + 20)))
+    sd.update(_prefixed("panoptic_head.mask_decoder.mask_decoder.", mask_decoder_state_dict(seed=seed + 1)))
+    pe = prompt_encoder_state_dict(seed=seed + 2)
+    sd.update({"panoptic_head.sam_" + k: v for k, v in pe.items() if k.startswith("mask_embed.")})
+    sd.update(_prefixed("shared_image_embedding.shared_image_embedding.",
+                        positional_embedding_state_dict(arch, seed + 3)))
+    return sd

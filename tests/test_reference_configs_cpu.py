@@ -55,3 +55,23 @@ def test_reference_anchor_configs_build(name, enc_cls):
     assert set(model.state_dict()) == set(sd)
     model.load_state_dict(sd, strict=True)
     assert model.roi_head.test_cfg.score_thr == 0.05 and model.rpn_head.test_cfg.nms_pre == 1000
+
+
+@pytest.mark.parametrize("name,enc_cls,nq", [("rsprompter_query-nwpu.py", "RSSamVisionEncoder", 70),
+                                             ("rsprompter_query-nwpu-peft-512.py", "MMPretrainSamVisionEncoder", 70)])
+def test_reference_query_configs_build(name, enc_cls, nq):
+    from rsprompter_b200 import synthetic
+    from rsprompter_b200.registry import MODELS, Config
+    cfg = Config.fromfile(os.path.join(REF_CFG, name))
+    model_cfg = _strip_init(cfg.to_dict()["model"])
+    model = MODELS.build(model_cfg)
+    assert type(model).__name__ == "RSPrompterQuery" and type(model.backbone).__name__ == enc_cls
+    head = model.panoptic_head
+    assert head.num_queries == nq and head.num_classes == 10 and head.per_pointset_point == 5
+    assert head.pixel_decoder.num_encoder_levels == 3 and head.pixel_decoder.num_points == 4 and head.num_layers == 6
+    assert model.panoptic_fusion_head.test_cfg.max_per_image == nq and model.test_cfg.instance_on
+    arch = model.backbone.vision_encoder.arch
+    pseudo = enc_cls == "MMPretrainSamVisionEncoder"
+    sd = synthetic.query_detector_state_dict(arch, 10, 0 if pseudo else 6, nq=nq, seed=0, pseudo_neck=pseudo)
+    assert set(model.state_dict()) == set(sd)
+    model.load_state_dict(sd, strict=True)
