@@ -210,15 +210,20 @@ int rsp_groupnorm_nhwc(const void* x, float* stats_ws, const float* gamma, const
 int rsp_ms_deform_attn_sample(const void* value, const float* ow, int ld_ow, const int32_t* hs, const int32_t* ws,
                               int L, int P, int B, int NQ, void* out, void* stream);
 
-/* nn.MultiheadAttention core, 8 heads x 16: Q bf16 [B,nq,ldq], K / V bf16 [B,nk,ld*], mask uint8 [B,nq,nk]
- * (1 = masked, shared by the heads) or NULL; out bf16 [B,nq,128].  Masked cross-attention / self-attention of
- * Mask2FormerTransformerDecoderLayer (mask2former_layers.py:113-135). */
-int rsp_mha_small(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const uint8_t* mask, int B,
-                  int nq, int nk, void* out, void* stream);
+/* nn.MultiheadAttention core, 8 heads x 16 (mma.sync flash form): Q bf16 [B,nq,ldq], K / V bf16 [B,nk,ld*],
+ * mask_bits uint64 [B*nq, ceil(nk/64)] (bit k%64 of word k/64 set = key k masked, shared by the heads) or NULL;
+ * out bf16 [B,nq,128].  Masked cross-attention / self-attention of Mask2FormerTransformerDecoderLayer
+ * (mask2former_layers.py:113-135). */
+int rsp_mha_small(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const uint64_t* mask_bits,
+                  int B, int nq, int nk, void* out, void* stream);
 
-/* attn_mask = sigmoid(bilinear(mask_pred_plus -> (h, w))) < 0.5 per (image, query) map, and a map that is entirely
- * masked is cleared (M:386-392, M:439-442).  mpp fp32 [n_maps, hm, wm] -> uint8 [n_maps, h*w]. */
-int rsp_attn_mask_build(const float* mpp, int n_maps, int hm, int wm, int h, int w, uint8_t* mask, void* stream);
+/* attn_mask = sigmoid(x) < 0.5 (= x < 0) per row of level-sized mask logits fp32 [rows, ld >= nk]; a row whose keys
+ * are all masked is cleared (M:386-392, M:439-442).  The logits are mask_embed x (bilinearly resized
+ * mask_feature)^T: F.interpolate is linear, so resizing the features once replaces resizing every query's map. */
+int rsp_attn_mask_bits(const float* logits, int ld, int rows, int nk, uint64_t* mask_bits, void* stream);
+
+/* F.interpolate(x, (h, w), mode='bilinear', align_corners=False) on bf16 NHWC maps (C % 8 == 0). */
+int rsp_resize_bilinear_nhwc(const void* x, int B, int H, int W, int C, int h, int w, void* out, void* stream);
 
 /* SamMaskEmbedding (HF:569-593) on mask_pred_plus + image embedding + key PE: for prompt n (image n / n_per_img)
  * src = emb[img] + mask_embed(mpp[n]) and src_pe = src + pos, both bf16 [N*h*w, 256] -- the mask decoder's two

@@ -75,7 +75,8 @@ _SIGNATURES = {
     "rsp_groupnorm_nhwc": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp], _i),
     "rsp_ms_deform_attn_sample": ([_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
     "rsp_mha_small": ([_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp], _i),
-    "rsp_attn_mask_build": ([_vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
+    "rsp_attn_mask_bits": ([_vp, _i, _i, _i, _vp, _vp], _i),
+    "rsp_resize_bilinear_nhwc": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "rsp_mask_embed_src": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp], _i),
     "rsp_query_postprocess": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "rsp_sin_fold": ([_vp, _vp, ctypes.c_longlong, _vp], _i),
@@ -594,13 +595,14 @@ def ms_deform_attn_sample(value: torch.Tensor, ow: torch.Tensor, shapes: list, p
 
 def mha_small(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, nq: int, nk: int,
               mask: torch.Tensor | None = None) -> torch.Tensor:
-    """q [B*nq, >=128], k / v [B*nk, >=128] bf16 row views (row stride = leading dim) -> bf16 [B*nq, 128]."""
+    """q [B*nq, >=128], k / v [B*nk, >=128] bf16 row views (row stride = leading dim); mask = bit words
+    int64 [B*nq, ceil(nk/64)] from attn_mask_bits -> bf16 [B*nq, 128]."""
     global launch_count
     _require_cuda(q, k, v, mask)
     for t in (q, k, v):
         assert t.dtype == torch.bfloat16 and t.stride(1) == 1
     if mask is not None:
-        assert mask.dtype == torch.uint8 and mask.is_contiguous() and mask.numel() == B * nq * nk
+        assert mask.dtype == torch.int64 and mask.is_contiguous() and mask.shape == (B * nq, (nk + 63) // 64)
     out = torch.empty(B * nq, 128, device=q.device, dtype=torch.bfloat16)
     _check(_lib.rsp_mha_small(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(mask), B, nq, nk,
                               _ptr(out), _stream()), "rsp_mha_small")
@@ -608,14 +610,27 @@ def mha_small(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, nq: int
     return out
 
 
-def attn_mask_build(mpp: torch.Tensor, hw: tuple) -> torch.Tensor:
-    """fp32 [n_maps, hm, wm] -> uint8 [n_maps, h*w] (1 = masked)."""
+def attn_mask_bits(logits: torch.Tensor) -> torch.Tensor:
+    """fp32 [rows, nk] level-sized mask logits -> int64 bit words [rows, ceil(nk/64)] (bit set = masked)."""
     global launch_count
-    _require_cuda(mpp)
-    assert mpp.dtype == torch.float32 and mpp.is_contiguous() and mpp.dim() == 3
-    n, hm, wm = mpp.shape
-    out = torch.empty(n, hw[0] * hw[1], device=mpp.device, dtype=torch.uint8)
-    _check(_lib.rsp_attn_mask_build(_ptr(mpp), n, hm, wm, hw[0], hw[1], _ptr(out), _stream()), "rsp_attn_mask_build")
+    _require_cuda(logits)
+    assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    rows, nk = logits.shape
+    out = torch.empty(rows, (nk + 63) // 64, device=logits.device, dtype=torch.int64)
+    _check(_lib.rsp_attn_mask_bits(_ptr(logits), logits.stride(0), rows, nk, _ptr(out), _stream()), "rsp_attn_mask_bits")
+    launch_count += 1
+    return out
+
+
+def resize_bilinear_nhwc(x: torch.Tensor, hw: tuple) -> torch.Tensor:
+    """bf16 [B, H, W, C] -> bf16 [B, h, w, C] (F.interpolate bilinear, align_corners=False)."""
+    global launch_count
+    _require_cuda(x)
+    B, H, W, C = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and C % 8 == 0
+    out = torch.empty(B, hw[0], hw[1], C, device=x.device, dtype=torch.bfloat16)
+    _check(_lib.rsp_resize_bilinear_nhwc(_ptr(x), B, H, W, C, hw[0], hw[1], _ptr(out), _stream()),
+           "rsp_resize_bilinear_nhwc")
     launch_count += 1
     return out
 

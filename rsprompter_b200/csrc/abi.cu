@@ -205,13 +205,18 @@ int rsp_ms_deform_attn_sample(const void* value, const float* ow, int ld_ow, con
   return ms_deform_attn_sample(value, ow, ld_ow, hs, ws, L, P, B, NQ, out, S(stream));
 }
 
-int rsp_mha_small(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const uint8_t* mask, int B,
-                  int nq, int nk, void* out, void* stream) {
-  return mha_small(Q, ldq, K, ldk, V, ldv, mask, B, nq, nk, out, S(stream));
+int rsp_mha_small(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const uint64_t* mask_bits,
+                  int B, int nq, int nk, void* out, void* stream) {
+  return mha_small(Q, ldq, K, ldk, V, ldv, reinterpret_cast<const unsigned long long*>(mask_bits), B, nq, nk, out,
+                   S(stream));
 }
 
-int rsp_attn_mask_build(const float* mpp, int n_maps, int hm, int wm, int h, int w, uint8_t* mask, void* stream) {
-  return attn_mask_build(mpp, n_maps, hm, wm, h, w, mask, S(stream));
+int rsp_attn_mask_bits(const float* logits, int ld, int rows, int nk, uint64_t* mask_bits, void* stream) {
+  return attn_mask_bits(logits, ld, rows, nk, reinterpret_cast<unsigned long long*>(mask_bits), S(stream));
+}
+
+int rsp_resize_bilinear_nhwc(const void* x, int B, int H, int W, int C, int h, int w, void* out, void* stream) {
+  return resize_bilinear_nhwc(x, B, H, W, C, h, w, out, S(stream));
 }
 
 int rsp_mask_embed_src(const float* mpp, const float* const* wts, const float* emb, const float* pos, int N,

@@ -202,107 +202,237 @@ int ms_deform_attn_sample(const void* value, const float* ow, int ld_ow, const i
 }
 
 // ------------------------------------------------------------------------------------ small MHA
-// thread = (batch, head, query); 8 heads x 16 channels; mask uint8 [B, nq, nk] (1 = masked) or null
-__global__ void mha_small_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* __restrict__ K,
-                                 int ldk, const __nv_bfloat16* __restrict__ V, int ldv,
-                                 const unsigned char* __restrict__ mask, int B, int nq, int nk,
-                                 __nv_bfloat16* __restrict__ out) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * 8 * nq) return;
-  const int q = idx % nq, h = (idx / nq) & 7, b = idx / (nq * 8);
-  float qf[16], t[8];
-  const __nv_bfloat16* qp = Q + (static_cast<size_t>(b) * nq + q) * ldq + h * 16;
-  unpack8f(*reinterpret_cast<const uint4*>(qp), t);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) qf[j] = t[j] * 0.25f;
-  unpack8f(*reinterpret_cast<const uint4*>(qp + 8), t);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) qf[8 + j] = t[j] * 0.25f;
-  const unsigned char* mrow = mask ? mask + (static_cast<size_t>(b) * nq + q) * nk : nullptr;
-  float m = -INFINITY, l = 0.f, o[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) o[j] = 0.f;
-  for (int k = 0; k < nk; ++k) {
-    if (mrow && mrow[k]) continue;
-    const __nv_bfloat16* kp = K + (static_cast<size_t>(b) * nk + k) * ldk + h * 16;
-    float kf[16];
-    unpack8f(*reinterpret_cast<const uint4*>(kp), t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) kf[j] = t[j];
-    unpack8f(*reinterpret_cast<const uint4*>(kp + 8), t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) kf[8 + j] = t[j];
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) s += qf[j] * kf[j];
-    const float mn = fmaxf(m, s);
-    const float a = __expf(m - mn), pe = __expf(s - mn);
-    l = l * a + pe;
-    const __nv_bfloat16* vp = V + (static_cast<size_t>(b) * nk + k) * ldv + h * 16;
-    float vf[16];
-    unpack8f(*reinterpret_cast<const uint4*>(vp), t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) vf[j] = t[j];
-    unpack8f(*reinterpret_cast<const uint4*>(vp + 8), t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) vf[8 + j] = t[j];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = o[j] * a + pe * vf[j];
-    m = mn;
-  }
-  const float inv = 1.0f / l;
-  __nv_bfloat16* op = out + (static_cast<size_t>(b) * nq + q) * 128 + h * 16;
-  reinterpret_cast<uint4*>(op)[0] = make_uint4(pack_bf16x2(o[0] * inv, o[1] * inv), pack_bf16x2(o[2] * inv, o[3] * inv),
-                                               pack_bf16x2(o[4] * inv, o[5] * inv), pack_bf16x2(o[6] * inv, o[7] * inv));
-  reinterpret_cast<uint4*>(op)[1] = make_uint4(pack_bf16x2(o[8] * inv, o[9] * inv), pack_bf16x2(o[10] * inv, o[11] * inv),
-                                               pack_bf16x2(o[12] * inv, o[13] * inv), pack_bf16x2(o[14] * inv, o[15] * inv));
+// nn.MultiheadAttention core, 8 heads x 16 channels, on mma.sync m16n8k16 (head_dim 16 = one k-step).
+// CTA = (batch, head, 64 queries): 4 warps x one 16-query tile each; keys stream through shared memory in
+// chunks of 64 (cp.async, double buffered).  S = Q K^T and O += P V keep P in registers (accumulator ->
+// A-fragment reuse); V's B-fragment comes from ldmatrix.trans.  mask: bit words [B*nq][ceil(nk/64)],
+// bit k%64 of word k/64 set = key k masked.
+__device__ __forceinline__ void mma_bf16_16816q(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16q(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
 }
 
-int mha_small(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const unsigned char* mask, int B,
-              int nq, int nk, void* out, cudaStream_t stream) {
+constexpr int MHA_KC = 64;     // keys per chunk
+constexpr int MHA_ROWB = 48;   // bytes per staged key row (16 bf16 + 16 B pad: conflict-free fragment reads)
+constexpr int MHA_WARPS = 4;
+
+__global__ void __launch_bounds__(MHA_WARPS * 32)
+mha16_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* __restrict__ K, int ldk,
+             const __nv_bfloat16* __restrict__ V, int ldv, const unsigned long long* __restrict__ mask, int mask_words,
+             int nq, int nk, __nv_bfloat16* __restrict__ out) {
+  __shared__ __align__(16) unsigned char sK[2][MHA_KC * MHA_ROWB];
+  __shared__ __align__(16) unsigned char sV[2][MHA_KC * MHA_ROWB];
+  const int b = blockIdx.x >> 3, h = blockIdx.x & 7;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int q0 = (blockIdx.y * MHA_WARPS + warp) * 16;
+  const bool active = q0 < nq;
+  const int r0 = min(q0 + g, nq - 1), r1 = min(q0 + g + 8, nq - 1);
+
+  uint32_t qa[4];
+  {
+    const __nv_bfloat162 sc = __float2bfloat162_rn(0.25f);   // 1/sqrt(16), exact in bf16
+    const __nv_bfloat16* p0 = Q + (static_cast<size_t>(b) * nq + r0) * ldq + h * 16 + 2 * t;
+    const __nv_bfloat16* p1 = Q + (static_cast<size_t>(b) * nq + r1) * ldq + h * 16 + 2 * t;
+    __nv_bfloat162 v;
+    v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(p0), sc);     qa[0] = *reinterpret_cast<uint32_t*>(&v);
+    v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(p1), sc);     qa[1] = *reinterpret_cast<uint32_t*>(&v);
+    v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(p0 + 8), sc); qa[2] = *reinterpret_cast<uint32_t*>(&v);
+    v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(p1 + 8), sc); qa[3] = *reinterpret_cast<uint32_t*>(&v);
+  }
+  const uint32_t sK0 = smem_u32(&sK[0][0]), sV0 = smem_u32(&sV[0][0]);
+  constexpr uint32_t BUF = MHA_KC * MHA_ROWB;
+  const int nchunks = (nk + MHA_KC - 1) / MHA_KC;
+  auto issue = [&](int c, int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int piece = threadIdx.x + i * MHA_WARPS * 32;       // 256 pieces of 16 B: K rows then V rows
+      const int which = piece >> 7, row = (piece & 127) >> 1, half = piece & 1;
+      const int key = min(c * MHA_KC + row, nk - 1);
+      const __nv_bfloat16* src = (which ? V + (static_cast<size_t>(b) * nk + key) * ldv
+                                        : K + (static_cast<size_t>(b) * nk + key) * ldk) + h * 16 + half * 8;
+      cp_async16q((which ? sV0 : sK0) + buf * BUF + row * MHA_ROWB + half * 16, src);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  issue(0, 0);
+  const unsigned long long* mr0 = mask ? mask + (static_cast<size_t>(b) * nq + r0) * mask_words : nullptr;
+  const unsigned long long* mr1 = mask ? mask + (static_cast<size_t>(b) * nq + r1) * mask_words : nullptr;
+  unsigned long long w0n = mask ? mr0[0] : 0ull, w1n = mask ? mr1[0] : 0ull;
+
+  constexpr float L2E = 1.4426950408889634f, NEG = -1e30f;
+  float m0 = NEG, m1 = NEG, l0 = 0.f, l1 = 0.f;
+  float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = c & 1;
+    asm volatile("cp.async.wait_all;\n" ::);
+    __syncthreads();
+    if (c + 1 < nchunks) issue(c + 1, buf ^ 1);
+    const unsigned long long w0 = w0n, w1 = w1n;
+    if (mask && c + 1 < nchunks) { w0n = mr0[c + 1]; w1n = mr1[c + 1]; }
+    if (!active) continue;
+    float s[8][4];
+    const unsigned char* kb = sK[buf];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t* kr = reinterpret_cast<const uint32_t*>(kb + (8 * j + g) * MHA_ROWB);
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      mma_bf16_16816q(s[j], qa, kr[t], kr[t + 4]);
+    }
+    const int kbase = c * MHA_KC;
+    float mx0 = NEG, mx1 = NEG;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = 8 * j + 2 * t;
+      const bool o0 = kbase + col >= nk, o1 = kbase + col + 1 >= nk;
+      if (o0 || ((w0 >> col) & 1ull)) s[j][0] = NEG;
+      if (o1 || ((w0 >> (col + 1)) & 1ull)) s[j][1] = NEG;
+      if (o0 || ((w1 >> col) & 1ull)) s[j][2] = NEG;
+      if (o1 || ((w1 >> (col + 1)) & 1ull)) s[j][3] = NEG;
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float a0 = exp2f((m0 - mn0) * L2E), a1 = exp2f((m1 - mn1) * L2E);
+    m0 = mn0; m1 = mn1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {   // (s - m) first: exact 0 for the -1e30 sentinels (an fma against m * log2e is not)
+      s[j][0] = exp2f((s[j][0] - mn0) * L2E); s[j][1] = exp2f((s[j][1] - mn0) * L2E);
+      s[j][2] = exp2f((s[j][2] - mn1) * L2E); s[j][3] = exp2f((s[j][3] - mn1) * L2E);
+      rs0 += s[j][0] + s[j][1];
+      rs1 += s[j][2] + s[j][3];
+    }
+    l0 = l0 * a0 + rs0; l1 = l1 * a1 + rs1;
+#pragma unroll
+    for (int n = 0; n < 2; ++n) { o[n][0] *= a0; o[n][1] *= a0; o[n][2] *= a1; o[n][3] *= a1; }
+    const uint32_t vb = sV0 + buf * BUF;
+    const int mi = lane >> 3, rr = lane & 7;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      uint32_t v0, v1, v2, v3;
+      const uint32_t addr = vb + (16 * kk + (mi & 1) * 8 + rr) * MHA_ROWB + (mi >> 1) * 16;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                   : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(addr));
+      mma_bf16_16816q(o[0], pa, v0, v1);
+      mma_bf16_16816q(o[1], pa, v2, v3);
+    }
+  }
+  if (!active) return;
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+  for (int n = 0; n < 2; ++n) {
+    if (q0 + g < nq)
+      *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * nq + q0 + g) * 128 + h * 16 + 8 * n + 2 * t) =
+          pack_bf16x2(o[n][0] * i0, o[n][1] * i0);
+    if (q0 + g + 8 < nq)
+      *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * nq + q0 + g + 8) * 128 + h * 16 + 8 * n + 2 * t) =
+          pack_bf16x2(o[n][2] * i1, o[n][3] * i1);
+  }
+}
+
+int mha_small(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const unsigned long long* mask,
+              int B, int nq, int nk, void* out, cudaStream_t stream) {
   RSP_CHECK_ARG(Q && K && V && out && B > 0 && nq > 0 && nk > 0, "mha_small: bad args");
   RSP_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0, "mha_small: leading dims must be multiples of 8");
-  const int total = B * 8 * nq;
-  mha_small_kernel<<<(total + 63) / 64, 64, 0, stream>>>(
+  dim3 grid(B * 8, (nq + MHA_WARPS * 16 - 1) / (MHA_WARPS * 16));
+  mha16_kernel<<<grid, MHA_WARPS * 32, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(Q), ldq, static_cast<const __nv_bfloat16*>(K), ldk,
-      static_cast<const __nv_bfloat16*>(V), ldv, mask, B, nq, nk, static_cast<__nv_bfloat16*>(out));
+      static_cast<const __nv_bfloat16*>(V), ldv, mask, (nk + 63) / 64, nq, nk, static_cast<__nv_bfloat16*>(out));
   RSP_CHECK_LAUNCH();
   return RSP_OK;
 }
 
 // ------------------------------------------------------------------------------------ attention mask
-// block = one (image, query) map: mask[k] = bilinear(mpp)[k] < 0 (== sigmoid < 0.5); cleared if all set
-__global__ void attn_mask_build_kernel(const float* __restrict__ mpp, int hm, int wm, int h, int w,
-                                       unsigned char* __restrict__ mask) {
-  const float* src = mpp + static_cast<size_t>(blockIdx.x) * hm * wm;
-  unsigned char* dst = mask + static_cast<size_t>(blockIdx.x) * h * w;
-  const float sy_s = static_cast<float>(hm) / h, sx_s = static_cast<float>(wm) / w;
-  int cnt = 0;
-  for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
-    const int y = i / w, x = i - y * w;
-    const float sy = fmaxf((y + 0.5f) * sy_s - 0.5f, 0.f), sx = fmaxf((x + 0.5f) * sx_s - 0.5f, 0.f);
-    const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
-    const int y1 = min(y0 + 1, hm - 1), x1 = min(x0 + 1, wm - 1);
-    const float ly = sy - y0, lx = sx - x0;
-    const float v = (1.f - ly) * ((1.f - lx) * src[y0 * wm + x0] + lx * src[y0 * wm + x1]) +
-                    ly * ((1.f - lx) * src[y1 * wm + x0] + lx * src[y1 * wm + x1]);
-    const unsigned char mk = v < 0.f;
-    dst[i] = mk;
-    cnt += mk;
+// F.interpolate(mask_pred_plus, level size, bilinear) is linear in the mask features, so the level-sized
+// logits are (mask_embed) x (bilinearly resized mask_feature)^T: resize_bilinear_nhwc produces the resized
+// features once per step, a small GEMM produces logits [B*nq, nk], and this kernel turns a row into bit
+// words: masked = sigmoid(x) < 0.5 = (x < 0); a row with every key masked is cleared (M:386-392, M:439-442).
+__global__ void attn_mask_bits_kernel(const float* __restrict__ logits, int ld, int nk, int words,
+                                      unsigned long long* __restrict__ out) {
+  __shared__ unsigned long long sw[64];
+  __shared__ int any_open;
+  const int row = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* lr = logits + static_cast<size_t>(row) * ld;
+  unsigned long long* orow = out + static_cast<size_t>(row) * words;
+  int open = 0;
+  for (int w0 = 0; w0 < words; w0 += 64) {
+    if (threadIdx.x == 0) any_open = 0;
+    __syncthreads();
+    for (int w = w0 + warp; w < min(words, w0 + 64); w += blockDim.x >> 5) {
+      const int k0 = 64 * w + lane, k1 = k0 + 32;
+      const bool in0 = k0 < nk, in1 = k1 < nk;
+      const bool m0 = in0 ? lr[k0] < 0.f : true, m1 = in1 ? lr[k1] < 0.f : true;
+      const unsigned lo = __ballot_sync(0xffffffffu, m0), hi = __ballot_sync(0xffffffffu, m1);
+      if ((in0 && !m0) || (in1 && !m1)) open = 1;
+      if (lane == 0) sw[w - w0] = static_cast<unsigned long long>(lo) | (static_cast<unsigned long long>(hi) << 32);
+    }
+    __syncthreads();
+    for (int w = w0 + threadIdx.x; w < min(words, w0 + 64); w += blockDim.x) orow[w] = sw[w - w0];
+    __syncthreads();
   }
-  __shared__ int total;
-  if (threadIdx.x == 0) total = 0;
+  if (open) any_open = 1;
   __syncthreads();
-  atomicAdd(&total, cnt);
-  __syncthreads();
-  if (total == h * w)
-    for (int i = threadIdx.x; i < h * w; i += blockDim.x) dst[i] = 0;
+  if (!any_open)
+    for (int w = threadIdx.x; w < words; w += blockDim.x) orow[w] = 0ull;
 }
 
-int attn_mask_build(const float* mpp, int n_maps, int hm, int wm, int h, int w, unsigned char* mask,
-                    cudaStream_t stream) {
-  RSP_CHECK_ARG(mpp && mask && n_maps > 0, "attn_mask_build: bad args");
-  attn_mask_build_kernel<<<n_maps, 256, 0, stream>>>(mpp, hm, wm, h, w, mask);
+int attn_mask_bits(const float* logits, int ld, int rows, int nk, unsigned long long* out, cudaStream_t stream) {
+  RSP_CHECK_ARG(logits && out && rows > 0 && nk > 0 && ld >= nk, "attn_mask_bits: bad args");
+  attn_mask_bits_kernel<<<rows, 128, 0, stream>>>(logits, ld, nk, (nk + 63) / 64, out);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
+// x bf16 [B, H, W, C] -> out bf16 [B, h, w, C], F.interpolate(mode='bilinear', align_corners=False); thread = 8 channels
+__global__ void resize_bilinear_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int h, int w,
+                                            __nv_bfloat16* __restrict__ out) {
+  const int c8 = C >> 3;
+  const size_t total = static_cast<size_t>(B) * h * w * c8;
+  const float sy = static_cast<float>(H) / h, sx = static_cast<float>(W) / w;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c8) * 8;
+    size_t r = i / c8;
+    const int ox = static_cast<int>(r % w); r /= w;
+    const int oy = static_cast<int>(r % h);
+    const int b = static_cast<int>(r / h);
+    const float fy = fmaxf((oy + 0.5f) * sy - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * sx - 0.5f, 0.f);
+    const int y0 = min(static_cast<int>(fy), H - 1), x0 = min(static_cast<int>(fx), W - 1);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float wy = fy - y0, wx = fx - x0;
+    const float wt[4] = {(1.f - wy) * (1.f - wx), (1.f - wy) * wx, wy * (1.f - wx), wy * wx};
+    const int ys[4] = {y0, y0, y1, y1}, xs[4] = {x0, x1, x0, x1};
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, v[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      unpack8f(*reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + ys[k]) * W + xs[k]) * C + c), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += wt[k] * v[j];
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                        pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+int resize_bilinear_nhwc(const void* x, int B, int H, int W, int C, int h, int w, void* out, cudaStream_t stream) {
+  RSP_CHECK_ARG(x && out && B > 0 && H > 0 && W > 0 && h > 0 && w > 0 && C % 8 == 0, "resize_bilinear_nhwc: bad args");
+  const size_t total = static_cast<size_t>(B) * h * w * (C / 8);
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  resize_bilinear_nhwc_kernel<<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), B, H, W, C, h, w,
+                                                         static_cast<__nv_bfloat16*>(out));
   RSP_CHECK_LAUNCH();
   return RSP_OK;
 }

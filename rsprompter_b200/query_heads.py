@@ -324,21 +324,27 @@ class RSMask2FormerHead(_PrepMixin, BaseModule):
         mf_rows = mask_feature.view(B, H0 * W0, -1)
         qf = p["qf"].unsqueeze(0).expand(B, -1, -1).reshape(B * nq, E).contiguous()      # fp32 query stream
 
-        def head(qf32: torch.Tensor, target_hw, final: bool):
+        # F.interpolate(mask_pred_plus, level size) = mask_embed x resize(mask_feature)^T (bilinear is linear):
+        # the intermediate layers only ever need level-sized logits, never the H0 x W0 maps (M:386-392)
+        mf_lvl = [_lib.resize_bilinear_nhwc(mask_feature, s).view(B, s[0] * s[1], -1) for s in shapes]
+
+        def head(qf32: torch.Tensor, lvl: int, final: bool):
             x = _lib.layernorm(qf32, *p["post"], 1e-5)                                    # post_norm -> bf16
             me = self._mlp(x, p["mask"])                                                  # [B*nq, 256]
+            if not final:
+                logits = torch.empty(B * nq, mf_lvl[lvl].shape[1], device=x.device, dtype=torch.float32)
+                for b in range(B):
+                    _lib.gemm(me[b * nq:(b + 1) * nq], mf_lvl[lvl][b], None, out=logits[b * nq:(b + 1) * nq])
+                return _lib.attn_mask_bits(logits), None, None, None
             mpp = torch.empty(B, nq, H0 * W0, device=x.device, dtype=torch.float32)
             for b in range(B):                                                            # einsum 'bqc,bchw->bqhw'
                 _lib.gemm(me[b * nq:(b + 1) * nq], mf_rows[b], None, out=mpp[b])
-            mpp = mpp.view(B * nq, H0, W0)
-            if not final:
-                return _lib.attn_mask_build(mpp, target_hw), mpp, None, None
             cls = self._mlp(x, p["cls"], out_dtype=torch.float32)
             pts = self._mlp(x, p["pts"], out_dtype=torch.float32).view(B * nq, self.per_pointset_point, -1)
             sparse = _lib.sin_fold(pts.contiguous()) if self.with_sincos else pts
-            return None, mpp, cls, sparse
+            return None, mpp.view(B * nq, H0, W0), cls, sparse
 
-        attn_mask, mpp, _, _ = head(qf, shapes[0], final=self.num_layers == 0)
+        attn_mask, mpp, cls, sparse = head(qf, 0, final=self.num_layers == 0)
         for i, d in enumerate(p["layers"]):
             lvl = i % self.num_levels
             hw = shapes[lvl][0] * shapes[lvl][1]
@@ -358,7 +364,7 @@ class RSMask2FormerHead(_PrepMixin, BaseModule):
             hdn = _lib.gemm(_lib.cast_bf16(qf), d["w1"], d["b1"], act="relu")
             qf = _lib.gemm(hdn, d["w2"], d["b2"], residual=qf, out_dtype=torch.float32, ln=(*d["norms"][2], 1e-5))
             last = i == self.num_layers - 1
-            attn_mask, mpp, cls, sparse = head(qf, shapes[(i + 1) % self.num_levels], final=last)
+            attn_mask, mpp, cls, sparse = head(qf, (i + 1) % self.num_levels, final=last)
         # the single live SAM-decoder invocation (M:359-378 of the last _forward_head)
         h, w = emb_hw
         src_pair = _lib.mask_embed_src(mpp, p["sam_me"], emb_rows, pos_rows, nq, (h, w))

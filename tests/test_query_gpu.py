@@ -66,19 +66,61 @@ def test_pixel_decoder_matches_oracle():
     assert _nerr(mf.permute(0, 3, 1, 2), mf_ref) < 2e-2
 
 
-def test_mha_small_masked():
+def _pack_bits(mask: torch.Tensor) -> torch.Tensor:
+    """bool [rows, nk] -> int64 words [rows, ceil(nk/64)], bit k%64 of word k/64."""
+    rows, nk = mask.shape
+    words = (nk + 63) // 64
+    m = torch.zeros(rows, words * 64, dtype=torch.int64)
+    m[:, :nk] = mask.to(torch.int64)
+    m = m.view(rows, words, 64)
+    w = torch.zeros(rows, words, dtype=torch.int64)
+    for k in range(64):
+        w |= m[:, :, k] << k          # bit 63 wraps into the sign bit: same 64-bit pattern
+    return w
+
+
+@pytest.mark.parametrize("nq,nk,masked", [(20, 300, True), (100, 4096, True), (100, 100, False), (130, 64, True)])
+def test_mha_small(nq, nk, masked):
     from rsprompter_b200 import _lib
     g = torch.Generator().manual_seed(9)
-    B, nq, nk, H, E = 2, 20, 300, 8, 128
+    B, H, E = 2, 8, 128
     q, k, v = (torch.randn(B * n, E, generator=g).to(torch.bfloat16) for n in (nq, nk, nk))
-    mask = torch.rand(B, nq, nk, generator=g) < 0.4
-    mask[0, 3] = False
     sp = lambda t, n: t.float().view(B, n, H, E // H).transpose(1, 2)  # noqa: E731
     s = (sp(q, nq) @ sp(k, nk).transpose(-1, -2)) * (E // H) ** -0.5
-    s = s.masked_fill(mask[:, None], float("-inf"))
+    bits = None
+    if masked:
+        mask = torch.rand(B, nq, nk, generator=g) < 0.6
+        mask[0, 3] = False
+        mask[1, 5, : nk - 1] = True
+        mask[1, 5, nk - 1] = False
+        s = s.masked_fill(mask[:, None], float("-inf"))
+        bits = _pack_bits(mask.view(B * nq, nk)).cuda()
     ref = (s.softmax(-1) @ sp(v, nk)).transpose(1, 2).reshape(B * nq, E)
-    out = _lib.mha_small(q.cuda(), k.cuda(), v.cuda(), B, nq, nk, mask=mask.to(torch.uint8).cuda().contiguous())
+    out = _lib.mha_small(q.cuda(), k.cuda(), v.cuda(), B, nq, nk, mask=bits)
     assert (out.float().cpu() - ref).abs().max().item() < 2e-2
+
+
+def test_attn_mask_bits_and_resize():
+    import torch.nn.functional as F
+    from rsprompter_b200 import _lib
+    g = torch.Generator().manual_seed(10)
+    for nk in (64, 1000, 4096):
+        x = torch.randn(37, nk, generator=g)
+        x[3] = -x[3].abs() - 0.1                      # fully masked row -> cleared (M:439-442)
+        ref = x < 0
+        ref[3] = False
+        got = _lib.attn_mask_bits(x.cuda()).cpu()
+        exp = _pack_bits(ref)
+        if nk % 64:
+            tail = ~((1 << (nk % 64)) - 1)          # bits past nk are "masked" unless the row was cleared
+            exp[:, -1] |= tail
+            exp[3, -1] = 0
+        assert torch.equal(got, exp)
+    x = torch.randn(2, 64, 48, 16, generator=g).to(torch.bfloat16)
+    for hw in ((16, 12), (8, 6), (4, 3), (24, 20)):
+        ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=hw, mode="bilinear", align_corners=False)
+        out = _lib.resize_bilinear_nhwc(x.cuda(), hw).float().cpu().permute(0, 3, 1, 2)
+        assert (out - ref).abs().max().item() < 2e-2
 
 
 def test_query_head_matches_oracle():
