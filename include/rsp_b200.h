@@ -47,6 +47,16 @@ int rsp_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int
                   int K, const float* bias, const void* residual, int ldr, int res_fp32, int res_mod,
                   const int32_t* row_map, int act, int out_fp32, void* stream);
 
+/* 3x3 / stride 1 / pad 1 convolution on a bf16 NHWC map as an implicit GEMM (replaces F.conv2d of the FPN / RPN /
+ * pixel-decoder ConvModules, e.g. M:1205-1216, dense_heads/rpn_head.py:60-75): x [B,H,W,C], Wt bf16 [N, 9*C] with
+ * K ordered (ky, kx, c), out [B*H*W, ldo] bf16 or fp32 = act(conv + bias) + residual.  No im2col matrix is built:
+ * each tap's A tile is one 4-D TMA box whose halo is zero-filled.  Needs C % 64 == 0 and a pixel grid whose
+ * 128-pixel tiles are boxes (rsp_conv3x3_geometry_ok); otherwise RSP_ERR_INVALID. */
+int rsp_conv3x3_nhwc_bf16(const void* x, int B, int H, int W, int C, const void* Wt, int ldw, void* out, int ldo,
+                          int N, const float* bias, const void* residual, int ldr, int res_fp32, int act,
+                          int out_fp32, void* stream);
+int rsp_conv3x3_geometry_ok(int B, int H, int W, int C);
+
 /* Same contract on CUDA cores (one thread per output); for contractions far below one
  * 128-row tile and as the independent check of the tensor-core kernel in tests. */
 int rsp_gemm_bf16_simt(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M,

@@ -75,6 +75,8 @@ _SIGNATURES = {
     "rsp_groupnorm_nhwc": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp], _i),
     "rsp_ms_deform_attn_sample": ([_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
     "rsp_mha_small": ([_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp], _i),
+    "rsp_conv3x3_nhwc_bf16": ([_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp], _i),
+    "rsp_conv3x3_geometry_ok": ([_i, _i, _i, _i], _i),
     "rsp_attn_mask_bits": ([_vp, _i, _i, _i, _vp, _vp], _i),
     "rsp_resize_bilinear_nhwc": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "rsp_mask_embed_src": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp], _i),
@@ -180,6 +182,34 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *,
                 _ptr(residual), ldr, res_fp32, res_mod, _ptr(row_map), ACT[act],
                 int(out.dtype == torch.float32), _stream())
     _check(st, "rsp_gemm_bf16")
+    launch_count += 1
+    return out
+
+
+def conv3x3_ok(B: int, H: int, W: int, C: int) -> bool:
+    return bool(_lib.rsp_conv3x3_geometry_ok(B, H, W, C))
+
+
+def conv3x3_nhwc(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *, act: str | None = None,
+                 residual: torch.Tensor | None = None, out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """3x3 / stride 1 / pad 1 convolution as an implicit GEMM: x bf16 [B,H,W,C], w bf16 [N, 9*C] (ky, kx, c)
+    -> [B*H*W, N] = act(conv + bias) + residual."""
+    global launch_count
+    _require_cuda(x, w, bias, residual)
+    B, H, W, C = x.shape
+    N = w.shape[0]
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and w.dtype == torch.bfloat16 and w.stride(1) == 1
+    assert w.shape[1] == 9 * C
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
+    ldr, res_fp32 = 0, 1
+    if residual is not None:
+        assert residual.dim() == 2 and residual.stride(1) == 1 and residual.shape[0] == B * H * W
+        ldr, res_fp32 = residual.stride(0), int(residual.dtype == torch.float32)
+    out = torch.empty(B * H * W, N, device=x.device, dtype=out_dtype)
+    _check(_lib.rsp_conv3x3_nhwc_bf16(_ptr(x), B, H, W, C, _ptr(w), w.stride(0), _ptr(out), out.stride(0), N, _ptr(bias),
+                                      _ptr(residual), ldr, res_fp32, ACT[act], int(out_dtype == torch.float32),
+                                      _stream()), "rsp_conv3x3_nhwc_bf16")
     launch_count += 1
     return out
 

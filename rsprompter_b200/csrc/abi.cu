@@ -34,6 +34,17 @@ int rsp_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int
                                   res_mod, row_map, act, out_fp32), S(stream));
 }
 
+int rsp_conv3x3_nhwc_bf16(const void* x, int B, int H, int W, int C, const void* Wt, int ldw, void* out, int ldo,
+                          int N, const float* bias, const void* residual, int ldr, int res_fp32, int act,
+                          int out_fp32, void* stream) {
+  GemmArgs a = make_gemm_args(x, C, Wt, ldw, out, ldo, B * H * W, N, 9 * C, bias, residual, ldr, res_fp32, 0,
+                              nullptr, act, out_fp32);
+  a.conv_b = B; a.conv_h = H; a.conv_w = W; a.conv_c = C;
+  return conv3x3_bf16(a, S(stream));
+}
+
+int rsp_conv3x3_geometry_ok(int B, int H, int W, int C) { return conv3x3_geometry_ok(B, H, W, C) ? 1 : 0; }
+
 int rsp_gemm_bf16_simt(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M,
                        int N, int K, const float* bias, const void* residual, int ldr, int res_fp32,
                        int res_mod, const int32_t* row_map, int act, int out_fp32, void* stream) {

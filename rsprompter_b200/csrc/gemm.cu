@@ -570,6 +570,39 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------
+// 3x3 / stride 1 / pad 1 convolution as an implicit GEMM (no im2col buffer): the A tile of tap (ky, kx) is the
+// output-pixel box shifted by (ky - 1, kx - 1), fetched by one 4-D TMA load whose out-of-range rows / columns
+// come back as zeros.  A 128-pixel tile must be a whole box of the [B, H, W] pixel grid.
+bool conv3x3_geometry_ok(int B, int H, int W, int C) {
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % BK != 0) return false;
+  const int tw = W < BM ? W : BM;
+  if (BM % tw != 0 || W % tw != 0) return false;
+  const int th = (BM / tw) < H ? BM / tw : H;
+  if (th > 1 && tw != W) return false;
+  if (H % th != 0 || BM % (tw * th) != 0) return false;
+  const int tb = BM / (tw * th);
+  if (tb > 1 && th != H) return false;
+  return tw <= 256 && th <= 256 && tb <= 256;
+}
+
+int conv3x3_bf16(const GemmArgs& a, cudaStream_t stream) {
+  RSP_CHECK_ARG(a.A && a.W && a.out, "conv3x3: null pointer");
+  RSP_CHECK_ARG(conv3x3_geometry_ok(a.conv_b, a.conv_h, a.conv_w, a.conv_c),
+                "conv3x3: unsupported geometry B=%d H=%d W=%d C=%d (C %% 64, 128-pixel tiles must be boxes)",
+                a.conv_b, a.conv_h, a.conv_w, a.conv_c);
+  RSP_CHECK_ARG(a.M == a.conv_b * a.conv_h * a.conv_w && a.K == 9 * a.conv_c && a.ldw % 8 == 0 && a.N > 0,
+                "conv3x3: M / K do not match the map");
+  RSP_CHECK_ARG(a.epi_mode == EPI_STD && !a.w_is_kn && !a.row_map && a.act >= 0 && a.act <= 2, "conv3x3: epilogue");
+  RSP_CHECK_ARG(gemm_v2_eligible(a), "conv3x3: output / residual alignment");
+  int bn = a.N > 128 ? 256 : a.N > 64 ? 128 : a.N > 32 ? 64 : 32;
+  if (bn == 256) {
+    const int t256 = ((a.M + BM - 1) / BM) * ((a.N + 255) / 256);
+    if ((a.N % 256 != 0 && a.N % 256 <= 128) || t256 < num_sms()) bn = 128;
+  }
+  return gemm_bf16_v2(a, bn, stream);
+}
+
+// ---------------------------------------------------------------------------------------
 // Plain SIMT GEMM with the same epilogue contract.  Used (a) by the device self-test as an
 // independent check of the tcgen05 path and (b) for contractions too small to fill one
 // 128-row tile (hypernetwork / IoU MLPs on a handful of tokens).

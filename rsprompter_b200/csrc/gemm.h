@@ -31,10 +31,15 @@ struct GemmArgs {
   const float* hyper = nullptr;       // fp32 [prompts, 32]
   float* mask_out = nullptr;          // fp32 [prompts, 4*grid_h, 4*grid_w]
   int grid_h = 0, grid_w = 0;
+  // implicit 3x3 / stride 1 / pad 1 convolution: A = bf16 NHWC [conv_b, conv_h, conv_w, conv_c], M = b*h*w,
+  // K = 9 * conv_c, W = [N, (ky, kx, c)]; the im2col matrix is never built (TMA zero-fills the halo)
+  int conv_b = 0, conv_h = 0, conv_w = 0, conv_c = 0;
 };
 
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream);
 int gemm_bf16_simt(const GemmArgs& a, cudaStream_t stream);
+bool conv3x3_geometry_ok(int B, int H, int W, int C);
+int conv3x3_bf16(const GemmArgs& a, cudaStream_t stream);   // conv_* set; standard epilogue only
 // coalesced-epilogue kernel (gemm_v2.cu); gemm_bf16 dispatches to it when eligible
 bool gemm_v2_eligible(const GemmArgs& a);
 int gemm_bf16_v2(const GemmArgs& a, int bn, cudaStream_t stream);

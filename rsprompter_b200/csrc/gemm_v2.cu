@@ -59,6 +59,7 @@ struct Dev {
   const float* hyper;
   float* mask_out;
   int grid_h, grid_w;
+  int conv_kb, conv_h, conv_w;   // conv_kb = Cin / 64 k-blocks per tap (0 = plain GEMM)
 };
 
 enum { EPI_STD = 0, EPI_LN64_GELU = 2, EPI_GELU_HYPER = 3 };
@@ -89,7 +90,7 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_kb = p.conv_kb > 0 ? 9 * p.conv_kb : (p.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_a);
@@ -117,12 +118,26 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a,
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile % p.num_n_blocks;
+      int cb = 0, cy = 0, cx = 0, tap = 0, ckb = 0;
+      if (p.conv_kb > 0) {   // the tile's 128 output pixels are a (images x rows x cols) box of the NHWC map
+        const int hw = p.conv_h * p.conv_w, p0 = m_blk * BM;
+        cb = p0 / hw;
+        const int rem = p0 - cb * hw;
+        cy = rem / p.conv_w;
+        cx = rem - cy * p.conv_w;
+      }
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
         const uint32_t full = smem_u32(&bar_full[stage]);
         const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
         mbar_expect_tx(full, C::STAGE_BYTES);
-        tma_load_2d(sa, &tma_a, full, kb * BK, m_blk * BM);
+        if (p.conv_kb > 0) {
+          const int ky = tap / 3, kx = tap - 3 * ky;
+          tma_load_4d(sa, &tma_a, full, ckb * BK, cx + kx - 1, cy + ky - 1, cb);   // halo -> zero fill
+          if (++ckb == p.conv_kb) { ckb = 0; ++tap; }
+        } else {
+          tma_load_2d(sa, &tma_a, full, kb * BK, m_blk * BM);
+        }
         tma_load_2d(sa + A_BYTES, &tma_b, full, kb * BK, n_blk * BN);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -436,9 +451,22 @@ template <int BN, int EPI>
 static int launch(const GemmArgs& a, cudaStream_t stream) {
   using C = Cfg<BN>;
   CUtensorMap ta, tb;
-  RSP_TRY(make_tmap_bf16_2d(&ta, a.A, a.M, a.K, static_cast<uint64_t>(a.lda) * 2, BM, BK));
-  RSP_TRY(make_tmap_bf16_2d(&tb, a.W, a.N, a.K, static_cast<uint64_t>(a.ldw) * 2, BN, BK));
   Dev p;
+  p.conv_kb = 0; p.conv_h = a.conv_h; p.conv_w = a.conv_w;
+  if (a.conv_c > 0) {
+    const uint64_t C_ = a.conv_c, W_ = a.conv_w, H_ = a.conv_h, B_ = a.conv_b;
+    const uint32_t tw = a.conv_w < BM ? a.conv_w : BM;
+    const uint32_t th = (BM / tw) < static_cast<uint32_t>(a.conv_h) ? BM / tw : a.conv_h;
+    const uint32_t tb = BM / (tw * th);
+    uint64_t dims[4] = {C_, W_, H_, B_};
+    uint64_t strides[3] = {C_ * 2, W_ * C_ * 2, H_ * W_ * C_ * 2};
+    uint32_t box[4] = {static_cast<uint32_t>(BK), tw, th, tb};
+    RSP_TRY(make_tmap_bf16(&ta, a.A, 4, dims, strides, box));
+    p.conv_kb = a.conv_c / BK;
+  } else {
+    RSP_TRY(make_tmap_bf16_2d(&ta, a.A, a.M, a.K, static_cast<uint64_t>(a.lda) * 2, BM, BK));
+  }
+  RSP_TRY(make_tmap_bf16_2d(&tb, a.W, a.N, a.K, static_cast<uint64_t>(a.ldw) * 2, BN, BK));
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.row_map = a.row_map;
   p.res_block_map = a.res_block_map; p.res_block_rows = a.res_block_rows;

@@ -444,12 +444,12 @@ struct MaskEmbedW {
   const float *w3, *b3;              // conv3 [256,16] (1x1), bias
 };
 
-// block = 256 threads = 256 output channels, 32 pixels of one prompt
+// block = 128 threads x 2 output channels, 32 pixels of one prompt (hidden vector read as 4 x 128-bit LDS)
 __global__ void mask_embed_src_kernel(const float* __restrict__ mpp, MaskEmbedW W, const float* __restrict__ emb,
                                       const float* __restrict__ pos, int n_per_img, int hm, int wm, int h, int w,
                                       float eps, __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ src_pe) {
   constexpr int PP = 32;
-  __shared__ float hid[PP][17];
+  __shared__ __align__(16) float hid[PP][16];
   const int n = blockIdx.y;
   const int p0 = blockIdx.x * PP;
   const int HW = h * w;
@@ -500,21 +500,31 @@ __global__ void mask_embed_src_kernel(const float* __restrict__ mpp, MaskEmbedW 
     for (int c = 0; c < 16; ++c) hid[threadIdx.x][c] = gelu_erf((a2[c] - mean) * rstd * W.g2[c] + W.be2[c]);
   }
   __syncthreads();
-  const int c = threadIdx.x;
-  float wc[16];
+  const int c = 2 * threadIdx.x;
+  float wa[16], wb[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) wc[k] = W.w3[c * 16 + k];
-  const float bc = W.b3[c];
+  for (int k = 0; k < 16; ++k) { wa[k] = W.w3[c * 16 + k]; wb[k] = W.w3[(c + 1) * 16 + k]; }
+  const float ba = W.b3[c], bb = W.b3[c + 1];
   const int img = n / n_per_img;
-  for (int pp = 0; pp < PP && p0 + pp < HW; ++pp) {
-    float s = bc;
+  const int npix = min(PP, HW - p0);
+#pragma unroll 4
+  for (int pp = 0; pp < npix; ++pp) {
+    float hv[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) s += wc[k] * hid[pp][k];
+    for (int k4 = 0; k4 < 4; ++k4) {
+      const float4 v = *reinterpret_cast<const float4*>(&hid[pp][4 * k4]);
+      hv[4 * k4] = v.x; hv[4 * k4 + 1] = v.y; hv[4 * k4 + 2] = v.z; hv[4 * k4 + 3] = v.w;
+    }
+    float sa = ba, sb = bb;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { sa = fmaf(wa[k], hv[k], sa); sb = fmaf(wb[k], hv[k], sb); }
     const int pix = p0 + pp;
-    s += emb[(static_cast<size_t>(img) * HW + pix) * 256 + c];
+    const float2 e = *reinterpret_cast<const float2*>(emb + (static_cast<size_t>(img) * HW + pix) * 256 + c);
+    const float2 ps = *reinterpret_cast<const float2*>(pos + static_cast<size_t>(pix) * 256 + c);
+    sa += e.x; sb += e.y;
     const size_t o = (static_cast<size_t>(n) * HW + pix) * 256 + c;
-    src[o] = __float2bfloat16_rn(s);
-    src_pe[o] = __float2bfloat16_rn(s + pos[static_cast<size_t>(pix) * 256 + c]);
+    *reinterpret_cast<uint32_t*>(src + o) = pack_bf16x2(sa, sb);
+    *reinterpret_cast<uint32_t*>(src_pe + o) = pack_bf16x2(sa + ps.x, sb + ps.y);
   }
 }
 
@@ -523,7 +533,7 @@ int mask_embed_src(const float* mpp, const float* const* wts, const float* emb, 
   RSP_CHECK_ARG(mpp && wts && emb && pos && src && src_pe && N > 0 && hm == 4 * h && wm == 4 * w, "mask_embed_src: bad args");
   MaskEmbedW W{wts[0], wts[1], wts[2], wts[3], wts[4], wts[5], wts[6], wts[7], wts[8], wts[9]};
   dim3 grid((h * w + 31) / 32, N);
-  mask_embed_src_kernel<<<grid, 256, 0, stream>>>(mpp, W, emb, pos, n_per_img, hm, wm, h, w, eps,
+  mask_embed_src_kernel<<<grid, 128, 0, stream>>>(mpp, W, emb, pos, n_per_img, hm, wm, h, w, eps,
                                                   static_cast<__nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(src_pe));
   RSP_CHECK_LAUNCH();
   return RSP_OK;

@@ -127,6 +127,9 @@ def conv1x1(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None, act=None, 
 def conv3x3(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None, act=None, residual=None, stride: int = 1,
             out_dtype=torch.bfloat16) -> torch.Tensor:
     B, H, W, C = x.shape
+    if stride == 1 and _lib.conv3x3_ok(B, H, W, C):      # implicit GEMM: no im2col matrix
+        res = residual.reshape(B * H * W, -1) if residual is not None else None
+        return _lib.conv3x3_nhwc(x.contiguous(), w, b, act=act, residual=res, out_dtype=out_dtype).view(B, H, W, -1)
     col = _lib.im2col_nhwc(x, 3, 3, stride, 1)
     Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
     res = residual.reshape(B * Ho * Wo, -1) if residual is not None else None

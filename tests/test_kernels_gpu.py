@@ -141,3 +141,34 @@ def test_wrong_device_raises():
     from rsprompter_b200 import _lib
     with pytest.raises(_lib.RspError):
         _lib.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+
+
+@pytest.mark.parametrize("B,H,W,C,N", [(2, 64, 64, 64, 96), (1, 256, 256, 64, 32), (3, 8, 8, 128, 256),
+                                       (2, 16, 16, 64, 24), (5, 4, 4, 64, 64), (1, 128, 128, 256, 256)])
+def test_conv3x3_implicit_gemm(B, H, W, C, N):
+    """rsp_conv3x3_nhwc_bf16 (4-D TMA taps, zero-filled halo) against F.conv2d on the same bf16 values."""
+    import torch.nn.functional as F
+    from rsprompter_b200 import _lib
+    from rsprompter_b200.necks import prep_conv
+    assert _lib.conv3x3_ok(B, H, W, C)
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    x = torch.randn(B, C, H, W, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, C, 3, 3, generator=g) / (3 * C ** 0.5)).to(torch.bfloat16)
+    b = torch.randn(N, generator=g)
+    res = torch.randn(B * H * W, N, generator=g)
+    wg, bg = prep_conv(w.float(), b)
+    xh = x.permute(0, 2, 3, 1).contiguous().cuda()
+    ref = F.conv2d(x.float(), w.float(), b, padding=1)
+    out = _lib.conv3x3_nhwc(xh, wg.cuda(), bg.cuda()).float().cpu().view(B, H, W, N).permute(0, 3, 1, 2)
+    assert (out - ref).abs().max().item() < 3e-2
+    ref2 = F.relu(ref).permute(0, 2, 3, 1).reshape(B * H * W, N) + res
+    out2 = _lib.conv3x3_nhwc(xh, wg.cuda(), bg.cuda(), act="relu", residual=res.cuda(), out_dtype=torch.float32).cpu()
+    assert (out2 - ref2).abs().max().item() < 2e-2
+
+
+def test_conv3x3_geometry_gate():
+    from rsprompter_b200 import _lib
+    assert not _lib.conv3x3_ok(1, 64, 64, 32)        # C % 64
+    assert not _lib.conv3x3_ok(1, 14, 14, 256)       # 14 x 14 RoI maps do not tile into 128-pixel boxes
+    assert not _lib.conv3x3_ok(1, 48, 48, 64)
+    assert _lib.conv3x3_ok(8, 256, 256, 256) and _lib.conv3x3_ok(8, 16, 16, 128)
