@@ -251,6 +251,10 @@ int rsp_query_postprocess(const float* logits, const int32_t* sel, const float* 
 /* fp32 -> bf16 (n % 4 == 0): feeds fp32 hidden states to the bf16 tensor-core GEMMs. */
 int rsp_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
 
+/* out = bf16(x + table[i % period]) on bf16 x: the RoI head's extra positional encoding added to one pyramid level
+ * (x = [xi + pe_i ...], M:1566-1574), table fp32 [H*W*C], n and period multiples of 8. */
+int rsp_add_table_bf16(const void* x, const float* table, void* out, long long n, long long period, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

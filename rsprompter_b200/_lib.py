@@ -58,6 +58,7 @@ _SIGNATURES = {
     "rsp_im2col_nhwc": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
     "rsp_nhwc_to_nchw": ([_vp, _i, _vp, _i, _i, _i, _vp], _i),
     "rsp_cast_f32_bf16": ([_vp, _vp, ctypes.c_longlong, _vp], _i),
+    "rsp_add_table_bf16": ([_vp, _vp, _vp, ctypes.c_longlong, ctypes.c_longlong, _vp], _i),
     "rsp_gemm_bf16_ex": ([_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i,
                           _i, _vp, _vp, _f, _vp, _i, _vp, _vp, _i, _i, _vp], _i),
     "rsp_add_cast_bf16": ([_vp, _vp, _vp, ctypes.c_longlong, ctypes.c_longlong, _vp], _i),
@@ -409,6 +410,19 @@ def cast_bf16(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
     assert out.is_contiguous() and out.numel() == x.numel() and out.dtype == torch.bfloat16
     _check(_lib.rsp_cast_f32_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "rsp_cast_f32_bf16")
+    launch_count += 1
+    return out
+
+
+def add_table_bf16(x: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    """bf16 x [B, ...] + fp32 table [...] (broadcast over the leading dim) -> bf16."""
+    global launch_count
+    _require_cuda(x, table)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and table.dtype == torch.float32 and table.is_contiguous()
+    assert x.numel() % table.numel() == 0 and table.numel() % 8 == 0
+    out = torch.empty_like(x)
+    _check(_lib.rsp_add_table_bf16(_ptr(x), _ptr(table), _ptr(out), x.numel(), table.numel(), _stream()),
+           "rsp_add_table_bf16")
     launch_count += 1
     return out
 

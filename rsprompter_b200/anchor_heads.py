@@ -356,6 +356,10 @@ class RSPrompterAnchorRoIPromptHead(BaseModule):
         B, K, _ = proposals.shape
         dev = proposals.device
         pes = self._extra_pe(feats)
+        if pes is not None:       # x = [xi + pe_i] once per level (M:1566-1574); both extractors then read bf16 only
+            n_lvl = max(self.bbox_roi_extractor.num_inputs, self.mask_roi_extractor.num_inputs)
+            feats = [_lib.add_table_bf16(f, t) for f, t in zip(feats[:n_lvl], pes[:n_lvl])] + list(feats[n_lvl:])
+            pes = None
         bidx = torch.arange(B, device=dev, dtype=torch.float32).view(B, 1, 1).expand(B, K, 1)
         rois = torch.cat([bidx, proposals], dim=2).reshape(B * K, 5).contiguous()
         valid = (torch.arange(K, device=dev).view(1, K) < prop_counts.view(B, 1)).reshape(-1).to(torch.uint8)

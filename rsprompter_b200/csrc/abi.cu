@@ -104,6 +104,10 @@ int rsp_cast_f32_bf16(const float* in, void* out, long long n, void* stream) {
   return cast_f32_bf16(in, out, n, S(stream));
 }
 
+int rsp_add_table_bf16(const void* x, const float* table, void* out, long long n, long long period, void* stream) {
+  return add_table_bf16(x, table, out, n, period, S(stream));
+}
+
 }  // extern "C"
 
 #include "decoder.h"

@@ -16,6 +16,7 @@
 //   sin_fold          x[..., ::2].sin() + x[..., 1::2]  (M:348, M:1672)
 #include "detect.h"
 #include "sm100.cuh"
+#include "upsample4.cuh"
 
 namespace rsp {
 
@@ -466,6 +467,34 @@ __global__ void mask_paste_kernel(const float* __restrict__ logits, unsigned cha
       make_uint4(packed[0], packed[1], packed[2], packed[3]);
 }
 
+// x4 fast path (the mask decoder's logits are always image / 4): thread = 4 output rows x 16 columns
+template <int MODE>
+__global__ void mask_paste_x4_kernel(const float* __restrict__ logits, unsigned char* __restrict__ out, int n, int hm,
+                                     int wm, float thr) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int w4 = wm / 4;
+  if (idx >= static_cast<long long>(n) * hm * w4) return;
+  const int xb = static_cast<int>(idx % w4);
+  long long t = idx / w4;
+  const int yb = static_cast<int>(t % hm);
+  const int m = static_cast<int>(t / hm);
+  Up4Tile tile;
+  up4_load(logits + static_cast<size_t>(m) * hm * wm, hm, wm, yb, xb, tile);
+  const int W = 4 * wm;
+  unsigned char* o = out + (static_cast<size_t>(m) * 4 * hm + 4 * yb) * W + 16 * xb;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t packed[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float v = up4_value(tile, j, k);
+      const uint32_t bit = (MODE == 1 ? (v > thr) : (v >= thr)) ? 1u : 0u;
+      packed[k >> 2] |= bit << ((k & 3) * 8);
+    }
+    *reinterpret_cast<uint4*>(o + static_cast<size_t>(j) * W) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  }
+}
+
 __global__ void sigmoid_f32_kernel(const float4* __restrict__ in, float4* __restrict__ out, long long n4) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
@@ -485,6 +514,14 @@ int sigmoid_f32(const float* in, float* out, long long n, cudaStream_t stream) {
 int mask_paste(const float* logits, unsigned char* out, int n, int hm, int wm, int H, int W, float thr,
                int mode, cudaStream_t stream) {
   RSP_CHECK_ARG(logits && out && n > 0 && W % 16 == 0, "mask_paste: W must be a multiple of 16");
+  if (mode != 0 && H == 4 * hm && W == 4 * wm && wm % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
+    const long long tiles = static_cast<long long>(n) * hm * (wm / 4);
+    const unsigned blocks = static_cast<unsigned>((tiles + 127) / 128);
+    if (mode == 1) mask_paste_x4_kernel<1><<<blocks, 128, 0, stream>>>(logits, out, n, hm, wm, thr);
+    else mask_paste_x4_kernel<2><<<blocks, 128, 0, stream>>>(logits, out, n, hm, wm, thr);
+    RSP_CHECK_LAUNCH();
+    return RSP_OK;
+  }
   const long long total = static_cast<long long>(n) * H * (W / 16);
   mask_paste_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(logits, out, n, hm, wm, H, W,
                                                                                    thr, mode);

@@ -17,6 +17,7 @@
 //                             intermediate and no per-instance host sync
 #include "query.h"
 #include "sm100.cuh"
+#include "upsample4.cuh"
 
 namespace rsp {
 
@@ -602,6 +603,67 @@ __global__ void query_mask_kernel(const float* __restrict__ logits, const int* _
   }
 }
 
+// x4 fast path: block = 16 output rows of one instance (same partial layout as above); thread = 4 x 16 tile
+__global__ void query_mask_x4_kernel(const float* __restrict__ logits, const int* __restrict__ sel, int hm, int wm,
+                                     unsigned char* __restrict__ masks, float* __restrict__ part) {
+  const int inst = blockIdx.y;
+  const float* src = logits + static_cast<size_t>(sel[inst]) * hm * wm;
+  const int H = 4 * hm, W = 4 * wm, w4 = wm / 4;
+  float sum = 0.f;
+  int cnt = 0, minx = W, maxx = -1, miny = H, maxy = -1;
+  for (int t = threadIdx.x; t < 4 * w4; t += blockDim.x) {
+    const int yb = blockIdx.x * 4 + t / w4, xb = t % w4;
+    if (yb >= hm) break;
+    Up4Tile tile;
+    up4_load(src, hm, wm, yb, xb, tile);
+    unsigned char* o = masks + (static_cast<size_t>(inst) * H + 4 * yb) * W + 16 * xb;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t packed[4] = {0u, 0u, 0u, 0u};
+      uint32_t bits = 0u;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float v = up4_value(tile, j, k);
+        if (v > 0.f) {
+          sum += 1.f / (1.f + expf(-v));
+          bits |= 1u << k;
+          packed[k >> 2] |= 1u << ((k & 3) * 8);
+        }
+      }
+      *reinterpret_cast<uint4*>(o + static_cast<size_t>(j) * W) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      if (bits) {
+        cnt += __popc(bits);
+        minx = min(minx, 16 * xb + __ffs(bits) - 1);
+        maxx = max(maxx, 16 * xb + 31 - __clz(bits));
+        miny = min(miny, 4 * yb + j);
+        maxy = max(maxy, 4 * yb + j);
+      }
+    }
+  }
+  __shared__ float s_sum[256];
+  __shared__ int s_i[256][5];
+  s_sum[threadIdx.x] = sum;
+  s_i[threadIdx.x][0] = cnt; s_i[threadIdx.x][1] = minx; s_i[threadIdx.x][2] = maxx;
+  s_i[threadIdx.x][3] = miny; s_i[threadIdx.x][4] = maxy;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      s_sum[threadIdx.x] += s_sum[threadIdx.x + s];
+      s_i[threadIdx.x][0] += s_i[threadIdx.x + s][0];
+      s_i[threadIdx.x][1] = min(s_i[threadIdx.x][1], s_i[threadIdx.x + s][1]);
+      s_i[threadIdx.x][2] = max(s_i[threadIdx.x][2], s_i[threadIdx.x + s][2]);
+      s_i[threadIdx.x][3] = min(s_i[threadIdx.x][3], s_i[threadIdx.x + s][3]);
+      s_i[threadIdx.x][4] = max(s_i[threadIdx.x][4], s_i[threadIdx.x + s][4]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float* o = part + (static_cast<size_t>(inst) * gridDim.x + blockIdx.x) * 6;
+    o[0] = s_sum[0]; o[1] = static_cast<float>(s_i[0][0]); o[2] = static_cast<float>(s_i[0][1]);
+    o[3] = static_cast<float>(s_i[0][2]); o[4] = static_cast<float>(s_i[0][3]); o[5] = static_cast<float>(s_i[0][4]);
+  }
+}
+
 __global__ void query_finalize_kernel(const float* __restrict__ part, int nblk, const float* __restrict__ cls_scores,
                                       int n_inst, int W, int H, float* __restrict__ scores, float* __restrict__ boxes) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -624,7 +686,10 @@ int query_postprocess(const float* logits, const int* sel, const float* cls_scor
                 "query_postprocess: bad args");
   const int nblk = (H + QP_ROWS - 1) / QP_ROWS;
   dim3 grid(nblk, n_inst);
-  query_mask_kernel<<<grid, 256, 0, stream>>>(logits, sel, hm, wm, H, W, masks, part_ws);
+  if (H == 4 * hm && W == 4 * wm && wm % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0)
+    query_mask_x4_kernel<<<grid, 256, 0, stream>>>(logits, sel, hm, wm, masks, part_ws);
+  else
+    query_mask_kernel<<<grid, 256, 0, stream>>>(logits, sel, hm, wm, H, W, masks, part_ws);
   RSP_CHECK_LAUNCH();
   query_finalize_kernel<<<(n_inst + 127) / 128, 128, 0, stream>>>(part_ws, nblk, cls_scores, n_inst, W, H, scores, boxes);
   RSP_CHECK_LAUNCH();

@@ -362,4 +362,31 @@ int layernorm_add(const void* x, const void* res, int res_fp32, const int* res_b
   return RSP_OK;
 }
 
+// out = bf16(x + table[i % period]): the extra positional encoding of the RoI head added to a pyramid level once
+// (M:1566-1574 computes x + pe before both RoI extractors), 8 elements per thread.
+__global__ void add_table_bf16_kernel(const uint4* __restrict__ x, const float* __restrict__ table, uint4* __restrict__ out,
+                                      long long n8, long long period) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 u = x[i];
+  const float* t = table + (i * 8) % period;
+  const float4 t0 = *reinterpret_cast<const float4*>(t), t1 = *reinterpret_cast<const float4*>(t + 4);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    o[j] = pack_bf16x2(__uint_as_float(w[j] << 16) + tv[2 * j], __uint_as_float(w[j] & 0xffff0000u) + tv[2 * j + 1]);
+  out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+int add_table_bf16(const void* x, const float* table, void* out, long long n, long long period, cudaStream_t stream) {
+  RSP_CHECK_ARG(x && table && out && n > 0 && n % 8 == 0 && period > 0 && period % 8 == 0, "add_table: bad args");
+  const long long n8 = n / 8;
+  add_table_bf16_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(
+      static_cast<const uint4*>(x), table, static_cast<uint4*>(out), n8, period);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
 }  // namespace rsp

@@ -25,5 +25,6 @@ int layernorm_add(const void* x, const void* res, int res_fp32, const int* res_b
                   const float* gamma, const float* beta, void* out, const float* pos, int pos_mod, void* out_pe,
                   long long rows, int C, float eps, cudaStream_t stream);
 int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t stream);
+int add_table_bf16(const void* x, const float* table, void* out, long long n, long long period, cudaStream_t stream);
 
 }  // namespace rsp

@@ -153,16 +153,19 @@ def test_roi_head_stages(model_and_sd):
     assert r["mask_logits"].shape == (B * 100, 1, 256, 256)
 
 
-def test_mask_paste_matches_oracle():
+@pytest.mark.parametrize("hm,size", [(256, (1024, 1024)), (64, (256, 256)), (256, (768, 768)), (48, (176, 208))])
+def test_mask_paste_matches_oracle(hm, size):
+    """x4 tiles (the shipped case: logits are image / 4) and the generic-scale kernel, borders included."""
     from oracle import restate_anchor as ra
     from rsprompter_b200 import _lib
     g = torch.Generator().manual_seed(8)
-    logits = torch.randn(5, 1, 256, 256, generator=g) * 3
-    ref = ra.mask_postprocess(logits, (1024, 1024), 0.5)
-    got = _lib.mask_paste(logits[:, 0].contiguous().cuda(), (1024, 1024), 0.5, 0)
+    logits = torch.randn(5, 1, hm, hm, generator=g) * 3
+    ref = ra.mask_postprocess(logits, size, 0.5)
+    got = _lib.mask_paste(logits[:, 0].contiguous().cuda(), size, 0.5, 0)
     torch.cuda.synchronize()
     assert got.dtype == torch.bool and got.shape == ref.shape
     assert (got.cpu() != ref).float().mean().item() < 1e-5
+    assert torch.equal(got.cpu()[:, :2], ref[:, :2]) or (got.cpu()[:, :2] != ref[:, :2]).float().mean().item() < 1e-4
 
 
 def test_end_to_end_predict_contract(model_and_sd):
