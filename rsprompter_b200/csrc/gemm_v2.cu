@@ -10,6 +10,8 @@
 //     epilogue-bound at ~35-55 % of the large-K rate).
 // All shared memory is dynamic (1024-byte aligned by declaration), barriers live at its end:
 //   [ STAGES x (A 16 KB + B BN*128 B) | 8 x 32 x 136 B staging | barriers ]
+#include <cstdlib>
+
 #include "gemm.h"
 #include "sm100.cuh"
 
@@ -60,6 +62,7 @@ struct Dev {
   float* mask_out;
   int grid_h, grid_w;
   int conv_kb, conv_h, conv_w;   // conv_kb = Cin / 64 k-blocks per tap (0 = plain GEMM)
+  int tma_store;                 // output leaves through tma_c (no residual / scatter, BN >= 64)
 };
 
 enum { EPI_STD = 0, EPI_LN64_GELU = 2, EPI_GELU_HYPER = 3 };
@@ -74,8 +77,8 @@ __device__ __forceinline__ int residual_row(const Dev& p, int orow) {
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a,
-                            const __grid_constant__ CUtensorMap tma_b, const Dev p) {
+gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                            const __grid_constant__ CUtensorMap tma_c, const Dev p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -292,6 +295,97 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a,
           }
           __syncwarp();
         }
+      } else if (p.tma_store) {
+        // ---- lean path: TMEM -> registers -> bias / activation -> 128-byte-swizzled staging -> one TMA store per
+        // 32 x 128 B slab.  No per-element address or bounds arithmetic: the tensor map clips rows >= M / cols >= N.
+        mbar_wait(smem_u32(&bar_tmem_full[as]), (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + hf * C::COLS_PER_WARP;
+        const int col_warp = n_blk * BN + hf * C::COLS_PER_WARP;
+        const int row0 = m_blk * BM + q * 32;
+        const uint32_t sbuf = smem_u32(stg_all) + e * 4096;
+        const uint32_t srow = sbuf + lane * 128;
+        const int sw = lane & 7;
+        const int act = p.act;
+        const float* bias = p.bias;
+        const int N = p.N;
+        auto bias_act = [&](float (&v)[32], int col0) {
+          if (bias) {
+            if (col0 + 32 <= N) {
+              const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 b = __ldg(b4 + i);
+                v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += (col0 + i < N) ? __ldg(bias + col0 + i) : 0.f;
+            }
+          }
+          if (act == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+          } else if (act == 2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+        };
+        if (p.out_fp32) {
+#pragma unroll 1
+          for (int ps = 0; ps < C::COLS_PER_WARP / 32; ++ps) {
+            const int col0 = col_warp + ps * 32;
+            if (col0 >= N) break;
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + ps * 32, r);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            bias_act(v, col0);
+            if (lane == 0) bulk_wait_read0();      // the previous slab has left the staging buffer
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ sw) << 4)), "f"(v[4 * j]),
+                           "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                           : "memory");
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&tma_c, sbuf, col0, row0); bulk_commit(); }
+          }
+        } else {
+#pragma unroll 1
+          for (int ps = 0; ps < C::COLS_PER_WARP / 64; ++ps) {
+            const int col0 = col_warp + ps * 64;
+            if (col0 >= N) break;
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32b_x32(t_row + ps * 64, r0);
+            tmem_ld_32x32b_x32(t_row + ps * 64 + 32, r1);
+            tmem_ld_wait();
+            float v0[32], v1[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v0[i] = __uint_as_float(r0[i]); v1[i] = __uint_as_float(r1[i]); }
+            bias_act(v0, col0);
+            if (col0 + 32 < N) bias_act(v1, col0 + 32);
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ sw) << 4)),
+                           "r"(pack_bf16x2(v0[8 * j], v0[8 * j + 1])), "r"(pack_bf16x2(v0[8 * j + 2], v0[8 * j + 3])),
+                           "r"(pack_bf16x2(v0[8 * j + 4], v0[8 * j + 5])), "r"(pack_bf16x2(v0[8 * j + 6], v0[8 * j + 7]))
+                           : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((j + 4) ^ sw) << 4)),
+                           "r"(pack_bf16x2(v1[8 * j], v1[8 * j + 1])), "r"(pack_bf16x2(v1[8 * j + 2], v1[8 * j + 3])),
+                           "r"(pack_bf16x2(v1[8 * j + 4], v1[8 * j + 5])), "r"(pack_bf16x2(v1[8 * j + 6], v1[8 * j + 7]))
+                           : "memory");
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&tma_c, sbuf, col0, row0); bulk_commit(); }
+          }
+        }
       } else {
       const int my_row = m_blk * BM + q * 32 + lane;
       int my_orow = -1;
@@ -437,6 +531,7 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a,
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[as]));
     }
+    if (p.tma_store && lane == 0) bulk_wait0();   // every slab is in global memory before the CTA retires
   }
 
   tc_fence_before();
@@ -467,6 +562,20 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
     RSP_TRY(make_tmap_bf16_2d(&ta, a.A, a.M, a.K, static_cast<uint64_t>(a.lda) * 2, BM, BK));
   }
   RSP_TRY(make_tmap_bf16_2d(&tb, a.W, a.N, a.K, static_cast<uint64_t>(a.ldw) * 2, BN, BK));
+  CUtensorMap tc = tb;
+  p.tma_store = 0;
+  {
+    const uint64_t esz = a.out_fp32 ? 4 : 2;
+    static const bool no_tma_store = getenv("RSP_GEMM_NO_TMA_STORE") != nullptr;
+    if (!no_tma_store && EPI == EPI_STD && BN >= 64 && !a.residual && !a.row_map && a.out &&
+        (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (static_cast<uint64_t>(a.ldo) * esz) % 16 == 0) {
+      uint64_t dims[2] = {static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.M)};
+      uint64_t strides[1] = {static_cast<uint64_t>(a.ldo) * esz};
+      uint32_t box[2] = {a.out_fp32 ? 32u : 64u, 32u};
+      RSP_TRY(make_tmap(&tc, a.out, 2, dims, strides, box, a.out_fp32));
+      p.tma_store = 1;
+    }
+  }
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.row_map = a.row_map;
   p.res_block_map = a.res_block_map; p.res_block_rows = a.res_block_rows;
@@ -484,7 +593,7 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
   }
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
-  kern<<<grid, THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  kern<<<grid, THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tc, p);
   RSP_CHECK_LAUNCH();
   return RSP_OK;
 }

@@ -36,6 +36,11 @@ static EncodeTiledFn get_encode_fn() {
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap(out, base, rank, dims, strides_bytes, box, 0);
+}
+
+int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, int is_f32) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -58,8 +63,8 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     RSP_CHECK_ARG((strides_bytes[i] & 15) == 0, "tensor map stride[%d]=%llu not 16B multiple", i,
                   (unsigned long long)strides_bytes[i]);
   }
-  RSP_CHECK_ARG(box[0] * 2 <= 128, "swizzle-128B inner box must be <= 64 bf16");
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+  RSP_CHECK_ARG(box[0] * (is_f32 ? 4 : 2) <= 128, "swizzle-128B inner box must be <= 128 bytes");
+  CUresult r = fn(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
                   gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
