@@ -62,7 +62,8 @@ struct Dev {
   float* mask_out;
   int grid_h, grid_w;
   int conv_kb, conv_h, conv_w;   // conv_kb = Cin / 64 k-blocks per tap (0 = plain GEMM)
-  int tma_store;                 // output leaves through tma_c (no residual / scatter, BN >= 64)
+  int tma_store;                 // output leaves through tma_c (no scatter, BN >= 64)
+  int tma_res;                   // residual slabs arrive through tma_r into the staging buffer (added in place)
 };
 
 enum { EPI_STD = 0, EPI_LN64_GELU = 2, EPI_GELU_HYPER = 3 };
@@ -78,7 +79,8 @@ __device__ __forceinline__ int residual_row(const Dev& p, int orow) {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                            const __grid_constant__ CUtensorMap tma_c, const Dev p) {
+                            const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r,
+                            const Dev p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -90,6 +92,7 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
   uint64_t* bar_tmem_full = bars + 2 * STAGES;
   uint64_t* bar_tmem_empty = bars + 2 * STAGES + 2;
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* bar_res = bars + 2 * STAGES + 5;   // one per epilogue warp: residual slab landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -106,6 +109,7 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
       mbar_init(smem_u32(&bar_tmem_full[s]), 1);
       mbar_init(smem_u32(&bar_tmem_empty[s]), 4 * C::NHALF);
     }
+    for (int s = 0; s < 8; ++s) mbar_init(smem_u32(&bar_res[s]), 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_base_s), C::TMEM_COLS);
@@ -183,6 +187,7 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
     const int rpi = 32 / lpr;                          // rows per write-out iteration
     const int epl = stage_f32 ? 2 : 4;                 // elements per lane (8 bytes)
     int it = 0;
+    uint32_t rphase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile % p.num_n_blocks;
@@ -298,14 +303,35 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
       } else if (p.tma_store) {
         // ---- lean path: TMEM -> registers -> bias / activation -> 128-byte-swizzled staging -> one TMA store per
         // 32 x 128 B slab.  No per-element address or bounds arithmetic: the tensor map clips rows >= M / cols >= N.
-        mbar_wait(smem_u32(&bar_tmem_full[as]), (it >> 1) & 1);
-        tc_fence_after();
+        // With a residual, its slab is TMA-loaded into the same staging buffer (issued as soon as the previous
+        // store has drained it), added in place by the lane that owns the row, and stored from there.
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + hf * C::COLS_PER_WARP;
         const int col_warp = n_blk * BN + hf * C::COLS_PER_WARP;
         const int row0 = m_blk * BM + q * 32;
         const uint32_t sbuf = smem_u32(stg_all) + e * 4096;
         const uint32_t srow = sbuf + lane * 128;
         const int sw = lane & 7;
+        const bool has_res = p.tma_res != 0 && row0 < p.M;
+        const uint32_t rbar = smem_u32(&bar_res[e]);
+        int rrow0 = row0;
+        if (has_res) {
+          if (p.res_block_map) {
+            const int blk = row0 / p.res_block_rows;
+            rrow0 = __ldg(p.res_block_map + blk) * p.res_block_rows + (row0 - blk * p.res_block_rows);
+          } else if (p.res_mod > 0) {
+            rrow0 = row0 % p.res_mod;
+          }
+        }
+        auto issue_res = [&](int col0) {
+          if (lane == 0) {
+            bulk_wait_read0();
+            mbar_expect_tx(rbar, 4096);
+            tma_load_2d(sbuf, &tma_r, rbar, col0, rrow0);
+          }
+        };
+        if (has_res && col_warp < p.N) issue_res(col_warp);
+        mbar_wait(smem_u32(&bar_tmem_full[as]), (it >> 1) & 1);
+        tc_fence_after();
         const int act = p.act;
         const float* bias = p.bias;
         const int N = p.N;
@@ -343,8 +369,20 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
             bias_act(v, col0);
-            if (lane == 0) bulk_wait_read0();      // the previous slab has left the staging buffer
-            __syncwarp();
+            if (has_res) {
+              mbar_wait(rbar, rphase);
+              rphase ^= 1;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float x0, x1, x2, x3;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(srow + ((j ^ sw) << 4)));
+                v[4 * j] += x0; v[4 * j + 1] += x1; v[4 * j + 2] += x2; v[4 * j + 3] += x3;
+              }
+            } else {
+              if (lane == 0) bulk_wait_read0();      // the previous slab has left the staging buffer
+              __syncwarp();
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ sw) << 4)), "f"(v[4 * j]),
@@ -353,6 +391,7 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) { tma_store_2d(&tma_c, sbuf, col0, row0); bulk_commit(); }
+            if (has_res && ps + 1 < C::COLS_PER_WARP / 32 && col0 + 32 < N) issue_res(col0 + 32);
           }
         } else {
 #pragma unroll 1
@@ -368,8 +407,24 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
             for (int i = 0; i < 32; ++i) { v0[i] = __uint_as_float(r0[i]); v1[i] = __uint_as_float(r1[i]); }
             bias_act(v0, col0);
             if (col0 + 32 < N) bias_act(v1, col0 + 32);
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
+            if (has_res) {
+              mbar_wait(rbar, rphase);
+              rphase ^= 1;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                uint32_t w0, w1, w2, w3;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(srow + ((j ^ sw) << 4)));
+                float* vv = j < 4 ? &v0[8 * j] : &v1[8 * (j - 4)];
+                vv[0] += __uint_as_float(w0 << 16); vv[1] += __uint_as_float(w0 & 0xffff0000u);
+                vv[2] += __uint_as_float(w1 << 16); vv[3] += __uint_as_float(w1 & 0xffff0000u);
+                vv[4] += __uint_as_float(w2 << 16); vv[5] += __uint_as_float(w2 & 0xffff0000u);
+                vv[6] += __uint_as_float(w3 << 16); vv[7] += __uint_as_float(w3 & 0xffff0000u);
+              }
+            } else {
+              if (lane == 0) bulk_wait_read0();
+              __syncwarp();
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ sw) << 4)),
@@ -384,6 +439,7 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) { tma_store_2d(&tma_c, sbuf, col0, row0); bulk_commit(); }
+            if (has_res && ps + 1 < C::COLS_PER_WARP / 64 && col0 + 64 < N) issue_res(col0 + 64);
           }
         }
       } else {
@@ -562,18 +618,35 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
     RSP_TRY(make_tmap_bf16_2d(&ta, a.A, a.M, a.K, static_cast<uint64_t>(a.lda) * 2, BM, BK));
   }
   RSP_TRY(make_tmap_bf16_2d(&tb, a.W, a.N, a.K, static_cast<uint64_t>(a.ldw) * 2, BN, BK));
-  CUtensorMap tc = tb;
+  CUtensorMap tc = tb, tr = tb;
   p.tma_store = 0;
+  p.tma_res = 0;
   {
     const uint64_t esz = a.out_fp32 ? 4 : 2;
     static const bool no_tma_store = getenv("RSP_GEMM_NO_TMA_STORE") != nullptr;
-    if (!no_tma_store && EPI == EPI_STD && BN >= 64 && !a.residual && !a.row_map && a.out &&
+    bool res_ok = true;
+    if (a.residual) {
+      static const bool no_tma_res = getenv("RSP_GEMM_NO_TMA_RES") != nullptr;
+      res_ok = !no_tma_res && (a.res_fp32 != 0) == (a.out_fp32 != 0) &&
+               (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0 && (static_cast<uint64_t>(a.ldr) * esz) % 16 == 0 &&
+               (a.res_block_map ? (a.res_block_rows % 32 == 0 && a.M % 32 == 0) : (a.res_mod == 0 || a.res_mod % 32 == 0));
+    }
+    if (!no_tma_store && EPI == EPI_STD && BN >= 64 && res_ok && !a.row_map && a.out &&
         (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (static_cast<uint64_t>(a.ldo) * esz) % 16 == 0) {
       uint64_t dims[2] = {static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.M)};
       uint64_t strides[1] = {static_cast<uint64_t>(a.ldo) * esz};
       uint32_t box[2] = {a.out_fp32 ? 32u : 64u, 32u};
       RSP_TRY(make_tmap(&tc, a.out, 2, dims, strides, box, a.out_fp32));
       p.tma_store = 1;
+      if (a.residual) {
+        // rows the map may address: the whole destination (identity), one period (res_mod) or an open bound
+        // (block map: the host guarantees map[blk] * res_block_rows + 31 stays inside the residual tensor)
+        const uint64_t rrows = a.res_block_map ? (1ull << 31) : (a.res_mod > 0 ? a.res_mod : a.M);
+        uint64_t rdims[2] = {static_cast<uint64_t>(a.N), rrows};
+        uint64_t rstrides[1] = {static_cast<uint64_t>(a.ldr) * esz};
+        RSP_TRY(make_tmap(&tr, a.residual, 2, rdims, rstrides, box, a.out_fp32));
+        p.tma_res = 1;
+      }
     }
   }
   p.M = a.M; p.N = a.N; p.K = a.K;
@@ -593,7 +666,7 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
   }
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
-  kern<<<grid, THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tc, p);
+  kern<<<grid, THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tc, tr, p);
   RSP_CHECK_LAUNCH();
   return RSP_OK;
 }
