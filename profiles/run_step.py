@@ -46,6 +46,16 @@ def main():
         model.predict(x)
     e1.record()
     torch.cuda.synchronize()
+    # host-side issue time of one step (no synchronisation inside): tells whether the step is launch-bound
+    import time
+    cpu_ms = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.predict_raw(x)
+        cpu_ms.append((time.perf_counter() - t0) * 1e3)
+        torch.cuda.synchronize()
+    print(json.dumps(dict(host_issue_ms_per_step=cpu_ms)))
     print(json.dumps(dict(variant=a.variant, arch=a.arch, batch=a.batch, size=a.size, steps=a.steps,
                           ms_per_step=e0.elapsed_time(e1) / a.steps, launches_per_step=(_lib.launch_count - l0) // a.steps,
                           images_per_s=a.batch * a.steps / (e0.elapsed_time(e1) * 1e-3))))

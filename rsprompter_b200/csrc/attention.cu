@@ -262,39 +262,82 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
         for (int k = 0; k < RPT; ++k) rh[k] = __half2float(relh_s[(RPT * j + k) * 128 + r]);
       }
       const int key0 = j * 128;
-      // ---- pass 1: row max of the biased, log2-scaled scores
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (!GLOBAL && key0 + c * 32 >= T) break;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tS + lane_off + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float t;
-          if (GLOBAL) {
-            t = fmaf(__uint_as_float(v[i]), scale2, rh[(c * 32) / (GLOBAL ? GS : 32)]) + relw[(c * 32) % (GLOBAL ? GS : 32) + i];
-          } else {
-            const int key = key0 + c * 32 + i;   // j in {0,1}: resolved after unrolling below
-            const int kh = key / 14, kw = key - kh * 14;
-            t = (key < T) ? fmaf(__uint_as_float(v[i]), scale2, relh[kh < 14 ? kh : 0]) + relw[kw]
-                            : -INFINITY;
-          }
-          mx = fmaxf(mx, t);
+      // biased, log2-scaled score of element i of 32-column chunk c
+      auto score = [&](uint32_t raw, int c, int i) -> float {
+        if (GLOBAL) {
+          return fmaf(__uint_as_float(raw), scale2, rh[(c * 32) / (GLOBAL ? GS : 32)]) + relw[(c * 32) % (GLOBAL ? GS : 32) + i];
+        } else {
+          const int key = key0 + c * 32 + i;   // j in {0,1}: resolved after unrolling
+          const int kh = key / 14, kw = key - kh * 14;
+          return (key < T) ? fmaf(__uint_as_float(raw), scale2, relh[kh < 14 ? kh : 0]) + relw[kw] : -INFINITY;
         }
-      }
-      // ---- running max with lazy rescale (only when it grows by more than 2^8)
-      float m_new = m_run;
-      bool need = false;
-      if (j == 0) m_new = mx;
-      else if (mx > m_run + 8.0f) { need = true; m_new = mx; }
-      if (j > 0) {
+      };
+      // ---- first tile only: row max up front (later tiles reuse the running max as the exponent reference
+      // and fall back to a second pass only when a score exceeds it by more than 2^8)
+      if (j == 0) {
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // 4 chains instead of one 128-long one
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (!GLOBAL && key0 + c * 32 >= T) break;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tS + lane_off + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], score(v[i], c, i));
+        }
+        m_run = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      } else {
         mbar_wait(bar(B_PV), (j - 1) & 1);   // O and the P buffer are free again
         tc_fence_after();
+      }
+      // ---- P = exp2(t - m_run), row sum, tile max; bf16 P into swizzled smem
+      float tile_max = -INFINITY, tile_sum = 0.f;
+      auto exp_pass = [&]() {
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        float ls4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+          if (!GLOBAL && key0 + c * 32 >= T) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          } else {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tS + lane_off + c * 32, v);
+            tmem_ld_wait();
+            float e[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float t = score(v[i], c, i);
+              mx4[i & 3] = fmaxf(mx4[i & 3], t);
+              e[i] = fast_exp2(t - m_run);
+              ls4[i & 3] += e[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+          }
+          // 32 keys = 64 B = 16-byte chunks (c&1)*4 .. +3 of atom (c>>1)
+          const uint32_t base = p_row + (c >> 1) * 16384;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t chunk = static_cast<uint32_t>(((c & 1) * 4 + q) ^ sw);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + chunk * 16),
+                         "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                         : "memory");
+          }
+        }
+        tile_max = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        tile_sum = (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
+      };
+      exp_pass();
+      if (j > 0) {
+        const bool need = tile_max > m_run + 8.0f;
         if (__any_sync(0xffffffffu, need)) {
-          const float alpha = need ? fast_exp2(m_run - m_new) : 1.0f;
+          // rare: the reference moves up, O / l are rescaled and this tile's exponentials are redone
+          const float m_new = need ? tile_max : m_run;
+          const float alpha = fast_exp2(m_run - m_new);
           l_run *= alpha;
+          m_run = m_new;
 #pragma unroll
           for (int c = 0; c < HD / 16; ++c) {
             uint32_t o[16];
@@ -305,48 +348,10 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
             tmem_st_32x32b_x16(tO + lane_off + c * 16, o);
           }
           tmem_st_wait();
+          exp_pass();
         }
       }
-      m_run = m_new;
-      // ---- pass 2: P = exp2(t - m), row sum, bf16 P into swizzled smem
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-        if (!GLOBAL && key0 + c * 32 >= T) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = 0u;
-        } else {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tS + lane_off + c * 32, v);
-          tmem_ld_wait();
-          float e[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float t;
-            if (GLOBAL) {
-              t = fmaf(__uint_as_float(v[i]), scale2, rh[(c * 32) / (GLOBAL ? GS : 32)]) + relw[(c * 32) % (GLOBAL ? GS : 32) + i];
-            } else {
-              const int key = key0 + c * 32 + i;
-              const int kh = key / 14, kw = key - kh * 14;
-              t = (key < T) ? fmaf(__uint_as_float(v[i]), scale2, relh[kh < 14 ? kh : 0]) + relw[kw]
-                              : -INFINITY;
-            }
-            e[i] = fast_exp2(t - m_run);
-            l_run += e[i];
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
-        }
-        // 32 keys = 64 B = 16-byte chunks (c&1)*4 .. +3 of atom (c>>1)
-        const uint32_t base = p_row + (c >> 1) * 16384;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t chunk = static_cast<uint32_t>(((c & 1) * 4 + q) ^ sw);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + chunk * 16),
-                       "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
-                       : "memory");
-        }
-      }
+      l_run += tile_sum;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar(B_PF));
