@@ -4,24 +4,30 @@
 // (:803-831), get_rel_pos / get_decomposed_rel_pos (:729-801); mmpretrain vit_sam.py
 // Attention.forward (:202-221), add_decomposed_rel_pos (:117-157).
 //
-// One CTA = 128 query rows of one (sequence, head); 192 threads:
-//   warps 0-3  softmax: thread r owns query row r (no cross-thread reductions); reads S
-//              from TMEM twice (max pass, exp pass), fp32 statistics, writes P (bf16) into
-//              128B-swizzled smem, rescales O in TMEM only when the running max grows by
-//              more than 2^8
-//   warp 4     TMA producer (Q once; K_j / V_j tiles; the two rel-pos tables) + TMEM alloc
-//   warp 5     tcgen05.mma issuer: S_j = Q K_j^T (128x128x hd), O += P_j V_j (128 x hd x128),
+// One CTA = 128 query rows of one (sequence, head); 320 threads:
+//   warps 0-7  softmax: thread (r, h) owns query row r and the 32-key chunks c with c % 2 == h of every
+//              128-key tile (warps w and w + 4 share TMEM lane quarter w).  The two key halves of a row are
+//              two independent online-softmax streams (own running max m_h, own sum l_h, own accumulator O_h
+//              in TMEM, the MMA warp routes each 16-key step of P V to the accumulator of the half that owns
+//              it), merged once at the end like a split-K flash decode:
+//                  O = (O_0 2^(m_0 - m) + O_1 2^(m_1 - m)) / (l_0 2^(m_0 - m) + l_1 2^(m_1 - m)).
+//              Nothing is exchanged inside the key loop, each thread keeps only 32 rel_w values in registers,
+//              and 16 softmax warps per SM (2 CTAs) hide the TMEM / MUFU latencies that 8 could not.
+//              Exponentials use the running max as reference and are redone only when a score exceeds it by
+//              more than 2^8 (O_h rescaled then); fp32 statistics; P (bf16) goes to 128B-swizzled smem.
+//   warp 8     TMA producer (Q once; K_j / V_j tiles; the two rel-pos tables) + TMEM alloc
+//   warp 9     tcgen05.mma issuer: S_j = Q K_j^T (128x128x hd), O_h += P_j V_j over the key steps of half h,
 //              V consumed straight from the qkv matrix as an MN-major operand
 // The decomposed relative-position bias is never materialised as a T x T tensor: a
 // prologue MMA computes Q (unscaled) x table^T for both tables (the reference's two
-// einsums), each thread gathers the <= 2S values its row needs, and the bias is added
+// einsums), each thread gathers the values its row / key half needs, and the bias is added
 // inside the softmax FMA.  Scores stay fp32 until the exp (reference: softmax in fp32).
 #include "attention.h"
 #include "sm100.cuh"
 
 namespace rsp {
 
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -37,7 +43,8 @@ struct AttCfg {
   static constexpr int P_BYTES = 32768;               // 128 x 128 bf16
   static constexpr int RELH_BYTES = 64 * 128 * 2;     // global: [kh][row] fp16
   static constexpr int SMEM_BYTES = 3 * TILE_BYTES + P_BYTES + RELH_BYTES + 1024;
-  static constexpr int TMEM_COLS = 256;               // S: [0,128)  O: [128, 128 + HD)
+  static constexpr int O_STRIDE = (HD <= 64) ? 64 : 96;   // column distance between the two accumulators
+  static constexpr int TMEM_COLS = (HD <= 64) ? 256 : 512;   // S: [0,128)  O_0: [128, ..)  O_1: [128 + O_STRIDE, ..)
 };
 
 struct AttDev {
@@ -94,18 +101,20 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_relh);
     tma_prefetch_desc(&tm_relw);
-    for (int i = 0; i < B_COUNT; ++i) mbar_init(bar(i), (i == B_RELC || i == B_PF) ? 128 : 1);
+    for (int i = 0; i < B_COUNT; ++i) mbar_init(bar(i), (i == B_RELC || i == B_PF) ? 256 : 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), Cfg::TMEM_COLS);
+  if (warp == 8) tmem_alloc(smem_u32(&tmem_base_s), Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t tS = tmem_base;
-  const uint32_t tO = tmem_base + 128;
+  const uint32_t tO = tmem_base + 128;                       // accumulator of key half 0 (and rel_w prologue)
+  const uint32_t tO1 = tmem_base + 128 + Cfg::O_STRIDE;      // accumulator of key half 1
+  __shared__ float2 xchg[2][128];                            // (m, l) of each half, exchanged once at the end
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
     mbar_expect_tx(bar(B_Q), Cfg::TILE_BYTES + 2 * NA * NREL * 128);
 #pragma unroll
@@ -127,7 +136,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
       for (int a = 0; a < NA; ++a)
         tma_load_2d(sV + a * 16384, &tm_qkv, bar(B_VF), colv + a * 64, row0 + j * 128);
     }
-  } else if (warp == 5 && lane == 0) {
+  } else if (warp == 9 && lane == 0) {
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t idesc_rel = make_idesc_bf16(128, NREL, 0, 0);
@@ -164,74 +173,86 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
       mbar_wait(bar(B_VF), par);
       tc_fence_after();
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
+      for (int ks = 0; ks < 8; ++ks) {   // 16 keys per step; 32-key chunk ks >> 1 belongs to half (ks >> 1) & 1
         const uint64_t adesc = make_sdesc(sP + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024);
         const uint64_t bdesc = make_sdesc(sV + ks * 2048, 16384, 1024);
-        umma_ss(tO, adesc, bdesc, idesc_pv, (j | ks) != 0);
+        const int hsel = (ks >> 1) & 1;
+        umma_ss(hsel ? tO1 : tO, adesc, bdesc, idesc_pv, (j | (ks & ~2)) != 0);
       }
       umma_commit(bar(B_PV));
       umma_commit(bar(B_VE));
     }
-  } else if (warp < 4) {
+  } else if (warp < 8) {
     // ------------------------------------------------------------ softmax / correction / output
-    const int r = warp * 32 + lane;          // query row inside the tile == TMEM lane
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const int q4 = warp & 3, hf = warp >> 2;
+    const int r = q4 * 32 + lane;            // query row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(q4 * 32) << 16;
     const int tq = q0 + r;                    // query index inside the sequence
     const int qh = tq / p.S;
     const int qw = tq - qh * p.S;
-    constexpr int NW = GLOBAL ? GS : 14;      // rel_w values kept in registers
+    constexpr int NW = GLOBAL ? 32 : 14;      // rel_w values kept in registers (this thread's key columns)
     constexpr int NH = GLOBAL ? 1 : 14;       // rel_h in registers (window) or smem (global)
     float relw[NW];
     float relh[NH];
     (void)relh;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q4) : "memory"); };
 
-    // ---- prologue: gather this row's rel-pos terms (pre-multiplied by log2 e)
+    // ---- prologue: gather this row's rel-pos terms (pre-multiplied by log2 e); half 0 takes rel_h, half 1 rel_w
     mbar_wait(bar(B_REL), 0);
     tc_fence_after();
     float* scratch = reinterpret_cast<float*>(gP);  // aliases the P buffer (unused yet)
     __half* relh_s = reinterpret_cast<__half*>(gRH);
     if (GLOBAL) {
       // table index t <-> key coordinate k: t = q - k + (GS - 1)
+      if (hf == 0) {
 #pragma unroll 1
-      for (int c = 0; c < NREL / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tS + lane_off + c * 32, v);
-        tmem_ld_wait();
+        for (int c = 0; c < NREL / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tS + lane_off + c * 32, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kh = qh + (GS - 1) - (c * 32 + i);
-          if (kh >= 0 && kh < GS) relh_s[kh * 128 + r] = __float2half_rn(__uint_as_float(v[i]) * LOG2E);
+          for (int i = 0; i < 32; ++i) {
+            const int kh = qh + (GS - 1) - (c * 32 + i);
+            if (kh >= 0 && kh < GS) relh_s[kh * 128 + r] = __float2half_rn(__uint_as_float(v[i]) * LOG2E);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < NREL / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tO + lane_off + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int kw = qw + (GS - 1) - (c * 32 + i);
+            if (kw >= 0 && kw < GS) scratch[kw * 128 + r] = __uint_as_float(v[i]) * LOG2E;
+          }
         }
       }
-#pragma unroll 1
-      for (int c = 0; c < NREL / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tO + lane_off + c * 32, v);
-        tmem_ld_wait();
+      pair_sync();
+      const int kw0 = (GS == 64) ? 32 * hf : 0;   // key column of this thread's chunks
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kw = qw + (GS - 1) - (c * 32 + i);
-          if (kw >= 0 && kw < GS) scratch[kw * 128 + r] = __uint_as_float(v[i]) * LOG2E;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < NW; ++i) relw[i] = scratch[i * 128 + r];
+      for (int i = 0; i < NW; ++i) relw[i] = scratch[(kw0 + i) * 128 + r];
     } else {
       uint32_t v[32];
-      tmem_ld_32x32b_x32(tS + lane_off, v);
-      tmem_ld_wait();
+      if (hf == 0) {
+        tmem_ld_32x32b_x32(tS + lane_off, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 27; ++i) {
-        const int kh = qh + 13 - i;
-        if (kh >= 0 && kh < 14) scratch[kh * 128 + r] = __uint_as_float(v[i]) * LOG2E;
-      }
-      tmem_ld_32x32b_x32(tO + lane_off, v);
-      tmem_ld_wait();
+        for (int i = 0; i < 27; ++i) {
+          const int kh = qh + 13 - i;
+          if (kh >= 0 && kh < 14) scratch[kh * 128 + r] = __uint_as_float(v[i]) * LOG2E;
+        }
+      } else {
+        tmem_ld_32x32b_x32(tO + lane_off, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 27; ++i) {
-        const int kw = qw + 13 - i;
-        if (kw >= 0 && kw < 14) scratch[(14 + kw) * 128 + r] = __uint_as_float(v[i]) * LOG2E;
+        for (int i = 0; i < 27; ++i) {
+          const int kw = qw + 13 - i;
+          if (kw >= 0 && kw < 14) scratch[(14 + kw) * 128 + r] = __uint_as_float(v[i]) * LOG2E;
+        }
       }
+      pair_sync();
       if (qh < 14) {
 #pragma unroll
         for (int i = 0; i < 14; ++i) { relh[i] = scratch[i * 128 + r]; relw[i] = scratch[(14 + i) * 128 + r]; }
@@ -249,6 +270,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
     const int n_kt = GLOBAL ? p.n_kt : 2;
     const uint32_t p_row = sP + r * 128;
     const int sw = r & 7;
+    const uint32_t tOme = hf ? tO1 : tO;
 
 #pragma unroll(GLOBAL ? 1 : 2)
     for (int j = 0; j < n_kt; ++j) {
@@ -262,32 +284,36 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
         for (int k = 0; k < RPT; ++k) rh[k] = __half2float(relh_s[(RPT * j + k) * 128 + r]);
       }
       const int key0 = j * 128;
-      // biased, log2-scaled score of element i of 32-column chunk c
-      auto score = [&](uint32_t raw, int c, int i) -> float {
+      // biased, log2-scaled score of element i (0..15) of 16-column piece h16 of chunk c
+      auto score = [&](uint32_t raw, int c, int h16, int i) -> float {
         if (GLOBAL) {
-          return fmaf(__uint_as_float(raw), scale2, rh[(c * 32) / (GLOBAL ? GS : 32)]) + relw[(c * 32) % (GLOBAL ? GS : 32) + i];
+          return fmaf(__uint_as_float(raw), scale2, rh[(c * 32) / (GLOBAL ? GS : 32)]) + relw[h16 * 16 + i];
         } else {
-          const int key = key0 + c * 32 + i;   // j in {0,1}: resolved after unrolling
+          const int key = key0 + c * 32 + h16 * 16 + i;   // j in {0,1}: resolved after unrolling
           const int kh = key / 14, kw = key - kh * 14;
           return (key < T) ? fmaf(__uint_as_float(raw), scale2, relh[kh < 14 ? kh : 0]) + relw[kw] : -INFINITY;
         }
       };
-      // ---- first tile only: row max up front (later tiles reuse the running max as the exponent reference
-      // and fall back to a second pass only when a score exceeds it by more than 2^8)
+      // ---- first tile only: max of this half up front (later tiles reuse the running max as the exponent
+      // reference and fall back to a second pass only when a score exceeds it by more than 2^8)
       if (j == 0) {
-        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // 4 chains instead of one 128-long one
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = hf + 2 * cc;
           if (!GLOBAL && key0 + c * 32 >= T) break;
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tS + lane_off + c * 32, v);
-          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], score(v[i], c, i));
+          for (int h16 = 0; h16 < 2; ++h16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(tS + lane_off + c * 32 + h16 * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], score(v[i], c, h16, i));
+          }
         }
         m_run = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       } else {
-        mbar_wait(bar(B_PV), (j - 1) & 1);   // O and the P buffer are free again
+        mbar_wait(bar(B_PV), (j - 1) & 1);   // the accumulators and the P buffer are free again
         tc_fence_after();
       }
       // ---- P = exp2(t - m_run), row sum, tile max; bf16 P into swizzled smem
@@ -296,34 +322,35 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         float ls4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
-          if (!GLOBAL && key0 + c * 32 >= T) {
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = hf + 2 * cc;
+          const uint32_t base = p_row + (c >> 1) * 16384;   // 32 keys = 16-byte chunks (c&1)*4 .. +3 of atom (c>>1)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = 0u;
-          } else {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tS + lane_off + c * 32, v);
-            tmem_ld_wait();
-            float e[32];
+          for (int h16 = 0; h16 < 2; ++h16) {
+            uint32_t pk[8];
+            if (!GLOBAL && key0 + c * 32 + h16 * 16 >= T) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float t = score(v[i], c, i);
-              mx4[i & 3] = fmaxf(mx4[i & 3], t);
-              e[i] = fast_exp2(t - m_run);
-              ls4[i & 3] += e[i];
+              for (int i = 0; i < 8; ++i) pk[i] = 0u;
+            } else {
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(tS + lane_off + c * 32 + h16 * 16, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float t0 = score(v[2 * i], c, h16, 2 * i), t1 = score(v[2 * i + 1], c, h16, 2 * i + 1);
+                mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(t0, t1));
+                const float e0 = fast_exp2(t0 - m_run), e1 = fast_exp2(t1 - m_run);
+                ls4[i & 3] += e0 + e1;
+                pk[i] = pack_bf16x2(e0, e1);
+              }
             }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
-          }
-          // 32 keys = 64 B = 16-byte chunks (c&1)*4 .. +3 of atom (c>>1)
-          const uint32_t base = p_row + (c >> 1) * 16384;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t chunk = static_cast<uint32_t>(((c & 1) * 4 + q) ^ sw);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + chunk * 16),
-                         "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
-                         : "memory");
+            for (int q = 0; q < 2; ++q) {
+              const uint32_t chunk = static_cast<uint32_t>(((c & 1) * 4 + h16 * 2 + q) ^ sw);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + chunk * 16),
+                           "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                           : "memory");
+            }
           }
         }
         tile_max = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
@@ -333,7 +360,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
       if (j > 0) {
         const bool need = tile_max > m_run + 8.0f;
         if (__any_sync(0xffffffffu, need)) {
-          // rare: the reference moves up, O / l are rescaled and this tile's exponentials are redone
+          // rare: the reference moves up, O_h / l_h are rescaled and this tile's exponentials are redone
           const float m_new = need ? tile_max : m_run;
           const float alpha = fast_exp2(m_run - m_new);
           l_run *= alpha;
@@ -341,11 +368,11 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
 #pragma unroll
           for (int c = 0; c < HD / 16; ++c) {
             uint32_t o[16];
-            tmem_ld_32x32b_x16(tO + lane_off + c * 16, o);
+            tmem_ld_32x32b_x16(tOme + lane_off + c * 16, o);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32b_x16(tO + lane_off + c * 16, o);
+            tmem_st_32x32b_x16(tOme + lane_off + c * 16, o);
           }
           tmem_st_wait();
           exp_pass();
@@ -357,25 +384,34 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
       mbar_arrive(bar(B_PF));
     }
 
-    // ---- epilogue: O / l -> out[token, head*HD .. ]
+    // ---- epilogue: merge the two key halves, O / l -> out[token, head*HD .. ]
     mbar_wait(bar(B_PV), (n_kt - 1) & 1);
     tc_fence_after();
-    const float inv = 1.0f / l_run;
+    xchg[hf][r] = make_float2(m_run, l_run);
+    pair_sync();
+    const float2 other = xchg[hf ^ 1][r];
+    const float m_all = fmaxf(m_run, other.x);
+    const float a_me = fast_exp2(m_run - m_all), a_ot = fast_exp2(other.x - m_all);
+    const float inv = 1.0f / (l_run * a_me + other.y * a_ot);
+    const float w_me = a_me * inv, w_ot = a_ot * inv;
+    const uint32_t tOot = hf ? tO : tO1;
     __nv_bfloat16* orow = p.out + static_cast<size_t>(row0 + tq) * p.D + colq;
-#pragma unroll
-    for (int c = 0; c < HD / 16; ++c) {
-      uint32_t o[16];
-      tmem_ld_32x32b_x16(tO + lane_off + c * 16, o);
+    constexpr int NC0 = (HD / 16 + 1) / 2;     // 16-column output chunks written by half 0
+    const int c_lo = hf ? NC0 : 0, c_hi = hf ? HD / 16 : NC0;
+#pragma unroll 1
+    for (int c = c_lo; c < c_hi; ++c) {
+      uint32_t o[16], o2[16];
+      tmem_ld_32x32b_x16(tOme + lane_off + c * 16, o);
+      tmem_ld_32x32b_x16(tOot + lane_off + c * 16, o2);
       tmem_ld_wait();
       if (tq < T) {
-        uint4 w0 = make_uint4(pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv),
-                              pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv),
-                              pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv),
-                              pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv));
-        uint4 w1 = make_uint4(pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv),
-                              pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv),
-                              pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv),
-                              pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv));
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(o[i]) * w_me + __uint_as_float(o2[i]) * w_ot;
+        uint4 w0 = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                              pack_bf16x2(f[6], f[7]));
+        uint4 w1 = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                              pack_bf16x2(f[14], f[15]));
         reinterpret_cast<uint4*>(orow + c * 16)[0] = w0;
         reinterpret_cast<uint4*>(orow + c * 16)[1] = w1;
       }
@@ -384,7 +420,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
