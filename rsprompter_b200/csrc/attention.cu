@@ -39,12 +39,14 @@ __device__ __forceinline__ float fast_exp2(float x) {
 template <int HD>
 struct AttCfg {
   static constexpr int NA = (HD + 63) / 64;           // 64-wide swizzle atoms per head
-  static constexpr int TILE_BYTES = NA * 16384;       // 128 rows x NA x 128 B
-  static constexpr int P_BYTES = 32768;               // 128 x 128 bf16
+  static constexpr int Q_BYTES = NA * 16384;          // 128 rows x NA x 128 B
+  static constexpr int KV_BYTES = NA * 8192;          // one 64-key stage of K or V
+  static constexpr int P_BYTES = 16384;               // 128 x 64 bf16 (one swizzle atom), two of them
   static constexpr int RELH_BYTES = 64 * 128 * 2;     // global: [kh][row] fp16
-  static constexpr int SMEM_BYTES = 3 * TILE_BYTES + P_BYTES + RELH_BYTES + 1024;
+  static constexpr int SMEM_BYTES = Q_BYTES + 4 * KV_BYTES + 2 * P_BYTES + RELH_BYTES + 1024;
   static constexpr int O_STRIDE = (HD <= 64) ? 64 : 96;   // column distance between the two accumulators
-  static constexpr int TMEM_COLS = (HD <= 64) ? 256 : 512;   // S: [0,128)  O_0: [128, ..)  O_1: [128 + O_STRIDE, ..)
+  // S_0: [0,64)  S_1: [64,128)  O_0: [128, ..)  O_1: [128 + O_STRIDE, ..)
+  static constexpr int TMEM_COLS = (HD <= 64) ? 256 : 512;
 };
 
 struct AttDev {
@@ -53,17 +55,18 @@ struct AttDev {
   int S;               // sqrt(T)
   int H;
   int D;
-  int n_qt;            // q tiles per sequence
-  int n_kt;            // key tiles per sequence
+  int n_qt;            // 128-query tiles per sequence
+  int n_kt;            // 64-key tiles per sequence
   float scale2;        // hd^-0.5 * log2(e)
 };
 
-// bar indices
-enum { B_Q = 0, B_REL, B_RELC, B_KF, B_KE, B_VF, B_VE, B_SF, B_PF, B_PV, B_COUNT };
+// barriers: two-slot rings indexed by tile parity; phase of slot use n is (n >> 1) & 1
+enum { B_Q = 0, B_REL, B_RELC, B_KF, B_KE = B_KF + 2, B_VF = B_KE + 2, B_VE = B_VF + 2, B_SF = B_VE + 2,
+       B_PF = B_SF + 2, B_PV = B_PF + 2, B_COUNT = B_PV + 2 };
 
 template <int HD, int GS>   // GS = 0: 14x14 windows; GS = 64 / 32: global attention over a GS x GS grid
 __global__ void __launch_bounds__(ATT_THREADS, (HD <= 64) ? 2 : 1)
-vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
+vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_kv,
                      const __grid_constant__ CUtensorMap tm_relh,
                      const __grid_constant__ CUtensorMap tm_relw, const AttDev p) {
   using Cfg = AttCfg<HD>;
@@ -73,12 +76,13 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[B_COUNT];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float2 xchg[2][128];            // (m, l) of each key half, exchanged once at the end
 
   const uint32_t sQ = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sK = sQ + Cfg::TILE_BYTES;
-  const uint32_t sV = sK + Cfg::TILE_BYTES;
-  const uint32_t sP = sV + Cfg::TILE_BYTES;
-  const uint32_t sRH = sP + Cfg::P_BYTES;
+  const uint32_t sK = sQ + Cfg::Q_BYTES;                 // 2 stages (prologue: the rel_h table)
+  const uint32_t sV = sK + 2 * Cfg::KV_BYTES;            // 2 stages (prologue: the rel_w table)
+  const uint32_t sP = sV + 2 * Cfg::KV_BYTES;            // 2 buffers
+  const uint32_t sRH = sP + 2 * Cfg::P_BYTES;
   uint8_t* gP = smem_raw + (sP - smem_u32(smem_raw));
   uint8_t* gRH = smem_raw + (sRH - smem_u32(smem_raw));
 
@@ -99,9 +103,11 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_kv);
     tma_prefetch_desc(&tm_relh);
     tma_prefetch_desc(&tm_relw);
-    for (int i = 0; i < B_COUNT; ++i) mbar_init(bar(i), (i == B_RELC || i == B_PF) ? 256 : 1);
+    for (int i = 0; i < B_COUNT; ++i)
+      mbar_init(bar(i), (i == B_RELC || i == B_PF || i == B_PF + 1) ? 256 : 1);
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc(smem_u32(&tmem_base_s), Cfg::TMEM_COLS);
@@ -109,36 +115,37 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t tS = tmem_base;
+  const uint32_t tS = tmem_base;                             // S_0 | S_1 (and the rel_h prologue product)
   const uint32_t tO = tmem_base + 128;                       // accumulator of key half 0 (and rel_w prologue)
   const uint32_t tO1 = tmem_base + 128 + Cfg::O_STRIDE;      // accumulator of key half 1
-  __shared__ float2 xchg[2][128];                            // (m, l) of each half, exchanged once at the end
+  const int n_kt = GLOBAL ? p.n_kt : 4;
 
   if (warp == 8 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
-    mbar_expect_tx(bar(B_Q), Cfg::TILE_BYTES + 2 * NA * NREL * 128);
+    mbar_expect_tx(bar(B_Q), Cfg::Q_BYTES + 2 * NA * NREL * 128);
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
       tma_load_2d(sQ + a * 16384, &tm_qkv, bar(B_Q), colq + a * 64, row0 + q0);
       tma_load_2d(sK + a * 16384, &tm_relh, bar(B_Q), a * 64, 0);
       tma_load_2d(sV + a * 16384, &tm_relw, bar(B_Q), a * 64, 0);
     }
-    for (int j = 0; j < p.n_kt; ++j) {
-      const uint32_t par = j & 1;
-      mbar_wait(bar(B_KE), par);
-      mbar_expect_tx(bar(B_KF), Cfg::TILE_BYTES);
+    for (int j = 0; j < n_kt; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(bar(B_KE + s), ph);           // phase 0 of the "empty" slots completes with the prologue MMAs
+      mbar_expect_tx(bar(B_KF + s), Cfg::KV_BYTES);
 #pragma unroll
       for (int a = 0; a < NA; ++a)
-        tma_load_2d(sK + a * 16384, &tm_qkv, bar(B_KF), colk + a * 64, row0 + j * 128);
-      mbar_wait(bar(B_VE), par);
-      mbar_expect_tx(bar(B_VF), Cfg::TILE_BYTES);
+        tma_load_2d(sK + s * Cfg::KV_BYTES + a * 8192, &tm_kv, bar(B_KF + s), colk + a * 64, row0 + j * 64);
+      mbar_wait(bar(B_VE + s), ph);
+      mbar_expect_tx(bar(B_VF + s), Cfg::KV_BYTES);
 #pragma unroll
       for (int a = 0; a < NA; ++a)
-        tma_load_2d(sV + a * 16384, &tm_qkv, bar(B_VF), colv + a * 64, row0 + j * 128);
+        tma_load_2d(sV + s * Cfg::KV_BYTES + a * 8192, &tm_kv, bar(B_VF + s), colv + a * 64, row0 + j * 64);
     }
   } else if (warp == 9 && lane == 0) {
     // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
     constexpr uint32_t idesc_rel = make_idesc_bf16(128, NREL, 0, 0);
     constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, 0, 1);
     mbar_wait(bar(B_Q), 0);
@@ -155,32 +162,42 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
     }
     umma_commit(bar(B_REL));
     umma_commit(bar(B_KE));
+    umma_commit(bar(B_KE + 1));
     umma_commit(bar(B_VE));
+    umma_commit(bar(B_VE + 1));
     mbar_wait(bar(B_RELC), 0);
     tc_fence_after();
-    for (int j = 0; j < p.n_kt; ++j) {
-      const uint32_t par = j & 1;
-      mbar_wait(bar(B_KF), par);
+    auto issue_qk = [&](int t) {   // S_{t&1} = Q K_t^T
+      const int s = t & 1;
+      mbar_wait(bar(B_KF + s), (t >> 1) & 1);
+      if (t >= 2) mbar_wait(bar(B_PV + s), ((t - 2) >> 1) & 1);   // P V of tile t-2 has consumed S_s / P_s
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < HD / 16; ++ks) {
-        const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
-        umma_ss(tS, make_sdesc(sQ + off, 0, 1024), make_sdesc(sK + off, 0, 1024), idesc_s, ks != 0);
+        const uint32_t qoff = (ks >> 2) * 16384 + (ks & 3) * 32;
+        const uint32_t koff = s * Cfg::KV_BYTES + (ks >> 2) * 8192 + (ks & 3) * 32;
+        umma_ss(tS + s * 64, make_sdesc(sQ + qoff, 0, 1024), make_sdesc(sK + koff, 0, 1024), idesc_s, ks != 0);
       }
-      umma_commit(bar(B_SF));
-      umma_commit(bar(B_KE));
-      mbar_wait(bar(B_PF), par);
-      mbar_wait(bar(B_VF), par);
+      umma_commit(bar(B_SF + s));
+      umma_commit(bar(B_KE + s));
+    };
+    issue_qk(0);
+    for (int j = 0; j < n_kt; ++j) {
+      if (j + 1 < n_kt) issue_qk(j + 1);      // runs while the softmax warps work on tile j
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(bar(B_PF + s), ph);
+      mbar_wait(bar(B_VF + s), ph);
       tc_fence_after();
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {   // 16 keys per step; 32-key chunk ks >> 1 belongs to half (ks >> 1) & 1
-        const uint64_t adesc = make_sdesc(sP + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024);
-        const uint64_t bdesc = make_sdesc(sV + ks * 2048, 16384, 1024);
-        const int hsel = (ks >> 1) & 1;
-        umma_ss(hsel ? tO1 : tO, adesc, bdesc, idesc_pv, (j | (ks & ~2)) != 0);
+      for (int ks = 0; ks < 4; ++ks) {   // 16 keys per step; 32-key chunk ks >> 1 belongs to key half ks >> 1
+        // A = P straight from TMEM: 8 packed bf16x2 columns per step, written in place over the chunk's scores
+        const uint32_t a_tmem = tS + s * 64 + (ks >> 1) * 32 + (ks & 1) * 8;
+        const uint64_t bdesc = make_sdesc(sV + s * Cfg::KV_BYTES + ks * 2048, 8192, 1024);
+        umma_ts((ks >> 1) ? tO1 : tO, a_tmem, bdesc, idesc_pv, (j | (ks & 1)) != 0);
       }
-      umma_commit(bar(B_PV));
-      umma_commit(bar(B_VE));
+      umma_commit(bar(B_PV + s));
+      umma_commit(bar(B_VE + s));
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------ softmax / correction / output
@@ -200,7 +217,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
     // ---- prologue: gather this row's rel-pos terms (pre-multiplied by log2 e); half 0 takes rel_h, half 1 rel_w
     mbar_wait(bar(B_REL), 0);
     tc_fence_after();
-    float* scratch = reinterpret_cast<float*>(gP);  // aliases the P buffer (unused yet)
+    float* scratch = reinterpret_cast<float*>(gP);  // aliases the P buffers (unused yet): [kw][128] fp32, 32 KB
     __half* relh_s = reinterpret_cast<__half*>(gRH);
     if (GLOBAL) {
       // table index t <-> key coordinate k: t = q - k + (GS - 1)
@@ -230,7 +247,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
         }
       }
       pair_sync();
-      const int kw0 = (GS == 64) ? 32 * hf : 0;   // key column of this thread's chunks
+      const int kw0 = (GS == 64) ? 32 * hf : 0;   // key column of this thread's 32-key chunk
 #pragma unroll
       for (int i = 0; i < NW; ++i) relw[i] = scratch[(kw0 + i) * 128 + r];
     } else {
@@ -267,104 +284,51 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
     float m_run = -INFINITY, l_run = 0.f;
     const float scale2 = p.scale2;
     const int T = GLOBAL ? p.T : 196;          // window: compile-time so key -> (kh, kw) folds
-    const int n_kt = GLOBAL ? p.n_kt : 2;
-    const uint32_t p_row = sP + r * 128;
-    const int sw = r & 7;
     const uint32_t tOme = hf ? tO1 : tO;
+    // largest bias this thread can add to a score (bounds the tile maximum from the raw accumulator maximum)
+    float bias_max = -INFINITY;
+    if (GLOBAL) {
+#pragma unroll
+      for (int i = 0; i < NW; ++i) bias_max = fmaxf(bias_max, relw[i]);
+    } else {
+      float a = -INFINITY, b = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 14; ++i) { a = fmaxf(a, relh[i]); b = fmaxf(b, relw[i]); }
+      bias_max = a + b;
+    }
 
-#pragma unroll(GLOBAL ? 1 : 2)
+#pragma unroll(GLOBAL ? 1 : 4)
     for (int j = 0; j < n_kt; ++j) {
-      const uint32_t par = j & 1;
-      mbar_wait(bar(B_SF), par);
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(bar(B_SF + s), ph);
       tc_fence_after();
-      constexpr int RPT = GLOBAL ? 128 / GS : 1;   // image rows of keys per 128-key tile
-      float rh[RPT];
-      if (GLOBAL) {
+      float rh = 0.f;
+      if (GLOBAL) rh = __half2float(relh_s[((GS == 64 ? j : 2 * j + hf)) * 128 + r]);   // image row of my chunk
+      const int key0 = j * 64 + hf * 32;                 // first key of my 32-key chunk
+      const uint32_t t_chunk = tS + lane_off + s * 64 + hf * 32;
+      // ---- upper bound of this chunk's scores from the raw accumulator maximum (scale2 > 0): the exponent
+      // reference only has to be an upper bound that is not absurdly loose, so no second look at the scores is
+      // ever needed and P can overwrite them in place
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int k = 0; k < RPT; ++k) rh[k] = __half2float(relh_s[(RPT * j + k) * 128 + r]);
+      for (int h16 = 0; h16 < 2; ++h16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_chunk + h16 * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
       }
-      const int key0 = j * 128;
-      // biased, log2-scaled score of element i (0..15) of 16-column piece h16 of chunk c
-      auto score = [&](uint32_t raw, int c, int h16, int i) -> float {
-        if (GLOBAL) {
-          return fmaf(__uint_as_float(raw), scale2, rh[(c * 32) / (GLOBAL ? GS : 32)]) + relw[h16 * 16 + i];
-        } else {
-          const int key = key0 + c * 32 + h16 * 16 + i;   // j in {0,1}: resolved after unrolling
-          const int kh = key / 14, kw = key - kh * 14;
-          return (key < T) ? fmaf(__uint_as_float(raw), scale2, relh[kh < 14 ? kh : 0]) + relw[kw] : -INFINITY;
-        }
-      };
-      // ---- first tile only: max of this half up front (later tiles reuse the running max as the exponent
-      // reference and fall back to a second pass only when a score exceeds it by more than 2^8)
-      if (j == 0) {
-        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = hf + 2 * cc;
-          if (!GLOBAL && key0 + c * 32 >= T) break;
-#pragma unroll
-          for (int h16 = 0; h16 < 2; ++h16) {
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(tS + lane_off + c * 32 + h16 * 16, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], score(v[i], c, h16, i));
-          }
-        }
-        m_run = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      } else {
-        mbar_wait(bar(B_PV), (j - 1) & 1);   // the accumulators and the P buffer are free again
-        tc_fence_after();
-      }
-      // ---- P = exp2(t - m_run), row sum, tile max; bf16 P into swizzled smem
-      float tile_max = -INFINITY, tile_sum = 0.f;
-      auto exp_pass = [&]() {
-        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        float ls4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = hf + 2 * cc;
-          const uint32_t base = p_row + (c >> 1) * 16384;   // 32 keys = 16-byte chunks (c&1)*4 .. +3 of atom (c>>1)
-#pragma unroll
-          for (int h16 = 0; h16 < 2; ++h16) {
-            uint32_t pk[8];
-            if (!GLOBAL && key0 + c * 32 + h16 * 16 >= T) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) pk[i] = 0u;
-            } else {
-              uint32_t v[16];
-              tmem_ld_32x32b_x16(tS + lane_off + c * 32 + h16 * 16, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float t0 = score(v[2 * i], c, h16, 2 * i), t1 = score(v[2 * i + 1], c, h16, 2 * i + 1);
-                mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(t0, t1));
-                const float e0 = fast_exp2(t0 - m_run), e1 = fast_exp2(t1 - m_run);
-                ls4[i & 3] += e0 + e1;
-                pk[i] = pack_bf16x2(e0, e1);
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const uint32_t chunk = static_cast<uint32_t>(((c & 1) * 4 + h16 * 2 + q) ^ sw);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + chunk * 16),
-                           "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
-                           : "memory");
-            }
-          }
-        }
-        tile_max = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-        tile_sum = (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
-      };
-      exp_pass();
-      if (j > 0) {
-        const bool need = tile_max > m_run + 8.0f;
-        if (__any_sync(0xffffffffu, need)) {
-          // rare: the reference moves up, O_h / l_h are rescaled and this tile's exponentials are redone
-          const float m_new = need ? tile_max : m_run;
-          const float alpha = fast_exp2(m_run - m_new);
-          l_run *= alpha;
-          m_run = m_new;
+      const float bound = fmaf(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])), scale2, rh + bias_max);
+      const bool need = bound > m_run + 8.0f;
+      if (__any_sync(0xffffffffu, need)) {
+        // the reference moves up (always on the first tile, rarely later): O_h / l_h are rescaled
+        const float alpha = need ? fast_exp2(m_run - bound) : 1.0f;
+        l_run *= alpha;
+        m_run = need ? bound : m_run;
+        if (j > 0) {
+          mbar_wait(bar(B_PV + (s ^ 1)), ((j - 1) >> 1) & 1);   // P V of tile j-1 has landed in O_h
+          tc_fence_after();
 #pragma unroll
           for (int c = 0; c < HD / 16; ++c) {
             uint32_t o[16];
@@ -375,17 +339,47 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv,
             tmem_st_32x32b_x16(tOme + lane_off + c * 16, o);
           }
           tmem_st_wait();
-          exp_pass();
         }
       }
-      l_run += tile_sum;
-      fence_proxy_async_smem();
+      // ---- P = exp2(t - m_run) (bf16, packed, written over the chunk's own scores), row sum
+      const float rhm = rh - m_run;
+      float ls4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[16];
+#pragma unroll
+      for (int h16 = 0; h16 < 2; ++h16) {
+        if (!GLOBAL && key0 + h16 * 16 >= T) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[h16 * 8 + i] = 0u;
+        } else {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_chunk + h16 * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float e0, e1;
+            if (GLOBAL) {
+              e0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), scale2, rhm) + relw[h16 * 16 + 2 * i]);
+              e1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), scale2, rhm) + relw[h16 * 16 + 2 * i + 1]);
+            } else {
+              const int k0 = key0 + h16 * 16 + 2 * i, k1 = k0 + 1;   // resolved after unrolling j
+              const int kh0 = k0 / 14, kw0 = k0 - kh0 * 14, kh1 = k1 / 14, kw1 = k1 - kh1 * 14;
+              e0 = (k0 < T) ? fast_exp2(fmaf(__uint_as_float(v[2 * i]), scale2, relh[kh0 < 14 ? kh0 : 0] - m_run) + relw[kw0]) : 0.f;
+              e1 = (k1 < T) ? fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), scale2, relh[kh1 < 14 ? kh1 : 0] - m_run) + relw[kw1]) : 0.f;
+            }
+            ls4[i & 3] += e0 + e1;
+            pk[h16 * 8 + i] = pack_bf16x2(e0, e1);
+          }
+        }
+      }
+      tmem_st_32x32b_x16(t_chunk, pk);
+      l_run += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
+      tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar(B_PF));
+      mbar_arrive(bar(B_PF + s));
     }
 
     // ---- epilogue: merge the two key halves, O / l -> out[token, head*HD .. ]
-    mbar_wait(bar(B_PV), (n_kt - 1) & 1);
+    mbar_wait(bar(B_PV + ((n_kt - 1) & 1)), ((n_kt - 1) >> 1) & 1);
     tc_fence_after();
     xchg[hf][r] = make_float2(m_run, l_run);
     pair_sync();
@@ -432,15 +426,16 @@ static int launch_att(const AttentionArgs& a, cudaStream_t stream) {
   constexpr int NREL = GS > 0 ? 2 * GS : 32;
   const int D = a.H * HD;
   const long long m_tok = static_cast<long long>(a.n_seq) * a.T;
-  CUtensorMap tq, th, tw;
+  CUtensorMap tq, tkv, th, tw;
   RSP_TRY(make_tmap_bf16_2d(&tq, a.qkv, m_tok, 3 * D, static_cast<uint64_t>(3 * D) * 2, 128, 64));
+  RSP_TRY(make_tmap_bf16_2d(&tkv, a.qkv, m_tok, 3 * D, static_cast<uint64_t>(3 * D) * 2, 64, 64));
   RSP_TRY(make_tmap_bf16_2d(&th, a.rel_h, 2 * a.S - 1, HD, static_cast<uint64_t>(HD) * 2, NREL, 64));
   RSP_TRY(make_tmap_bf16_2d(&tw, a.rel_w, 2 * a.S - 1, HD, static_cast<uint64_t>(HD) * 2, NREL, 64));
   AttDev p;
   p.out = static_cast<__nv_bfloat16*>(a.out);
   p.T = a.T; p.S = a.S; p.H = a.H; p.D = D;
   p.n_qt = (a.T + 127) / 128;
-  p.n_kt = (a.T + 127) / 128;
+  p.n_kt = (a.T + 63) / 64;
   p.scale2 = (1.0f / sqrtf(static_cast<float>(HD))) * LOG2E;
   auto kern = vit_attention_kernel<HD, GS>;
   static bool attr_set = false;
@@ -451,7 +446,7 @@ static int launch_att(const AttentionArgs& a, cudaStream_t stream) {
   }
   const long long grid = static_cast<long long>(a.n_seq) * a.H * p.n_qt;
   RSP_CHECK_ARG(grid > 0 && grid < (1ll << 31), "attention: grid %lld", grid);
-  kern<<<static_cast<unsigned>(grid), ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tq, th, tw, p);
+  kern<<<static_cast<unsigned>(grid), ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tkv, th, tw, p);
   RSP_CHECK_LAUNCH();
   return RSP_OK;
 }
