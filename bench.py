@@ -278,8 +278,18 @@ def run_ours(args) -> None:
         t_ms = sum(a.elapsed_time(b) for a, b, _ in records)
         fl = sum(f for _, _, f in records)
         ach = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
+        traffic, traffic_src = None, None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic_anchor_vitb.json")
+        if os.path.exists(tpath):      # ncu dram__bytes_read.sum + dram__bytes_write.sum of the same step, per launch
+            with open(tpath) as f:
+                tj = json.load(f)
+            g = [k for k in tj["kernels"] if "gemm_bf16_tcgen05" in k["kernel"]]
+            if g:
+                traffic = sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in g) / sum(k["launches"] for k in g)
+                traffic_src = "profiles/r01_traffic_anchor_vitb.json (ncu capture of one step, mean bytes per GEMM launch)"
         roof = dict(bound="tensor", kernel="gemm_bf16_tcgen05_kernel (all tile shapes)", achieved=ach,
-                    peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"], traffic=None,
+                    peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"], traffic=traffic,
+                    traffic_source=traffic_src,
                     peak_source=peaks["source"], launches_per_step=len(records) // max(inst_steps, 1),
                     gemm_ms_per_step=t_ms / max(inst_steps, 1),
                     algorithmic_tflop_per_step=fl / max(inst_steps, 1) / 1e12,
