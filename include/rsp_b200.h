@@ -71,6 +71,12 @@ int rsp_gemm_bf16_simt(const void* A, int lda, const void* W, int ldw, void* out
  * HF:729-801) / Attention.forward + add_decomposed_rel_pos (VS:202-221, VS:117-157). */
 int rsp_vit_attention(const void* qkv, const void* rel_h, const void* rel_w, void* out, int n_seq,
                       int T, int S, int H, int hd, void* stream);
+/* rsp_vit_attention with window_unpartition + crop (HF:925-952) fused into the store: output row r of the
+ * (window-ordered) sequences goes to row out_row_map[r] of `out` (int32 [n_seq*T], -1 = padding token, dropped),
+ * so the projection that follows is a plain GEMM over the B*g*g token rows. */
+int rsp_vit_attention_scatter(const void* qkv, const void* rel_h, const void* rel_w, void* out, int n_seq, int T,
+                              int Sg, int H, int hd, const int32_t* out_row_map, void* stream);
+
 int rsp_vit_attention_simt(const void* qkv, const void* rel_h, const void* rel_w, void* out,
                            int n_seq, int T, int S, int H, int hd, void* stream);
 
@@ -131,11 +137,12 @@ int rsp_add_cast_bf16(const float* a, const float* b, void* out, long long n, lo
 /* SamAttention core (HF:253-267) for the three shapes the two-way transformer uses; q/k/v are the
  * already-projected bf16 matrices, softmax in fp32, scale = c^-0.5.
  *   token self-attention: q,k,v [N, T, heads*c], T <= 16, c = 32 (or 16)
- *   t2i: q [N, Tq, 128] (8 heads x 16) attends to K,V [*, 128] rows kv_block[n]*HW .. +HW (NULL: n)
+ *   t2i: q [N, Tq, 128] (8 heads x 16) attends to K,V rows kv_block[n]*HW .. +HW (NULL: n); K / V are 128-column
+ *        slices with row stride ldkv (both halves of one fused k|v projection, or two [*,128] matrices)
  *   i2t: Q [*, 128] rows q_block[n]*HW .. +HW attend to ktok,vtok [N, Tq, 128]; out [N*HW, 128] */
 int rsp_token_self_attention(const void* q, const void* k, const void* v, void* out, int N, int T,
                              int heads, int c, void* stream);
-int rsp_t2i_attention(const void* q, const void* K, const void* V, const int32_t* kv_block, void* out,
+int rsp_t2i_attention(const void* q, const void* K, const void* V, int ldkv, const int32_t* kv_block, void* out,
                       int N, int Tq, int HW, void* stream);
 int rsp_i2t_attention(const void* Q, const int32_t* q_block, const void* ktok, const void* vtok,
                       void* out, int N, int Tq, int HW, void* stream);
@@ -236,8 +243,8 @@ int rsp_attn_mask_bits(const float* logits, int ld, int rows, int nk, uint64_t* 
 int rsp_resize_bilinear_nhwc(const void* x, int B, int H, int W, int C, int h, int w, void* out, void* stream);
 
 /* SamMaskEmbedding (HF:569-593) on mask_pred_plus + image embedding + key PE: for prompt n (image n / n_per_img)
- * src = emb[img] + mask_embed(mpp[n]) and src_pe = src + pos, both bf16 [N*h*w, 256] -- the mask decoder's two
- * source tensors (M:359-368, HF:499).  wts = HOST array of 10 device pointers (conv1 w,b, ln1 g,b, conv2 w,b,
+ * src = emb[img] + mask_embed(mpp[n]) bf16 [N*h*w, 256], the mask decoder's source tensor (M:359-368, HF:499), and
+ * optionally (src_pe != NULL) src + pos.  wts = HOST array of 10 device pointers (conv1 w,b, ln1 g,b, conv2 w,b,
  * ln2 g,b, conv3 w,b).  emb fp32 [imgs*h*w, 256], pos fp32 [h*w, 256], mpp fp32 [N, 4h, 4w]. */
 int rsp_mask_embed_src(const float* mpp, const float* const* wts, const float* emb, const float* pos, int N,
                        int n_per_img, int hm, int wm, int h, int w, float eps, void* src, void* src_pe, void* stream);

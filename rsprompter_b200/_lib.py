@@ -51,6 +51,7 @@ _SIGNATURES = {
     "rsp_gemm_bf16": ([_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "rsp_gemm_bf16_simt": ([_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "rsp_vit_attention": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    "rsp_vit_attention_scatter": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "rsp_vit_attention_simt": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "rsp_layernorm": ([_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _f, _i, _vp], _i),
     "rsp_patchify16": ([_vp, _vp, _i, _i, _i, _vp], _i),
@@ -63,7 +64,7 @@ _SIGNATURES = {
                           _i, _vp, _vp, _f, _vp, _i, _vp, _vp, _i, _i, _vp], _i),
     "rsp_add_cast_bf16": ([_vp, _vp, _vp, ctypes.c_longlong, ctypes.c_longlong, _vp], _i),
     "rsp_token_self_attention": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
-    "rsp_t2i_attention": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
+    "rsp_t2i_attention": ([_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp], _i),
     "rsp_i2t_attention": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
     "rsp_rpn_decode": ([_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _f, _f, _f, _i, _i, _vp, _vp, _vp], _i),
     "rsp_bbox_cls_decode": ([_vp, _i, _vp, _i, _vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp], _i),
@@ -271,19 +272,21 @@ def token_self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, head
 
 def t2i_attention(q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, hw: int,
                   kv_block: torch.Tensor | None = None) -> torch.Tensor:
-    """q bf16 [N, Tq, 128]; K, V bf16 [blocks*hw, 128]; kv_block int32 [N] -> bf16 [N, Tq, 128]."""
+    """q bf16 [N, Tq, 128]; K, V bf16 [blocks*hw, 128] (row views with a common stride, e.g. the two halves of a
+    fused k|v projection); kv_block int32 [N] -> bf16 [N, Tq, 128]."""
     global launch_count
     _require_cuda(q, K, V, kv_block)
     N, Tq, C = q.shape
     assert C == 128 and q.dtype == torch.bfloat16 and q.is_contiguous()
-    assert K.dtype == torch.bfloat16 and V.dtype == torch.bfloat16 and K.is_contiguous() and V.is_contiguous()
+    assert K.dtype == torch.bfloat16 and V.dtype == torch.bfloat16 and K.stride(1) == 1 and V.stride(1) == 1
+    assert K.stride(0) == V.stride(0)
     assert K.shape[1] == 128 and V.shape == K.shape and K.shape[0] % hw == 0
     if kv_block is not None:
         assert kv_block.dtype == torch.int32 and kv_block.numel() == N and kv_block.is_contiguous()
     else:
         assert K.shape[0] == N * hw
     out = torch.empty_like(q)
-    _check(_lib.rsp_t2i_attention(_ptr(q), _ptr(K), _ptr(V), _ptr(kv_block), _ptr(out), N, Tq, hw, _stream()),
+    _check(_lib.rsp_t2i_attention(_ptr(q), _ptr(K), _ptr(V), K.stride(0), _ptr(kv_block), _ptr(out), N, Tq, hw, _stream()),
            "rsp_t2i_attention")
     launch_count += 1
     return out
@@ -310,8 +313,10 @@ def i2t_attention(Q: torch.Tensor, ktok: torch.Tensor, vtok: torch.Tensor, hw: i
 
 
 def vit_attention(qkv: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor, n_seq: int, S: int,
-                  H: int, hd: int, *, out: torch.Tensor | None = None, simt: bool = False) -> torch.Tensor:
-    """softmax(q k^T / sqrt(hd) + decomposed rel-pos) v for n_seq sequences of S*S tokens."""
+                  H: int, hd: int, *, out: torch.Tensor | None = None, simt: bool = False,
+                  out_row_map: torch.Tensor | None = None, out_rows: int | None = None) -> torch.Tensor:
+    """softmax(q k^T / sqrt(hd) + decomposed rel-pos) v for n_seq sequences of S*S tokens.
+    out_row_map (int32 [n_seq*T], -1 = drop) scatters the rows into an [out_rows, D] tensor (window un-partition)."""
     global launch_count
     _require_cuda(qkv, rel_h, rel_w, out)
     T = S * S
@@ -319,6 +324,17 @@ def vit_attention(qkv: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor, n
     assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (n_seq * T, 3 * D)
     assert rel_h.dtype == torch.bfloat16 and rel_h.is_contiguous() and rel_h.shape == (2 * S - 1, hd)
     assert rel_w.dtype == torch.bfloat16 and rel_w.is_contiguous() and rel_w.shape == (2 * S - 1, hd)
+    if out_row_map is not None:
+        assert not simt and out_row_map.dtype == torch.int32 and out_row_map.is_contiguous()
+        assert out_row_map.numel() == n_seq * T and out_rows is not None
+        _require_cuda(out_row_map)
+        if out is None:
+            out = torch.empty((out_rows, D), device=qkv.device, dtype=torch.bfloat16)
+        assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.shape == (out_rows, D)
+        _check(_lib.rsp_vit_attention_scatter(_ptr(qkv), _ptr(rel_h), _ptr(rel_w), _ptr(out), n_seq, T, S, H, hd,
+                                              _ptr(out_row_map), _stream()), "rsp_vit_attention_scatter")
+        launch_count += 1
+        return out
     if out is None:
         out = torch.empty((n_seq * T, D), device=qkv.device, dtype=torch.bfloat16)
     assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.shape == (n_seq * T, D)
@@ -680,7 +696,7 @@ def resize_bilinear_nhwc(x: torch.Tensor, hw: tuple) -> torch.Tensor:
 
 
 def mask_embed_src(mpp: torch.Tensor, weights: list, emb_rows: torch.Tensor, pos_rows: torch.Tensor, n_per_img: int,
-                   hw: tuple, eps: float = 1e-6):
+                   hw: tuple, eps: float = 1e-6, want_pe: bool = False):
     """-> (src, src_pe) bf16 [N*h*w, 256]; weights = 10 fp32 tensors (conv1 w,b, ln1 g,b, conv2 w,b, ln2 g,b, conv3 w,b)."""
     global launch_count
     _require_cuda(mpp, emb_rows, pos_rows, *weights)
@@ -692,7 +708,7 @@ def mask_embed_src(mpp: torch.Tensor, weights: list, emb_rows: torch.Tensor, pos
     assert emb_rows.dtype == torch.float32 and emb_rows.is_contiguous() and pos_rows.dtype == torch.float32
     wp = (ctypes.c_void_p * 10)(*[t.data_ptr() for t in weights])
     src = torch.empty(N * h * w, 256, device=mpp.device, dtype=torch.bfloat16)
-    src_pe = torch.empty_like(src)
+    src_pe = torch.empty_like(src) if want_pe else None
     _check(_lib.rsp_mask_embed_src(_ptr(mpp), ctypes.cast(wp, _vp), _ptr(emb_rows), _ptr(pos_rows), N, n_per_img, hm, wm,
                                    h, w, float(eps), _ptr(src), _ptr(src_pe), _stream()), "rsp_mask_embed_src")
     launch_count += 1

@@ -53,16 +53,21 @@ int rsp_gemm_bf16_simt(const void* A, int lda, const void* W, int ldw, void* out
 }
 
 static AttentionArgs make_att_args(const void* qkv, const void* rel_h, const void* rel_w, void* out,
-                                   int n_seq, int T, int Sg, int H, int hd) {
+                                   int n_seq, int T, int Sg, int H, int hd, const int32_t* out_row_map = nullptr) {
   AttentionArgs a;
   a.qkv = qkv; a.rel_h = rel_h; a.rel_w = rel_w; a.out = out;
-  a.n_seq = n_seq; a.T = T; a.S = Sg; a.H = H; a.hd = hd;
+  a.n_seq = n_seq; a.T = T; a.S = Sg; a.H = H; a.hd = hd; a.out_row_map = out_row_map;
   return a;
 }
 
 int rsp_vit_attention(const void* qkv, const void* rel_h, const void* rel_w, void* out, int n_seq,
                       int T, int Sg, int H, int hd, void* stream) {
   return vit_attention(make_att_args(qkv, rel_h, rel_w, out, n_seq, T, Sg, H, hd), S(stream));
+}
+
+int rsp_vit_attention_scatter(const void* qkv, const void* rel_h, const void* rel_w, void* out, int n_seq, int T,
+                              int Sg, int H, int hd, const int32_t* out_row_map, void* stream) {
+  return vit_attention(make_att_args(qkv, rel_h, rel_w, out, n_seq, T, Sg, H, hd, out_row_map), S(stream));
 }
 
 int rsp_vit_attention_simt(const void* qkv, const void* rel_h, const void* rel_w, void* out,
@@ -138,9 +143,9 @@ int rsp_token_self_attention(const void* q, const void* k, const void* v, void* 
   return token_self_attention(q, k, v, out, N, T, heads, c, S(stream));
 }
 
-int rsp_t2i_attention(const void* q, const void* K, const void* V, const int32_t* kv_block, void* out,
+int rsp_t2i_attention(const void* q, const void* K, const void* V, int ldkv, const int32_t* kv_block, void* out,
                       int N, int Tq, int HW, void* stream) {
-  return t2i_attention(q, K, V, kv_block, out, N, Tq, HW, S(stream));
+  return t2i_attention(q, K, V, ldkv, kv_block, out, N, Tq, HW, S(stream));
 }
 
 int rsp_i2t_attention(const void* Q, const int32_t* q_block, const void* ktok, const void* vtok,

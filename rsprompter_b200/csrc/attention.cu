@@ -58,6 +58,7 @@ struct AttDev {
   int n_qt;            // 128-query tiles per sequence
   int n_kt;            // 64-key tiles per sequence
   float scale2;        // hd^-0.5 * log2(e)
+  const int* out_row_map;   // window_unpartition + crop fused into the store (HF:925-952), or null
 };
 
 // barriers: two-slot rings indexed by tile parity; phase of slot use n is (n >> 1) & 1
@@ -389,7 +390,10 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     const float inv = 1.0f / (l_run * a_me + other.y * a_ot);
     const float w_me = a_me * inv, w_ot = a_ot * inv;
     const uint32_t tOot = hf ? tO : tO1;
-    __nv_bfloat16* orow = p.out + static_cast<size_t>(row0 + tq) * p.D + colq;
+    int dst_row = row0 + tq;
+    if (p.out_row_map && tq < T) dst_row = __ldg(p.out_row_map + dst_row);
+    const bool store = tq < T && dst_row >= 0;
+    __nv_bfloat16* orow = p.out + static_cast<size_t>(store ? dst_row : 0) * p.D + colq;
     constexpr int NC0 = (HD / 16 + 1) / 2;     // 16-column output chunks written by half 0
     const int c_lo = hf ? NC0 : 0, c_hi = hf ? HD / 16 : NC0;
 #pragma unroll 1
@@ -398,7 +402,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       tmem_ld_32x32b_x16(tOme + lane_off + c * 16, o);
       tmem_ld_32x32b_x16(tOot + lane_off + c * 16, o2);
       tmem_ld_wait();
-      if (tq < T) {
+      if (store) {
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(o[i]) * w_me + __uint_as_float(o2[i]) * w_ot;
@@ -437,6 +441,7 @@ static int launch_att(const AttentionArgs& a, cudaStream_t stream) {
   p.n_qt = (a.T + 127) / 128;
   p.n_kt = (a.T + 63) / 64;
   p.scale2 = (1.0f / sqrtf(static_cast<float>(HD))) * LOG2E;
+  p.out_row_map = a.out_row_map;
   auto kern = vit_attention_kernel<HD, GS>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -479,7 +484,7 @@ __global__ void vit_attention_simt_kernel(const __nv_bfloat16* __restrict__ qkv,
                                           const __nv_bfloat16* __restrict__ rel_h,
                                           const __nv_bfloat16* __restrict__ rel_w,
                                           __nv_bfloat16* __restrict__ out, int T, int S, int H,
-                                          int hd, float scale) {
+                                          int hd, float scale, const int* __restrict__ out_row_map) {
   const int D = H * hd;
   const int tq = blockIdx.x * blockDim.x + threadIdx.x;
   const int head = blockIdx.y;
@@ -515,7 +520,10 @@ __global__ void vit_attention_simt_kernel(const __nv_bfloat16* __restrict__ qkv,
     for (int d = 0; d < hd; ++d) o[d] = o[d] * a + pe * __bfloat162float(vp[d]);
     m = mn;
   }
-  __nv_bfloat16* op = out + (static_cast<size_t>(seq) * T + tq) * D + head * hd;
+  int dst = seq * T + tq;
+  if (out_row_map) dst = out_row_map[dst];
+  if (dst < 0) return;
+  __nv_bfloat16* op = out + static_cast<size_t>(dst) * D + head * hd;
   for (int d = 0; d < hd; ++d) op[d] = __float2bfloat16_rn(o[d] / l);
 }
 
@@ -527,7 +535,7 @@ int vit_attention_simt(const AttentionArgs& a, cudaStream_t stream) {
   vit_attention_simt_kernel<<<grid, block, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(a.qkv), static_cast<const __nv_bfloat16*>(a.rel_h),
       static_cast<const __nv_bfloat16*>(a.rel_w), static_cast<__nv_bfloat16*>(a.out), a.T, a.S, a.H,
-      a.hd, 1.0f / sqrtf(static_cast<float>(a.hd)));
+      a.hd, 1.0f / sqrtf(static_cast<float>(a.hd)), a.out_row_map);
   RSP_CHECK_LAUNCH();
   return RSP_OK;
 }

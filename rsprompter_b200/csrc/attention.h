@@ -16,6 +16,7 @@ struct AttentionArgs {
   int S = 0;      // 14 (window) or 64 (global, 1024^2 input)
   int H = 0;
   int hd = 0;     // 64 (ViT-B/L) or 80 (ViT-H)
+  const int* out_row_map = nullptr;   // int32 [n_seq * T]: destination row of each output row (-1 = drop), or null
 };
 
 int vit_attention(const AttentionArgs& a, cudaStream_t stream);

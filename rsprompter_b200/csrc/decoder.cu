@@ -157,13 +157,13 @@ t2i_attention_kernel(const __nv_bfloat16* __restrict__ q,   // [N, Tq, 128]
                      const __nv_bfloat16* __restrict__ V,
                      const int* __restrict__ kv_block,      // [N] or null
                      __nv_bfloat16* __restrict__ out,       // [N, Tq, 128]
-                     int Tq, int HW, float scale) {
+                     int Tq, int HW, int ldkv, float scale) {
   extern __shared__ __align__(16) uint8_t t2i_smem[];
   const uint32_t s_base = smem_u32(t2i_smem);
   const int n = blockIdx.x;
   const int blk = kv_block ? kv_block[n] : n;
-  const __nv_bfloat16* Kb = K + static_cast<size_t>(blk) * HW * 128;
-  const __nv_bfloat16* Vb = V + static_cast<size_t>(blk) * HW * 128;
+  const __nv_bfloat16* Kb = K + static_cast<size_t>(blk) * HW * ldkv;
+  const __nv_bfloat16* Vb = V + static_cast<size_t>(blk) * HW * ldkv;
   const int tid = threadIdx.x, lane = tid & 31, h = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int n_tiles = (HW + T2I_TILE - 1) / T2I_TILE;
@@ -177,7 +177,7 @@ t2i_attention_kernel(const __nv_bfloat16* __restrict__ q,   // [N, Tq, 128]
       const int which = idx >> 10, j = idx & 1023;
       const int row = j >> 4, ch = j & 15;
       const int grow = min(t0 + row, HW - 1);   // rows past the end are masked in the softmax
-      const __nv_bfloat16* src = (which ? Vb : Kb) + static_cast<size_t>(grow) * 128 + ch * 8;
+      const __nv_bfloat16* src = (which ? Vb : Kb) + static_cast<size_t>(grow) * ldkv + ch * 8;
       cp_async16(s_base + stage * T2I_STAGE + which * (T2I_TILE * T2I_ROWB) + row * T2I_ROWB + ch * 16, src);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -288,9 +288,11 @@ t2i_attention_kernel(const __nv_bfloat16* __restrict__ q,   // [N, Tq, 128]
   }
 }
 
-int t2i_attention(const void* q, const void* K, const void* V, const int* kv_block, void* out, int N,
+int t2i_attention(const void* q, const void* K, const void* V, int ldkv, const int* kv_block, void* out, int N,
                   int Tq, int HW, cudaStream_t stream) {
   RSP_CHECK_ARG(q && K && V && out && N > 0 && Tq > 0 && Tq <= 16 && HW > 0, "t2i_attention: bad args");
+  RSP_CHECK_ARG(ldkv >= 128 && ldkv % 8 == 0 && (reinterpret_cast<uintptr_t>(K) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(V) & 15) == 0, "t2i_attention: K / V row stride / alignment");
   const int smem = 2 * T2I_STAGE;
   static bool attr_set = false;
   if (!attr_set) {
@@ -299,7 +301,7 @@ int t2i_attention(const void* q, const void* K, const void* V, const int* kv_blo
   }
   t2i_attention_kernel<<<N, 256, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(K),
-      static_cast<const __nv_bfloat16*>(V), kv_block, static_cast<__nv_bfloat16*>(out), Tq, HW, 0.25f);
+      static_cast<const __nv_bfloat16*>(V), kv_block, static_cast<__nv_bfloat16*>(out), Tq, HW, ldkv, 0.25f);
   RSP_CHECK_LAUNCH();
   return RSP_OK;
 }

@@ -7,7 +7,7 @@ int add_cast_bf16(const float* a, const float* b, void* out, long long n, long l
                   cudaStream_t stream);
 int token_self_attention(const void* q, const void* k, const void* v, void* out, int N, int T,
                          int heads, int c, cudaStream_t stream);
-int t2i_attention(const void* q, const void* K, const void* V, const int* kv_block, void* out, int N,
+int t2i_attention(const void* q, const void* K, const void* V, int ldkv, const int* kv_block, void* out, int N,
                   int Tq, int HW, cudaStream_t stream);
 int i2t_attention(const void* Q, const int* q_block, const void* ktok, const void* vtok, void* out,
                   int N, int Tq, int HW, cudaStream_t stream);

@@ -525,13 +525,13 @@ __global__ void mask_embed_src_kernel(const float* __restrict__ mpp, MaskEmbedW 
     sa += e.x; sb += e.y;
     const size_t o = (static_cast<size_t>(n) * HW + pix) * 256 + c;
     *reinterpret_cast<uint32_t*>(src + o) = pack_bf16x2(sa, sb);
-    *reinterpret_cast<uint32_t*>(src_pe + o) = pack_bf16x2(sa + ps.x, sb + ps.y);
+    if (src_pe) *reinterpret_cast<uint32_t*>(src_pe + o) = pack_bf16x2(sa + ps.x, sb + ps.y);
   }
 }
 
 int mask_embed_src(const float* mpp, const float* const* wts, const float* emb, const float* pos, int N, int n_per_img,
                    int hm, int wm, int h, int w, float eps, void* src, void* src_pe, cudaStream_t stream) {
-  RSP_CHECK_ARG(mpp && wts && emb && pos && src && src_pe && N > 0 && hm == 4 * h && wm == 4 * w, "mask_embed_src: bad args");
+  RSP_CHECK_ARG(mpp && wts && emb && pos && src && N > 0 && hm == 4 * h && wm == 4 * w, "mask_embed_src: bad args");
   MaskEmbedW W{wts[0], wts[1], wts[2], wts[3], wts[4], wts[5], wts[6], wts[7], wts[8], wts[9]};
   dim3 grid((h * w + 31) / 32, N);
   mask_embed_src_kernel<<<grid, 128, 0, stream>>>(mpp, W, emb, pos, n_per_img, hm, wm, h, w, eps,

@@ -124,7 +124,10 @@ class SamMaskDecoderB200(nn.Module):
         def attn(m: _SamAttention) -> dict:
             return dict(qw=bf(m.q_proj.weight), qb=f32(m.q_proj.bias), kw=bf(m.k_proj.weight),
                         kb=f32(m.k_proj.bias), vw=bf(m.v_proj.weight), vb=f32(m.v_proj.bias),
-                        ow=bf(m.out_proj.weight), ob=f32(m.out_proj.bias))
+                        ow=bf(m.out_proj.weight), ob=f32(m.out_proj.bias),
+                        # k | v of the image tokens as one projection (the keys are read once)
+                        kvw=bf(torch.cat([m.k_proj.weight, m.v_proj.weight], dim=0)),
+                        kvb=f32(torch.cat([m.k_proj.bias, m.v_proj.bias], dim=0)))
 
         def ln(m: _Affine) -> tuple:
             return (f32(m.weight), f32(m.bias))
@@ -154,8 +157,27 @@ class SamMaskDecoderB200(nn.Module):
         p["hyper"] = [ff(m) for m in self.output_hypernetworks_mlps]
         p["iou"] = ff(self.iou_prediction_head)
         p["out_tokens"] = f32(torch.cat([self.iou_token.weight, self.mask_tokens.weight], dim=0))
+        p["pos_terms"] = {}
         self._prep = p
         return p
+
+    def _pos_terms(self, p: dict, pos_rows: torch.Tensor) -> dict:
+        """"keys + key_point_embedding" (HF:326, 339-340) never exists as a tensor:
+        (keys + pos) W^T = keys W^T + pos W^T, and pos W^T (bf16 [HW, n], a constant of the weights and the map
+        size) enters the projection as a broadcast residual slab of the GEMM epilogue."""
+        key = (pos_rows.data_ptr(), pos_rows.shape[0])
+        if key not in p["pos_terms"]:
+            pb = _lib.cast_bf16(pos_rows)
+            layers = [L["t2i"] for L in p["layers"]] + [p["final"]]
+            kv = []
+            for a in layers:
+                t = torch.zeros(pos_rows.shape[0], a["kvw"].shape[0], device=pos_rows.device, dtype=torch.bfloat16)
+                n_k = a["kw"].shape[0]
+                t[:, :n_k] = _lib.gemm(pb, a["kw"])                  # v half stays 0
+                kv.append(t)
+            q = [_lib.gemm(pb, L["i2t"]["qw"]) for L in p["layers"]]
+            p["pos_terms"] = {key: dict(kv=kv, q=q)}
+        return p["pos_terms"][key]
 
     @staticmethod
     def _ff(x_bf: torch.Tensor, layers: list) -> torch.Tensor:
@@ -190,8 +212,8 @@ class SamMaskDecoderB200(nn.Module):
         pos_rows = pos_rows.contiguous()
         # ---- src = image_embeddings + dense (HF:499)
         if src_pair is not None:
-            # per-prompt sources already built on the device (rsp_mask_embed_src): bf16 src and src + pe
-            src_b, src_pe_b = src_pair
+            # per-prompt sources already built on the device (rsp_mask_embed_src): bf16 src
+            src_b = src_pair[0]
             src32, blk = src_b, None
         elif dense_rows is not None:
             if prompt_img is not None:  # per-prompt dense on per-image embeddings: expand once
@@ -204,22 +226,20 @@ class SamMaskDecoderB200(nn.Module):
         if src_pair is None:
             src32 = src32.contiguous()
             src_b = _lib.cast_bf16(src32)
-            # "keys + key_point_embedding" (HF:326,339) is kept as a second bf16 tensor next to the keys, so
-            # the k / q projections are plain GEMMs; later layers get it from the LayerNorm kernel for free
-            src_pe_b = _lib.add_cast_bf16(src32, pos_rows)
+        pt = self._pos_terms(p, pos_rows)
         tokens = torch.cat([p["out_tokens"].unsqueeze(0).expand(N, -1, -1), sparse.to(torch.float32)], dim=1)
         tokens = tokens.reshape(N * Tt, C).contiguous()
 
-        def t2i(layer: dict, queries: torch.Tensor, keys_b: torch.Tensor, keys_pe_b: torch.Tensor, kv_blk, ln):
+        def t2i(layer: dict, queries: torch.Tensor, keys_b: torch.Tensor, pos_kv: torch.Tensor, kv_blk, ln):
             qin = _lib.add_cast_bf16(queries, tokens)
             q = _lib.gemm(qin, layer["qw"], layer["qb"])
-            K = _lib.gemm(keys_pe_b, layer["kw"], layer["kb"])
-            V = _lib.gemm(keys_b, layer["vw"], layer["vb"])
-            att = _lib.t2i_attention(q.view(N, Tt, -1), K, V, HW, kv_block=kv_blk)
+            KV = _lib.gemm(keys_b, layer["kvw"], layer["kvb"], residual=pos_kv, res_mod=HW)   # [rows, k | v]
+            n_k = layer["kw"].shape[0]
+            att = _lib.t2i_attention(q.view(N, Tt, -1), KV[:, :n_k], KV[:, n_k:], HW, kv_block=kv_blk)
             return _lib.gemm(att.view(N * Tt, -1), layer["ow"], layer["ob"], residual=queries,
                              out_dtype=torch.float32, ln=ln)
 
-        keys_b, keys_pe_b, keys_res, kblk = src_b, src_pe_b, src32, blk
+        keys_b, keys_res, kblk = src_b, src32, blk
         queries = None
         for li, L in enumerate(p["layers"]):
             sa = L["sa"]
@@ -240,7 +260,7 @@ class SamMaskDecoderB200(nn.Module):
                 queries = _lib.gemm(att.view(N * Tt, C), sa["ow"], sa["ob"], residual=queries,
                                     out_dtype=torch.float32, ln=(*L["ln1"], a.layer_norm_eps))
             # tokens -> image cross attention (HF:323-333)
-            queries = t2i(L["t2i"], queries, keys_b, keys_pe_b, kblk, (*L["ln2"], a.layer_norm_eps))
+            queries = t2i(L["t2i"], queries, keys_b, pt["kv"][li], kblk, (*L["ln2"], a.layer_norm_eps))
             # MLP (HF:335-338)
             hdn = _lib.gemm(_lib.cast_bf16(queries), L["w1"], L["b1"], act="relu")
             queries = _lib.gemm(hdn, L["w2"], L["b2"], residual=queries, out_dtype=torch.float32,
@@ -250,15 +270,15 @@ class SamMaskDecoderB200(nn.Module):
             qin = _lib.add_cast_bf16(queries, tokens)
             ktok = _lib.gemm(qin, i2t["kw"], i2t["kb"])
             vtok = _lib.gemm(_lib.cast_bf16(queries), i2t["vw"], i2t["vb"])
-            Qimg = _lib.gemm(keys_pe_b, i2t["qw"], i2t["qb"])
+            Qimg = _lib.gemm(keys_b, i2t["qw"], i2t["qb"], residual=pt["q"][li], res_mod=HW)
             att = _lib.i2t_attention(Qimg, ktok.view(N, Tt, -1), vtok.view(N, Tt, -1), HW, q_block=kblk)
             # out_proj as a plain bf16 GEMM (HBM-roofline epilogue), then keys = LN4(keys + attn_out) in
             # one row kernel that also applies the prompt -> image block map of the residual
             proj = _lib.gemm(att, i2t["ow"], i2t["ob"])
-            keys_b, keys_pe_b = _lib.layernorm_add(proj, keys_res, *L["ln4"], a.layer_norm_eps, res_block_map=kblk,
-                                                   res_block_rows=HW if kblk is not None else 0, pos=pos_rows)
+            keys_b = _lib.layernorm_add(proj, keys_res, *L["ln4"], a.layer_norm_eps, res_block_map=kblk,
+                                        res_block_rows=HW if kblk is not None else 0)
             keys_res, kblk = keys_b, None
-        queries = t2i(p["final"], queries, keys_b, keys_pe_b, None, (*p["lnf"], 1e-5))
+        queries = t2i(p["final"], queries, keys_b, pt["kv"][-1], None, (*p["lnf"], 1e-5))
         qv = queries.view(N, Tt, C)
         iou_tok = _lib.cast_bf16(qv[:, 0].contiguous())
         iou = self._ff(iou_tok, p["iou"])                                   # [N, num_mask_tokens]

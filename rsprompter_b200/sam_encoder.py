@@ -210,9 +210,10 @@ class SamVisionEncoderB200(nn.Module):
             else:
                 xn = _lib.layernorm(h, lw["ln1_w"], lw["ln1_b"], a.layer_norm_eps, src_map=wmap)
                 qkv = _lib.gemm(xn, lw["qkv_w"], lw["qkv_b"])
-                att = _lib.vit_attention(qkv, lw["rel_h"], lw["rel_w"], B * n_win, ws, H, hd)
-                x1 = _lib.gemm(att, lw["proj_w"], lw["proj_b"], residual=h, row_map=wmap,
-                               out_rows=M, out_dtype=torch.float32)
+                # window_unpartition + crop happen in the attention store: the projection is a plain GEMM
+                att = _lib.vit_attention(qkv, lw["rel_h"], lw["rel_w"], B * n_win, ws, H, hd, out_row_map=wmap,
+                                         out_rows=M)
+                x1 = _lib.gemm(att, lw["proj_w"], lw["proj_b"], residual=h, out_dtype=torch.float32)
             xn2 = _lib.layernorm(x1, lw["ln2_w"], lw["ln2_b"], a.layer_norm_eps)
             y = _lib.gemm(xn2, lw["lin1_w"], lw["lin1_b"], act="gelu")
             h = _lib.gemm(y, lw["lin2_w"], lw["lin2_b"], residual=x1, out_dtype=torch.float32)
@@ -221,8 +222,10 @@ class SamVisionEncoderB200(nn.Module):
         hb = _lib.cast_bf16(h)
         c1 = _lib.gemm(hb, p["n1_w"])
         l1 = _lib.layernorm(c1, p["nln1_w"], p["nln1_b"], 1e-6)
-        col = _lib.im2col_nhwc(l1.view(B, g, g, C), 3, 3, 1, 1)
-        c2 = _lib.gemm(col, p["n2_w"])
+        if _lib.conv3x3_ok(B, g, g, C):
+            c2 = _lib.conv3x3_nhwc(l1.view(B, g, g, C), p["n2_w"])
+        else:
+            c2 = _lib.gemm(_lib.im2col_nhwc(l1.view(B, g, g, C), 3, 3, 1, 1), p["n2_w"])
         l2 = _lib.layernorm(c2, p["nln2_w"], p["nln2_b"], 1e-6, out_dtype=torch.float32)
         emb = _lib.nhwc_to_nchw(l2.view(B, g, g, C))
         hs = tuple(t.view(B, g, g, D) for t in hidden) if want_hidden else None
