@@ -515,6 +515,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
     RSP_CHECK_ARG(a.N % 32 == 0 && a.N <= 256 && a.ln_gamma && a.ln_beta && !a.w_is_kn && !a.row_map,
                   "gemm: row-LN epilogue needs N %% 32 == 0, N <= 256, gamma/beta");
     RSP_CHECK_ARG(a.ldo % 8 == 0 && (!a.residual || a.ldr % 8 == 0), "gemm: row-LN epilogue alignment");
+    if (gemm_v2_ln_row_eligible(a)) return gemm_bf16_v2_ln_row(a, stream);
     if (a.N > 128) return launch_gemm<256, false>(a, stream);
     if (a.N > 64) return launch_gemm<128, false>(a, stream);
     return launch_gemm<64, false>(a, stream);

@@ -43,6 +43,8 @@ int conv3x3_bf16(const GemmArgs& a, cudaStream_t stream);   // conv_* set; stand
 // coalesced-epilogue kernel (gemm_v2.cu); gemm_bf16 dispatches to it when eligible
 bool gemm_v2_eligible(const GemmArgs& a);
 int gemm_bf16_v2(const GemmArgs& a, int bn, cudaStream_t stream);
+bool gemm_v2_ln_row_eligible(const GemmArgs& a);
+int gemm_bf16_v2_ln_row(const GemmArgs& a, cudaStream_t stream);             // N == 256, bf16 residual / out
 int gemm_bf16_v2_ln64_gelu(const GemmArgs& a, cudaStream_t stream);     // N % 128 == 0
 int gemm_bf16_v2_gelu_hyper(const GemmArgs& a, cudaStream_t stream);    // N == 128
 

@@ -66,7 +66,7 @@ struct Dev {
   int tma_res;                   // residual slabs arrive through tma_r into the staging buffer (added in place)
 };
 
-enum { EPI_STD = 0, EPI_LN64_GELU = 2, EPI_GELU_HYPER = 3 };
+enum { EPI_STD = 0, EPI_LN_ROW = 1, EPI_LN64_GELU = 2, EPI_GELU_HYPER = 3 };
 
 __device__ __forceinline__ int residual_row(const Dev& p, int orow) {
   if (p.res_block_map) {
@@ -237,6 +237,120 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
           const int Y = 4 * y + 2 * (tap1 >> 1) + hf, X = 4 * x + 2 * (tap1 & 1);
           *reinterpret_cast<float2*>(p.mask_out + (static_cast<size_t>(n) * 4 * p.grid_h + Y) * W4 + X) =
               make_float2(m2[0], m2[1]);
+        }
+      } else if constexpr (EPI == EPI_LN_ROW) {
+        // out = LayerNorm_256(acc + bias + residual), bf16 (N == BN == 256: the tile holds whole rows).  Two warps
+        // share a row (128 columns each).  Pass 1: v = acc + bias + residual (residual slabs arrive by TMA in the
+        // staging buffer) is written back over the accumulator in TMEM while sum / sum of squares accumulate;
+        // the pair exchanges its partial statistics through shared memory; pass 2 re-reads v from TMEM (TMEM
+        // reads are ~900 B/clk/SM), normalises, and leaves through the same staging buffer as TMA stores.
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + hf * 128;
+        const int col_warp = hf * 128;
+        const int row0 = m_blk * BM + q * 32;
+        const uint32_t sbuf = smem_u32(stg_all) + e * 4096;
+        const uint32_t srow = sbuf + lane * 128;
+        const int sw = lane & 7;
+        float2* xchg = reinterpret_cast<float2*>(stg_all + 8 * 4096);   // [2][128] (sum, sumsq)
+        const bool valid = row0 < p.M;
+        const uint32_t rbar = smem_u32(&bar_res[e]);
+        int rrow0 = row0;
+        if (valid && p.res_block_map) {
+          const int blk = row0 / p.res_block_rows;
+          rrow0 = __ldg(p.res_block_map + blk) * p.res_block_rows + (row0 - blk * p.res_block_rows);
+        }
+        auto issue_res = [&](int col0) {
+          if (lane == 0) {
+            bulk_wait_read0();
+            mbar_expect_tx(rbar, 4096);
+            tma_load_2d(sbuf, &tma_r, rbar, col0, rrow0);
+          }
+        };
+        if (valid) issue_res(col_warp);
+        mbar_wait(smem_u32(&bar_tmem_full[as]), (it >> 1) & 1);
+        tc_fence_after();
+        float sum = 0.f, sumsq = 0.f;
+        if (valid) {
+#pragma unroll 1
+          for (int ps = 0; ps < 2; ++ps) {
+            const int col0 = col_warp + ps * 64;
+            mbar_wait(rbar, rphase);
+            rphase ^= 1;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t r[32];
+              tmem_ld_32x32b_x32(t_row + ps * 64 + c * 32, r);
+              tmem_ld_wait();
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + c * 32);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint32_t w0, w1, w2, w3;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(srow + (((c * 4 + j) ^ sw) << 4)));
+                const float4 ba = __ldg(b4 + 2 * j), bb = __ldg(b4 + 2 * j + 1);
+                float v[8];
+                v[0] = __uint_as_float(r[8 * j]) + ba.x + __uint_as_float(w0 << 16);
+                v[1] = __uint_as_float(r[8 * j + 1]) + ba.y + __uint_as_float(w0 & 0xffff0000u);
+                v[2] = __uint_as_float(r[8 * j + 2]) + ba.z + __uint_as_float(w1 << 16);
+                v[3] = __uint_as_float(r[8 * j + 3]) + ba.w + __uint_as_float(w1 & 0xffff0000u);
+                v[4] = __uint_as_float(r[8 * j + 4]) + bb.x + __uint_as_float(w2 << 16);
+                v[5] = __uint_as_float(r[8 * j + 5]) + bb.y + __uint_as_float(w2 & 0xffff0000u);
+                v[6] = __uint_as_float(r[8 * j + 6]) + bb.z + __uint_as_float(w3 << 16);
+                v[7] = __uint_as_float(r[8 * j + 7]) + bb.w + __uint_as_float(w3 & 0xffff0000u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  sum += v[k];
+                  sumsq = fmaf(v[k], v[k], sumsq);
+                  r[8 * j + k] = __float_as_uint(v[k]);
+                }
+              }
+              tmem_st_32x32b_x32(t_row + ps * 64 + c * 32, r);
+            }
+            __syncwarp();                         // every lane has read its residual row: the buffer is free
+            if (ps == 0) issue_res(col0 + 64);
+          }
+          tmem_st_wait();
+        }
+        xchg[hf * 128 + q * 32 + lane] = make_float2(sum, sumsq);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        const float2 ot = xchg[(hf ^ 1) * 128 + q * 32 + lane];
+        const float mean = (sum + ot.x) * (1.0f / 256.0f);
+        const float var = fmaxf((sumsq + ot.y) * (1.0f / 256.0f) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + p.ln_eps);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // xchg may be rewritten by the next tile
+        if (valid) {
+#pragma unroll 1
+          for (int ps = 0; ps < 2; ++ps) {
+            const int col0 = col_warp + ps * 64;
+            uint32_t pk[32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t r[32];
+              tmem_ld_32x32b_x32(t_row + ps * 64 + c * 32, r);
+              tmem_ld_wait();
+              const float4* g4 = reinterpret_cast<const float4*>(p.ln_gamma + col0 + c * 32);
+              const float4* e4 = reinterpret_cast<const float4*>(p.ln_beta + col0 + c * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 g = __ldg(g4 + j), bt = __ldg(e4 + j);
+                const float y0 = fmaf((__uint_as_float(r[4 * j]) - mean) * rstd, g.x, bt.x);
+                const float y1 = fmaf((__uint_as_float(r[4 * j + 1]) - mean) * rstd, g.y, bt.y);
+                const float y2 = fmaf((__uint_as_float(r[4 * j + 2]) - mean) * rstd, g.z, bt.z);
+                const float y3 = fmaf((__uint_as_float(r[4 * j + 3]) - mean) * rstd, g.w, bt.w);
+                pk[c * 16 + 2 * j] = pack_bf16x2(y0, y1);
+                pk[c * 16 + 2 * j + 1] = pack_bf16x2(y2, y3);
+              }
+            }
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ sw) << 4)), "r"(pk[4 * j]),
+                           "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                           : "memory");
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&tma_c, sbuf, col0, row0); bulk_commit(); }
+          }
         }
       } else if constexpr (EPI == EPI_LN64_GELU) {
         // this warp owns two 64-column groups (taps); per group: bias, LayerNorm over the 64
@@ -631,7 +745,7 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
                (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0 && (static_cast<uint64_t>(a.ldr) * esz) % 16 == 0 &&
                (a.res_block_map ? (a.res_block_rows % 32 == 0 && a.M % 32 == 0) : (a.res_mod == 0 || a.res_mod % 32 == 0));
     }
-    if (!no_tma_store && EPI == EPI_STD && BN >= 64 && res_ok && !a.row_map && a.out &&
+    if (!no_tma_store && (EPI == EPI_STD || EPI == EPI_LN_ROW) && BN >= 64 && res_ok && !a.row_map && a.out &&
         (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (static_cast<uint64_t>(a.ldo) * esz) % 16 == 0) {
       uint64_t dims[2] = {static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.M)};
       uint64_t strides[1] = {static_cast<uint64_t>(a.ldo) * esz};
@@ -648,6 +762,10 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
         p.tma_res = 1;
       }
     }
+  }
+  if (EPI == EPI_LN_ROW && !(p.tma_store && p.tma_res)) {
+    set_last_error("gemm_v2: fused row LayerNorm needs TMA-eligible bf16 output and residual");
+    return RSP_ERR_INVALID;
   }
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.row_map = a.row_map;
@@ -697,6 +815,18 @@ int gemm_bf16_v2(const GemmArgs& a, int bn, cudaStream_t stream) {
     default: set_last_error("gemm_v2: unsupported BN %d", bn); return RSP_ERR_INVALID;
   }
 }
+
+// out = LayerNorm_256(acc + bias + residual), bf16 in / bf16 residual / bf16 out (mask decoder: LN4(keys + attn))
+bool gemm_v2_ln_row_eligible(const GemmArgs& a) {
+  static const bool off = getenv("RSP_GEMM_NO_LN_FUSED") != nullptr;
+  return !off && a.N == 256 && !a.out_fp32 && a.residual && !a.res_fp32 && a.bias && a.ln_gamma && a.ln_beta && !a.row_map &&
+         !a.w_is_kn && a.res_mod == 0 && a.act == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && a.ldo % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0 && a.ldr % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.ln_gamma) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(a.ln_beta) & 15) == 0 &&
+         (a.res_block_map ? (a.res_block_rows % 32 == 0 && a.M % 32 == 0) : true);
+}
+int gemm_bf16_v2_ln_row(const GemmArgs& a, cudaStream_t stream) { return v2::launch<256, v2::EPI_LN_ROW>(a, stream); }
 
 // mask-decoder upscaler epilogues on the 8-warp kernel (called from gemm_bf16 for epi_mode 2 / 3)
 int gemm_bf16_v2_ln64_gelu(const GemmArgs& a, cudaStream_t stream) {

@@ -239,7 +239,7 @@ class SamMaskDecoderB200(nn.Module):
             return _lib.gemm(att.view(N * Tt, -1), layer["ow"], layer["ob"], residual=queries,
                              out_dtype=torch.float32, ln=ln)
 
-        keys_b, keys_res, kblk = src_b, src32, blk
+        keys_b, keys_res, kblk = src_b, src_b, blk
         queries = None
         for li, L in enumerate(p["layers"]):
             sa = L["sa"]
@@ -272,11 +272,11 @@ class SamMaskDecoderB200(nn.Module):
             vtok = _lib.gemm(_lib.cast_bf16(queries), i2t["vw"], i2t["vb"])
             Qimg = _lib.gemm(keys_b, i2t["qw"], i2t["qb"], residual=pt["q"][li], res_mod=HW)
             att = _lib.i2t_attention(Qimg, ktok.view(N, Tt, -1), vtok.view(N, Tt, -1), HW, q_block=kblk)
-            # out_proj as a plain bf16 GEMM (HBM-roofline epilogue), then keys = LN4(keys + attn_out) in
-            # one row kernel that also applies the prompt -> image block map of the residual
-            proj = _lib.gemm(att, i2t["ow"], i2t["ob"])
-            keys_b = _lib.layernorm_add(proj, keys_res, *L["ln4"], a.layer_norm_eps, res_block_map=kblk,
-                                        res_block_rows=HW if kblk is not None else 0)
+            # keys = LN4(keys + out_proj(attn)) (HF:346-347) in the out_proj GEMM's epilogue: the residual slab
+            # (block-mapped prompt -> image in the first layer) arrives by TMA, the row statistics are taken on
+            # the fp32 accumulator, and only the normalised bf16 keys are written
+            keys_b = _lib.gemm(att, i2t["ow"], i2t["ob"], residual=keys_res, ln=(*L["ln4"], a.layer_norm_eps),
+                               res_block_map=kblk, res_block_rows=HW if kblk is not None else 0)
             keys_res, kblk = keys_b, None
         queries = t2i(p["final"], queries, keys_b, pt["kv"][-1], None, (*p["lnf"], 1e-5))
         qv = queries.view(N, Tt, C)
