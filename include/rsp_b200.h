@@ -249,6 +249,19 @@ int rsp_resize_bilinear_nhwc(const void* x, int B, int H, int W, int C, int h, i
 int rsp_mask_embed_src(const float* mpp, const float* const* wts, const float* emb, const float* pos, int N,
                        int n_per_img, int hm, int wm, int h, int w, float eps, void* src, void* src_pe, void* stream);
 
+/* Mask resize of RSPrompterAnchorMaskHead._predict_by_feat_single for resized / padded images (M:1763-1777): maps
+ * fp32 [n, hm, wm] (mode 2: already sigmoid-activated, >= thr; mode 1: raw, > thr) -> bilinear to (Hb, Wb) =
+ * batch_input_shape -> crop [:crop_h, :crop_w] (the resized, unpadded image) -> bilinear to (H, W) = ori_shape ->
+ * threshold.  The intermediate map is never formed.  out uint8 [n, H, W]. */
+int rsp_mask_paste_rescale(const float* maps, uint8_t* out, int n, int hm, int wm, int Hb, int Wb, int crop_h, int crop_w,
+                           int H, int W, float thr, int mode, void* stream);
+
+/* rsp_query_postprocess for resized / padded images (M:652-656 + 679-691): logits -> (Hb, Wb) -> crop -> (H, W), then
+ * mask = > 0, score, tight box as below.  part_ws fp32 [n_inst, ceil(H/16), 6]. */
+int rsp_query_postprocess_rescale(const float* logits, const int32_t* sel, const float* cls_scores, int n_inst, int hm,
+                                  int wm, int Hb, int Wb, int crop_h, int crop_w, int H, int W, uint8_t* masks,
+                                  float* part_ws, float* scores, float* boxes, void* stream);
+
 /* Instance post-processing of the query variant (M:652-656; maskformer_fusion_head.py:149-182; mask/utils.py:56-77):
  * for instance i (map sel[i] of logits fp32 [*, hm, wm]): bilinear to H x W, mask = > 0, score = cls_scores[i] *
  * mean sigmoid over the positive pixels, tight box.  part_ws fp32 [n_inst, ceil(H/16), 6]. */

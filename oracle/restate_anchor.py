@@ -294,6 +294,21 @@ def mask_postprocess(mask_logits: torch.Tensor, size, thr: float = 0.5) -> torch
     return m >= thr
 
 
+def mask_postprocess_rescale(mask_logits: torch.Tensor, bboxes: torch.Tensor, meta: dict, thr: float = 0.5):
+    """RSPrompterAnchorMaskHead._predict_by_feat_single with rescale=True (M:1746-1784) for one image:
+    boxes back to the original image (/ scale_factor), masks: sigmoid -> bilinear to batch_input_shape ->
+    crop to the resized (unpadded) image -> bilinear to ori_shape -> >= thr."""
+    sf_w, sf_h = meta["scale_factor"]
+    scale = bboxes.new_tensor([sf_w, sf_h]).repeat(1, 2)
+    boxes = bboxes / scale
+    img_h, img_w = meta["ori_shape"][:2]
+    m = F.interpolate(mask_logits.sigmoid(), size=tuple(meta["batch_input_shape"]), mode="bilinear",
+                      align_corners=False).squeeze(1)
+    m = m[:, :int(img_h * sf_h), :int(img_w * sf_w)]
+    m = F.interpolate(m.unsqueeze(1), size=(img_h, img_w), mode="bilinear", align_corners=False).squeeze(1)
+    return m >= thr, boxes
+
+
 # --------------------------------------------------------------------------------------------
 # whole detector
 # --------------------------------------------------------------------------------------------

@@ -195,3 +195,15 @@ def instance_postprocess(mask_cls: torch.Tensor, mask_pred: torch.Tensor, num_cl
     binary = (mp > 0).float()
     mscore = (mp.sigmoid() * binary).flatten(1).sum(1) / (binary.flatten(1).sum(1) + 1e-6)
     return dict(bboxes=mask2bbox(binary.bool()), labels=lab, scores=sc * mscore, masks=binary.bool(), query=qidx)
+
+
+def fusion_rescale(mask_pred: torch.Tensor, meta: dict, rescale: bool = True) -> torch.Tensor:
+    """RSMask2FormerHead.predict up-sampling + RSMaskFormerFusionHead.predict crop / rescale for one image
+    (M:652-656, 679-691): logits [nq, hm, wm] -> batch_input_shape -> crop to the resized image -> ori_shape."""
+    m = F.interpolate(mask_pred[None], size=tuple(meta["batch_input_shape"]), mode="bilinear", align_corners=False)[0]
+    ori_h, ori_w = meta["ori_shape"][:2]
+    sf_w, sf_h = meta["scale_factor"]
+    m = m[:, :int(ori_h * sf_h), :int(ori_w * sf_w)]
+    if rescale:
+        m = F.interpolate(m[:, None], size=(ori_h, ori_w), mode="bilinear", align_corners=False)[:, 0]
+    return m

@@ -79,6 +79,8 @@ _SIGNATURES = {
     "rsp_mha_small": ([_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp], _i),
     "rsp_conv3x3_nhwc_bf16": ([_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "rsp_conv3x3_geometry_ok": ([_i, _i, _i, _i], _i),
+    "rsp_mask_paste_rescale": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, ctypes.c_float, _i, _vp], _i),
+    "rsp_query_postprocess_rescale": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "rsp_attn_mask_bits": ([_vp, _i, _i, _i, _vp, _vp], _i),
     "rsp_resize_bilinear_nhwc": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "rsp_mask_embed_src": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp], _i),
@@ -567,6 +569,22 @@ def mask_paste(logits: torch.Tensor, size: tuple, thr: float, mode: int) -> torc
     return out.view(torch.bool)
 
 
+def mask_paste_rescale(logits: torch.Tensor, batch_hw: tuple, crop_hw: tuple, ori_hw: tuple, thr: float) -> torch.Tensor:
+    """M:1763-1777 for a resized / padded image: sigmoid -> bilinear to batch_hw -> crop -> bilinear to ori_hw -> >= thr.
+    logits fp32 [n, hm, wm] -> bool [n, ori_h, ori_w]."""
+    global launch_count
+    _require_cuda(logits)
+    n, hm, wm = logits.shape
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and n > 0
+    act = torch.empty_like(logits)
+    _check(_lib.rsp_sigmoid_f32(_ptr(logits), _ptr(act), logits.numel(), _stream()), "rsp_sigmoid_f32")
+    out = torch.empty(n, ori_hw[0], ori_hw[1], device=logits.device, dtype=torch.uint8)
+    _check(_lib.rsp_mask_paste_rescale(_ptr(act), _ptr(out), n, hm, wm, batch_hw[0], batch_hw[1], crop_hw[0], crop_hw[1],
+                                       ori_hw[0], ori_hw[1], float(thr), 2, _stream()), "rsp_mask_paste_rescale")
+    launch_count += 2
+    return out.view(torch.bool)
+
+
 def pool2_nhwc(x: torch.Tensor, mode: int) -> torch.Tensor:
     """bf16 NHWC: mode 0 = 2x2 max pool stride 2, mode 1 = stride-2 subsample."""
     global launch_count
@@ -713,6 +731,26 @@ def mask_embed_src(mpp: torch.Tensor, weights: list, emb_rows: torch.Tensor, pos
                                    h, w, float(eps), _ptr(src), _ptr(src_pe), _stream()), "rsp_mask_embed_src")
     launch_count += 1
     return src, src_pe
+
+
+def query_postprocess_rescale(logits: torch.Tensor, sel: torch.Tensor, cls_scores: torch.Tensor, batch_hw: tuple,
+                              crop_hw: tuple, out_hw: tuple):
+    """query_postprocess for a resized / padded image: logits -> batch_hw -> crop -> out_hw, then mask / score / box."""
+    global launch_count
+    _require_cuda(logits, sel, cls_scores)
+    n = sel.numel()
+    _, hm, wm = logits.shape
+    H, W = out_hw
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and sel.dtype == torch.int32 and cls_scores.dtype == torch.float32
+    masks = torch.empty(n, H, W, device=logits.device, dtype=torch.uint8)
+    part = torch.empty(n * ((H + 15) // 16) * 6, device=logits.device, dtype=torch.float32)
+    scores = torch.empty(n, device=logits.device, dtype=torch.float32)
+    boxes = torch.empty(n, 4, device=logits.device, dtype=torch.float32)
+    _check(_lib.rsp_query_postprocess_rescale(_ptr(logits), _ptr(sel), _ptr(cls_scores), n, hm, wm, batch_hw[0], batch_hw[1],
+                                              crop_hw[0], crop_hw[1], H, W, _ptr(masks), _ptr(part), _ptr(scores),
+                                              _ptr(boxes), _stream()), "rsp_query_postprocess_rescale")
+    launch_count += 2
+    return masks.view(torch.bool), scores, boxes
 
 
 def query_postprocess(logits: torch.Tensor, sel: torch.Tensor, cls_scores: torch.Tensor, size: tuple):

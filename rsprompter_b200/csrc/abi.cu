@@ -244,6 +244,18 @@ int rsp_mask_embed_src(const float* mpp, const float* const* wts, const float* e
   return mask_embed_src(mpp, wts, emb, pos, N, n_per_img, hm, wm, h, w, eps, src, src_pe, S(stream));
 }
 
+int rsp_mask_paste_rescale(const float* maps, uint8_t* out, int n, int hm, int wm, int Hb, int Wb, int crop_h, int crop_w,
+                           int H, int W, float thr, int mode, void* stream) {
+  return mask_paste_rescale(maps, out, n, hm, wm, Hb, Wb, crop_h, crop_w, H, W, thr, mode, S(stream));
+}
+
+int rsp_query_postprocess_rescale(const float* logits, const int32_t* sel, const float* cls_scores, int n_inst, int hm,
+                                  int wm, int Hb, int Wb, int crop_h, int crop_w, int H, int W, uint8_t* masks,
+                                  float* part_ws, float* scores, float* boxes, void* stream) {
+  return query_postprocess_rescale(logits, sel, cls_scores, n_inst, hm, wm, Hb, Wb, crop_h, crop_w, H, W, masks, part_ws,
+                                   scores, boxes, S(stream));
+}
+
 int rsp_query_postprocess(const float* logits, const int32_t* sel, const float* cls_scores, int n_inst, int hm, int wm,
                           int H, int W, uint8_t* masks, float* part_ws, float* scores, float* boxes, void* stream) {
   return query_postprocess(logits, sel, cls_scores, n_inst, hm, wm, H, W, masks, part_ws, scores, boxes, S(stream));

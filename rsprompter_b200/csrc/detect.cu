@@ -495,6 +495,42 @@ __global__ void mask_paste_x4_kernel(const float* __restrict__ logits, unsigned 
   }
 }
 
+// general case: resized / padded images (two chained resizes with a crop); thread = 4 output pixels of one row
+template <int MODE>
+__global__ void mask_paste_rescale_kernel(const float* __restrict__ maps, unsigned char* __restrict__ out, int n,
+                                          Resize2 g, float thr) {
+  const int w4 = (g.W + 3) / 4;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(n) * g.H * w4) return;
+  const int xb = static_cast<int>(idx % w4);
+  long long t = idx / w4;
+  const int y = static_cast<int>(t % g.H);
+  const int m = static_cast<int>(t / g.H);
+  const float* src = maps + static_cast<size_t>(m) * g.hm * g.wm;
+  unsigned char* o = out + (static_cast<size_t>(m) * g.H + y) * g.W;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = 4 * xb + k;
+    if (x >= g.W) break;
+    const float v = resize2_at(src, g, y, x);
+    o[x] = (MODE == 1 ? (v > thr) : (v >= thr)) ? 1 : 0;
+  }
+}
+
+int mask_paste_rescale(const float* maps, unsigned char* out, int n, int hm, int wm, int Hb, int Wb, int crop_h,
+                       int crop_w, int H, int W, float thr, int mode, cudaStream_t stream) {
+  RSP_CHECK_ARG(maps && out && n > 0 && hm > 0 && wm > 0 && Hb > 0 && Wb > 0 && crop_h > 0 && crop_w > 0 &&
+                crop_h <= Hb && crop_w <= Wb && H > 0 && W > 0 && (mode == 1 || mode == 2),
+                "mask_paste_rescale: bad args (mode 1: > thr on raw maps, 2: >= thr on activated maps)");
+  Resize2 g{hm, wm, Hb, Wb, crop_h, crop_w, H, W};
+  const long long total = static_cast<long long>(n) * H * ((W + 3) / 4);
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (mode == 1) mask_paste_rescale_kernel<1><<<blocks, 256, 0, stream>>>(maps, out, n, g, thr);
+  else mask_paste_rescale_kernel<2><<<blocks, 256, 0, stream>>>(maps, out, n, g, thr);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
 __global__ void sigmoid_f32_kernel(const float4* __restrict__ in, float4* __restrict__ out, long long n4) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;

@@ -17,6 +17,8 @@ int compact_keep(const unsigned char* keep, const float* boxes, const float* sco
 int roi_align_nhwc(const void* const* feats, const float* const* pes, const int* Hs, const int* Ws,
                    const float* scales, int num_levels, const float* rois, int n, int C, int P,
                    float finest_scale, void* out, cudaStream_t stream);
+int mask_paste_rescale(const float* maps, unsigned char* out, int n, int hm, int wm, int Hb, int Wb, int crop_h,
+                       int crop_w, int H, int W, float thr, int mode, cudaStream_t stream);
 int mask_paste(const float* logits, unsigned char* out, int n, int hm, int wm, int H, int W, float thr,
                int mode, cudaStream_t stream);
 int sigmoid_f32(const float* in, float* out, long long n, cudaStream_t stream);

@@ -664,6 +664,50 @@ __global__ void query_mask_x4_kernel(const float* __restrict__ logits, const int
   }
 }
 
+// general case (resized / padded images): same partial layout, two chained resizes per pixel
+__global__ void query_mask_rescale_kernel(const float* __restrict__ logits, const int* __restrict__ sel, Resize2 g,
+                                          unsigned char* __restrict__ masks, float* __restrict__ part) {
+  const int inst = blockIdx.y;
+  const float* src = logits + static_cast<size_t>(sel[inst]) * g.hm * g.wm;
+  float sum = 0.f;
+  int cnt = 0, minx = g.W, maxx = -1, miny = g.H, maxy = -1;
+  const int y_base = blockIdx.x * QP_ROWS;
+  for (int i = threadIdx.x; i < QP_ROWS * g.W; i += blockDim.x) {
+    const int y = y_base + i / g.W, x = i % g.W;
+    if (y >= g.H) break;
+    const float v = resize2_at(src, g, y, x);
+    const bool on = v > 0.f;
+    masks[(static_cast<size_t>(inst) * g.H + y) * g.W + x] = on;
+    if (on) {
+      sum += 1.f / (1.f + expf(-v));
+      ++cnt;
+      minx = min(minx, x); maxx = max(maxx, x); miny = min(miny, y); maxy = max(maxy, y);
+    }
+  }
+  __shared__ float s_sum[256];
+  __shared__ int s_i[256][5];
+  s_sum[threadIdx.x] = sum;
+  s_i[threadIdx.x][0] = cnt; s_i[threadIdx.x][1] = minx; s_i[threadIdx.x][2] = maxx;
+  s_i[threadIdx.x][3] = miny; s_i[threadIdx.x][4] = maxy;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      s_sum[threadIdx.x] += s_sum[threadIdx.x + s];
+      s_i[threadIdx.x][0] += s_i[threadIdx.x + s][0];
+      s_i[threadIdx.x][1] = min(s_i[threadIdx.x][1], s_i[threadIdx.x + s][1]);
+      s_i[threadIdx.x][2] = max(s_i[threadIdx.x][2], s_i[threadIdx.x + s][2]);
+      s_i[threadIdx.x][3] = min(s_i[threadIdx.x][3], s_i[threadIdx.x + s][3]);
+      s_i[threadIdx.x][4] = max(s_i[threadIdx.x][4], s_i[threadIdx.x + s][4]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float* o = part + (static_cast<size_t>(inst) * gridDim.x + blockIdx.x) * 6;
+    o[0] = s_sum[0]; o[1] = static_cast<float>(s_i[0][0]); o[2] = static_cast<float>(s_i[0][1]);
+    o[3] = static_cast<float>(s_i[0][2]); o[4] = static_cast<float>(s_i[0][3]); o[5] = static_cast<float>(s_i[0][4]);
+  }
+}
+
 __global__ void query_finalize_kernel(const float* __restrict__ part, int nblk, const float* __restrict__ cls_scores,
                                       int n_inst, int W, int H, float* __restrict__ scores, float* __restrict__ boxes) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -690,6 +734,21 @@ int query_postprocess(const float* logits, const int* sel, const float* cls_scor
     query_mask_x4_kernel<<<grid, 256, 0, stream>>>(logits, sel, hm, wm, masks, part_ws);
   else
     query_mask_kernel<<<grid, 256, 0, stream>>>(logits, sel, hm, wm, H, W, masks, part_ws);
+  RSP_CHECK_LAUNCH();
+  query_finalize_kernel<<<(n_inst + 127) / 128, 128, 0, stream>>>(part_ws, nblk, cls_scores, n_inst, W, H, scores, boxes);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
+int query_postprocess_rescale(const float* logits, const int* sel, const float* cls_scores, int n_inst, int hm, int wm,
+                              int Hb, int Wb, int crop_h, int crop_w, int H, int W, unsigned char* masks, float* part_ws,
+                              float* scores, float* boxes, cudaStream_t stream) {
+  RSP_CHECK_ARG(logits && sel && cls_scores && masks && part_ws && scores && boxes && n_inst > 0 && crop_h > 0 &&
+                crop_w > 0 && crop_h <= Hb && crop_w <= Wb && H > 0 && W > 0, "query_postprocess_rescale: bad args");
+  Resize2 g{hm, wm, Hb, Wb, crop_h, crop_w, H, W};
+  const int nblk = (H + QP_ROWS - 1) / QP_ROWS;
+  dim3 grid(nblk, n_inst);
+  query_mask_rescale_kernel<<<grid, 256, 0, stream>>>(logits, sel, g, masks, part_ws);
   RSP_CHECK_LAUNCH();
   query_finalize_kernel<<<(n_inst + 127) / 128, 128, 0, stream>>>(part_ws, nblk, cls_scores, n_inst, W, H, scores, boxes);
   RSP_CHECK_LAUNCH();

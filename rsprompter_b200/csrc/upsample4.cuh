@@ -56,4 +56,38 @@ __device__ __forceinline__ float up4_value(const Up4Tile& t, int j, int k) {
   return (1.f - ly) * top + ly * bot;
 }
 
+// Two chained F.interpolate(bilinear, align_corners=False) calls with a crop in between (the reference's mask
+// path when the image was resized / padded: low-res map -> batch_input_shape -> crop to the resized image ->
+// ori_shape; M:1763-1777, M:652-656 + 679-691), evaluated per output pixel without the intermediate map: the
+// 4 intermediate taps are themselves bilinear samples of the source, with fp32 rounding at the same places.
+struct Resize2 {
+  int hm, wm;      // source map
+  int Hb, Wb;      // intermediate (batch_input_shape)
+  int ch, cw;      // crop of the intermediate that is resized (<= Hb, Wb)
+  int H, W;        // output (ori_shape)
+};
+
+__device__ __forceinline__ float bilinear_at(const float* __restrict__ src, int h, int w, int H, int W, int y, int x) {
+  const float sy = fmaxf((y + 0.5f) * (static_cast<float>(h) / H) - 0.5f, 0.f);
+  const float sx = fmaxf((x + 0.5f) * (static_cast<float>(w) / W) - 0.5f, 0.f);
+  const int y0 = min(static_cast<int>(sy), h - 1), x0 = min(static_cast<int>(sx), w - 1);
+  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  const float ly = sy - y0, lx = sx - x0;
+  return (1.f - ly) * ((1.f - lx) * __ldg(src + y0 * w + x0) + lx * __ldg(src + y0 * w + x1)) +
+         ly * ((1.f - lx) * __ldg(src + y1 * w + x0) + lx * __ldg(src + y1 * w + x1));
+}
+
+__device__ __forceinline__ float resize2_at(const float* __restrict__ src, const Resize2& g, int y, int x) {
+  // second resize: (ch, cw) -> (H, W)
+  const float sy = fmaxf((y + 0.5f) * (static_cast<float>(g.ch) / g.H) - 0.5f, 0.f);
+  const float sx = fmaxf((x + 0.5f) * (static_cast<float>(g.cw) / g.W) - 0.5f, 0.f);
+  const int y0 = min(static_cast<int>(sy), g.ch - 1), x0 = min(static_cast<int>(sx), g.cw - 1);
+  const int y1 = min(y0 + 1, g.ch - 1), x1 = min(x0 + 1, g.cw - 1);
+  const float ly = sy - y0, lx = sx - x0;
+  // first resize (hm, wm) -> (Hb, Wb), sampled at the 4 taps
+  const float v00 = bilinear_at(src, g.hm, g.wm, g.Hb, g.Wb, y0, x0), v01 = bilinear_at(src, g.hm, g.wm, g.Hb, g.Wb, y0, x1);
+  const float v10 = bilinear_at(src, g.hm, g.wm, g.Hb, g.Wb, y1, x0), v11 = bilinear_at(src, g.hm, g.wm, g.Hb, g.Wb, y1, x1);
+  return (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+}
+
 }  // namespace rsp

@@ -46,16 +46,22 @@ class _SamDetectorBase(BaseModule):
         return x, image_embeddings, pe
 
     @staticmethod
-    def _check_metas(batch_data_samples, batch_inputs):
-        hw = tuple(batch_inputs.shape[-2:])
+    def _metas(batch_data_samples, batch_inputs):
+        """-> (batch hw, per-image list of None (ori_shape == img_shape == batch shape, scale_factor 1: the fast
+        batched post-process applies) or dict(ori_hw, crop_hw, scale_factor) for resized / padded images)."""
+        hw = tuple(int(v) for v in batch_inputs.shape[-2:])
+        out = []
         for ds in batch_data_samples:
             m = ds.metainfo
             sf = tuple(float(s) for s in m.get("scale_factor", (1.0, 1.0)))
-            if tuple(m.get("ori_shape", hw))[:2] != hw or tuple(m.get("img_shape", hw))[:2] != hw or sf != (1.0, 1.0):
-                raise NotImplementedError(
-                    "rsprompter_b200 post-processing currently handles ori_shape == img_shape == batch shape "
-                    "with scale_factor 1 (the resize-to-original step of M:1763-1777 is listed as next work)")
-        return hw
+            ori = tuple(int(v) for v in tuple(m.get("ori_shape", hw))[:2])
+            if ori == hw and sf == (1.0, 1.0):
+                out.append(None)
+                continue
+            # crop of the batch-sized map that holds the resized, unpadded image (M:1771-1773, M:681-685)
+            crop = (min(int(ori[0] * sf[1]), hw[0]), min(int(ori[1] * sf[0]), hw[1]))
+            out.append(dict(ori_hw=ori, crop_hw=crop, scale_factor=sf))
+        return hw, out
 
 
 @MODELS.register_module(force=True)
@@ -97,17 +103,28 @@ class RSPrompterAnchor(_SamDetectorBase):
     def predict(self, batch_inputs: torch.Tensor, batch_data_samples=None, rescale: bool = True):
         if batch_data_samples is None:
             batch_data_samples = make_data_samples(batch_inputs.shape[0], tuple(batch_inputs.shape[-2:]))
-        hw = self._check_metas(batch_data_samples, batch_inputs)
+        hw, metas = self._metas(batch_data_samples, batch_inputs)
         r = self.predict_raw(batch_inputs)
         thr = float(self.test_cfg.rcnn.get("mask_thr_binary", 0.5))
         B, M = r["scores"].shape
         logits = r["mask_logits"][:, 0].contiguous()
-        masks = _lib.mask_paste(logits, hw, thr, 0).view(B, M, hw[0], hw[1])
+        fast = all(m is None for m in metas)
+        masks = _lib.mask_paste(logits, hw, thr, 0).view(B, M, hw[0], hw[1]) if fast else None
         counts = r["counts"].cpu().tolist()          # the only device->host read
         for b, ds in enumerate(batch_data_samples):
-            n = counts[b]
-            ds.pred_instances = InstanceData(bboxes=r["bboxes"][b, :n], scores=r["scores"][b, :n],
-                                             labels=r["labels"][b, :n], masks=masks[b, :n])
+            n, m = counts[b], metas[b]
+            boxes = r["bboxes"][b, :n]
+            if m is None:
+                mk = masks[b, :n] if fast else _lib.mask_paste(logits[b * M:b * M + max(n, 1)], hw, thr, 0)[:n]
+            else:   # resized / padded image: boxes back to the original image, masks through the two resizes
+                sf, crop = m["scale_factor"], m["crop_hw"]
+                if rescale:
+                    boxes = boxes / boxes.new_tensor(sf).repeat(2)
+                else:   # M:1756-1760 scales img_h / img_w once more before the crop; the output stays ori_shape
+                    ih, iw = int(round(m["ori_hw"][0] * sf[1])), int(round(m["ori_hw"][1] * sf[0]))
+                    crop = (min(int(ih * sf[1]), hw[0]), min(int(iw * sf[0]), hw[1]))
+                mk = _lib.mask_paste_rescale(logits[b * M:b * M + max(n, 1)], hw, crop, m["ori_hw"], thr)[:n]
+            ds.pred_instances = InstanceData(bboxes=boxes, scores=r["scores"][b, :n], labels=r["labels"][b, :n], masks=mk)
         return batch_data_samples
 
     def forward(self, inputs, data_samples=None, mode: str = "predict"):
@@ -157,11 +174,12 @@ class RSPrompterQuery(_SamDetectorBase):
     def predict(self, batch_inputs: torch.Tensor, batch_data_samples=None, rescale: bool = True):
         if batch_data_samples is None:
             batch_data_samples = make_data_samples(batch_inputs.shape[0], tuple(batch_inputs.shape[-2:]))
-        hw = self._check_metas(batch_data_samples, batch_inputs)
+        hw, metas = self._metas(batch_data_samples, batch_inputs)
         if self.test_cfg.get("panoptic_on", True) or self.test_cfg.get("semantic_on", False):
             raise NotImplementedError("rsprompter_b200 implements instance_on post-processing (every RSPrompter config)")
         r = self.predict_raw(batch_inputs)
-        out = self.panoptic_fusion_head.instance_postprocess_batched(r["cls"], r["mask_logits"], hw)
+        out = self.panoptic_fusion_head.instance_postprocess_batched(r["cls"], r["mask_logits"], hw, metas=metas,
+                                                                     rescale=rescale)
         stuff = self.panoptic_fusion_head.num_stuff_classes > 0
         for b, ds in enumerate(batch_data_samples):
             inst = dict(bboxes=out["bboxes"][b], scores=out["scores"][b], labels=out["labels"][b], masks=out["masks"][b])

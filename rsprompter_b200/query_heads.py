@@ -387,9 +387,11 @@ class RSMaskFormerFusionHead(BaseModule):
         self.test_cfg = _cfg(test_cfg)
 
     @torch.no_grad()
-    def instance_postprocess_batched(self, cls: torch.Tensor, mask_pred: torch.Tensor, size: tuple):
+    def instance_postprocess_batched(self, cls: torch.Tensor, mask_pred: torch.Tensor, size: tuple, metas: list | None = None,
+                                     rescale: bool = True):
         """cls fp32 [B, nq, C+1]; mask_pred fp32 [B*nq, hm, wm] low-res logits (the bilinear up-sampling of
-        M:652-656 is fused into the mask kernel).  -> dict of [B, K, ...] tensors."""
+        M:652-656 and the crop / rescale of M:679-691 are fused into the mask kernel).
+        -> dict of per-image lists / [B, K, ...] tensors (all images at the batch shape: stacked tensors)."""
         B, nq, _ = cls.shape
         C = self.num_classes
         K = int(self.test_cfg.get("max_per_image", 100))
@@ -397,11 +399,22 @@ class RSMaskFormerFusionHead(BaseModule):
         sc, top = scores.topk(K, dim=1, sorted=False)
         labels = top % C
         query = top // C
-        sel = (query + torch.arange(B, device=cls.device).view(B, 1) * nq).to(torch.int32).reshape(-1).contiguous()
-        masks, det, boxes = _lib.query_postprocess(mask_pred, sel, sc.reshape(-1).contiguous(), size)
+        sel = (query + torch.arange(B, device=cls.device).view(B, 1) * nq).to(torch.int32).contiguous()
         keep_thing = labels < self.num_things_classes
-        return dict(masks=masks.view(B, K, *size), scores=det.view(B, K), bboxes=boxes.view(B, K, 4), labels=labels,
-                    query=query, is_thing=keep_thing)
+        if metas is None or all(m is None for m in metas):
+            masks, det, boxes = _lib.query_postprocess(mask_pred, sel.reshape(-1), sc.reshape(-1).contiguous(), size)
+            return dict(masks=masks.view(B, K, *size), scores=det.view(B, K), bboxes=boxes.view(B, K, 4), labels=labels,
+                        query=query, is_thing=keep_thing)
+        ms, ds, bs = [], [], []
+        for b, m in enumerate(metas):      # image sizes differ: one launch pair per image, no host sync
+            if m is None:
+                mk, det, bx = _lib.query_postprocess(mask_pred, sel[b].contiguous(), sc[b].contiguous(), size)
+            else:
+                out_hw = m["ori_hw"] if rescale else m["crop_hw"]
+                mk, det, bx = _lib.query_postprocess_rescale(mask_pred, sel[b].contiguous(), sc[b].contiguous(), size,
+                                                             m["crop_hw"], out_hw)
+            ms.append(mk); ds.append(det); bs.append(bx)
+        return dict(masks=ms, scores=ds, bboxes=bs, labels=labels, query=query, is_thing=keep_thing)
 
 
 __all__ = ["MSDeformAttnPixelDecoder", "RSMask2FormerHead", "RSMaskFormerFusionHead"]

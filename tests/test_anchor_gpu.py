@@ -185,3 +185,43 @@ def test_end_to_end_predict_contract(model_and_sd):
         assert (p.scores[:-1] >= p.scores[1:]).all()
     out2 = m.predict(x, make_data_samples(2, 1024))
     assert torch.equal(out[0].pred_instances.bboxes, out2[0].pred_instances.bboxes)
+
+
+@pytest.mark.parametrize("ori,batch", [((120, 200), (256, 256)), ((512, 512), (1024, 1024)), ((300, 180), (256, 256))])
+def test_mask_paste_rescale_matches_oracle(ori, batch):
+    """Resized + padded images (M:1763-1777): sigmoid -> batch shape -> crop -> ori_shape -> threshold, no intermediate."""
+    from oracle import restate_anchor as ra
+    from rsprompter_b200 import _lib
+    g = torch.Generator().manual_seed(9)
+    hm = batch[0] // 4
+    s = min(batch[0] / ori[0], batch[1] / ori[1])
+    new_hw = (int(ori[0] * s + 0.5), int(ori[1] * s + 0.5))
+    meta = dict(ori_shape=ori, batch_input_shape=batch, scale_factor=(new_hw[1] / ori[1], new_hw[0] / ori[0]))
+    logits = torch.randn(4, 1, hm, hm, generator=g) * 3
+    boxes = torch.rand(4, 4, generator=g) * 200
+    ref, ref_boxes = ra.mask_postprocess_rescale(logits, boxes.clone(), meta, 0.5)
+    sf = meta["scale_factor"]
+    crop = (min(int(ori[0] * sf[1]), batch[0]), min(int(ori[1] * sf[0]), batch[1]))
+    got = _lib.mask_paste_rescale(logits[:, 0].contiguous().cuda(), batch, crop, ori, 0.5)
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape and got.dtype == torch.bool
+    assert (got.cpu() != ref).float().mean().item() < 2e-5
+
+
+def test_predict_rescales_to_original_image(model_and_sd):
+    """predict() with the metainfo of a keep-ratio resized, padded image: boxes / scale_factor, masks at ori_shape."""
+    from rsprompter_b200.registry import make_data_samples
+    m, _ = model_and_sd
+    torch.manual_seed(5)
+    x = torch.randn(2, 3, 1024, 1024).cuda()
+    base = m.predict(x)
+    samples = make_data_samples(2, (1024, 1024))
+    samples[1].set_metainfo(dict(ori_shape=(600, 800), img_shape=(768, 1024), scale_factor=(1.28, 1.28),
+                                 batch_input_shape=(1024, 1024)))
+    out = m.predict(x, samples)
+    torch.cuda.synchronize()
+    p0, p1, b1 = out[0].pred_instances, out[1].pred_instances, base[1].pred_instances
+    assert torch.equal(p0.masks, base[0].pred_instances.masks)            # untouched image: same fast-path result
+    n = p1.scores.numel()
+    assert p1.masks.shape == (n, 600, 800) and torch.equal(p1.scores, b1.scores)
+    assert torch.allclose(p1.bboxes, b1.bboxes / 1.28, rtol=1e-6, atol=1e-4)

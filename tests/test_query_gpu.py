@@ -202,3 +202,40 @@ def test_query_detector_predict():
                 assert torch.equal(p.bboxes[i].cpu(), exp)
             else:
                 assert p.bboxes[i].abs().sum().item() == 0
+
+
+def test_instance_postprocess_rescale_matches_oracle():
+    """Resized + padded image (M:652-656, 679-691): logits -> batch shape -> crop -> ori_shape, then mask / score / box."""
+    from oracle import restate_query
+    from rsprompter_b200.registry import MODELS
+    g = torch.Generator().manual_seed(19)
+    B, nq, hm, K = 2, 12, 64, 9
+    batch, ori = (256, 256), (150, 210)
+    s = min(batch[0] / ori[0], batch[1] / ori[1])
+    new_hw = (int(ori[0] * s + 0.5), int(ori[1] * s + 0.5))
+    meta = dict(ori_shape=ori, batch_input_shape=batch, scale_factor=(new_hw[1] / ori[1], new_hw[0] / ori[0]))
+    sf = meta["scale_factor"]
+    metas = [None, dict(ori_hw=ori, crop_hw=(min(int(ori[0] * sf[1]), batch[0]), min(int(ori[1] * sf[0]), batch[1])), scale_factor=sf)]
+    fh = MODELS.build(dict(type="RSMaskFormerFusionHead", num_things_classes=NCLS, num_stuff_classes=0,
+                           test_cfg=dict(max_per_image=K, instance_on=True, panoptic_on=False)))
+    cls = torch.randn(B, nq, NCLS + 1, generator=g) * 2
+    yy, xx = torch.meshgrid(torch.arange(hm), torch.arange(hm), indexing="ij")
+    cy, cx, r = (torch.rand(B * nq, 1, 1, generator=g) * hm for _ in range(3))
+    logit = (r * 0.4 + 3 - ((yy - cy) ** 2 + (xx - cx) ** 2).sqrt()) * 1.7 + 0.05 * torch.randn(B * nq, hm, hm, generator=g)
+    out = fh.instance_postprocess_batched(cls.cuda(), logit.cuda().contiguous(), batch, metas=metas, rescale=True)
+    torch.cuda.synchronize()
+    up = restate_query.fusion_rescale(logit.view(B, nq, hm, hm)[1], meta)            # [nq, 150, 210]
+    ref = restate_query.instance_postprocess(cls[1], up, NCLS, K)
+    key = lambda q, l: (q * NCLS + l).tolist()  # noqa: E731
+    order_ref = {k: i for i, k in enumerate(key(ref["query"], ref["labels"]))}
+    got = key(out["query"][1].cpu(), out["labels"][1].cpu())
+    assert sorted(got) == sorted(order_ref)
+    idx = torch.tensor([order_ref[k] for k in got])
+    m = out["masks"][1].cpu()
+    assert m.shape == (K, *ori) and out["masks"][0].shape == (K, *batch)
+    m_ref = ref["masks"][idx]
+    near = up[ref["query"][idx]].abs() < 1e-4
+    assert ((m != m_ref) & ~near).sum().item() == 0
+    assert torch.allclose(out["scores"][1].cpu(), ref["scores"][idx], rtol=2e-3, atol=1e-5)
+    clean = ~((m != m_ref).flatten(1).any(1))
+    assert torch.equal(out["bboxes"][1].cpu()[clean], ref["bboxes"][idx][clean])
