@@ -21,6 +21,38 @@ def _cfg(d) -> ConfigDict:
 
 
 class _SamDetectorBase(BaseModule):
+    # ---- CUDA-graph replay of the device-resident forward ----------------------------------------------------
+    # predict_raw() is ~420 launches with static shapes and no host synchronisation, so one captured graph per
+    # input shape replays it without per-launch host work or inter-kernel launch gaps.  Opt-in
+    # (enable_cuda_graphs()): capture allocates a private memory pool per shape.
+    def enable_cuda_graphs(self, enabled: bool = True):
+        self._graphs = {} if enabled else None
+        return self
+
+    def _raw(self, batch_inputs: torch.Tensor) -> dict:
+        graphs = getattr(self, "_graphs", None)
+        if graphs is None:
+            return self.predict_raw(batch_inputs)
+        key = (tuple(batch_inputs.shape), batch_inputs.dtype)
+        if key not in graphs:
+            static_in = batch_inputs.to(next(self.parameters()).device, copy=True)   # also accepts a pinned host batch
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):          # warm-up: one-time attribute calls, caches, constant tables
+                for _ in range(2):
+                    self.predict_raw(static_in)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count
+            with torch.cuda.graph(g):
+                out = self.predict_raw(static_in)
+            graphs[key] = (g, static_in, out, _lib.launch_count - n0)
+        g, static_in, out, n_launch = graphs[key]
+        static_in.copy_(batch_inputs, non_blocking=True)
+        g.replay()
+        _lib.launch_count += n_launch      # the replay launches the library's kernels again
+        return out      # static output buffers: valid until the next call with this shape
+
     def _encode(self, batch_inputs: torch.Tensor):
         """-> (emb_rows fp32 [B*g*g, C], pos_rows fp32 [g*g, C], (g, g), emb_nhwc_bf16 | None, hidden | None)."""
         enc = self.backbone.vision_encoder
@@ -104,7 +136,7 @@ class RSPrompterAnchor(_SamDetectorBase):
         if batch_data_samples is None:
             batch_data_samples = make_data_samples(batch_inputs.shape[0], tuple(batch_inputs.shape[-2:]))
         hw, metas = self._metas(batch_data_samples, batch_inputs)
-        r = self.predict_raw(batch_inputs)
+        r = self._raw(batch_inputs)
         thr = float(self.test_cfg.rcnn.get("mask_thr_binary", 0.5))
         B, M = r["scores"].shape
         logits = r["mask_logits"][:, 0].contiguous()
@@ -177,7 +209,7 @@ class RSPrompterQuery(_SamDetectorBase):
         hw, metas = self._metas(batch_data_samples, batch_inputs)
         if self.test_cfg.get("panoptic_on", True) or self.test_cfg.get("semantic_on", False):
             raise NotImplementedError("rsprompter_b200 implements instance_on post-processing (every RSPrompter config)")
-        r = self.predict_raw(batch_inputs)
+        r = self._raw(batch_inputs)
         out = self.panoptic_fusion_head.instance_postprocess_batched(r["cls"], r["mask_logits"], hw, metas=metas,
                                                                      rescale=rescale)
         stuff = self.panoptic_fusion_head.num_stuff_classes > 0

@@ -225,3 +225,23 @@ def test_predict_rescales_to_original_image(model_and_sd):
     n = p1.scores.numel()
     assert p1.masks.shape == (n, 600, 800) and torch.equal(p1.scores, b1.scores)
     assert torch.allclose(p1.bboxes, b1.bboxes / 1.28, rtol=1e-6, atol=1e-4)
+
+
+def test_cuda_graph_replay_equals_eager(model_and_sd):
+    """enable_cuda_graphs(): the captured forward replays to the same detections as the eager launch sequence."""
+    m, _ = model_and_sd
+    torch.manual_seed(11)
+    xs = [torch.randn(2, 3, 1024, 1024).cuda() for _ in range(2)]
+    eager = [m.predict(x) for x in xs]
+    eager = [[(d.pred_instances.bboxes.clone(), d.pred_instances.scores.clone(), d.pred_instances.masks.clone())
+              for d in out] for out in eager]
+    m.enable_cuda_graphs()
+    try:
+        for rep in range(2):
+            for x, ref in zip(xs, eager):
+                out = m.predict(x)
+                for d, (b, s, k) in zip(out, ref):
+                    assert torch.equal(d.pred_instances.bboxes, b) and torch.equal(d.pred_instances.scores, s)
+                    assert torch.equal(d.pred_instances.masks, k)
+    finally:
+        m.enable_cuda_graphs(False)
