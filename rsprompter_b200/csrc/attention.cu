@@ -44,14 +44,20 @@ __device__ __forceinline__ float fast_exp2(float x) {
 template <int HD>
 struct AttCfg {
   static constexpr int NA = (HD + 63) / 64;           // 64-wide swizzle atoms per head
+  static constexpr bool SB = HD > 64;                 // single-buffered S / K / V (hd 80): fits 2 CTAs per SM
+  static constexpr int NBUF = SB ? 1 : 2;
   static constexpr int Q_BYTES = NA * 16384;          // 128 rows x NA x 128 B
   static constexpr int KV_BYTES = NA * 8192;          // one 64-key stage of K or V
-  static constexpr int P_BYTES = 16384;               // 128 x 64 bf16 (one swizzle atom), two of them
+  static constexpr int TAB_BYTES = NA * 16384;        // a rel-pos table in the prologue (<= 128 rows x NA x 128 B)
+  static constexpr int SCRATCH_BYTES = 32768;         // prologue gather scratch: [kw <= 64][128] fp32
   static constexpr int RELH_BYTES = 64 * 128 * 2;     // global: [kh][row] fp16
-  static constexpr int SMEM_BYTES = Q_BYTES + 4 * KV_BYTES + 2 * P_BYTES + RELH_BYTES + 1024;
+  // hd 64: [Q | K x2 (rel_h table) | V x2 (rel_w table) | scratch | relh_s]
+  // hd 80: [Q | A: rel_h table -> scratch -> K, V | B: rel_w table -> relh_s]   (K / V loads wait for the gather)
+  static constexpr int SMEM_BYTES = SB ? Q_BYTES + 2 * TAB_BYTES + 1024
+                                       : Q_BYTES + 4 * KV_BYTES + SCRATCH_BYTES + RELH_BYTES + 1024;
   static constexpr int O_STRIDE = (HD <= 64) ? 64 : 96;   // column distance between the two accumulators
-  // S_0: [0,64)  S_1: [64,128)  O_0: [128, ..)  O_1: [128 + O_STRIDE, ..)
-  static constexpr int TMEM_COLS = (HD <= 64) ? 256 : 512;
+  static constexpr int O_COL = SB ? 64 : 128;         // hd 64: S_0 [0,64) S_1 [64,128) O_0 [128,192) O_1 [192,256)
+  static constexpr int TMEM_COLS = 256;               // hd 80: S [0,64) O_0 [64,144) O_1 [160,240)
 };
 
 struct AttDev {
@@ -71,7 +77,7 @@ enum { B_Q = 0, B_REL, B_RELC, B_KF, B_KE = B_KF + 2, B_VF = B_KE + 2, B_VE = B_
        B_PF = B_SF + 2, B_PV = B_PF + 2, B_COUNT = B_PV + 2 };
 
 template <int HD, int GS>   // GS = 0: 14x14 windows; GS = 64 / 32: global attention over a GS x GS grid
-__global__ void __launch_bounds__(ATT_THREADS, (HD <= 64) ? 2 : 1)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_kv,
                      const __grid_constant__ CUtensorMap tm_relh,
                      const __grid_constant__ CUtensorMap tm_relw, const AttDev p) {
@@ -84,13 +90,20 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   __shared__ uint32_t tmem_base_s;
   __shared__ float2 xchg[2][128];            // (m, l) of each key half, exchanged once at the end
 
+  constexpr bool SB = Cfg::SB;
+  constexpr int NBUF = Cfg::NBUF;
   const uint32_t sQ = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sK = sQ + Cfg::Q_BYTES;                 // 2 stages (prologue: the rel_h table)
-  const uint32_t sV = sK + 2 * Cfg::KV_BYTES;            // 2 stages (prologue: the rel_w table)
-  const uint32_t sP = sV + 2 * Cfg::KV_BYTES;            // 2 buffers
-  const uint32_t sRH = sP + 2 * Cfg::P_BYTES;
-  uint8_t* gP = smem_raw + (sP - smem_u32(smem_raw));
+  const uint32_t sTabH = sQ + Cfg::Q_BYTES;                               // rel_h table (prologue)
+  const uint32_t sTabW = sTabH + (SB ? Cfg::TAB_BYTES : 2 * Cfg::KV_BYTES);   // rel_w table (prologue)
+  const uint32_t sK = sTabH;                                             // K stage(s)
+  const uint32_t sV = SB ? sTabH + Cfg::KV_BYTES : sTabW;                // V stage(s)
+  const uint32_t sScr = SB ? sTabH : sTabW + 2 * Cfg::KV_BYTES;          // gather scratch
+  const uint32_t sRH = SB ? sTabW : sScr + Cfg::SCRATCH_BYTES;           // relh_s
+  uint8_t* gP = smem_raw + (sScr - smem_u32(smem_raw));
   uint8_t* gRH = smem_raw + (sRH - smem_u32(smem_raw));
+  // ring slot / mbarrier phase of tile t (two slots for hd 64, one for hd 80)
+  auto slot = [](int t) { return SB ? 0 : (t & 1); };
+  auto phase = [](int t) -> uint32_t { return SB ? (t & 1) : ((t >> 1) & 1); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -122,8 +135,9 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t tS = tmem_base;                             // S_0 | S_1 (and the rel_h prologue product)
-  const uint32_t tO = tmem_base + 128;                       // accumulator of key half 0 (and rel_w prologue)
-  const uint32_t tO1 = tmem_base + 128 + Cfg::O_STRIDE;      // accumulator of key half 1
+  const uint32_t tOpro = tmem_base + 128;                    // rel_w prologue product
+  const uint32_t tO = tmem_base + Cfg::O_COL;                // accumulator of key half 0
+  const uint32_t tO1 = tO + Cfg::O_STRIDE;                   // accumulator of key half 1
   const int n_kt = GLOBAL ? p.n_kt : 4;
 
   if (warp == 8 && lane == 0) {
@@ -132,12 +146,13 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
       tma_load_2d(sQ + a * 16384, &tm_qkv, bar(B_Q), colq + a * 64, row0 + q0);
-      tma_load_2d(sK + a * 16384, &tm_relh, bar(B_Q), a * 64, 0);
-      tma_load_2d(sV + a * 16384, &tm_relw, bar(B_Q), a * 64, 0);
+      tma_load_2d(sTabH + a * 16384, &tm_relh, bar(B_Q), a * 64, 0);
+      tma_load_2d(sTabW + a * 16384, &tm_relw, bar(B_Q), a * 64, 0);
     }
+    if (SB) mbar_wait(bar(B_RELC), 0);        // the gather scratch / relh_s live where K / V land
     for (int j = 0; j < n_kt; ++j) {
-      const int s = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
+      const int s = slot(j);
+      const uint32_t ph = phase(j);
       mbar_wait(bar(B_KE + s), ph);           // phase 0 of the "empty" slots completes with the prologue MMAs
       mbar_expect_tx(bar(B_KF + s), Cfg::KV_BYTES);
 #pragma unroll
@@ -160,12 +175,12 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 #pragma unroll
     for (int ks = 0; ks < HD / 16; ++ks) {
       const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
-      umma_ss(tS, make_sdesc(sQ + off, 0, 1024), make_sdesc(sK + off, 0, 1024), idesc_rel, ks != 0);
+      umma_ss(tS, make_sdesc(sQ + off, 0, 1024), make_sdesc(sTabH + off, 0, 1024), idesc_rel, ks != 0);
     }
 #pragma unroll
     for (int ks = 0; ks < HD / 16; ++ks) {
       const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
-      umma_ss(tO, make_sdesc(sQ + off, 0, 1024), make_sdesc(sV + off, 0, 1024), idesc_rel, ks != 0);
+      umma_ss(tOpro, make_sdesc(sQ + off, 0, 1024), make_sdesc(sTabW + off, 0, 1024), idesc_rel, ks != 0);
     }
     umma_commit(bar(B_REL));
     umma_commit(bar(B_KE));
@@ -174,10 +189,10 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     umma_commit(bar(B_VE + 1));
     mbar_wait(bar(B_RELC), 0);
     tc_fence_after();
-    auto issue_qk = [&](int t) {   // S_{t&1} = Q K_t^T
-      const int s = t & 1;
-      mbar_wait(bar(B_KF + s), (t >> 1) & 1);
-      if (t >= 2) mbar_wait(bar(B_PV + s), ((t - 2) >> 1) & 1);   // P V of tile t-2 has consumed S_s / P_s
+    auto issue_qk = [&](int t) {   // S_slot(t) = Q K_t^T
+      const int s = slot(t);
+      mbar_wait(bar(B_KF + s), phase(t));
+      if (t >= NBUF) mbar_wait(bar(B_PV + s), phase(t - NBUF));   // P V of the previous user has consumed S_s / P_s
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < HD / 16; ++ks) {
@@ -190,9 +205,9 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     };
     issue_qk(0);
     for (int j = 0; j < n_kt; ++j) {
-      if (j + 1 < n_kt) issue_qk(j + 1);      // runs while the softmax warps work on tile j
-      const int s = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
+      if (!SB && j + 1 < n_kt) issue_qk(j + 1);      // runs while the softmax warps work on tile j
+      const int s = slot(j);
+      const uint32_t ph = phase(j);
       mbar_wait(bar(B_PF + s), ph);
       mbar_wait(bar(B_VF + s), ph);
       tc_fence_after();
@@ -205,6 +220,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       }
       umma_commit(bar(B_PV + s));
       umma_commit(bar(B_VE + s));
+      if (SB && j + 1 < n_kt) issue_qk(j + 1);       // single S: the next scores follow P V
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------ softmax / correction / output
@@ -244,7 +260,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 #pragma unroll 1
         for (int c = 0; c < NREL / 16; ++c) {
           uint32_t v[16];
-          tmem_ld_32x32b_x16(tO + lane_off + c * 16, v);
+          tmem_ld_32x32b_x16(tOpro + lane_off + c * 16, v);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -268,7 +284,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           if (kh >= 0 && kh < 14) scratch[kh * 128 + r] = __uint_as_float(v[i]) * LOG2E;
         }
       } else {
-        tmem_ld_32x32b_x32(tO + lane_off, v);
+        tmem_ld_32x32b_x32(tOpro + lane_off, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 27; ++i) {
@@ -306,8 +322,8 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 
 #pragma unroll(GLOBAL ? 1 : 4)
     for (int j = 0; j < n_kt; ++j) {
-      const int s = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
+      const int s = slot(j);
+      const uint32_t ph = phase(j);
       mbar_wait(bar(B_SF + s), ph);
       tc_fence_after();
       float rh = 0.f;
@@ -334,7 +350,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         l_run *= alpha;
         m_run = need ? bound : m_run;
         if (j > 0) {
-          mbar_wait(bar(B_PV + (s ^ 1)), ((j - 1) >> 1) & 1);   // P V of tile j-1 has landed in O_h
+          mbar_wait(bar(B_PV + slot(j - 1)), phase(j - 1));     // P V of tile j-1 has landed in O_h
           tc_fence_after();
 #pragma unroll
           for (int c = 0; c < HD / 16; ++c) {
@@ -386,7 +402,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     }
 
     // ---- epilogue: merge the two key halves, O / l -> out[token, head*HD .. ]
-    mbar_wait(bar(B_PV + ((n_kt - 1) & 1)), ((n_kt - 1) >> 1) & 1);
+    mbar_wait(bar(B_PV + slot(n_kt - 1)), phase(n_kt - 1));
     tc_fence_after();
     xchg[hf][r] = make_float2(m_run, l_run);
     pair_sync();
