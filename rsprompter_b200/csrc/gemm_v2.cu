@@ -387,6 +387,35 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
 #pragma unroll
           for (int i = 0; i < 64; ++i) { const float d = v[i] - mean; var += d * d; }
           const float rstd = rsqrtf(var * (1.0f / 64.0f) + p.ln_eps);
+          if (p.tma_store) {
+            // swizzled 32 x 128 B slab -> one TMA store (rows >= M are clipped by the tensor map)
+            const uint32_t sbuf = smem_u32(stg_all) + e * 4096;
+            const uint32_t srow = sbuf + lane * 128;
+            const int sw = lane & 7;
+            uint32_t pk[32];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma) + i);
+              const float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_beta) + i);
+              const float y0 = gelu_fast((v[4 * i] - mean) * rstd * g.x + bt.x);
+              const float y1 = gelu_fast((v[4 * i + 1] - mean) * rstd * g.y + bt.y);
+              const float y2 = gelu_fast((v[4 * i + 2] - mean) * rstd * g.z + bt.z);
+              const float y3 = gelu_fast((v[4 * i + 3] - mean) * rstd * g.w + bt.w);
+              pk[2 * i] = pack_bf16x2(y0, y1);
+              pk[2 * i + 1] = pack_bf16x2(y2, y3);
+            }
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ sw) << 4)), "r"(pk[4 * j]),
+                           "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                           : "memory");
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&tma_c, sbuf, col0, m_blk * BM + q * 32); bulk_commit(); }
+            continue;
+          }
           const uint32_t a = stg_s + lane * STG_ROW;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -745,7 +774,8 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
                (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0 && (static_cast<uint64_t>(a.ldr) * esz) % 16 == 0 &&
                (a.res_block_map ? (a.res_block_rows % 32 == 0 && a.M % 32 == 0) : (a.res_mod == 0 || a.res_mod % 32 == 0));
     }
-    if (!no_tma_store && (EPI == EPI_STD || EPI == EPI_LN_ROW) && BN >= 64 && res_ok && !a.row_map && a.out &&
+    if (!no_tma_store && (EPI == EPI_STD || EPI == EPI_LN_ROW || EPI == EPI_LN64_GELU) && BN >= 64 && res_ok && !a.row_map &&
+        a.out &&
         (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (static_cast<uint64_t>(a.ldo) * esz) % 16 == 0) {
       uint64_t dims[2] = {static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.M)};
       uint64_t strides[1] = {static_cast<uint64_t>(a.ldo) * esz};
