@@ -22,6 +22,8 @@
 // prologue MMA computes Q (unscaled) x table^T for both tables (the reference's two
 // einsums), each thread gathers the values its row / key half needs, and the bias is added
 // inside the softmax FMA.  Scores stay fp32 until the exp (reference: softmax in fp32).
+#include <cstdlib>
+
 #include "attention.h"
 #include "sm100.cuh"
 
@@ -484,6 +486,10 @@ int vit_attention(const AttentionArgs& a, cudaStream_t stream) {
   RSP_CHECK_ARG(a.n_seq > 0 && a.H > 0, "attention: bad n_seq/H");
   if (a.S != 14 && a.S != 32 && a.S != 64)   // other grids (768^2 / 1280^2 inputs): CUDA-core kernel
     return vit_attention_simt(a, stream);
+  if (a.S == 14 && (a.hd == 64 || a.hd == 80)) {
+    static const bool old_path = getenv("RSP_ATT_WINDOW_GENERIC") != nullptr;   // A/B switch for the self-test
+    if (!old_path) return vit_window_attention(a, stream);
+  }
   if (a.hd == 64) {
     if (a.S == 64) return launch_att<64, 64>(a, stream);
     if (a.S == 32) return launch_att<64, 32>(a, stream);

@@ -21,5 +21,6 @@ struct AttentionArgs {
 
 int vit_attention(const AttentionArgs& a, cudaStream_t stream);
 int vit_attention_simt(const AttentionArgs& a, cudaStream_t stream);
+int vit_window_attention(const AttentionArgs& a, cudaStream_t stream);   // S = 14 sequences (attention_window.cu)
 
 }  // namespace rsp
