@@ -280,7 +280,9 @@ def run_ours(args) -> None:
                 # park the GPU (~50 ms) so the host enqueues the whole instrumented step ahead of it: each event
                 # pair then brackets exactly one GEMM on a never-starved stream (without this the eager, event-laden
                 # pass is host-bound and the pairs would include launch gaps)
-                torch.cuda._sleep(100_000_000)
+                park = getattr(torch.cuda, "_sleep", None)
+                if park is not None:
+                    park(100_000_000)
                 model.predict_raw(resident[i % N_INPUT_SETS])
                 torch.cuda.synchronize()
         finally:
