@@ -111,6 +111,43 @@ def main():
     fx["ln2d"] = dict(x=xx, weight=w, bias=b, eps=1e-6,
                       out=ln["forward"](SimpleNamespace(weight=w, bias=b, eps=1e-6), xx))
 
+    # ---- mmdet/models/seg_heads/panoptic_fusion_heads/maskformer_fusion_head.py:126-182 instance_postprocess
+    class _Inst(SimpleNamespace):
+        pass
+    fh = load_defs("mmdet/models/seg_heads/panoptic_fusion_heads/maskformer_fusion_head.py", ["instance_postprocess"],
+                   cls="MaskFormerFusionHead")
+    fh["instance_postprocess"].__globals__.update(mask2bbox=mu["mask2bbox"], InstanceData=_Inst)
+    nq, ncls = 12, 5
+    mask_cls = torch.randn(nq, ncls + 1, generator=g) * 2
+    yy, xx2 = torch.meshgrid(torch.arange(40), torch.arange(48), indexing="ij")
+    cy, cx, rr = torch.rand(nq, 1, 1, generator=g) * 40, torch.rand(nq, 1, 1, generator=g) * 48, torch.rand(nq, 1, 1, generator=g) * 12
+    mask_pred = (rr + 2 - ((yy - cy) ** 2 + (xx2 - cx) ** 2).sqrt()) * 1.3 + 0.1 * torch.randn(nq, 40, 48, generator=g)
+    self_ = SimpleNamespace(test_cfg=dict(max_per_image=7), num_classes=ncls, num_things_classes=ncls)
+    res = fh["instance_postprocess"](self_, mask_cls, mask_pred)
+    fx["instance_postprocess"] = dict(mask_cls=mask_cls, mask_pred=mask_pred, num_classes=ncls, max_per_image=7,
+                                      bboxes=res.bboxes, labels=res.labels, scores=res.scores, masks=res.masks)
+
+    # ---- mmdet/rsprompter/models.py:661-715 RSMaskFormerFusionHead.predict (crop to the resized image + rescale)
+    rf = load_defs("mmdet/rsprompter/models.py", ["predict"], cls="RSMaskFormerFusionHead")
+    meta = dict(img_shape=(60, 96), ori_shape=(50, 80), scale_factor=(1.2, 1.2), batch_input_shape=(96, 96))
+    self_ = SimpleNamespace(test_cfg=dict(panoptic_on=False, semantic_on=False, instance_on=True, max_per_image=7),
+                            num_classes=ncls, num_things_classes=ncls)
+    self_.instance_postprocess = lambda c, m: fh["instance_postprocess"](self_, c, m)
+    mp_b = torch.randn(1, nq, 96, 96, generator=g) * 2
+    out = rf["predict"](self_, mask_cls[None], mp_b, [SimpleNamespace(metainfo=meta)], rescale=True)[0]["ins_results"]
+    fx["fusion_predict_rescale"] = dict(mask_cls=mask_cls, mask_pred=mp_b[0], meta=meta, num_classes=ncls, max_per_image=7,
+                                        bboxes=out.bboxes, labels=out.labels, scores=out.scores, masks=out.masks)
+
+    # ---- mmdet/rsprompter/models.py:1746-1784 RSPrompterAnchorMaskHead._predict_by_feat_single (rescale=True)
+    mh = load_defs("mmdet/rsprompter/models.py", ["_predict_by_feat_single"], cls="RSPrompterAnchorMaskHead")
+    meta2 = dict(ori_shape=(50, 80), scale_factor=(1.2, 1.2), batch_input_shape=(96, 96))
+    logits = torch.randn(5, 1, 24, 24, generator=g) * 3
+    boxes = torch.rand(5, 4, generator=g) * 90
+    b_in = boxes.clone()
+    im = mh["_predict_by_feat_single"](SimpleNamespace(), logits, b_in, torch.zeros(5, dtype=torch.long), meta2,
+                                       SimpleNamespace(mask_thr_binary=0.5), rescale=True)
+    fx["anchor_mask_rescale"] = dict(logits=logits, boxes=boxes, meta=meta2, masks=im, boxes_out=b_in)
+
     torch.save(fx, OUT)
     print("wrote", OUT, {k: list(v.keys()) for k, v in fx.items()})
 

@@ -74,3 +74,41 @@ def test_ln2d():
 def test_mask2bbox():
     f = FX["mask2bbox"]
     assert torch.equal(ra.mask2bbox(f["masks"]), f["out"])
+
+
+def _by_score(d):
+    o = torch.argsort(d["scores"], descending=True, stable=True)
+    return {k: d[k][o] for k in ("scores", "labels", "bboxes", "masks")}
+
+
+def test_instance_postprocess_matches_reference():
+    """oracle/restate_query.instance_postprocess vs MaskFormerFusionHead.instance_postprocess executed from the
+    reference tree (maskformer_fusion_head.py:126-182)."""
+    from oracle import restate_query
+    f = FX["instance_postprocess"]
+    got = restate_query.instance_postprocess(f["mask_cls"], f["mask_pred"], f["num_classes"], f["max_per_image"])
+    a, b = _by_score(got), _by_score(f)
+    assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["masks"], b["masks"])
+    assert torch.equal(a["bboxes"], b["bboxes"]) and torch.allclose(a["scores"], b["scores"], rtol=1e-6, atol=1e-7)
+
+
+def test_fusion_head_rescale_matches_reference():
+    """fusion_rescale + instance_postprocess vs RSMaskFormerFusionHead.predict(rescale=True) (M:661-715) on a
+    keep-ratio resized, padded image."""
+    from oracle import restate_query
+    f = FX["fusion_predict_rescale"]
+    up = restate_query.fusion_rescale(f["mask_pred"], f["meta"])
+    assert tuple(up.shape[-2:]) == tuple(f["meta"]["ori_shape"])
+    got = restate_query.instance_postprocess(f["mask_cls"], up, f["num_classes"], f["max_per_image"])
+    a, b = _by_score(got), _by_score(f)
+    assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["masks"], b["masks"])
+    assert torch.equal(a["bboxes"], b["bboxes"]) and torch.allclose(a["scores"], b["scores"], rtol=1e-6, atol=1e-7)
+
+
+def test_anchor_mask_rescale_matches_reference():
+    """mask_postprocess_rescale vs RSPrompterAnchorMaskHead._predict_by_feat_single(rescale=True) (M:1746-1784)."""
+    from oracle import restate_anchor as ra
+    f = FX["anchor_mask_rescale"]
+    masks, boxes = ra.mask_postprocess_rescale(f["logits"], f["boxes"].clone(), f["meta"], 0.5)
+    assert torch.equal(masks, f["masks"])
+    assert torch.allclose(boxes, f["boxes_out"], rtol=1e-6, atol=1e-6)
