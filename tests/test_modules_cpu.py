@@ -78,3 +78,19 @@ def test_window_map_matches_window_partition():
     ref, _ = restate.window_partition(tok, ws)
     ref = ref.reshape(-1).long() - 1          # padding (0) -> -1
     assert n_win == 25 and torch.equal(wmap.long(), ref)
+
+
+def test_metas_crop_geometry_follows_reference_formulas():
+    """detectors._SamDetectorBase._metas: fast path only for untouched images; crop = int(ori * scale_factor)
+    clipped to the batch shape (M:1771-1773, M:681-685)."""
+    import torch
+    from rsprompter_b200.detectors import _SamDetectorBase
+    from rsprompter_b200.registry import make_data_samples
+    x = torch.empty(3, 3, 1024, 1024)
+    ds = make_data_samples(3, (1024, 1024))
+    ds[1].set_metainfo(dict(ori_shape=(512, 512), img_shape=(1024, 1024), scale_factor=(2.0, 2.0)))
+    ds[2].set_metainfo(dict(ori_shape=(600, 800), img_shape=(768, 1024), scale_factor=(1.28, 1.28)))
+    hw, metas = _SamDetectorBase._metas(ds, x)
+    assert hw == (1024, 1024) and metas[0] is None
+    assert metas[1] == dict(ori_hw=(512, 512), crop_hw=(1024, 1024), scale_factor=(2.0, 2.0))
+    assert metas[2]["crop_hw"] == (int(600 * 1.28), int(800 * 1.28)) == (768, 1024) and metas[2]["ori_hw"] == (600, 800)
