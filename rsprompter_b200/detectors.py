@@ -29,6 +29,17 @@ class _SamDetectorBase(BaseModule):
         self._graphs = {} if enabled else None
         return self
 
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        if getattr(self, "_graphs", None):
+            self._graphs = {}          # captured graphs hold the previous prepared weights: recapture on next use
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        if getattr(self, "_graphs", None):
+            self._graphs = {}          # .to() / .cuda() / .half() move the parameters the graphs point at
+        return super()._apply(fn, *args, **kwargs)
+
     def _raw(self, batch_inputs: torch.Tensor) -> dict:
         graphs = getattr(self, "_graphs", None)
         if graphs is None:

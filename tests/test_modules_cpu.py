@@ -94,3 +94,19 @@ def test_metas_crop_geometry_follows_reference_formulas():
     assert hw == (1024, 1024) and metas[0] is None
     assert metas[1] == dict(ori_hw=(512, 512), crop_hw=(1024, 1024), scale_factor=(2.0, 2.0))
     assert metas[2]["crop_hw"] == (int(600 * 1.28), int(800 * 1.28)) == (768, 1024) and metas[2]["ori_hw"] == (600, 800)
+
+
+def test_cuda_graph_cache_is_dropped_when_weights_change():
+    """Captured graphs reference the prepared (bf16, re-laid-out) weights: loading a state dict must invalidate them."""
+    from rsprompter_b200 import model_configs, sam_config, synthetic
+    from rsprompter_b200.registry import MODELS
+    m = MODELS.build(model_configs.anchor_model_cfg("base", 3, mmpretrain_img_size=512))
+    m.enable_cuda_graphs()
+    m._graphs[("fake",)] = object()
+    arch = m.backbone.vision_encoder.arch
+    m.load_state_dict(synthetic.anchor_detector_state_dict(arch, 3, 0, seed=1, pseudo_neck=True))
+    assert m._graphs == {}
+    m._graphs[("fake",)] = object()
+    m.float()
+    assert m._graphs == {}
+    assert m.enable_cuda_graphs(False)._graphs is None
