@@ -82,13 +82,11 @@ class ClockSampler:
                     reasons=sorted(self.reasons), samples=len(self.samples))
 
 
-def _workload_config(n_gpus: int, ours: bool = False) -> dict:
+def _workload_config(n_gpus: int) -> dict:
     cfg = dict(workload=f"RSPrompter-anchor ViT-B bf16, bs={BATCH}/GPU, {SIZE}x{SIZE} synthetic (BASELINE.json configs[1])",
                 num_classes=NUM_CLASSES, global_batch=BATCH * n_gpus, parallelism=f"dp{n_gpus} (batch-sharded)",
                 l2_policy=f"{N_INPUT_SETS} distinct input batches rotated (> L2); activations per step >> L2",
                 weights="seeded random init of the exact architecture")
-    if ours:
-        cfg["cuda_graph"] = not os.environ.get("RSP_BENCH_NO_GRAPH")
     return cfg
 
 
@@ -321,7 +319,7 @@ def run_ours(args) -> None:
         line = dict(metric="images/sec", value=value, unit="images/s", n_gpus=world, steps=args.steps,
                     warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True,
                     scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-                    config=_workload_config(world, ours=True), clocks=clk.summary(),
+                    config=_workload_config(world), clocks=clk.summary(), cuda_graph=use_graph,
                     e2e=dict(value=e2e_val, unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=ms_e2e / args.steps,
                              note="pinned host batch -> predict() -> detection records + counts read back; "
