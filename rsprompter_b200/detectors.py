@@ -128,6 +128,7 @@ class RSPrompterAnchor(_SamDetectorBase):
         self.decoder_freeze = decoder_freeze
         self.test_cfg = test_cfg
         self.data_preprocessor_cfg = data_preprocessor
+        self.data_preprocessor = MODELS.build(dict(data_preprocessor)) if data_preprocessor else None
         self.eval()
 
     @torch.no_grad()
@@ -176,6 +177,9 @@ class RSPrompterAnchor(_SamDetectorBase):
         raise NotImplementedError("rsprompter_b200 implements the inference path only (mode='predict')")
 
     def test_step(self, data):
+        """BaseModel.test_step: data_preprocessor(data, False) then forward(mode='predict')."""
+        if self.data_preprocessor is not None:
+            data = self.data_preprocessor(data, False)
         return self.predict(data["inputs"], data.get("data_samples"))
 
 
@@ -200,6 +204,7 @@ class RSPrompterQuery(_SamDetectorBase):
         self.decoder_freeze = decoder_freeze
         self.test_cfg = test_cfg
         self.data_preprocessor_cfg = data_preprocessor
+        self.data_preprocessor = MODELS.build(dict(data_preprocessor)) if data_preprocessor else None
         self.eval()
 
     @torch.no_grad()
@@ -238,6 +243,9 @@ class RSPrompterQuery(_SamDetectorBase):
         raise NotImplementedError("rsprompter_b200 implements the inference path only (mode='predict')")
 
     def test_step(self, data):
+        """BaseModel.test_step: data_preprocessor(data, False) then forward(mode='predict')."""
+        if self.data_preprocessor is not None:
+            data = self.data_preprocessor(data, False)
         return self.predict(data["inputs"], data.get("data_samples"))
 
 

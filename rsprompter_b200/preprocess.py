@@ -1,0 +1,77 @@
+"""DetDataPreprocessor for inference (mmdet/models/data_preprocessors/data_preprocessor.py:29-149 over mmengine's
+ImgDataPreprocessor): collate -> BGR->RGB -> float -> (x - mean) / std -> pad bottom/right to a multiple of
+``pad_size_divisor`` -> stack, and ``batch_input_shape`` / ``pad_shape`` written into the data samples.
+
+This sits in front of the hot path (SURVEY.md 8f "next"): it is host-side glue expressed with a handful of
+device-side torch ops on the model's device (one H2D copy per image, no CPU arithmetic), so ``test_step(data)`` keeps
+the reference contract.  Training-time batch augmentations (``BatchFixedSizePad`` ...) are ignored: the reference
+applies them only when ``training=True`` (data_preprocessor.py:145-147)."""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from .registry import MODELS, BaseModule, DetDataSample
+
+
+@MODELS.register_module(force=True)
+class DetDataPreprocessor(BaseModule):
+    def __init__(self, mean=None, std=None, pad_size_divisor: int = 1, pad_value: float = 0, pad_mask: bool = False,
+                 mask_pad_value: int = 0, pad_seg: bool = False, seg_pad_value: int = 255, bgr_to_rgb: bool = False,
+                 rgb_to_bgr: bool = False, boxtype2tensor: bool = True, non_blocking: bool = False,
+                 batch_augments=None, init_cfg=None, **kwargs):
+        BaseModule.__init__(self, init_cfg=None)
+        assert not (bgr_to_rgb and rgb_to_bgr), "bgr_to_rgb and rgb_to_bgr cannot both be set"
+        assert (mean is None) == (std is None), "mean and std come together"
+        self.channel_conversion = bool(bgr_to_rgb or rgb_to_bgr)
+        self.pad_size_divisor, self.pad_value = int(pad_size_divisor), float(pad_value)
+        self._enable_normalize = mean is not None
+        if self._enable_normalize:
+            assert len(mean) in (1, 3) and len(std) in (1, 3)
+            self.register_buffer("mean", torch.tensor(mean, dtype=torch.float32).view(-1, 1, 1), persistent=False)
+            self.register_buffer("std", torch.tensor(std, dtype=torch.float32).view(-1, 1, 1), persistent=False)
+        self.register_buffer("_dev", torch.zeros(1), persistent=False)
+
+    @property
+    def device(self) -> torch.device:
+        return self._dev.device
+
+    def _one(self, img: torch.Tensor) -> torch.Tensor:
+        x = img.to(self.device, non_blocking=True)
+        if self.channel_conversion and x.shape[0] == 3:
+            x = x[[2, 1, 0], ...]
+        x = x.float()
+        if self._enable_normalize:
+            x = (x - self.mean) / self.std
+        return x
+
+    @torch.no_grad()
+    def forward(self, data: dict, training: bool = False) -> dict:
+        if training:
+            raise NotImplementedError("rsprompter_b200 implements the inference path only")
+        inputs, samples = data["inputs"], data.get("data_samples")
+        d = self.pad_size_divisor
+        if isinstance(inputs, torch.Tensor):          # default_collate: already a batch [N, C, H, W]
+            assert inputs.dim() == 4, "inputs must be NCHW or a list of CHW tensors"
+            imgs = [inputs[i] for i in range(inputs.shape[0])]
+        else:
+            imgs = list(inputs)
+            assert all(t.dim() == 3 for t in imgs), "inputs must be NCHW or a list of CHW tensors"
+        pad_shapes = [(int(math.ceil(t.shape[1] / d)) * d, int(math.ceil(t.shape[2] / d)) * d) for t in imgs]
+        xs = [self._one(t) for t in imgs]
+        H = int(math.ceil(max(t.shape[1] for t in xs) / d)) * d
+        W = int(math.ceil(max(t.shape[2] for t in xs) / d)) * d
+        batch = torch.full((len(xs), xs[0].shape[0], H, W), self.pad_value, dtype=torch.float32, device=self.device)
+        for i, t in enumerate(xs):                    # stack_batch: pad bottom / right
+            batch[i, :, :t.shape[1], :t.shape[2]] = t
+        if samples is None:
+            samples = [DetDataSample(metainfo=dict(img_shape=tuple(t.shape[1:]), ori_shape=tuple(t.shape[1:]),
+                                                   scale_factor=(1.0, 1.0))) for t in imgs]
+        for ds, ps in zip(samples, pad_shapes):
+            ds.set_metainfo(dict(batch_input_shape=(H, W), pad_shape=ps))
+        return dict(inputs=batch, data_samples=samples)
+
+
+__all__ = ["DetDataPreprocessor"]

@@ -110,3 +110,30 @@ def test_cuda_graph_cache_is_dropped_when_weights_change():
     m.float()
     assert m._graphs == {}
     assert m.enable_cuda_graphs(False)._graphs is None
+
+
+def test_det_data_preprocessor_matches_documented_semantics():
+    """BGR->RGB, float, (x - mean) / std, pad bottom/right to the divisor, metainfo (data_preprocessor.py:110-149 over
+    mmengine ImgDataPreprocessor.forward / stack_batch, restated with numpy)."""
+    import numpy as np
+    import torch
+    from rsprompter_b200.registry import MODELS, make_data_samples
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    pp = MODELS.build(dict(type="DetDataPreprocessor", mean=mean, std=std, bgr_to_rgb=True, pad_mask=True,
+                           pad_size_divisor=32, batch_augments=[dict(type="BatchFixedSizePad", size=(64, 64))]))
+    assert list(pp.state_dict()) == []                       # nothing a reference checkpoint would not have
+    g = torch.Generator().manual_seed(0)
+    imgs = [torch.randint(0, 256, (3, 50, 70), generator=g, dtype=torch.uint8),
+            torch.randint(0, 256, (3, 64, 33), generator=g, dtype=torch.uint8)]
+    ds = make_data_samples(2, (64, 64))
+    out = pp(dict(inputs=imgs, data_samples=ds))
+    m, s = np.array(mean, np.float32).reshape(3, 1, 1), np.array(std, np.float32).reshape(3, 1, 1)
+    ref = np.zeros((2, 3, 64, 96), np.float32)
+    for i, t in enumerate(imgs):
+        a = (t.numpy()[::-1].astype(np.float32) - m) / s
+        ref[i, :, :a.shape[1], :a.shape[2]] = a
+    assert out["inputs"].shape == (2, 3, 64, 96) and np.abs(out["inputs"].numpy() - ref).max() < 1e-6
+    assert [d.metainfo["pad_shape"] for d in out["data_samples"]] == [(64, 96), (64, 64)]
+    assert all(d.metainfo["batch_input_shape"] == (64, 96) for d in out["data_samples"])
+    batched = pp(dict(inputs=torch.stack([imgs[0], imgs[0]]), data_samples=None))      # default_collate form
+    assert batched["inputs"].shape == (2, 3, 64, 96) and torch.equal(batched["inputs"][0], out["inputs"][0])
