@@ -132,6 +132,28 @@ class SamVisionEncoderB200(nn.Module):
         self._prep: dict | None = None
         self._maps: dict = {}
         self.register_load_state_dict_post_hook(lambda *_: self._invalidate())
+        self._register_load_state_dict_pre_hook(self._resize_checkpoint_tables)
+
+    def _resize_checkpoint_tables(self, state_dict, prefix, *args):
+        """A checkpoint trained at another image size (a 1024^2 SAM checkpoint into the 512^2 model of the *-peft-512
+        configs): absolute position embedding resized bicubically, relative-position tables linearly, exactly as
+        mmpretrain ViTSAM does at load time (VS:611-662, mmpretrain/models/utils/embed.py:16-59)."""
+        import torch.nn.functional as F
+        k = prefix + "pos_embed"
+        if k in state_dict and tuple(state_dict[k].shape) != tuple(self.pos_embed.shape):
+            src = state_dict[k]
+            dst = F.interpolate(src.permute(0, 3, 1, 2).float(), size=tuple(self.pos_embed.shape[1:3]), mode="bicubic",
+                                align_corners=False)
+            state_dict[k] = dst.permute(0, 2, 3, 1).to(src.dtype).contiguous()
+        for name, own in self.named_parameters():
+            if "rel_pos_" not in name:
+                continue
+            ck = prefix + name
+            if ck in state_dict and state_dict[ck].shape[0] != own.shape[0]:
+                t = state_dict[ck]
+                L1, L2 = t.shape[0], own.shape[0]
+                new = F.interpolate(t.reshape(1, L1, -1).permute(0, 2, 1), size=L2, mode="linear")
+                state_dict[ck] = new.reshape(-1, L2).permute(1, 0).contiguous()
 
     def _invalidate(self) -> None:
         self._prep = None

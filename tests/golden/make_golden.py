@@ -148,6 +148,28 @@ def main():
                                        SimpleNamespace(mask_thr_binary=0.5), rescale=True)
     fx["anchor_mask_rescale"] = dict(logits=logits, boxes=boxes, meta=meta2, masks=im, boxes_out=b_in)
 
+    # ---- mmpretrain checkpoint resize at load time (VS:611-662, mmpretrain/models/utils/embed.py:16-59)
+    import types
+    fake_log = types.ModuleType("mmengine.logging")
+    fake_log.MMLogger = SimpleNamespace(get_current_instance=lambda: SimpleNamespace(info=lambda *a, **k: None))
+    sys.modules.setdefault("mmengine", types.ModuleType("mmengine"))
+    sys.modules["mmengine.logging"] = fake_log
+    em = load_defs("mmpretrain/models/utils/embed.py", ["resize_pos_embed"])
+    vsl = load_defs("mmpretrain/models/backbones/vit_sam.py", ["_prepare_pos_embed", "_prepare_relative_position"],
+                    cls="ViTSAM")
+    vsl["_prepare_pos_embed"].__globals__.update(resize_pos_embed=em["resize_pos_embed"])
+    ck_pos = torch.randn(1, 8, 8, 12, generator=g)
+    ck_rel = torch.randn(15, 6, generator=g)
+    ck_win = torch.randn(5, 6, generator=g)
+    own = {"layers.0.attn.rel_pos_h": torch.zeros(7, 6), "layers.1.attn.rel_pos_w": torch.zeros(5, 6)}
+    self_ = SimpleNamespace(pos_embed=torch.zeros(1, 4, 4, 12), patch_embed=SimpleNamespace(init_out_size=(4, 4)),
+                            interpolate_mode="bicubic", embed_dims=12, state_dict=lambda: own)
+    sd_ck = {"pos_embed": ck_pos.clone(), "layers.0.attn.rel_pos_h": ck_rel.clone(), "layers.1.attn.rel_pos_w": ck_win.clone()}
+    vsl["_prepare_pos_embed"](self_, sd_ck, "")
+    vsl["_prepare_relative_position"](self_, sd_ck, "")
+    fx["ckpt_resize"] = dict(pos_embed=ck_pos, rel_pos=ck_rel, rel_win=ck_win, pos_embed_out=sd_ck["pos_embed"],
+                             rel_pos_out=sd_ck["layers.0.attn.rel_pos_h"], rel_win_out=sd_ck["layers.1.attn.rel_pos_w"])
+
     torch.save(fx, OUT)
     print("wrote", OUT, {k: list(v.keys()) for k, v in fx.items()})
 

@@ -112,3 +112,24 @@ def test_anchor_mask_rescale_matches_reference():
     masks, boxes = ra.mask_postprocess_rescale(f["logits"], f["boxes"].clone(), f["meta"], 0.5)
     assert torch.equal(masks, f["masks"])
     assert torch.allclose(boxes, f["boxes_out"], rtol=1e-6, atol=1e-6)
+
+
+def test_checkpoint_tables_resize_like_mmpretrain():
+    """SamVisionEncoderB200's load hook vs ViTSAM._prepare_pos_embed / _prepare_relative_position executed from the
+    reference tree (VS:611-662): a checkpoint of another image size loads with bicubic / linear resizing."""
+    from rsprompter_b200.sam_config import SamVisionArch
+    from rsprompter_b200.sam_encoder import SamVisionEncoderB200
+    f = FX["ckpt_resize"]
+    arch = SamVisionArch("t", hidden_size=12, num_layers=2, num_heads=2, mlp_dim=24, global_attn_indexes=(0,),
+                         image_size=64, window_size=3)
+    enc = SamVisionEncoderB200(arch)
+    assert enc.pos_embed.shape == (1, 4, 4, 12) and enc.layers[0].attn.rel_pos_h.shape == (7, 6)
+    assert enc.layers[1].attn.rel_pos_w.shape == (5, 6)
+    sd = {k: torch.zeros_like(v) for k, v in enc.state_dict().items()}
+    sd["pos_embed"] = f["pos_embed"].clone()
+    sd["layers.0.attn.rel_pos_h"] = f["rel_pos"].clone()
+    sd["layers.1.attn.rel_pos_w"] = f["rel_win"].clone()
+    enc.load_state_dict(sd, strict=True)
+    assert torch.allclose(enc.pos_embed, f["pos_embed_out"], rtol=1e-6, atol=1e-6)
+    assert torch.allclose(enc.layers[0].attn.rel_pos_h, f["rel_pos_out"], rtol=1e-6, atol=1e-6)
+    assert torch.equal(enc.layers[1].attn.rel_pos_w, f["rel_win_out"])        # same length: untouched
