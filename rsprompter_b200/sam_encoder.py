@@ -288,6 +288,26 @@ def merge_lora_into_qkv(state_dict: dict, r_alpha: tuple[int, int] = (16, 32)) -
     return out
 
 
+def _install_lora_merge_hook(wrapper: nn.Module, peft_config: dict | None) -> None:
+    """Checkpoints of the reference's peft-wrapped encoder (M:785-797: keys ``vision_encoder.base_model.model.*``,
+    ``qkv.base_layer.weight``, ``qkv.lora_A/B.default.weight``) load into the plain module with the LoRA update
+    folded into qkv.weight - inference needs no adapter branch."""
+    cfg = dict(r=16, lora_alpha=32)
+    cfg.update(peft_config or {})
+    r_alpha = (int(cfg["r"]), int(cfg["lora_alpha"]))
+
+    def hook(state_dict, prefix, *args):
+        pre = prefix + "vision_encoder."
+        keys = [k for k in state_dict if k.startswith(pre)]
+        if not any("lora_" in k or ".base_layer." in k or "base_model.model." in k for k in keys):
+            return
+        sub = OrderedDict((k[len(pre):], state_dict.pop(k)) for k in keys)
+        for k, v in merge_lora_into_qkv(sub, r_alpha).items():
+            state_dict[pre + k] = v
+
+    wrapper._register_load_state_dict_pre_hook(hook)
+
+
 def _load_pretrained(module: nn.Module, init_cfg: dict | None, revise_keys) -> None:
     if not init_cfg or not init_cfg.get("checkpoint"):
         return
@@ -311,6 +331,7 @@ class RSSamVisionEncoder(BaseModule):
         arch = vision_arch(hf_pretrain_name, extra_config)
         self.vision_encoder = SamVisionEncoderB200(arch)
         self.peft_config = peft_config  # LoRA is merged at load time for inference
+        _install_lora_merge_hook(self, peft_config)
         _load_pretrained(self.vision_encoder, init_cfg, [(r"^module\.", ""), (r"^vision_encoder\.", "")])
         self.vision_encoder.is_init = True
 
@@ -345,11 +366,25 @@ class MMPretrainSamVisionEncoder(BaseModule):
                            img_size=img_size)
         self.vision_encoder = SamVisionEncoderB200(arch)
         self.peft_config = peft_config
+        _install_lora_merge_hook(self, peft_config)
+        self._register_load_state_dict_pre_hook(self._rename_mmpretrain_keys)
         _load_pretrained(self.vision_encoder, init_cfg, [(r"^module\.", ""), (r"^vision_encoder\.", "")])
         self.vision_encoder.is_init = True
 
     def init_weights(self):
         pass
+
+    @staticmethod
+    def _rename_mmpretrain_keys(state_dict, prefix, *args):
+        """A checkpoint saved from the reference module carries mmpretrain ViTSAM parameter names (ln1, ffn.layers,
+        channel_reduction: the forward direction of the revise_keys at M:840-851); map them onto this module's."""
+        pre = prefix + "vision_encoder."
+        for k in [k for k in state_dict if k.startswith(pre)]:
+            k2 = k[len(pre):]
+            for pat, rep in _MMPRETRAIN_TO_HF:
+                k2 = re.sub(pat, rep, k2)
+            if pre + k2 != k:
+                state_dict[pre + k2] = state_dict.pop(k)
 
     def load_mmpretrain_state_dict(self, sd: dict) -> None:
         out = OrderedDict()

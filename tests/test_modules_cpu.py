@@ -137,3 +137,57 @@ def test_det_data_preprocessor_matches_documented_semantics():
     assert all(d.metainfo["batch_input_shape"] == (64, 96) for d in out["data_samples"])
     batched = pp(dict(inputs=torch.stack([imgs[0], imgs[0]]), data_samples=None))      # default_collate form
     assert batched["inputs"].shape == (2, 3, 64, 96) and torch.equal(batched["inputs"][0], out["inputs"][0])
+
+
+def test_peft_lora_checkpoint_is_merged_on_load():
+    """A state dict with the reference's peft key layout (M:785-797) loads into the plain encoder with
+    W_qkv += (lora_alpha / r) * B @ A."""
+    import torch
+    from rsprompter_b200 import synthetic
+    from rsprompter_b200.registry import MODELS
+    enc = MODELS.build(dict(type="MMPretrainSamVisionEncoder", hf_pretrain_name="work_dirs/sam_cache/sam_vit_base",
+                            img_size=512, peft_config=dict(peft_type="LORA", r=16, target_modules=["qkv"], lora_alpha=32,
+                                                           lora_dropout=0.05, bias="none")))
+    arch = enc.vision_encoder.arch
+    base = synthetic.vision_encoder_state_dict(arch, seed=4)
+    g = torch.Generator().manual_seed(5)
+    ck = {}
+    for k, v in base.items():
+        if k.endswith("attn.qkv.weight"):
+            stem = "vision_encoder.base_model.model." + k[:-len(".weight")]
+            A, B = torch.randn(16, v.shape[1], generator=g) * 0.02, torch.randn(v.shape[0], 16, generator=g) * 0.02
+            ck[stem + ".base_layer.weight"] = v
+            ck[stem + ".lora_A.default.weight"], ck[stem + ".lora_B.default.weight"] = A, B
+            base[k] = v + 2.0 * (B @ A)
+        elif k.endswith("attn.qkv.bias"):
+            ck["vision_encoder.base_model.model." + k[:-len(".bias")] + ".base_layer.bias"] = v
+        else:
+            ck["vision_encoder.base_model.model." + k] = v
+    enc.load_state_dict(ck, strict=True)
+    got = enc.vision_encoder.state_dict()
+    assert set(got) == set(base)
+    for k in base:
+        assert torch.allclose(got[k], base[k], rtol=1e-6, atol=1e-7), k
+
+
+def test_mmpretrain_named_checkpoint_loads_through_load_state_dict():
+    """Keys as the reference's MMPretrainSamVisionEncoder saves them (mmpretrain ViTSAM names) load without a helper."""
+    import re
+    import torch
+    from rsprompter_b200 import synthetic
+    from rsprompter_b200.registry import MODELS
+    enc = MODELS.build(dict(type="MMPretrainSamVisionEncoder", hf_pretrain_name="work_dirs/sam_cache/sam_vit_base", img_size=512))
+    base = synthetic.vision_encoder_state_dict(enc.vision_encoder.arch, seed=6)
+    back = [(r"^neck\.conv1\.", "channel_reduction.0."), (r"^neck\.layer_norm1\.", "channel_reduction.1."),
+            (r"^neck\.conv2\.", "channel_reduction.2."), (r"^neck\.layer_norm2\.", "channel_reduction.3."),
+            (r"\.layer_norm1\.", ".ln1."), (r"\.layer_norm2\.", ".ln2."), (r"\.mlp\.lin1\.", ".ffn.layers.0.0."),
+            (r"\.mlp\.lin2\.", ".ffn.layers.1.")]
+    ck = {}
+    for k, v in base.items():
+        for pat, rep in back:
+            k = re.sub(pat, rep, k)
+        ck["vision_encoder." + k] = v
+    assert any(".ln1." in k for k in ck) and any("channel_reduction.3." in k for k in ck)
+    enc.load_state_dict(ck, strict=True)
+    got = enc.vision_encoder.state_dict()
+    assert all(torch.equal(got[k], base[k]) for k in base)
