@@ -315,7 +315,11 @@ def _load_pretrained(module: nn.Module, init_cfg: dict | None, revise_keys) -> N
     path = os.path.expanduser(init_cfg["checkpoint"])
     if not os.path.isfile(path):
         raise FileNotFoundError(f"init_cfg checkpoint {path} not found")
-    sd = torch.load(path, map_location="cpu")
+    if path.endswith(".safetensors"):           # HF hub snapshots ship model.safetensors next to pytorch_model.bin
+        from safetensors.torch import load_file
+        sd = load_file(path, device="cpu")
+    else:
+        sd = torch.load(path, map_location="cpu")
     sd = sd.get("state_dict", sd)
     sd = strip_checkpoint_prefixes(sd, revise_keys)
     own = module.state_dict()

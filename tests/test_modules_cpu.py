@@ -191,3 +191,35 @@ def test_mmpretrain_named_checkpoint_loads_through_load_state_dict():
     enc.load_state_dict(ck, strict=True)
     got = enc.vision_encoder.state_dict()
     assert all(torch.equal(got[k], base[k]) for k in base)
+
+
+@pytest.mark.parametrize("fmt", ["bin", "safetensors"])
+def test_init_cfg_pretrained_picks_submodule_by_prefix(tmp_path, fmt):
+    """One HF-style SamModel checkpoint file (prefixes vision_encoder. / mask_decoder. / prompt_encoder. /
+    shared_image_embedding.) initialises each registry module through init_cfg, as the reference configs do
+    (_base_/rsprompter_anchor.py:61-70,135-138; revise_keys at M:783, M:909)."""
+    import torch
+    from rsprompter_b200 import synthetic
+    from rsprompter_b200.registry import MODELS
+    from rsprompter_b200.sam_config import VISION_ARCHS
+    dec = synthetic.mask_decoder_state_dict(seed=31)
+    pe = synthetic.prompt_encoder_state_dict(seed=32)
+    pos = synthetic.positional_embedding_state_dict(VISION_ARCHS["base"], 33)
+    ck = {"mask_decoder." + k: v for k, v in dec.items()}
+    ck.update({"prompt_encoder." + k: v for k, v in pe.items()})
+    ck.update({"shared_image_embedding." + k: v for k, v in pos.items()})
+    ck["vision_encoder.pos_embed"] = torch.zeros(1, 2, 2, 4)          # ignored by the non-encoder modules
+    path = str(tmp_path / ("model." + fmt))
+    if fmt == "bin":
+        torch.save(ck, path)
+    else:
+        from safetensors.torch import save_file
+        save_file({k: v.contiguous() for k, v in ck.items()}, path)
+    init = dict(type="Pretrained", checkpoint=path)
+    d = MODELS.build(dict(type="RSSamMaskDecoder", hf_pretrain_name="facebook/sam-vit-base", init_cfg=init))
+    e = MODELS.build(dict(type="RSSamPromptEncoder", hf_pretrain_name="facebook/sam-vit-base", init_cfg=init))
+    s = MODELS.build(dict(type="RSSamPositionalEmbedding", hf_pretrain_name="facebook/sam-vit-base", init_cfg=init))
+    got = d.mask_decoder.state_dict()
+    assert all(torch.equal(got[k], v) for k, v in dec.items())
+    assert torch.equal(e.prompt_encoder.mask_embed.conv3.weight, pe["mask_embed.conv3.weight"])
+    assert torch.equal(s.shared_image_embedding.positional_embedding, pos["positional_embedding"])
