@@ -177,7 +177,7 @@ def run_ours(args) -> None:
     from rsprompter_b200 import _lib, model_configs, synthetic
     from rsprompter_b200.model_configs import SELECT_LAYERS
     from rsprompter_b200.registry import MODELS, make_data_samples
-    from rsprompter_b200.results import gather_records, pack_records
+    from rsprompter_b200.results import gather_mask_logits, gather_records, pack_records
     from rsprompter_b200.sam_config import VISION_ARCHS
 
     rank = int(os.environ.get("RANK", "0"))
@@ -201,6 +201,7 @@ def run_ours(args) -> None:
     thr = 0.5
     M = 100
 
+    gather_masks = bool(os.environ.get("RSP_BENCH_GATHER_MASKS"))
     use_graph = not os.environ.get("RSP_BENCH_NO_GRAPH")
     if use_graph:
         model.enable_cuda_graphs()      # the device-resident forward is captured once per input shape and replayed
@@ -211,6 +212,8 @@ def run_ours(args) -> None:
         masks = _lib.mask_paste(r["mask_logits"][:, 0].contiguous(), (SIZE, SIZE), thr, 0)
         rec = pack_records(r["bboxes"], r["scores"], r["labels"])      # [B, M, 6]
         rec, cnt = gather_records(rec, r["counts"])                    # the one collective of the path
+        if gather_masks:                                               # opt-in: fp16 256^2 logits ride along
+            gather_mask_logits(r["mask_logits"][:, 0])
         return masks, rec, cnt
 
     def step_e2e(i):

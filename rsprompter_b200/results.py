@@ -27,6 +27,17 @@ def gather_records(records: torch.Tensor, counts: torch.Tensor):
     return out, cnt
 
 
+def gather_mask_logits(mask_logits: torch.Tensor) -> torch.Tensor:
+    """Optional second part of the record: the low-resolution mask logits [B*M, h, w] as fp16, gathered
+    over the default process group; the consumer resizes / thresholds them.  100 x 256^2 fp16 = 13 MB per image."""
+    x = mask_logits.to(torch.float16).contiguous()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return x
+    out = torch.empty((dist.get_world_size() * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x)
+    return out
+
+
 def unpack_records(records: torch.Tensor, counts: torch.Tensor) -> list:
     out = []
     for r, n in zip(records, counts.tolist()):

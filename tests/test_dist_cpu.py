@@ -20,7 +20,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from rsprompter_b200.results import gather_records, pack_records, unpack_records
+    from rsprompter_b200.results import gather_mask_logits, gather_records, pack_records, unpack_records
     B, M = 3, 5
     g = torch.Generator().manual_seed(rank)
     boxes = torch.rand(B, M, 4, generator=g)
@@ -34,6 +34,10 @@ def _worker(rank, world, port, q):
     mine = unpack_records(all_rec[rank * B:(rank + 1) * B], all_cnt[rank * B:(rank + 1) * B])
     ok = all(torch.equal(mine[i]["bboxes"], boxes[i, :counts[i]]) and
              torch.equal(mine[i]["labels"], labels[i, :counts[i]]) for i in range(B))
+    logits = torch.randn(B * M, 8, 8, generator=g)
+    all_logits = gather_mask_logits(logits)
+    ok = ok and all_logits.dtype == torch.float16 and all_logits.shape == (world * B * M, 8, 8)
+    ok = ok and torch.equal(all_logits[rank * B * M:(rank + 1) * B * M], logits.half())
     q.put((rank, ok, all_cnt.tolist()))
     dist.destroy_process_group()
 
