@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RSP_ABI_VERSION 1
+#define RSP_ABI_VERSION 2
 
 int rsp_abi_version(void);
 const char* rsp_last_error(void);
@@ -156,19 +156,20 @@ int rsp_i2t_attention(const void* Q, const int32_t* q_block, const void* ktok, c
  * scores[B, out_ld] at column out_off.  head_out fp32 [B*H*W, ld]: columns [0,A) objectness logits,
  * [A, 5A) deltas.  Anchors are generated analytically (AnchorGenerator, anchor_generator.py:161-301,
  * base_anchors fp32 [A, 4]); boxes failing min_bbox_size get score -1 (rpn_head.py:267-271).
+ * stds4: HOST array of the coder's 4 target_stds (bbox_coder.stds; means must be 0).
  * Replaces RPNHead._predict_by_feat_single's per-level body + DeltaXYWHBBoxCoder.decode
  * (rpn_head.py:188-226; delta_xywh_bbox_coder.py:325-359). */
 int rsp_rpn_decode(const float* head_out, int ld, const int64_t* topk_idx, int K, int B, int H, int W,
-                   int A, int stride, const float* base_anchors, float img_h, float img_w,
+                   int A, int stride, const float* base_anchors, const float* stds4, float img_h, float img_w,
                    float min_size, int out_off, int out_ld, float* boxes, float* scores, void* stream);
 
-/* RoI bbox head post-processing before NMS: softmax over C+1 logits, per-class delta2bbox with stds
- * (.1,.1,.2,.2), score_thr filter; rois fp32 [n, 5], roi_valid uint8 [n] or NULL.  Outputs
+/* RoI bbox head post-processing before NMS: softmax over C+1 logits, per-class delta2bbox with the
+ * coder's target_stds (stds4: HOST array of 4 floats), score_thr filter; rois fp32 [n, 5], roi_valid uint8 [n] or NULL.  Outputs
  * scores [n*C] (-1 = filtered), boxes [n*C, 4], labels int64 [n*C].
  * Replaces BBoxHead._predict_by_feat_single up to multiclass_nms (bbox_head.py:520-555,
  * bbox_nms.py:45-75). */
 int rsp_bbox_cls_decode(const float* cls, int ld_cls, const float* reg, int ld_reg, const float* rois,
-                        const uint8_t* roi_valid, int n, int C, float img_h, float img_w,
+                        const uint8_t* roi_valid, int n, int C, const float* stds4, float img_h, float img_w,
                         float score_thr, float* scores, float* boxes, int64_t* labels, void* stream);
 
 /* mmcv.ops.batched_nms semantics on score-sorted candidates: boxes fp32 [B, n, 4], ids int64 [B, n]
@@ -267,6 +268,40 @@ int rsp_query_postprocess_rescale(const float* logits, const int32_t* sel, const
  * mean sigmoid over the positive pixels, tight box.  part_ws fp32 [n_inst, ceil(H/16), 6]. */
 int rsp_query_postprocess(const float* logits, const int32_t* sel, const float* cls_scores, int n_inst, int hm, int wm,
                           int H, int W, uint8_t* masks, float* part_ws, float* scores, float* boxes, void* stream);
+
+/* ---- result record payload: masks leave the device bit-packed.  Bit layout everywhere: a mask
+ * row of W pixels is ceil(W/8) bytes, pixel x = bit (x % 8) of byte x / 8 (numpy.packbits(bitorder='little')).  This
+ * is the device-side stand-in for encode_mask_results + collect_results (coco_metric.py:346-400, :365). ---- */
+
+/* rsp_query_postprocess with H = 4*hm, W = 4*wm (the mask decoder always emits image/4 logits) and the mask written
+ * bit-packed: bits uint8 [n_inst, H, W/8].  Scores / boxes as rsp_query_postprocess.  part_ws fp32 [n_inst, H/16, 6]. */
+int rsp_query_postprocess_bits(const float* logits, const int32_t* sel, const float* cls_scores, int n_inst, int hm,
+                               int wm, uint8_t* bits, float* part_ws, float* scores, float* boxes, void* stream);
+
+/* x4 bilinear + threshold of rsp_mask_paste (modes 1, 2) with bit-packed output: bits uint8 [n, 4*hm, 4*wm/8]
+ * (anchor variant, M:1758-1780 when ori_shape == batch shape). */
+int rsp_mask_paste_bits(const float* maps, uint8_t* bits, int n, int hm, int wm, float thr, int mode, void* stream);
+
+/* Generic pack / unpack between uint8 {0,1} masks [rows, W] and the payload [rows, ceil(W/8)] (masks produced by the
+ * *_rescale entry points; unpack is for consumers that want torch.bool masks back). */
+int rsp_pack_mask_bits(const uint8_t* masks, uint8_t* bits, long long rows, int W, void* stream);
+int rsp_unpack_mask_bits(const uint8_t* bits, uint8_t* masks, long long rows, int W, void* stream);
+
+/* ---- DetDataPreprocessor on the device (data_preprocessor.py:110-148, ImgDataPreprocessor.forward,
+ * BatchFixedSizePad :300).  mean3 / std3: HOST arrays of 3 floats in OUTPUT channel order. ---- */
+
+/* One image: uint8 pixels addressed by byte strides (stride_c, stride_y, stride_x): CHW planes as PackDetInputs emits
+ * them = (h*w, w, 1), decoded HWC = (1, 3w, 3) -> fp32 planes out[3, H, W]: channel c = input channel
+ * (swap_rb ? 2 - c : c), (x - mean[c]) / std[c] with true fp32 division, pixels outside (h, w) = pad_value. */
+int rsp_preprocess_u8(const uint8_t* img, int h, int w, long long stride_c, long long stride_y, long long stride_x,
+                      float* out, int H, int W, const float* mean3, const float* std3, int swap_rb, float pad_value,
+                      void* stream);
+
+/* The same arithmetic fused into the patch-embed operand loader: uint8 batch [B, 3, H, W] (hwc = 0) or [B, H, W, 3]
+ * (hwc = 1), contiguous, 16-byte aligned, H, W % 16 == 0 -> bf16 patch rows [B*(H/16)*(W/16), 768] in (c, ky, kx)
+ * order = rsp_patchify16(rsp_preprocess_u8(img)) bit for bit; the fp32 image never exists. */
+int rsp_patchify16_u8(const uint8_t* img, int hwc, void* out, int B, int H, int W, const float* mean3, const float* std3,
+                      int swap_rb, void* stream);
 
 /* fp32 -> bf16 (n % 4 == 0): feeds fp32 hidden states to the bf16 tensor-core GEMMs. */
 int rsp_cast_f32_bf16(const float* in, void* out, long long n, void* stream);

@@ -84,6 +84,9 @@ def vit_layer(sd: dict, p: str, x: torch.Tensor, window: int, heads: int, eps: f
         y, padded = window_partition(y, window)
     n, h, w, _ = y.shape
     qkv = F.linear(y, sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"])
+    if p + "attn.qkv.lora_A" in sd:     # peft LoRA on qkv, UNMERGED (M:785-797): y = Wx + b + (alpha/r) B(A x)
+        A, Bm, scale = sd[p + "attn.qkv.lora_A"], sd[p + "attn.qkv.lora_B"], sd[p + "attn.qkv.lora_scale"]
+        qkv = qkv + float(scale) * F.linear(F.linear(y, A), Bm)
     qkv = qkv.reshape(n, h * w, 3, heads, hd).permute(2, 0, 3, 1, 4).reshape(3, n * heads, h * w, hd)
     o = vit_attention_core(qkv[0], qkv[1], qkv[2], sd[p + "attn.rel_pos_h"], sd[p + "attn.rel_pos_w"], h)
     o = o.reshape(n, heads, h, w, hd).permute(0, 2, 3, 1, 4).reshape(n, h, w, D)

@@ -318,15 +318,20 @@ def _sub(sd: dict, prefix: str) -> dict:
 
 def anchor_predict(sd: dict, vision_arch, decoder_arch, images: torch.Tensor, num_classes: int,
                    select_layers, strides=(4, 8, 16, 32, 64), scales=(4, 8), ratios=(0.5, 1.0, 2.0),
-                   points: int = 5, timings: dict | None = None):
+                   points: int = 5, timings: dict | None = None, pseudo_neck: bool = False):
     """RSPrompterAnchor.predict (M:148-170) for metainfo img_shape == ori_shape == batch shape,
-    scale_factor 1: returns a list of per-image dicts(bboxes, scores, labels, masks, mask_logits)."""
+    scale_factor 1: returns a list of per-image dicts(bboxes, scores, labels, masks, mask_logits).
+    pseudo_neck: the *-peft-512 configs (MMPretrainSamVisionEncoder + PseudoFeatureAggregator, M:944-984): the neck
+    consumes the image embedding instead of the hidden states."""
     import time
     t0 = time.perf_counter()
     B, _, H, W = images.shape
     emb, hidden = restate.vit_encoder(_sub(sd, "backbone.vision_encoder."), vision_arch, images)
     t1 = time.perf_counter()
-    agg = feature_aggregator(_sub(sd, "neck.feature_aggregator."), hidden, list(select_layers))
+    if pseudo_neck:
+        agg = pseudo_feature_aggregator(_sub(sd, "neck.feature_aggregator."), emb)
+    else:
+        agg = feature_aggregator(_sub(sd, "neck.feature_aggregator."), hidden, list(select_layers))
     feats = simple_fpn(_sub(sd, "neck.feature_spliter."), agg)
     pe = restate.image_wide_positional_embedding(
         sd["shared_image_embedding.shared_image_embedding.positional_embedding"], emb.shape[-1])

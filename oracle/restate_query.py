@@ -207,3 +207,41 @@ def fusion_rescale(mask_pred: torch.Tensor, meta: dict, rescale: bool = True) ->
     if rescale:
         m = F.interpolate(m[:, None], size=(ori_h, ori_w), mode="bilinear", align_corners=False)[:, 0]
     return m
+
+
+def _sub(sd: dict, prefix: str) -> dict:
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def query_predict(sd: dict, vision_arch, decoder_arch, images: torch.Tensor, num_classes: int, select_layers,
+                  points: int = 5, max_per_image: int = 100, timings: dict | None = None):
+    """RSPrompterQuery.predict (M:249-272) for metainfo img_shape == ori_shape == batch shape, scale_factor 1:
+    extract_feat (M:217-234) -> RSMask2FormerHead.predict (M:633-658: last-layer cls / SAM-decoder masks, bilinear to
+    the batch shape) -> RSMaskFormerFusionHead.predict (M:663-715, instance_on only) -> per-image dicts(bboxes, scores,
+    labels, masks, query, mask_logits [low-res logits of every query], cls)."""
+    import time
+    from . import restate, restate_anchor
+    t0 = time.perf_counter()
+    B, _, H, W = images.shape
+    emb, hidden = restate.vit_encoder(_sub(sd, "backbone.vision_encoder."), vision_arch, images)
+    t1 = time.perf_counter()
+    agg = restate_anchor.feature_aggregator(_sub(sd, "neck.feature_aggregator."), hidden, list(select_layers))
+    feats = restate_anchor.simple_fpn(_sub(sd, "neck.feature_spliter."), agg)
+    pe = restate.image_wide_positional_embedding(
+        sd["shared_image_embedding.shared_image_embedding.positional_embedding"], emb.shape[-1])
+    t2 = time.perf_counter()
+    hsd = _sub(sd, "panoptic_head.")
+    dec_sd = _sub(hsd, "mask_decoder.mask_decoder.")
+    pe_sd = {k[len("sam_"):]: v for k, v in hsd.items() if k.startswith("sam_mask_embed.")}
+    cls, mp, mpp = mask2former_head(hsd, decoder_arch, dec_sd, pe_sd, feats, emb, pe.expand(B, -1, -1, -1), points=points)
+    t3 = time.perf_counter()
+    up = F.interpolate(mp, size=(H, W), mode="bilinear", align_corners=False)
+    out = []
+    for b in range(B):
+        r = instance_postprocess(cls[b], up[b], num_classes, max_per_image)
+        r.update(mask_logits=mp[b], cls=cls[b])
+        out.append(r)
+    t4 = time.perf_counter()
+    if timings is not None:
+        timings.update(encoder=t1 - t0, neck=t2 - t1, head=t3 - t2, post=t4 - t3)
+    return out

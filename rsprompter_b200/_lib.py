@@ -66,8 +66,8 @@ _SIGNATURES = {
     "rsp_token_self_attention": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "rsp_t2i_attention": ([_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp], _i),
     "rsp_i2t_attention": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
-    "rsp_rpn_decode": ([_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _f, _f, _f, _i, _i, _vp, _vp, _vp], _i),
-    "rsp_bbox_cls_decode": ([_vp, _i, _vp, _i, _vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp], _i),
+    "rsp_rpn_decode": ([_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _f, _f, _i, _i, _vp, _vp, _vp], _i),
+    "rsp_bbox_cls_decode": ([_vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _f, _f, _f, _vp, _vp, _vp, _vp], _i),
     "rsp_nms_batched": ([_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp], _i),
     "rsp_compact_keep": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "rsp_roi_align_nhwc": ([_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _f, _vp, _vp], _i),
@@ -86,6 +86,13 @@ _SIGNATURES = {
     "rsp_mask_embed_src": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp], _i),
     "rsp_query_postprocess": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "rsp_sin_fold": ([_vp, _vp, ctypes.c_longlong, _vp], _i),
+    "rsp_query_postprocess_bits": ([_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "rsp_mask_paste_bits": ([_vp, _vp, _i, _i, _i, _f, _i, _vp], _i),
+    "rsp_pack_mask_bits": ([_vp, _vp, ctypes.c_longlong, _i, _vp], _i),
+    "rsp_unpack_mask_bits": ([_vp, _vp, ctypes.c_longlong, _i, _vp], _i),
+    "rsp_preprocess_u8": ([_vp, _i, _i, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _vp, _i, _i, _vp, _vp,
+                           _i, _f, _vp], _i),
+    "rsp_patchify16_u8": ([_vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp], _i),
 }
 
 
@@ -103,6 +110,16 @@ ABI_VERSION = _lib.rsp_abi_version()
 
 # number of kernel launches issued through this binding (bench.py reports it)
 launch_count = 0
+
+# optional launch log of the tensor-core kernels: when `trace` is a list every GEMM / attention wrapper appends
+# dict(kind, scope, flops) in launch order (bench.py maps CUPTI kernel records onto it for the roofline)
+trace: list | None = None
+trace_scope = ""
+
+
+def _log(kind: str, flops: float) -> None:
+    if trace is not None:
+        trace.append(dict(kind=kind, scope=trace_scope, flops=float(flops)))
 
 
 def _check(status: int, what: str) -> None:
@@ -125,6 +142,13 @@ def _require_cuda(*ts: torch.Tensor | None) -> None:
     for t in ts:
         if t is not None and not t.is_cuda:
             raise RspError("rsprompter_b200 kernels take CUDA tensors only (there is no CPU path)")
+
+
+def _host_f4(v):
+    """4 floats as a host C array (DeltaXYWHBBoxCoder target_stds and similar by-value parameters)."""
+    v = tuple(float(x) for x in v)
+    assert len(v) == 4
+    return (ctypes.c_float * 4)(*v)
 
 
 ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2}
@@ -187,6 +211,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *,
                 int(out.dtype == torch.float32), _stream())
     _check(st, "rsp_gemm_bf16")
     launch_count += 1
+    if not simt:
+        _log("gemm", 2.0 * M * N * K)
     return out
 
 
@@ -215,6 +241,7 @@ def conv3x3_nhwc(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = N
                                       _ptr(residual), ldr, res_fp32, ACT[act], int(out_dtype == torch.float32),
                                       _stream()), "rsp_conv3x3_nhwc_bf16")
     launch_count += 1
+    _log("gemm", 2.0 * B * H * W * N * 9 * C)
     return out
 
 
@@ -239,6 +266,7 @@ def gemm_upscale_mask(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, hype
                                _ptr(out), grid_h, grid_w, _stream())
     _check(st, "rsp_gemm_bf16_ex(upscale_mask)")
     launch_count += 1
+    _log("gemm", 2.0 * M * 128 * K)
     return out
 
 
@@ -323,6 +351,8 @@ def vit_attention(qkv: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor, n
     _require_cuda(qkv, rel_h, rel_w, out)
     T = S * S
     D = H * hd
+    if not simt and S in (14, 32, 64):     # QK^T + PV on the tensor cores (rel-pos prologue not counted)
+        _log("attention_window" if S == 14 else "attention_global", 4.0 * n_seq * H * T * T * hd)
     assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (n_seq * T, 3 * D)
     assert rel_h.dtype == torch.bfloat16 and rel_h.is_contiguous() and rel_h.shape == (2 * S - 1, hd)
     assert rel_w.dtype == torch.bfloat16 and rel_w.is_contiguous() and rel_w.shape == (2 * S - 1, hd)
@@ -448,7 +478,7 @@ def add_table_bf16(x: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------ detection ops
 def rpn_decode(head_out: torch.Tensor, topk_idx: torch.Tensor, B: int, H: int, W: int, A: int, stride: int,
                base_anchors: torch.Tensor, img_hw: tuple, min_size: float, boxes: torch.Tensor,
-               scores: torch.Tensor, out_off: int) -> None:
+               scores: torch.Tensor, out_off: int, stds=(1.0, 1.0, 1.0, 1.0)) -> None:
     """Decode the K top anchors of one level into boxes[B, n, 4] / scores[B, n] at column out_off."""
     global launch_count
     _require_cuda(head_out, topk_idx, base_anchors, boxes, scores)
@@ -457,13 +487,13 @@ def rpn_decode(head_out: torch.Tensor, topk_idx: torch.Tensor, B: int, H: int, W
     assert boxes.is_contiguous() and scores.is_contiguous() and boxes.dtype == torch.float32
     K = topk_idx.shape[1]
     _check(_lib.rsp_rpn_decode(_ptr(head_out), head_out.stride(0), _ptr(topk_idx), K, B, H, W, A, stride,
-                               _ptr(base_anchors), float(img_hw[0]), float(img_hw[1]), float(min_size),
+                               _ptr(base_anchors), _host_f4(stds), float(img_hw[0]), float(img_hw[1]), float(min_size),
                                out_off, scores.shape[1], _ptr(boxes), _ptr(scores), _stream()), "rsp_rpn_decode")
     launch_count += 1
 
 
 def bbox_cls_decode(cls: torch.Tensor, reg: torch.Tensor, rois: torch.Tensor, roi_valid: torch.Tensor | None,
-                    C: int, img_hw: tuple, score_thr: float):
+                    C: int, img_hw: tuple, score_thr: float, stds=(0.1, 0.1, 0.2, 0.2)):
     """-> scores fp32 [n*C] (-1 filtered), boxes fp32 [n*C, 4], labels int64 [n*C]."""
     global launch_count
     _require_cuda(cls, reg, rois, roi_valid)
@@ -476,7 +506,7 @@ def bbox_cls_decode(cls: torch.Tensor, reg: torch.Tensor, rois: torch.Tensor, ro
     if roi_valid is not None:
         assert roi_valid.dtype == torch.uint8 and roi_valid.numel() == n
     _check(_lib.rsp_bbox_cls_decode(_ptr(cls), cls.stride(0), _ptr(reg), reg.stride(0), _ptr(rois),
-                                    _ptr(roi_valid), n, C, float(img_hw[0]), float(img_hw[1]),
+                                    _ptr(roi_valid), n, C, _host_f4(stds), float(img_hw[0]), float(img_hw[1]),
                                     float(score_thr), _ptr(scores), _ptr(boxes), _ptr(labels), _stream()),
            "rsp_bbox_cls_decode")
     launch_count += 1
@@ -769,3 +799,125 @@ def query_postprocess(logits: torch.Tensor, sel: torch.Tensor, cls_scores: torch
                                       _ptr(scores), _ptr(boxes), _stream()), "rsp_query_postprocess")
     launch_count += 2
     return masks.view(torch.bool), scores, boxes
+
+
+# ------------------------------------------------------------------------------ result-record payload
+def query_postprocess_bits(logits: torch.Tensor, sel: torch.Tensor, cls_scores: torch.Tensor, bits: torch.Tensor | None = None,
+                           scores: torch.Tensor | None = None, boxes: torch.Tensor | None = None):
+    """query_postprocess at 4x the logit size with bit-packed masks: -> (bits uint8 [n, 4hm, 4wm/8], scores [n], boxes [n,4]).
+    Outputs may be preallocated views of a result record."""
+    global launch_count
+    _require_cuda(logits, sel, cls_scores, bits, scores, boxes)
+    n = sel.numel()
+    _, hm, wm = logits.shape
+    H, W = 4 * hm, 4 * wm
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and sel.dtype == torch.int32 and cls_scores.dtype == torch.float32
+    assert sel.is_contiguous() and cls_scores.is_contiguous() and cls_scores.numel() == n
+    if bits is None:
+        bits = torch.empty(n, H, W // 8, device=logits.device, dtype=torch.uint8)
+    if scores is None:
+        scores = torch.empty(n, device=logits.device, dtype=torch.float32)
+    if boxes is None:
+        boxes = torch.empty(n, 4, device=logits.device, dtype=torch.float32)
+    assert bits.dtype == torch.uint8 and bits.is_contiguous() and bits.numel() == n * H * W // 8
+    assert scores.is_contiguous() and boxes.is_contiguous() and scores.numel() == n and boxes.numel() == 4 * n
+    part = torch.empty(n * ((H + 15) // 16) * 6, device=logits.device, dtype=torch.float32)
+    _check(_lib.rsp_query_postprocess_bits(_ptr(logits), _ptr(sel), _ptr(cls_scores), n, hm, wm, _ptr(bits), _ptr(part),
+                                           _ptr(scores), _ptr(boxes), _stream()), "rsp_query_postprocess_bits")
+    launch_count += 2
+    return bits, scores, boxes
+
+
+def mask_paste_bits(logits: torch.Tensor, thr: float, mode: int, bits: torch.Tensor | None = None) -> torch.Tensor:
+    """fp32 [n, hm, wm] -> bit-packed uint8 [n, 4hm, 4wm/8]; mode 0 sigmoid+bilinear >= thr, mode 1 bilinear > thr."""
+    global launch_count
+    _require_cuda(logits, bits)
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and logits.dim() == 3
+    n, hm, wm = logits.shape
+    if bits is None:
+        bits = torch.empty(n, 4 * hm, wm // 2, device=logits.device, dtype=torch.uint8)
+    assert bits.dtype == torch.uint8 and bits.is_contiguous() and bits.numel() == n * 4 * hm * (wm // 2)
+    if n == 0:
+        return bits
+    src = logits
+    if mode == 0:
+        src = torch.empty_like(logits)
+        _check(_lib.rsp_sigmoid_f32(_ptr(logits), _ptr(src), logits.numel(), _stream()), "rsp_sigmoid_f32")
+        launch_count += 1
+        mode = 2
+    _check(_lib.rsp_mask_paste_bits(_ptr(src), _ptr(bits), n, hm, wm, float(thr), mode, _stream()), "rsp_mask_paste_bits")
+    launch_count += 1
+    return bits
+
+
+def pack_mask_bits(masks: torch.Tensor, bits: torch.Tensor | None = None) -> torch.Tensor:
+    """bool / uint8 [..., W] -> uint8 [..., ceil(W/8)], pixel x = bit x % 8 of byte x // 8."""
+    global launch_count
+    _require_cuda(masks, bits)
+    m = masks.view(torch.uint8) if masks.dtype == torch.bool else masks
+    assert m.dtype == torch.uint8 and m.is_contiguous()
+    W = m.shape[-1]
+    rows = m.numel() // W
+    if bits is None:
+        bits = torch.empty(*m.shape[:-1], (W + 7) // 8, device=m.device, dtype=torch.uint8)
+    assert bits.dtype == torch.uint8 and bits.is_contiguous() and bits.numel() == rows * ((W + 7) // 8)
+    if rows:
+        _check(_lib.rsp_pack_mask_bits(_ptr(m), _ptr(bits), rows, W, _stream()), "rsp_pack_mask_bits")
+        launch_count += 1
+    return bits
+
+
+def unpack_mask_bits(bits: torch.Tensor, W: int) -> torch.Tensor:
+    """uint8 [..., ceil(W/8)] -> bool [..., W]."""
+    global launch_count
+    _require_cuda(bits)
+    assert bits.dtype == torch.uint8 and bits.is_contiguous() and bits.shape[-1] == (W + 7) // 8
+    out = torch.empty(*bits.shape[:-1], W, device=bits.device, dtype=torch.uint8)
+    rows = out.numel() // W
+    if rows:
+        _check(_lib.rsp_unpack_mask_bits(_ptr(bits), _ptr(out), rows, W, _stream()), "rsp_unpack_mask_bits")
+        launch_count += 1
+    return out.view(torch.bool)
+
+
+# ------------------------------------------------------------------------------ DetDataPreprocessor
+def _host_f3(v):
+    v = tuple(float(x) for x in v)
+    assert len(v) == 3
+    return (ctypes.c_float * 3)(*v)
+
+
+def preprocess_u8(img: torch.Tensor, out: torch.Tensor, mean, std, swap_rb: bool, pad_value: float) -> torch.Tensor:
+    """img uint8 [3, h, w] (any strides, e.g. a permuted HWC array) -> out fp32 [3, H, W] (a slot of the batch tensor)."""
+    global launch_count
+    _require_cuda(img, out)
+    assert img.dtype == torch.uint8 and img.dim() == 3 and img.shape[0] == 3
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.dim() == 3 and out.shape[0] == 3
+    _, h, w = img.shape
+    sc, sy, sx = img.stride()
+    _check(_lib.rsp_preprocess_u8(_ptr(img), h, w, sc, sy, sx, _ptr(out), out.shape[1], out.shape[2], _host_f3(mean),
+                                  _host_f3(std), int(swap_rb), float(pad_value), _stream()), "rsp_preprocess_u8")
+    launch_count += 1
+    return out
+
+
+def patchify16_u8(img: torch.Tensor, mean, std, swap_rb: bool, out: torch.Tensor | None = None) -> torch.Tensor:
+    """uint8 [B,3,H,W] (contiguous, or channels-last memory = decoded HWC images) -> bf16 [B*(H/16)*(W/16), 768]
+    normalised patch rows (DetDataPreprocessor fused into the patch-embed operand)."""
+    global launch_count
+    _require_cuda(img, out)
+    assert img.dtype == torch.uint8 and img.dim() == 4 and img.shape[1] == 3
+    B, _, H, W = img.shape
+    if img.is_contiguous():
+        hwc = 0
+    else:
+        assert img.permute(0, 2, 3, 1).is_contiguous(), "uint8 batch must be NCHW-contiguous or channels-last"
+        hwc = 1
+    rows = B * (H // 16) * (W // 16)
+    if out is None:
+        out = torch.empty((rows, 768), device=img.device, dtype=torch.bfloat16)
+    assert out.shape == (rows, 768) and out.is_contiguous() and out.dtype == torch.bfloat16
+    _check(_lib.rsp_patchify16_u8(_ptr(img), hwc, _ptr(out), B, H, W, _host_f3(mean), _host_f3(std), int(swap_rb),
+                                  _stream()), "rsp_patchify16_u8")
+    launch_count += 1
+    return out

@@ -161,7 +161,8 @@ class RPNHead(_PrepMixin, BaseModule):
             # rpn_head.py:206-212: descending sort, first nms_pre
             _, idx = torch.topk(logits, k, dim=1, largest=True, sorted=True)
             _lib.rpn_decode(out, idx.contiguous(), B, H, W, A, self.prior_generator.strides[l],
-                            p["anchors"][l], img_hw, float(cfg.get("min_bbox_size", 0)), boxes, scores, off)
+                            p["anchors"][l], img_hw, float(cfg.get("min_bbox_size", 0)), boxes, scores, off,
+                            stds=self.bbox_coder.stds)
             ids[:, off:off + k] = l
             off += k
         # batched_nms sorts by score internally; filtered boxes (score -1) sink to the end
@@ -368,7 +369,8 @@ class RSPrompterAnchorRoIPromptHead(BaseModule):
         if capture is not None:
             capture.update(roi_feats7=feats7, cls=cls, reg=reg, rois=rois)
         C = self.bbox_head.num_classes
-        s, b, lab = _lib.bbox_cls_decode(cls, reg, rois, valid.contiguous(), C, img_hw, float(cfg.get("score_thr", 0.05)))
+        s, b, lab = _lib.bbox_cls_decode(cls, reg, rois, valid.contiguous(), C, img_hw, float(cfg.get("score_thr", 0.05)),
+                                         stds=self.bbox_head.bbox_coder.stds)
         n = K * C
         s, b, lab = s.view(B, n), b.view(B, n, 4), lab.view(B, n)
         s_sorted, order = torch.sort(s, dim=1, descending=True, stable=True)

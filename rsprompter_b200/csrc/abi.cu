@@ -160,16 +160,16 @@ int rsp_i2t_attention(const void* Q, const int32_t* q_block, const void* ktok, c
 extern "C" {
 
 int rsp_rpn_decode(const float* head_out, int ld, const int64_t* topk_idx, int K, int B, int H, int W,
-                   int A, int stride, const float* base_anchors, float img_h, float img_w,
+                   int A, int stride, const float* base_anchors, const float* stds4, float img_h, float img_w,
                    float min_size, int out_off, int out_ld, float* boxes, float* scores, void* stream) {
   return rpn_decode(head_out, ld, reinterpret_cast<const long long*>(topk_idx), K, B, H, W, A, stride,
-                    base_anchors, img_h, img_w, min_size, out_off, out_ld, boxes, scores, S(stream));
+                    base_anchors, stds4, img_h, img_w, min_size, out_off, out_ld, boxes, scores, S(stream));
 }
 
 int rsp_bbox_cls_decode(const float* cls, int ld_cls, const float* reg, int ld_reg, const float* rois,
-                        const uint8_t* roi_valid, int n, int C, float img_h, float img_w,
+                        const uint8_t* roi_valid, int n, int C, const float* stds4, float img_h, float img_w,
                         float score_thr, float* scores, float* boxes, int64_t* labels, void* stream) {
-  return bbox_cls_decode(cls, ld_cls, reg, ld_reg, rois, roi_valid, n, C, img_h, img_w, score_thr, scores,
+  return bbox_cls_decode(cls, ld_cls, reg, ld_reg, rois, roi_valid, n, C, stds4, img_h, img_w, score_thr, scores,
                          boxes, reinterpret_cast<long long*>(labels), S(stream));
 }
 
@@ -259,6 +259,40 @@ int rsp_query_postprocess_rescale(const float* logits, const int32_t* sel, const
 int rsp_query_postprocess(const float* logits, const int32_t* sel, const float* cls_scores, int n_inst, int hm, int wm,
                           int H, int W, uint8_t* masks, float* part_ws, float* scores, float* boxes, void* stream) {
   return query_postprocess(logits, sel, cls_scores, n_inst, hm, wm, H, W, masks, part_ws, scores, boxes, S(stream));
+}
+
+int rsp_query_postprocess_bits(const float* logits, const int32_t* sel, const float* cls_scores, int n_inst, int hm,
+                               int wm, uint8_t* bits, float* part_ws, float* scores, float* boxes, void* stream) {
+  return query_postprocess_bits(logits, sel, cls_scores, n_inst, hm, wm, bits, part_ws, scores, boxes, S(stream));
+}
+
+int rsp_mask_paste_bits(const float* maps, uint8_t* bits, int n, int hm, int wm, float thr, int mode, void* stream) {
+  return mask_paste_bits(maps, bits, n, hm, wm, thr, mode, S(stream));
+}
+
+}  // extern "C"
+
+#include "records.h"
+
+extern "C" {
+
+int rsp_pack_mask_bits(const uint8_t* masks, uint8_t* bits, long long rows, int W, void* stream) {
+  return pack_mask_bits(masks, bits, rows, W, S(stream));
+}
+
+int rsp_unpack_mask_bits(const uint8_t* bits, uint8_t* masks, long long rows, int W, void* stream) {
+  return unpack_mask_bits(bits, masks, rows, W, S(stream));
+}
+
+int rsp_preprocess_u8(const uint8_t* img, int h, int w, long long stride_c, long long stride_y, long long stride_x,
+                      float* out, int H, int W, const float* mean3, const float* std3, int swap_rb, float pad_value,
+                      void* stream) {
+  return preprocess_u8(img, h, w, stride_c, stride_y, stride_x, out, H, W, mean3, std3, swap_rb, pad_value, S(stream));
+}
+
+int rsp_patchify16_u8(const uint8_t* img, int hwc, void* out, int B, int H, int W, const float* mean3, const float* std3,
+                      int swap_rb, void* stream) {
+  return patchify16_u8(img, hwc, out, B, H, W, mean3, std3, swap_rb, S(stream));
 }
 
 }  // extern "C"

@@ -25,6 +25,8 @@ __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b)
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 
+struct Stds4 { float v[4]; };   // DeltaXYWHBBoxCoder target_stds (host array -> kernel parameter)
+
 __device__ __forceinline__ void delta2bbox_one(const float r[4], const float d[4], const float stds[4],
                                                float max_h, float max_w, float out[4]) {
   const float max_ratio = 4.135166556742356f;  // |log(16/1000)|
@@ -46,7 +48,7 @@ __device__ __forceinline__ void delta2bbox_one(const float r[4], const float d[4
 // head_out: fp32 [B*H*W, ld] rows = pixels, columns [0, A) cls logits, [A, 5A) box deltas (a*4 + k)
 __global__ void rpn_decode_kernel(const float* __restrict__ head_out, int ld,
                                   const long long* __restrict__ topk_idx, int K, int B, int H, int W,
-                                  int A, int stride, const float* __restrict__ base_anchors,
+                                  int A, int stride, const float* __restrict__ base_anchors, Stds4 sd,
                                   float img_h, float img_w, float min_size, int out_off, int out_ld,
                                   float* __restrict__ boxes, float* __restrict__ scores) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -62,7 +64,7 @@ __global__ void rpn_decode_kernel(const float* __restrict__ head_out, int ld,
   const float sx = static_cast<float>(x * stride), sy = static_cast<float>(y * stride);
   const float r[4] = {base_anchors[a * 4] + sx, base_anchors[a * 4 + 1] + sy,
                       base_anchors[a * 4 + 2] + sx, base_anchors[a * 4 + 3] + sy};
-  const float stds[4] = {1.f, 1.f, 1.f, 1.f};
+  const float stds[4] = {sd.v[0], sd.v[1], sd.v[2], sd.v[3]};
   float o[4];
   delta2bbox_one(r, d, stds, img_h, img_w, o);
   float s = 1.0f / (1.0f + expf(-logit));
@@ -73,12 +75,14 @@ __global__ void rpn_decode_kernel(const float* __restrict__ head_out, int ld,
 }
 
 int rpn_decode(const float* head_out, int ld, const long long* topk_idx, int K, int B, int H, int W,
-               int A, int stride, const float* base_anchors, float img_h, float img_w, float min_size,
-               int out_off, int out_ld, float* boxes, float* scores, cudaStream_t stream) {
-  RSP_CHECK_ARG(head_out && topk_idx && base_anchors && boxes && scores && B > 0 && K > 0, "rpn_decode: bad args");
+               int A, int stride, const float* base_anchors, const float* stds4, float img_h, float img_w,
+               float min_size, int out_off, int out_ld, float* boxes, float* scores, cudaStream_t stream) {
+  RSP_CHECK_ARG(head_out && topk_idx && base_anchors && stds4 && boxes && scores && B > 0 && K > 0,
+                "rpn_decode: bad args");
   const int n = B * K;
+  Stds4 sd{{stds4[0], stds4[1], stds4[2], stds4[3]}};
   rpn_decode_kernel<<<(n + 127) / 128, 128, 0, stream>>>(head_out, ld, topk_idx, K, B, H, W, A, stride,
-                                                         base_anchors, img_h, img_w, min_size, out_off,
+                                                         base_anchors, sd, img_h, img_w, min_size, out_off,
                                                          out_ld, boxes, scores);
   RSP_CHECK_LAUNCH();
   return RSP_OK;
@@ -90,7 +94,7 @@ int rpn_decode(const float* head_out, int ld, const long long* topk_idx, int K, 
 __global__ void bbox_cls_decode_kernel(const float* __restrict__ cls, int ld_cls,
                                        const float* __restrict__ reg, int ld_reg,
                                        const float* __restrict__ rois, const unsigned char* __restrict__ roi_valid,
-                                       int n, int C, float img_h, float img_w, float score_thr,
+                                       int n, int C, Stds4 sd, float img_h, float img_w, float score_thr,
                                        float* __restrict__ scores, float* __restrict__ boxes,
                                        long long* __restrict__ labels) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,7 +110,7 @@ __global__ void bbox_cls_decode_kernel(const float* __restrict__ cls, int ld_cls
   const float roi[4] = {rr[1], rr[2], rr[3], rr[4]};
   const float* dp = reg + static_cast<size_t>(r) * ld_reg + c * 4;
   const float d[4] = {dp[0], dp[1], dp[2], dp[3]};
-  const float stds[4] = {0.1f, 0.1f, 0.2f, 0.2f};
+  const float stds[4] = {sd.v[0], sd.v[1], sd.v[2], sd.v[3]};
   float o[4];
   delta2bbox_one(roi, d, stds, img_h, img_w, o);
   if (!(s > score_thr) || (roi_valid && !roi_valid[r])) s = -1.0f;
@@ -117,11 +121,12 @@ __global__ void bbox_cls_decode_kernel(const float* __restrict__ cls, int ld_cls
 }
 
 int bbox_cls_decode(const float* cls, int ld_cls, const float* reg, int ld_reg, const float* rois,
-                    const unsigned char* roi_valid, int n, int C, float img_h, float img_w,
+                    const unsigned char* roi_valid, int n, int C, const float* stds4, float img_h, float img_w,
                     float score_thr, float* scores, float* boxes, long long* labels, cudaStream_t stream) {
-  RSP_CHECK_ARG(cls && reg && rois && scores && boxes && labels && n > 0 && C > 0, "bbox_cls_decode: bad args");
+  RSP_CHECK_ARG(cls && reg && rois && stds4 && scores && boxes && labels && n > 0 && C > 0, "bbox_cls_decode: bad args");
   const int t = n * C;
-  bbox_cls_decode_kernel<<<(t + 127) / 128, 128, 0, stream>>>(cls, ld_cls, reg, ld_reg, rois, roi_valid, n, C,
+  Stds4 sd{{stds4[0], stds4[1], stds4[2], stds4[3]}};
+  bbox_cls_decode_kernel<<<(t + 127) / 128, 128, 0, stream>>>(cls, ld_cls, reg, ld_reg, rois, roi_valid, n, C, sd,
                                                               img_h, img_w, score_thr, scores, boxes, labels);
   RSP_CHECK_LAUNCH();
   return RSP_OK;
@@ -468,7 +473,8 @@ __global__ void mask_paste_kernel(const float* __restrict__ logits, unsigned cha
 }
 
 // x4 fast path (the mask decoder's logits are always image / 4): thread = 4 output rows x 16 columns
-template <int MODE>
+// PACKED: out holds W/8 bytes per row, pixel x = bit x%8 of byte x/8 (the result-record payload)
+template <int MODE, bool PACKED>
 __global__ void mask_paste_x4_kernel(const float* __restrict__ logits, unsigned char* __restrict__ out, int n, int hm,
                                      int wm, float thr) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -481,17 +487,21 @@ __global__ void mask_paste_x4_kernel(const float* __restrict__ logits, unsigned 
   Up4Tile tile;
   up4_load(logits + static_cast<size_t>(m) * hm * wm, hm, wm, yb, xb, tile);
   const int W = 4 * wm;
-  unsigned char* o = out + (static_cast<size_t>(m) * 4 * hm + 4 * yb) * W + 16 * xb;
+  const int ldm = PACKED ? W / 8 : W;
+  unsigned char* o = out + (static_cast<size_t>(m) * 4 * hm + 4 * yb) * ldm + (PACKED ? 2 : 16) * xb;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     uint32_t packed[4] = {0u, 0u, 0u, 0u};
+    uint32_t bits = 0u;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const float v = up4_value(tile, j, k);
       const uint32_t bit = (MODE == 1 ? (v > thr) : (v >= thr)) ? 1u : 0u;
-      packed[k >> 2] |= bit << ((k & 3) * 8);
+      if (PACKED) bits |= bit << k;
+      else packed[k >> 2] |= bit << ((k & 3) * 8);
     }
-    *reinterpret_cast<uint4*>(o + static_cast<size_t>(j) * W) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    if (PACKED) *reinterpret_cast<uint16_t*>(o + static_cast<size_t>(j) * ldm) = static_cast<uint16_t>(bits);
+    else *reinterpret_cast<uint4*>(o + static_cast<size_t>(j) * W) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
   }
 }
 
@@ -547,14 +557,27 @@ int sigmoid_f32(const float* in, float* out, long long n, cudaStream_t stream) {
   return RSP_OK;
 }
 
+int mask_paste_bits(const float* maps, unsigned char* bits, int n, int hm, int wm, float thr, int mode,
+                    cudaStream_t stream) {
+  RSP_CHECK_ARG(maps && bits && n > 0 && wm % 4 == 0 && (mode == 1 || mode == 2) &&
+                (reinterpret_cast<uintptr_t>(maps) & 15) == 0 && (reinterpret_cast<uintptr_t>(bits) & 1) == 0,
+                "mask_paste_bits: x4 path only (wm % 4 == 0, mode 1: > thr on raw maps, 2: >= thr on activated maps)");
+  const long long tiles = static_cast<long long>(n) * hm * (wm / 4);
+  const unsigned blocks = static_cast<unsigned>((tiles + 127) / 128);
+  if (mode == 1) mask_paste_x4_kernel<1, true><<<blocks, 128, 0, stream>>>(maps, bits, n, hm, wm, thr);
+  else mask_paste_x4_kernel<2, true><<<blocks, 128, 0, stream>>>(maps, bits, n, hm, wm, thr);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
 int mask_paste(const float* logits, unsigned char* out, int n, int hm, int wm, int H, int W, float thr,
                int mode, cudaStream_t stream) {
   RSP_CHECK_ARG(logits && out && n > 0 && W % 16 == 0, "mask_paste: W must be a multiple of 16");
   if (mode != 0 && H == 4 * hm && W == 4 * wm && wm % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
     const long long tiles = static_cast<long long>(n) * hm * (wm / 4);
     const unsigned blocks = static_cast<unsigned>((tiles + 127) / 128);
-    if (mode == 1) mask_paste_x4_kernel<1><<<blocks, 128, 0, stream>>>(logits, out, n, hm, wm, thr);
-    else mask_paste_x4_kernel<2><<<blocks, 128, 0, stream>>>(logits, out, n, hm, wm, thr);
+    if (mode == 1) mask_paste_x4_kernel<1, false><<<blocks, 128, 0, stream>>>(logits, out, n, hm, wm, thr);
+    else mask_paste_x4_kernel<2, false><<<blocks, 128, 0, stream>>>(logits, out, n, hm, wm, thr);
     RSP_CHECK_LAUNCH();
     return RSP_OK;
   }

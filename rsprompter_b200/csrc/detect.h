@@ -4,10 +4,10 @@
 namespace rsp {
 
 int rpn_decode(const float* head_out, int ld, const long long* topk_idx, int K, int B, int H, int W,
-               int A, int stride, const float* base_anchors, float img_h, float img_w, float min_size,
-               int out_off, int out_ld, float* boxes, float* scores, cudaStream_t stream);
+               int A, int stride, const float* base_anchors, const float* stds4, float img_h, float img_w,
+               float min_size, int out_off, int out_ld, float* boxes, float* scores, cudaStream_t stream);
 int bbox_cls_decode(const float* cls, int ld_cls, const float* reg, int ld_reg, const float* rois,
-                    const unsigned char* roi_valid, int n, int C, float img_h, float img_w,
+                    const unsigned char* roi_valid, int n, int C, const float* stds4, float img_h, float img_w,
                     float score_thr, float* scores, float* boxes, long long* labels, cudaStream_t stream);
 int nms_batched(const float* boxes, const long long* ids, const int* nvalid, int B, int n, float thr,
                 unsigned long long* mask_ws, float* max_coord_ws, unsigned char* keep, cudaStream_t stream);
@@ -21,6 +21,8 @@ int mask_paste_rescale(const float* maps, unsigned char* out, int n, int hm, int
                        int crop_w, int H, int W, float thr, int mode, cudaStream_t stream);
 int mask_paste(const float* logits, unsigned char* out, int n, int hm, int wm, int H, int W, float thr,
                int mode, cudaStream_t stream);
+int mask_paste_bits(const float* maps, unsigned char* bits, int n, int hm, int wm, float thr, int mode,
+                    cudaStream_t stream);
 int sigmoid_f32(const float* in, float* out, long long n, cudaStream_t stream);
 int pool2_nhwc(const void* in, void* out, int B, int H, int W, int C, int mode, cudaStream_t stream);
 int sin_fold(const float* in, float* out, long long n_out, cudaStream_t stream);

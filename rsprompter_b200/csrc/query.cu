@@ -604,6 +604,9 @@ __global__ void query_mask_kernel(const float* __restrict__ logits, const int* _
 }
 
 // x4 fast path: block = 16 output rows of one instance (same partial layout as above); thread = 4 x 16 tile
+// PACKED: masks is the bit-packed record payload (H rows of W/8 bytes, pixel x = bit x%8 of byte x/8, i.e.
+// numpy packbits(bitorder='little')); a thread writes its 16 pixels of a row as one uint16.
+template <bool PACKED>
 __global__ void query_mask_x4_kernel(const float* __restrict__ logits, const int* __restrict__ sel, int hm, int wm,
                                      unsigned char* __restrict__ masks, float* __restrict__ part) {
   const int inst = blockIdx.y;
@@ -616,7 +619,8 @@ __global__ void query_mask_x4_kernel(const float* __restrict__ logits, const int
     if (yb >= hm) break;
     Up4Tile tile;
     up4_load(src, hm, wm, yb, xb, tile);
-    unsigned char* o = masks + (static_cast<size_t>(inst) * H + 4 * yb) * W + 16 * xb;
+    const int ldm = PACKED ? W / 8 : W;       // bytes per mask row
+    unsigned char* o = masks + (static_cast<size_t>(inst) * H + 4 * yb) * ldm + (PACKED ? 2 : 16) * xb;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint32_t packed[4] = {0u, 0u, 0u, 0u};
@@ -627,10 +631,11 @@ __global__ void query_mask_x4_kernel(const float* __restrict__ logits, const int
         if (v > 0.f) {
           sum += 1.f / (1.f + expf(-v));
           bits |= 1u << k;
-          packed[k >> 2] |= 1u << ((k & 3) * 8);
+          if (!PACKED) packed[k >> 2] |= 1u << ((k & 3) * 8);
         }
       }
-      *reinterpret_cast<uint4*>(o + static_cast<size_t>(j) * W) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      if (PACKED) *reinterpret_cast<uint16_t*>(o + static_cast<size_t>(j) * ldm) = static_cast<uint16_t>(bits);
+      else *reinterpret_cast<uint4*>(o + static_cast<size_t>(j) * W) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
       if (bits) {
         cnt += __popc(bits);
         minx = min(minx, 16 * xb + __ffs(bits) - 1);
@@ -731,9 +736,24 @@ int query_postprocess(const float* logits, const int* sel, const float* cls_scor
   const int nblk = (H + QP_ROWS - 1) / QP_ROWS;
   dim3 grid(nblk, n_inst);
   if (H == 4 * hm && W == 4 * wm && wm % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0)
-    query_mask_x4_kernel<<<grid, 256, 0, stream>>>(logits, sel, hm, wm, masks, part_ws);
+    query_mask_x4_kernel<false><<<grid, 256, 0, stream>>>(logits, sel, hm, wm, masks, part_ws);
   else
     query_mask_kernel<<<grid, 256, 0, stream>>>(logits, sel, hm, wm, H, W, masks, part_ws);
+  RSP_CHECK_LAUNCH();
+  query_finalize_kernel<<<(n_inst + 127) / 128, 128, 0, stream>>>(part_ws, nblk, cls_scores, n_inst, W, H, scores, boxes);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
+int query_postprocess_bits(const float* logits, const int* sel, const float* cls_scores, int n_inst, int hm, int wm,
+                           unsigned char* bits, float* part_ws, float* scores, float* boxes, cudaStream_t stream) {
+  RSP_CHECK_ARG(logits && sel && cls_scores && bits && part_ws && scores && boxes && n_inst > 0 && wm % 4 == 0 &&
+                (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (reinterpret_cast<uintptr_t>(bits) & 1) == 0,
+                "query_postprocess_bits: needs wm % 4 == 0 and 16-byte aligned logits (x4 path only)");
+  const int H = 4 * hm, W = 4 * wm;
+  const int nblk = (H + QP_ROWS - 1) / QP_ROWS;
+  dim3 grid(nblk, n_inst);
+  query_mask_x4_kernel<true><<<grid, 256, 0, stream>>>(logits, sel, hm, wm, bits, part_ws);
   RSP_CHECK_LAUNCH();
   query_finalize_kernel<<<(n_inst + 127) / 128, 128, 0, stream>>>(part_ws, nblk, cls_scores, n_inst, W, H, scores, boxes);
   RSP_CHECK_LAUNCH();

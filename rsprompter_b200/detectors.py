@@ -13,6 +13,7 @@ import torch
 from . import _lib
 from .necks import PseudoFeatureAggregator
 from .registry import MODELS, BaseModule, ConfigDict, DetDataSample, InstanceData, make_data_samples
+from .results import ResultRecord
 from .sam_encoder import MMPretrainSamVisionEncoder, SamVisionEncoderOutput
 
 
@@ -26,6 +27,9 @@ class _SamDetectorBase(BaseModule):
     # input shape replays it without per-launch host work or inter-kernel launch gaps.  Opt-in
     # (enable_cuda_graphs()): capture allocates a private memory pool per shape.
     def enable_cuda_graphs(self, enabled: bool = True):
+        """Replay the device-resident forward as one CUDA graph per input shape.  The graph's output buffers are
+        reused by the next call with the same shape: predict() / predict_records() copy what they hand back, callers
+        of _raw() must consume the result before calling again."""
         self._graphs = {} if enabled else None
         return self
 
@@ -44,9 +48,12 @@ class _SamDetectorBase(BaseModule):
         graphs = getattr(self, "_graphs", None)
         if graphs is None:
             return self.predict_raw(batch_inputs)
-        key = (tuple(batch_inputs.shape), batch_inputs.dtype)
+        key = (tuple(batch_inputs.shape), batch_inputs.dtype, tuple(batch_inputs.stride()),
+               getattr(batch_inputs, "rsp_norm", None))
         if key not in graphs:
             static_in = batch_inputs.to(next(self.parameters()).device, copy=True)   # also accepts a pinned host batch
+            if hasattr(batch_inputs, "rsp_norm"):      # uint8 batch: normalisation rides along (DetDataPreprocessor)
+                static_in.rsp_norm = batch_inputs.rsp_norm
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):          # warm-up: one-time attribute calls, caches, constant tables
@@ -87,6 +94,24 @@ class _SamDetectorBase(BaseModule):
         pe = pe.view(size, size, -1).permute(2, 0, 1).unsqueeze(0).repeat(image_embeddings.shape[0], 1, 1, 1)
         x = self.neck(hidden)
         return x, image_embeddings, pe
+
+    def _preprocess(self, data: dict) -> dict:
+        """BaseModel.test_step's data_preprocessor(data, False); the detector lets its own preprocessor hand over the
+        uint8 batch when the normalisation can be fused into the patch-embed operand loader."""
+        if self.data_preprocessor is None:
+            return data
+        return self.data_preprocessor(data, False, fuse_patch_embed=True)
+
+    def _new_record(self, B: int, M: int, hw: tuple, device) -> ResultRecord:
+        """With CUDA graphs on, records alternate between two buffers per shape so that the previous step's record can
+        still be in flight (side-stream gather / D2H) while this step writes the next one."""
+        if getattr(self, "_graphs", None) is None:
+            return ResultRecord(B, M, hw, device=device)
+        pool = self.__dict__.setdefault("_rec_pool", {})
+        key = (B, M, tuple(hw), str(device))
+        slot = pool.setdefault(key, dict(i=0, recs=[ResultRecord(B, M, hw, device=device) for _ in range(2)]))
+        slot["i"] ^= 1
+        return slot["recs"][slot["i"]]
 
     @staticmethod
     def _metas(batch_data_samples, batch_inputs):
@@ -149,6 +174,8 @@ class RSPrompterAnchor(_SamDetectorBase):
             batch_data_samples = make_data_samples(batch_inputs.shape[0], tuple(batch_inputs.shape[-2:]))
         hw, metas = self._metas(batch_data_samples, batch_inputs)
         r = self._raw(batch_inputs)
+        if getattr(self, "_graphs", None) is not None:     # graph buffers are overwritten by the next replay
+            r = dict(r, bboxes=r["bboxes"].clone(), scores=r["scores"].clone(), labels=r["labels"].clone())
         thr = float(self.test_cfg.rcnn.get("mask_thr_binary", 0.5))
         B, M = r["scores"].shape
         logits = r["mask_logits"][:, 0].contiguous()
@@ -171,6 +198,20 @@ class RSPrompterAnchor(_SamDetectorBase):
             ds.pred_instances = InstanceData(bboxes=boxes, scores=r["scores"][b, :n], labels=r["labels"][b, :n], masks=mk)
         return batch_data_samples
 
+    @torch.no_grad()
+    def predict_records(self, batch_inputs: torch.Tensor, record: ResultRecord | None = None) -> ResultRecord:
+        """predict() for images at the batch shape with the result left on the device as one ResultRecord
+        (bit-packed masks + rows + counts): what a distributed test loop gathers / copies to the host."""
+        r = self._raw(batch_inputs)
+        hw = tuple(int(v) for v in batch_inputs.shape[-2:])
+        B, M = r["scores"].shape
+        rec = record or self._new_record(B, M, hw, r["scores"].device)
+        thr = float(self.test_cfg.rcnn.get("mask_thr_binary", 0.5))
+        _lib.mask_paste_bits(r["mask_logits"][:, 0].contiguous(), thr, 0, bits=rec.mask_bits)
+        torch.cat([r["bboxes"], r["scores"][..., None], r["labels"].to(torch.float32)[..., None]], dim=2, out=rec.rows)
+        rec.counts.copy_(r["counts"])
+        return rec
+
     def forward(self, inputs, data_samples=None, mode: str = "predict"):
         if mode == "predict":
             return self.predict(inputs, data_samples)
@@ -178,8 +219,7 @@ class RSPrompterAnchor(_SamDetectorBase):
 
     def test_step(self, data):
         """BaseModel.test_step: data_preprocessor(data, False) then forward(mode='predict')."""
-        if self.data_preprocessor is not None:
-            data = self.data_preprocessor(data, False)
+        data = self._preprocess(data)
         return self.predict(data["inputs"], data.get("data_samples"))
 
 
@@ -237,6 +277,17 @@ class RSPrompterQuery(_SamDetectorBase):
             ds.pred_instances = InstanceData(**inst)
         return batch_data_samples
 
+    @torch.no_grad()
+    def predict_records(self, batch_inputs: torch.Tensor, record: ResultRecord | None = None) -> ResultRecord:
+        """predict() for images at the batch shape with the result left on the device as one ResultRecord."""
+        r = self._raw(batch_inputs)
+        hw = tuple(int(v) for v in batch_inputs.shape[-2:])
+        B = r["cls"].shape[0]
+        K = int(self.test_cfg.get("max_per_image", 100))
+        rec = record or self._new_record(B, K, hw, r["cls"].device)
+        self.panoptic_fusion_head.instance_postprocess_record(r["cls"], r["mask_logits"], rec)
+        return rec
+
     def forward(self, inputs, data_samples=None, mode: str = "predict"):
         if mode == "predict":
             return self.predict(inputs, data_samples)
@@ -244,8 +295,7 @@ class RSPrompterQuery(_SamDetectorBase):
 
     def test_step(self, data):
         """BaseModel.test_step: data_preprocessor(data, False) then forward(mode='predict')."""
-        if self.data_preprocessor is not None:
-            data = self.data_preprocessor(data, False)
+        data = self._preprocess(data)
         return self.predict(data["inputs"], data.get("data_samples"))
 
 

@@ -2,10 +2,14 @@
 ImgDataPreprocessor): collate -> BGR->RGB -> float -> (x - mean) / std -> pad bottom/right to a multiple of
 ``pad_size_divisor`` -> stack, and ``batch_input_shape`` / ``pad_shape`` written into the data samples.
 
-This sits in front of the hot path (SURVEY.md 8f "next"): it is host-side glue expressed with a handful of
-device-side torch ops on the model's device (one H2D copy per image, no CPU arithmetic), so ``test_step(data)`` keeps
-the reference contract.  Training-time batch augmentations (``BatchFixedSizePad`` ...) are ignored: the reference
-applies them only when ``training=True`` (data_preprocessor.py:145-147)."""
+This sits in front of the hot path.  uint8 images (what ``PackDetInputs`` emits) are uploaded as
+bytes and converted by ``rsp_preprocess_u8`` (channel flip, normalise with true fp32 division, pad) straight into
+their slot of the batch tensor - one kernel per image, no CPU arithmetic.  When the consumer is one of this package's
+detectors (``fuse_patch_embed=True``) and the images already have the batch shape, the uint8 batch itself is handed
+over with the normalisation attached (``tensor.rsp_norm``): ``rsp_patchify16_u8`` then applies it inside the
+patch-embed operand loader and the fp32 image never exists.  Float inputs keep the round-1 torch expression.
+Training-time batch augmentations (``BatchFixedSizePad`` ...) are ignored: the reference applies them only when
+``training=True`` (data_preprocessor.py:145-147)."""
 from __future__ import annotations
 
 import math
@@ -13,6 +17,7 @@ import math
 import torch
 from torch import nn
 
+from . import _lib
 from .registry import MODELS, BaseModule, DetDataSample
 
 
@@ -28,8 +33,11 @@ class DetDataPreprocessor(BaseModule):
         self.channel_conversion = bool(bgr_to_rgb or rgb_to_bgr)
         self.pad_size_divisor, self.pad_value = int(pad_size_divisor), float(pad_value)
         self._enable_normalize = mean is not None
+        self._mean3 = self._std3 = None
         if self._enable_normalize:
             assert len(mean) in (1, 3) and len(std) in (1, 3)
+            self._mean3 = tuple(float(m) for m in (mean if len(mean) == 3 else list(mean) * 3))
+            self._std3 = tuple(float(m) for m in (std if len(std) == 3 else list(std) * 3))
             self.register_buffer("mean", torch.tensor(mean, dtype=torch.float32).view(-1, 1, 1), persistent=False)
             self.register_buffer("std", torch.tensor(std, dtype=torch.float32).view(-1, 1, 1), persistent=False)
         self.register_buffer("_dev", torch.zeros(1), persistent=False)
@@ -47,8 +55,11 @@ class DetDataPreprocessor(BaseModule):
             x = (x - self.mean) / self.std
         return x
 
+    def _norm3(self):
+        return (self._mean3 or (0.0, 0.0, 0.0), self._std3 or (1.0, 1.0, 1.0), self.channel_conversion)
+
     @torch.no_grad()
-    def forward(self, data: dict, training: bool = False) -> dict:
+    def forward(self, data: dict, training: bool = False, fuse_patch_embed: bool = False) -> dict:
         if training:
             raise NotImplementedError("rsprompter_b200 implements the inference path only")
         inputs, samples = data["inputs"], data.get("data_samples")
@@ -60,12 +71,26 @@ class DetDataPreprocessor(BaseModule):
             imgs = list(inputs)
             assert all(t.dim() == 3 for t in imgs), "inputs must be NCHW or a list of CHW tensors"
         pad_shapes = [(int(math.ceil(t.shape[1] / d)) * d, int(math.ceil(t.shape[2] / d)) * d) for t in imgs]
-        xs = [self._one(t) for t in imgs]
-        H = int(math.ceil(max(t.shape[1] for t in xs) / d)) * d
-        W = int(math.ceil(max(t.shape[2] for t in xs) / d)) * d
-        batch = torch.full((len(xs), xs[0].shape[0], H, W), self.pad_value, dtype=torch.float32, device=self.device)
-        for i, t in enumerate(xs):                    # stack_batch: pad bottom / right
-            batch[i, :, :t.shape[1], :t.shape[2]] = t
+        H = int(math.ceil(max(t.shape[1] for t in imgs) / d)) * d
+        W = int(math.ceil(max(t.shape[2] for t in imgs) / d)) * d
+        u8 = self.device.type == "cuda" and all(t.dtype == torch.uint8 and t.shape[0] == 3 for t in imgs)
+        if u8 and fuse_patch_embed and H % 16 == 0 and W % 16 == 0 and all(tuple(t.shape[1:]) == (H, W) for t in imgs):
+            # the raw bytes are the batch: normalisation happens inside the patch-embed operand loader
+            if isinstance(inputs, torch.Tensor) and (inputs.is_contiguous() or inputs.permute(0, 2, 3, 1).is_contiguous()):
+                batch = inputs.to(self.device, non_blocking=True)
+            else:
+                batch = torch.stack([t.to(self.device, non_blocking=True) for t in imgs]).contiguous()
+            batch.rsp_norm = self._norm3()
+        elif u8:
+            batch = torch.empty((len(imgs), 3, H, W), dtype=torch.float32, device=self.device)
+            mean, std, swap = self._norm3()
+            for i, t in enumerate(imgs):              # one kernel per image: flip + normalise + pad into its slot
+                _lib.preprocess_u8(t.to(self.device, non_blocking=True), batch[i], mean, std, swap, self.pad_value)
+        else:
+            xs = [self._one(t) for t in imgs]
+            batch = torch.full((len(xs), xs[0].shape[0], H, W), self.pad_value, dtype=torch.float32, device=self.device)
+            for i, t in enumerate(xs):                # stack_batch: pad bottom / right
+                batch[i, :, :t.shape[1], :t.shape[2]] = t
         if samples is None:
             samples = [DetDataSample(metainfo=dict(img_shape=tuple(t.shape[1:]), ori_shape=tuple(t.shape[1:]),
                                                    scale_factor=(1.0, 1.0))) for t in imgs]

@@ -416,5 +416,22 @@ class RSMaskFormerFusionHead(BaseModule):
             ms.append(mk); ds.append(det); bs.append(bx)
         return dict(masks=ms, scores=ds, bboxes=bs, labels=labels, query=query, is_thing=keep_thing)
 
+    @torch.no_grad()
+    def instance_postprocess_record(self, cls: torch.Tensor, mask_pred: torch.Tensor, rec) -> None:
+        """instance_postprocess for images at the batch shape (4x the logit size), written into a ResultRecord: the
+        masks go out bit-packed, rows = (tight box, cls * mask score, label) (maskformer_fusion_head.py:149-182)."""
+        B, nq, _ = cls.shape
+        C = self.num_classes
+        K = rec.slots
+        assert self.num_stuff_classes == 0, "records hold fixed-size instance lists (no stuff filtering)"
+        scores = torch.softmax(cls, dim=-1)[:, :, :-1].reshape(B, nq * C)
+        sc, top = scores.topk(K, dim=1, sorted=False)
+        labels, query = top % C, top // C
+        sel = (query + torch.arange(B, device=cls.device).view(B, 1) * nq).to(torch.int32).contiguous()
+        _, det, boxes = _lib.query_postprocess_bits(mask_pred, sel.reshape(-1), sc.reshape(-1).contiguous(),
+                                                    bits=rec.mask_bits.view(B * K, rec.hw[0], rec.hw[1] // 8))
+        torch.cat([boxes.view(B, K, 4), det.view(B, K, 1), labels.to(torch.float32)[..., None]], dim=2, out=rec.rows)
+        rec.counts.fill_(K)
+
 
 __all__ = ["MSDeformAttnPixelDecoder", "RSMask2FormerHead", "RSMaskFormerFusionHead"]

@@ -1,35 +1,107 @@
-"""Fixed-size per-image result records and their cross-rank gather.
+"""Fixed-size per-rank result records and their cross-rank gather.
 
-The inference path shards images across GPUs with no collective inside forward; the only exchange is
-one all-gather of compact per-image records after predict (the B200 counterpart of mmengine's
-``collect_results`` after ``CocoMetric.process``, mmdet/evaluation/metrics/coco_metric.py:346-400).
-A record row is (x1, y1, x2, y2, score, label); each image has ``max_per_img`` rows plus a count."""
+The inference path shards images across GPUs with no collective inside forward; the only exchange is ONE
+all-gather of a compact result record after predict (the B200 counterpart of mmengine's ``collect_results`` after
+``CocoMetric.process`` has encoded the masks, mmdet/evaluation/metrics/coco_metric.py:346-400, ``encode_mask_results``
+:365).  A record is one flat byte buffer per rank holding, for its B images with M instance slots each:
+
+    mask_bits  uint8  [B, M, H, W/8]   thresholded masks, bit-packed (pixel x = bit x % 8 of byte x // 8)
+    rows       fp32   [B, M, 6]        x1, y1, x2, y2, score, label
+    counts     int32  [B]              valid slots per image (slots >= count are padding)
+
+The kernels write straight into views of the buffer (no packing pass); sections are 16-byte aligned."""
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
 
 
+def _align16(n: int) -> int:
+    return (n + 15) // 16 * 16
+
+
+class ResultRecord:
+    def __init__(self, batch: int, slots: int, hw: tuple, device=None, buf: torch.Tensor | None = None):
+        H, W = int(hw[0]), int(hw[1])
+        assert W % 8 == 0, "record payload needs W % 8 == 0"
+        self.batch, self.slots, self.hw = int(batch), int(slots), (H, W)
+        nb = batch * slots * H * (W // 8)
+        self._o_rows = _align16(nb)
+        self._o_cnt = self._o_rows + _align16(batch * slots * 24)
+        self.nbytes = self._o_cnt + _align16(batch * 4)
+        if buf is None:
+            buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        assert buf.dtype == torch.uint8 and buf.is_contiguous() and buf.numel() == self.nbytes
+        self.buf = buf
+        self.mask_bits = buf[:nb].view(batch, slots, H, W // 8)
+        self.rows = buf[self._o_rows:self._o_rows + batch * slots * 24].view(torch.float32).view(batch, slots, 6)
+        self.counts = buf[self._o_cnt:self._o_cnt + batch * 4].view(torch.int32)
+
+    def like(self, buf: torch.Tensor) -> "ResultRecord":
+        """The same layout over another buffer (a gathered slice, a pinned host copy)."""
+        return ResultRecord(self.batch, self.slots, self.hw, buf=buf)
+
+    def gather(self, out: torch.Tensor | None = None, group=None) -> torch.Tensor:
+        """The one collective of the path: uint8 [world, nbytes]; row r = rank r's record."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return self.buf.view(1, -1)
+        world = dist.get_world_size(group)
+        if out is None:
+            out = torch.empty(world, self.nbytes, dtype=torch.uint8, device=self.buf.device)
+        dist.all_gather_into_tensor(out.view(-1), self.buf, group=group)
+        return out
+
+    def split(self, gathered: torch.Tensor) -> list:
+        return [self.like(gathered[r]) for r in range(gathered.shape[0])]
+
+    def to_host(self, host: torch.Tensor | None = None, non_blocking: bool = True) -> "ResultRecord":
+        if host is None:
+            host = torch.empty(self.nbytes, dtype=torch.uint8, pin_memory=self.buf.is_cuda)
+        host.copy_(self.buf, non_blocking=non_blocking)
+        return self.like(host)
+
+    def instances(self) -> list:
+        """Per image: dict(bboxes [n,4], scores [n], labels int64 [n], masks bool [n,H,W]) - masks unpacked on the
+        device the record lives on (numpy.unpackbits(bitorder='little') semantics on the host)."""
+        H, W = self.hw
+        out = []
+        for b, n in enumerate(self.counts.tolist()):
+            bits = self.mask_bits[b, :n]
+            if bits.is_cuda:
+                from . import _lib
+                masks = _lib.unpack_mask_bits(bits.contiguous(), W)
+            else:
+                import numpy as np
+                masks = torch.from_numpy(np.unpackbits(bits.numpy(), axis=-1, bitorder="little")[..., :W].astype(bool))
+            r = self.rows[b, :n]
+            out.append(dict(bboxes=r[:, :4], scores=r[:, 4], labels=r[:, 5].long(), masks=masks))
+        return out
+
+
+# ---- round-1 helpers kept for callers that only exchange the detection rows -------------------------------------
 def pack_records(bboxes: torch.Tensor, scores: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
     """[B,M,4], [B,M], [B,M] -> fp32 [B, M, 6]."""
     return torch.cat([bboxes.float(), scores.float()[..., None], labels.float()[..., None]], dim=2).contiguous()
 
 
 def gather_records(records: torch.Tensor, counts: torch.Tensor):
-    """All-gather [B, M, 6] records and int32 [B] counts over the default process group."""
+    """All-gather [B, M, 6] rows with the int32 [B] counts appended, in one collective."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return records, counts
     world = dist.get_world_size()
-    out = torch.empty((world * records.shape[0],) + tuple(records.shape[1:]), dtype=records.dtype, device=records.device)
-    cnt = torch.empty(world * counts.shape[0], dtype=counts.dtype, device=counts.device)
-    dist.all_gather_into_tensor(out, records.contiguous())
-    dist.all_gather_into_tensor(cnt, counts.contiguous())
-    return out, cnt
+    B = records.shape[0]
+    flat = torch.cat([records.reshape(-1), counts.view(torch.float32).reshape(-1)])
+    out = torch.empty(world, flat.numel(), dtype=flat.dtype, device=flat.device)
+    dist.all_gather_into_tensor(out.view(-1), flat)
+    n = records.numel()
+    rec = out[:, :n].reshape((world * B,) + tuple(records.shape[1:]))
+    cnt = out[:, n:].contiguous().view(torch.int32).reshape(world * B)
+    return rec, cnt
 
 
 def gather_mask_logits(mask_logits: torch.Tensor) -> torch.Tensor:
-    """Optional second part of the record: the low-resolution mask logits [B*M, h, w] as fp16, gathered
-    over the default process group; the consumer resizes / thresholds them.  100 x 256^2 fp16 = 13 MB per image."""
+    """Alternative payload: the low-resolution mask logits [B*M, h, w] as fp16, gathered over the default
+    process group; the consumer resizes / thresholds them.  100 x 256^2 fp16 = 13 MB per image."""
     x = mask_logits.to(torch.float16).contiguous()
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return x

@@ -215,8 +215,17 @@ class SamVisionEncoderB200(nn.Module):
         D, g, H, hd, C = a.hidden_size, a.grid, a.num_heads, a.head_dim, a.output_channels
         T = g * g
         M = B * T
-        x = pixel_values.to(dtype=torch.float32).contiguous()
-        patches = _lib.patchify16(x)
+        if pixel_values.dtype == torch.uint8:
+            # DetDataPreprocessor fused into the operand loader: raw uint8 pixels (NCHW or channels-last memory) ->
+            # normalised bf16 patch rows; (mean, std, swap_rb) ride on the tensor (preprocess.py)
+            norm = getattr(pixel_values, "rsp_norm", None)
+            if norm is None:
+                raise _lib.RspError("uint8 pixel_values need the DetDataPreprocessor normalisation (tensor.rsp_norm)")
+            x = pixel_values
+            patches = _lib.patchify16_u8(x, norm[0], norm[1], norm[2])
+        else:
+            x = pixel_values.to(dtype=torch.float32).contiguous()
+            patches = _lib.patchify16(x)
         h = _lib.gemm(patches, p["pe_w"], p["pe_b"], residual=p["pos"], res_mod=T,
                       out_dtype=torch.float32)
         hidden = [h]

@@ -38,6 +38,22 @@ def _worker(rank, world, port, q):
     all_logits = gather_mask_logits(logits)
     ok = ok and all_logits.dtype == torch.float16 and all_logits.shape == (world * B * M, 8, 8)
     ok = ok and torch.equal(all_logits[rank * B * M:(rank + 1) * B * M], logits.half())
+    # the full record (bit-packed masks + rows + counts) in ONE collective
+    import numpy as np
+    from rsprompter_b200.results import ResultRecord
+    H, W = 16, 24
+    rr = ResultRecord(B, M, (H, W), device="cpu")
+    masks = torch.rand(B, M, H, W, generator=g) > 0.5
+    rr.mask_bits.copy_(torch.from_numpy(np.packbits(masks.numpy(), axis=-1, bitorder="little")))
+    rr.rows.copy_(rec)
+    rr.counts.copy_(counts)
+    parts = rr.split(rr.gather())
+    ok = ok and len(parts) == world and torch.equal(parts[rank].buf, rr.buf)
+    inst = parts[rank].instances()
+    ok = ok and all(torch.equal(inst[i]["masks"], masks[i, :counts[i]]) and
+                    torch.equal(inst[i]["bboxes"], boxes[i, :counts[i]]) for i in range(B))
+    other = parts[1 - rank].counts.tolist()
+    ok = ok and other == (torch.tensor([M, 2, 0]) + (1 - rank)).clamp(max=M).tolist()
     q.put((rank, ok, all_cnt.tolist()))
     dist.destroy_process_group()
 

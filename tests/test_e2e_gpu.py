@@ -1,0 +1,244 @@
+"""End to end: image -> instances on the GPU (predict()) against the CPU oracle's whole-detector functions
+(oracle.restate_anchor.anchor_predict, oracle.restate_query.query_predict), plus the contracts
+around it: the result record equals predict(), graph-mode results stay valid across calls, uint8 test_step.
+
+What "identical instance set" can mean here: the GPU path computes in bf16, the oracle in fp32, so two detections whose
+scores differ by less than the bf16 noise may swap ranks / flip an NMS or top-k decision (SURVEY hard parts).  The
+stage-wise tests (test_anchor_gpu / test_query_gpu) pin the index arithmetic EXACTLY on identical inputs; here the
+instance sets are matched (query variant: by the (query, label) key; anchor variant: by label + box IoU) and the test
+asserts (i) the matched fraction, (ii) mask logits of matched instances within the bf16 tolerance, (iii) boolean
+masks of matched instances equal away from the decision boundary.  Diagnostics go to gpurun_out/parity_e2e_*.json."""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NUM_CLASSES = 10
+MEAN, STD = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+
+
+def _dump(name: str, obj) -> None:
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", name), "w") as f:
+            json.dump(obj, f, indent=1)
+    except OSError:
+        pass
+
+
+def _iou(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    lt = torch.maximum(a[:, None, :2], b[None, :, :2])
+    rb = torch.minimum(a[:, None, 2:], b[None, :, 2:])
+    inter = (rb - lt).clamp(min=0).prod(-1)
+    area = lambda x: (x[:, 2] - x[:, 0]).clamp(min=0) * (x[:, 3] - x[:, 1]).clamp(min=0)  # noqa: E731
+    return inter / (area(a)[:, None] + area(b)[None, :] - inter + 1e-9)
+
+
+def _match_boxes(gb, gl, rb, rl, thr=0.9):
+    """greedy one-to-one matching of GPU detections to oracle detections: same label, IoU >= thr."""
+    if gb.numel() == 0 or rb.numel() == 0:
+        return []
+    iou = _iou(gb, rb)
+    iou[gl[:, None] != rl[None, :]] = 0
+    pairs, used = [], set()
+    for i in iou.max(dim=1).values.argsort(descending=True).tolist():
+        j = int(iou[i].argmax())
+        if iou[i, j] >= thr and j not in used:
+            used.add(j)
+            pairs.append((i, j))
+    return pairs
+
+
+def _anchor_case(arch_name, size, mmpretrain, seed, name):
+    from oracle import restate_anchor as ra
+    from rsprompter_b200 import model_configs, sam_config, synthetic
+    from rsprompter_b200.model_configs import SELECT_LAYERS
+    from rsprompter_b200.registry import MODELS
+    cfg = model_configs.anchor_model_cfg(arch_name, NUM_CLASSES, mmpretrain_img_size=size if mmpretrain else None)
+    m = MODELS.build(cfg)
+    arch = m.backbone.vision_encoder.arch
+    sel = SELECT_LAYERS[arch_name]
+    sd = synthetic.anchor_detector_state_dict(arch, NUM_CLASSES, 0 if mmpretrain else len(sel), seed=seed,
+                                              pseudo_neck=mmpretrain)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    torch.manual_seed(seed)
+    x = torch.randn(1, 3, size, size)
+    with torch.no_grad():
+        ref = ra.anchor_predict(sd, arch, sam_config.SamDecoderArch(), x, NUM_CLASSES, sel, pseudo_neck=mmpretrain)[0]
+    out = m.predict(x.cuda())[0].pred_instances
+    raw = m.predict_raw(x.cuda())
+    torch.cuda.synchronize()
+    n = int(raw["counts"][0])
+    gb, gs, gl = out.bboxes.cpu(), out.scores.cpu(), out.labels.cpu()
+    glog = raw["mask_logits"][:n, 0].cpu()
+    assert len(out) == n and out.masks.shape == (n, size, size)
+    pairs = _match_boxes(gb, gl, ref["bboxes"], ref["labels"])
+    rep = dict(n_gpu=n, n_ref=int(ref["bboxes"].shape[0]), matched=len(pairs))
+    if pairs:
+        gi, ri = torch.tensor([p[0] for p in pairs]), torch.tensor([p[1] for p in pairs])
+        dl = (glog[gi] - ref["mask_logits"][ri]).abs()
+        rep.update(score_max_diff=(gs[gi] - ref["scores"][ri]).abs().max().item(),
+                   box_max_diff=(gb[gi] - ref["bboxes"][ri]).abs().max().item(),
+                   logit_max_diff=dl.max().item(), logit_mean_diff=dl.mean().item(),
+                   logit_scale=ref["mask_logits"][ri].abs().max().item(),
+                   mask_disagree=(out.masks.cpu()[gi] != ref["masks"][ri]).float().mean().item())
+    _dump(f"parity_e2e_{name}.json", rep)
+    print(name, rep)
+    return rep
+
+
+def test_anchor_c1_end_to_end_matches_oracle():
+    """BASELINE configs[0]: RSPrompter-anchor ViT-B, 1 x 512^2, MMPretrainSamVisionEncoder + PseudoFeatureAggregator."""
+    rep = _anchor_case("base", 512, True, 4, "anchor_c1_vitb_512")
+    assert rep["n_gpu"] > 0 and rep["n_ref"] > 0
+    assert rep["matched"] >= 0.8 * max(rep["n_gpu"], rep["n_ref"])
+    assert rep["logit_mean_diff"] <= 2e-2 * max(1.0, rep["logit_scale"])
+    assert rep["mask_disagree"] <= 2e-3
+
+
+def test_anchor_1024_end_to_end_matches_oracle():
+    """configs[1] shape at bs 1: RSSamVisionEncoder ViT-B 1024^2 + RSFeatureAggregator."""
+    rep = _anchor_case("base", 1024, False, 3, "anchor_vitb_1024")
+    assert rep["n_gpu"] > 0 and rep["n_ref"] > 0
+    assert rep["matched"] >= 0.8 * max(rep["n_gpu"], rep["n_ref"])
+    assert rep["logit_mean_diff"] <= 2e-2 * max(1.0, rep["logit_scale"])
+    assert rep["mask_disagree"] <= 2e-3
+
+
+def test_query_1024_end_to_end_matches_oracle():
+    """RSPrompter-query ViT-B 1024^2, 100 queries, bs 1: instance keys, scores, every query's mask logits."""
+    from oracle import restate_query as rq
+    from rsprompter_b200 import model_configs, sam_config, synthetic
+    from rsprompter_b200.model_configs import SELECT_LAYERS
+    from rsprompter_b200.registry import MODELS
+    nq, size = 100, 1024
+    cfg = model_configs.query_model_cfg("base", NUM_CLASSES, prompt_shape=(nq, 5))
+    m = MODELS.build(cfg)
+    arch = sam_config.VISION_ARCHS["base"]
+    sel = SELECT_LAYERS["base"]
+    sd = synthetic.query_detector_state_dict(arch, NUM_CLASSES, len(sel), nq=nq, seed=6)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    torch.manual_seed(6)
+    x = torch.randn(1, 3, size, size)
+    with torch.no_grad():
+        ref = rq.query_predict(sd, arch, sam_config.SamDecoderArch(), x, NUM_CLASSES, sel, max_per_image=nq)[0]
+    raw = m.predict_raw(x.cuda())
+    res = m.panoptic_fusion_head.instance_postprocess_batched(raw["cls"], raw["mask_logits"], (size, size))
+    torch.cuda.synchronize()
+    dl = (raw["mask_logits"].cpu() - ref["mask_logits"]).abs()            # every query, low-res logits
+    dc = (raw["cls"][0].cpu() - ref["cls"]).abs()
+    key = lambda q, l: (q * NUM_CLASSES + l).tolist()  # noqa: E731
+    kr = {k: i for i, k in enumerate(key(ref["query"], ref["labels"]))}
+    kg = key(res["query"][0].cpu(), res["labels"][0].cpu())
+    shared = [(i, kr[k]) for i, k in enumerate(kg) if k in kr]
+    gi, ri = torch.tensor([p[0] for p in shared]), torch.tensor([p[1] for p in shared])
+    gm, rm = res["masks"][0].cpu()[gi], ref["masks"][ri]
+    rep = dict(keys_gpu=len(kg), keys_ref=len(kr), shared=len(shared), logit_max_diff=dl.max().item(),
+               logit_mean_diff=dl.mean().item(), logit_scale=ref["mask_logits"].abs().max().item(),
+               cls_max_diff=dc.max().item(), cls_scale=ref["cls"].abs().max().item(),
+               score_max_diff=(res["scores"][0].cpu()[gi] - ref["scores"][ri]).abs().max().item(),
+               mask_disagree=(gm != rm).float().mean().item(),
+               box_equal_frac=(res["bboxes"][0].cpu()[gi] == ref["bboxes"][ri]).all(dim=1).float().mean().item())
+    _dump("parity_e2e_query_vitb_1024.json", rep)
+    print("query e2e", rep)
+    assert rep["shared"] >= 0.9 * nq
+    assert rep["logit_max_diff"] <= 2e-2 * max(1.0, rep["logit_scale"])
+    assert rep["cls_max_diff"] <= 2e-2 * max(1.0, rep["cls_scale"])
+    assert rep["mask_disagree"] <= 2e-3
+    assert rep["score_max_diff"] <= 2e-2
+
+
+def _anchor_model(seed=3, graphs=False):
+    from rsprompter_b200 import model_configs, synthetic
+    from rsprompter_b200.registry import MODELS
+    from rsprompter_b200.sam_config import VISION_ARCHS
+    cfg = model_configs.anchor_model_cfg("base", NUM_CLASSES)
+    cfg["data_preprocessor"] = dict(type="DetDataPreprocessor", mean=MEAN, std=STD, bgr_to_rgb=True, pad_size_divisor=32)
+    m = MODELS.build(cfg)
+    m.load_state_dict(synthetic.anchor_detector_state_dict(VISION_ARCHS["base"], NUM_CLASSES, 6, seed=seed), strict=True)
+    m = m.cuda()
+    if graphs:
+        m.enable_cuda_graphs()
+    return m
+
+
+def test_graph_mode_results_survive_the_next_call():
+    """predict() under enable_cuda_graphs() must not hand out views of the graph's output buffers."""
+    m = _anchor_model(graphs=True)
+    torch.manual_seed(21)
+    x1, x2 = torch.randn(1, 3, 1024, 1024).cuda(), torch.randn(1, 3, 1024, 1024).cuda()
+    p1 = m.predict(x1)[0].pred_instances
+    snap = (p1.bboxes.clone(), p1.scores.clone(), p1.labels.clone(), p1.masks.clone())
+    p2 = m.predict(x2)[0].pred_instances
+    torch.cuda.synchronize()
+    assert not torch.equal(p2.scores[:5], snap[1][:5]) or len(p2) != len(p1)     # a different image, different result
+    assert torch.equal(p1.bboxes, snap[0]) and torch.equal(p1.scores, snap[1])
+    assert torch.equal(p1.labels, snap[2]) and torch.equal(p1.masks, snap[3])
+
+
+def test_anchor_record_equals_predict_and_u8_test_step():
+    """predict_records(): bit-packed masks / rows / counts == predict(); test_step on uint8 CHW images (the fused
+    DetDataPreprocessor hand-over) == predict() on the torch-preprocessed float batch."""
+    m = _anchor_model()
+    g = torch.Generator().manual_seed(22)
+    u8 = torch.randint(0, 256, (2, 3, 1024, 1024), generator=g, dtype=torch.uint8)
+    xf = ((u8[:, [2, 1, 0]].float() - torch.tensor(MEAN).view(1, 3, 1, 1)) / torch.tensor(STD).view(1, 3, 1, 1)).cuda()
+    ref = m.predict(xf)
+    out = m.test_step(dict(inputs=u8.clone()))
+    rec = m.predict_records(xf)
+    inst = rec.instances()
+    host = rec.to_host(non_blocking=False).instances()
+    torch.cuda.synchronize()
+    for b in range(2):
+        r, o, i, h = ref[b].pred_instances, out[b].pred_instances, inst[b], host[b]
+        assert len(r) > 0
+        for a in (o, i, h):
+            bb, ss, ll, mm = (a.bboxes, a.scores, a.labels, a.masks) if not isinstance(a, dict) else \
+                (a["bboxes"], a["scores"], a["labels"], a["masks"])
+            assert torch.equal(bb.cpu(), r.bboxes.cpu()) and torch.equal(ss.cpu(), r.scores.cpu())
+            assert torch.equal(ll.cpu(), r.labels.cpu()) and torch.equal(mm.cpu(), r.masks.cpu())
+
+
+def test_query_record_equals_predict():
+    from rsprompter_b200 import model_configs, sam_config, synthetic
+    from rsprompter_b200.registry import MODELS
+    nq = 20
+    cfg = model_configs.query_model_cfg("base", NUM_CLASSES, prompt_shape=(nq, 5))
+    m = MODELS.build(cfg)
+    m.load_state_dict(synthetic.query_detector_state_dict(sam_config.VISION_ARCHS["base"], NUM_CLASSES, 6, nq=nq, seed=8))
+    m = m.cuda()
+    torch.manual_seed(8)
+    x = torch.randn(2, 3, 1024, 1024).cuda()
+    ref = m.predict(x)
+    inst = m.predict_records(x).instances()
+    torch.cuda.synchronize()
+    for b in range(2):
+        r, i = ref[b].pred_instances, inst[b]
+        assert torch.equal(i["bboxes"], r.bboxes) and torch.equal(i["scores"], r.scores)
+        assert torch.equal(i["labels"], r.labels) and torch.equal(i["masks"], r.masks)
+
+
+def test_pseudo_feature_aggregator_matches_oracle():
+    """SURVEY 8 row a13 (M:944-984)."""
+    from oracle import restate_anchor as ra
+    from rsprompter_b200 import synthetic
+    from rsprompter_b200.registry import MODELS
+    agg = MODELS.build(dict(type="PseudoFeatureAggregator", in_channels=256, hidden_channels=512, out_channels=256))
+    sd = synthetic.pseudo_aggregator_state_dict(seed=11)
+    agg.load_state_dict(sd, strict=True)
+    agg = agg.cuda()
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(2, 256, 32, 32, generator=g).to(torch.bfloat16).float()
+    with torch.no_grad():
+        ref = ra.pseudo_feature_aggregator(sd, x)
+    out = agg.forward_nhwc(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda())
+    torch.cuda.synchronize()
+    got = out.float().cpu().reshape(2, 32, 32, -1).permute(0, 3, 1, 2)
+    err = (got - ref).abs().max().item()
+    assert got.shape == ref.shape and err <= 4e-2 * max(1.0, ref.abs().max().item()), err

@@ -22,7 +22,7 @@ def test_header_and_binding_export_the_same_symbols():
     lib = ctypes.CDLL(str(_lib.LIB_PATH))
     for name in declared:
         assert hasattr(lib, name), f"{name} missing from librsp_b200.so"
-    assert lib.rsp_abi_version() == 1
+    assert lib.rsp_abi_version() == 2
 
 
 def test_arch_name_parsing():
