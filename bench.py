@@ -103,7 +103,7 @@ class ClockSampler:
                             self.reasons.add(nm)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._thr = threading.Thread(target=self._run, daemon=True)
@@ -553,7 +553,7 @@ def run_ours(args) -> None:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="query_vith", choices=sorted(CONFIGS))

@@ -318,11 +318,14 @@ def _sub(sd: dict, prefix: str) -> dict:
 
 def anchor_predict(sd: dict, vision_arch, decoder_arch, images: torch.Tensor, num_classes: int,
                    select_layers, strides=(4, 8, 16, 32, 64), scales=(4, 8), ratios=(0.5, 1.0, 2.0),
-                   points: int = 5, timings: dict | None = None, pseudo_neck: bool = False):
+                   points: int = 5, timings: dict | None = None, pseudo_neck: bool = False,
+                   extra_boxes: list | None = None):
     """RSPrompterAnchor.predict (M:148-170) for metainfo img_shape == ori_shape == batch shape,
     scale_factor 1: returns a list of per-image dicts(bboxes, scores, labels, masks, mask_logits).
     pseudo_neck: the *-peft-512 configs (MMPretrainSamVisionEncoder + PseudoFeatureAggregator, M:944-984): the neck
-    consumes the image embedding instead of the hidden states."""
+    consumes the image embedding instead of the hidden states.
+    extra_boxes (per-image [n, 4] tensors): the mask branch (M:1511-1550, 1659-1698) is evaluated a second time on these
+    boxes -> results[b]["extra_mask_logits"]; lets a test compare mask logits conditioned on identical box decisions."""
     import time
     t0 = time.perf_counter()
     B, _, H, W = images.shape
@@ -372,6 +375,20 @@ def anchor_predict(sd: dict, vision_arch, decoder_arch, images: torch.Tensor, nu
             r["mask_logits"] = logits[off:off + n]
             r["masks"] = mask_postprocess(logits[off:off + n], (H, W))
             off += n
+    if extra_boxes is not None:
+        xrois = torch.cat([torch.cat([bx.new_full((bx.shape[0], 1), b), bx], dim=1) for b, bx in enumerate(extra_boxes)])
+        if xrois.shape[0] > 0:
+            msd = _sub(sd, "roi_head.mask_head.")
+            xsparse = mask_head_prompts(msd, roi_extract(feats_pe[:4], xrois, 14), points, prefix="")
+            xids = xrois[:, 0].long()
+            xdense = sd["roi_head.mask_head.no_mask_embed.weight"].reshape(1, -1, 1, 1).expand(
+                xids.numel(), -1, emb.shape[-2], emb.shape[-1])
+            xl, _ = restate.mask_decoder(_sub(msd, "mask_decoder.mask_decoder."), decoder_arch, emb[xids],
+                                         pe.expand(xids.numel(), -1, -1, -1), xsparse[:, None], xdense, False)
+            off = 0
+            for r, bx in zip(results, extra_boxes):
+                r["extra_mask_logits"] = xl[off:off + bx.shape[0], 0]
+                off += bx.shape[0]
     t5 = time.perf_counter()
     if timings is not None:
         timings.update(encoder=t1 - t0, neck=t2 - t1, rpn=t3 - t2, roi=t4 - t3, mask=t5 - t4)

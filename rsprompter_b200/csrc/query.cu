@@ -15,6 +15,8 @@
 //   query_postprocess         bilinear 256^2 -> S^2 + (> 0) + mask score + tight box per selected instance
 //                             (M:652-656, maskformer_fusion_head.py:149-182, mask/utils.py:56-77), no S^2 fp32
 //                             intermediate and no per-instance host sync
+#include <cstdlib>
+
 #include "query.h"
 #include "sm100.cuh"
 #include "upsample4.cuh"
@@ -529,10 +531,126 @@ __global__ void mask_embed_src_kernel(const float* __restrict__ mpp, MaskEmbedW 
   }
 }
 
+// Tensor-core form of the same op for whole 128-pixel blocks (the shipped 64 x 64 embedding grid): thread = pixel for
+// the two tiny stride-2 convs (coalesced float4 reads of the 4 x 4 logit patch), then the 16 -> 256 1x1 conv of the
+// block runs as mma.sync m16n8k16 tiles (A = the block's 128 x 16 hidden vectors, bf16, from shared memory; B = conv3
+// weight [256][16]), and  + bias + image embedding  happens on the accumulator fragments, stored as bf16x2.
+// The round-1 kernel above spent 2.7 ms per step on fp32 FMAs with 25 % of the threads idle in the first phase.
+__global__ void __launch_bounds__(128)
+mask_embed_src_mma_kernel(const float* __restrict__ mpp, MaskEmbedW W, const float* __restrict__ emb, int n_per_img,
+                          int hm, int wm, int h, int w, float eps, __nv_bfloat16* __restrict__ src) {
+  __shared__ __align__(16) __nv_bfloat16 hid[128][24];      // 16 used + 8 pad: conflict-free fragment reads
+  __shared__ __align__(16) __nv_bfloat16 w3s[256][24];
+  __shared__ float b3s[256];
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * 128;
+  const int HW = h * w;
+  for (int i = threadIdx.x; i < 256 * 16; i += 128) w3s[i >> 4][i & 15] = __float2bfloat16(W.w3[i]);
+  for (int i = threadIdx.x; i < 256; i += 128) b3s[i] = W.b3[i];
+  {
+    const int pix = p0 + threadIdx.x, y = pix / w, x = pix - y * w;
+    const float* in = mpp + (static_cast<size_t>(n) * hm + 4 * y) * wm + 4 * x;
+    float v[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(in + static_cast<size_t>(r) * wm));
+      v[r][0] = t.x; v[r][1] = t.y; v[r][2] = t.z; v[r][3] = t.w;
+    }
+    float h1[2][2][4];
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        float a[4], mean = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float s = W.b1[c];
+#pragma unroll
+          for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 2; ++kx) s += W.w1[c * 4 + ky * 2 + kx] * v[2 * py + ky][2 * px + kx];
+          a[c] = s; mean += s;
+        }
+        mean *= 0.25f;
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) var += (a[c] - mean) * (a[c] - mean);
+        const float rstd = rsqrtf(var * 0.25f + eps);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) h1[py][px][c] = gelu_erf((a[c] - mean) * rstd * W.g1[c] + W.be1[c]);
+      }
+    float a2[16], mean = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float s = W.b2[c];
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 2; ++kx) s += W.w2[((c * 4 + ci) * 2 + ky) * 2 + kx] * h1[ky][kx][ci];
+      a2[c] = s; mean += s;
+    }
+    mean *= (1.0f / 16.0f);
+    float var = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) var += (a2[c] - mean) * (a2[c] - mean);
+    const float rstd = rsqrtf(var * (1.0f / 16.0f) + eps);
+    uint32_t pk[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      pk[c] = pack_bf16x2(gelu_erf((a2[2 * c] - mean) * rstd * W.g2[2 * c] + W.be2[2 * c]),
+                          gelu_erf((a2[2 * c + 1] - mean) * rstd * W.g2[2 * c + 1] + W.be2[2 * c + 1]));
+    uint4* hp = reinterpret_cast<uint4*>(&hid[threadIdx.x][0]);
+    hp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    hp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const int img = n / n_per_img;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int r0 = warp * 32 + mt * 16;              // first pixel (row) of this 16-row tile inside the block
+    uint32_t a[4];                                   // A fragment: rows g / g+8, k = 2q..2q+1 and 2q+8..2q+9
+    a[0] = *reinterpret_cast<const uint32_t*>(&hid[r0 + g][2 * q]);
+    a[1] = *reinterpret_cast<const uint32_t*>(&hid[r0 + g + 8][2 * q]);
+    a[2] = *reinterpret_cast<const uint32_t*>(&hid[r0 + g][2 * q + 8]);
+    a[3] = *reinterpret_cast<const uint32_t*>(&hid[r0 + g + 8][2 * q + 8]);
+    const size_t pixA = static_cast<size_t>(p0 + r0 + g), pixB = pixA + 8;
+    const float* eA = emb + (static_cast<size_t>(img) * HW + pixA) * 256;
+    const float* eB = emb + (static_cast<size_t>(img) * HW + pixB) * 256;
+    __nv_bfloat16* oA = src + (static_cast<size_t>(n) * HW + pixA) * 256;
+    __nv_bfloat16* oB = src + (static_cast<size_t>(n) * HW + pixB) * 256;
+#pragma unroll 4
+    for (int nt = 0; nt < 32; ++nt) {
+      const int c0 = nt * 8;
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&w3s[c0 + g][2 * q]);        // B(k, n) = w3[c0 + n][k]
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&w3s[c0 + g][2 * q + 8]);
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_bf16_16816q(d, a, b0, b1);
+      const int c = c0 + 2 * q;                       // this thread's two output channels
+      const float2 ea = __ldg(reinterpret_cast<const float2*>(eA + c));
+      const float2 eb = __ldg(reinterpret_cast<const float2*>(eB + c));
+      const float ba = b3s[c], bb = b3s[c + 1];
+      *reinterpret_cast<uint32_t*>(oA + c) = pack_bf16x2(d[0] + ba + ea.x, d[1] + bb + ea.y);
+      *reinterpret_cast<uint32_t*>(oB + c) = pack_bf16x2(d[2] + ba + eb.x, d[3] + bb + eb.y);
+    }
+  }
+}
+
 int mask_embed_src(const float* mpp, const float* const* wts, const float* emb, const float* pos, int N, int n_per_img,
                    int hm, int wm, int h, int w, float eps, void* src, void* src_pe, cudaStream_t stream) {
   RSP_CHECK_ARG(mpp && wts && emb && pos && src && N > 0 && hm == 4 * h && wm == 4 * w, "mask_embed_src: bad args");
   MaskEmbedW W{wts[0], wts[1], wts[2], wts[3], wts[4], wts[5], wts[6], wts[7], wts[8], wts[9]};
+  static const bool fp32_path = getenv("RSP_MASK_EMBED_FP32") != nullptr;     // A/B switch (tests compare the two)
+  if (!src_pe && (h * w) % 128 == 0 && w % 4 == 0 && (reinterpret_cast<uintptr_t>(mpp) & 15) == 0 && !fp32_path) {
+    dim3 grid(h * w / 128, N);
+    mask_embed_src_mma_kernel<<<grid, 128, 0, stream>>>(mpp, W, emb, n_per_img, hm, wm, h, w, eps,
+                                                        static_cast<__nv_bfloat16*>(src));
+    RSP_CHECK_LAUNCH();
+    return RSP_OK;
+  }
   dim3 grid((h * w + 31) / 32, N);
   mask_embed_src_kernel<<<grid, 128, 0, stream>>>(mpp, W, emb, pos, n_per_img, hm, wm, h, w, eps,
                                                   static_cast<__nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(src_pe));

@@ -6,8 +6,11 @@ What "identical instance set" can mean here: the GPU path computes in bf16, the 
 scores differ by less than the bf16 noise may swap ranks / flip an NMS or top-k decision (SURVEY hard parts).  The
 stage-wise tests (test_anchor_gpu / test_query_gpu) pin the index arithmetic EXACTLY on identical inputs; here the
 instance sets are matched (query variant: by the (query, label) key; anchor variant: by label + box IoU) and the test
-asserts (i) the matched fraction, (ii) mask logits of matched instances within the bf16 tolerance, (iii) boolean
-masks of matched instances equal away from the decision boundary.  Diagnostics go to gpurun_out/parity_e2e_*.json."""
+asserts (i) the matched fraction and the agreement of matched scores / boxes, (ii) mask logits within the bf16
+tolerance CONDITIONED ON THE SAME BOXES: the anchor variant's prompts are a (chaotic, random-weight) function of the
+RoI box, so a 2-pixel box difference moves the logits by O(1); the oracle therefore also evaluates its fp32 mask branch
+(RoIAlign 14x14 -> prompt head -> SAM decoder, on its own fp32 encoder / neck outputs) on the boxes the GPU path
+emitted, (iii) boolean masks equal away from the decision boundary.  Diagnostics: gpurun_out/parity_e2e_*.json."""
 import json
 import os
 
@@ -68,8 +71,6 @@ def _anchor_case(arch_name, size, mmpretrain, seed, name):
     m = m.cuda()
     torch.manual_seed(seed)
     x = torch.randn(1, 3, size, size)
-    with torch.no_grad():
-        ref = ra.anchor_predict(sd, arch, sam_config.SamDecoderArch(), x, NUM_CLASSES, sel, pseudo_neck=mmpretrain)[0]
     out = m.predict(x.cuda())[0].pred_instances
     raw = m.predict_raw(x.cuda())
     torch.cuda.synchronize()
@@ -77,16 +78,24 @@ def _anchor_case(arch_name, size, mmpretrain, seed, name):
     gb, gs, gl = out.bboxes.cpu(), out.scores.cpu(), out.labels.cpu()
     glog = raw["mask_logits"][:n, 0].cpu()
     assert len(out) == n and out.masks.shape == (n, size, size)
+    with torch.no_grad():
+        ref = ra.anchor_predict(sd, arch, sam_config.SamDecoderArch(), x, NUM_CLASSES, sel, pseudo_neck=mmpretrain,
+                                extra_boxes=[gb])[0]
     pairs = _match_boxes(gb, gl, ref["bboxes"], ref["labels"])
     rep = dict(n_gpu=n, n_ref=int(ref["bboxes"].shape[0]), matched=len(pairs))
     if pairs:
         gi, ri = torch.tensor([p[0] for p in pairs]), torch.tensor([p[1] for p in pairs])
-        dl = (glog[gi] - ref["mask_logits"][ri]).abs()
         rep.update(score_max_diff=(gs[gi] - ref["scores"][ri]).abs().max().item(),
                    box_max_diff=(gb[gi] - ref["bboxes"][ri]).abs().max().item(),
-                   logit_max_diff=dl.max().item(), logit_mean_diff=dl.mean().item(),
-                   logit_scale=ref["mask_logits"][ri].abs().max().item(),
-                   mask_disagree=(out.masks.cpu()[gi] != ref["masks"][ri]).float().mean().item())
+                   box_median_diff=(gb[gi] - ref["bboxes"][ri]).abs().amax(dim=1).median().item())
+    xl = ref["extra_mask_logits"]                       # oracle mask branch on the GPU path's own boxes
+    dl = (glog - xl).abs()
+    xm = ra.mask_postprocess(xl, (size, size))
+    near = torch.nn.functional.interpolate(xl.sigmoid()[:, None], size=(size, size), mode="bilinear",
+                                           align_corners=False)[:, 0].sub(0.5).abs() < 5e-3
+    rep.update(logit_max_diff=dl.max().item(), logit_mean_diff=dl.mean().item(), logit_scale=xl.abs().max().item(),
+               mask_disagree=(out.masks.cpu() != xm).float().mean().item(),
+               mask_disagree_off_boundary=((out.masks.cpu() != xm) & ~near).float().mean().item())
     _dump(f"parity_e2e_{name}.json", rep)
     print(name, rep)
     return rep
@@ -97,8 +106,9 @@ def test_anchor_c1_end_to_end_matches_oracle():
     rep = _anchor_case("base", 512, True, 4, "anchor_c1_vitb_512")
     assert rep["n_gpu"] > 0 and rep["n_ref"] > 0
     assert rep["matched"] >= 0.8 * max(rep["n_gpu"], rep["n_ref"])
-    assert rep["logit_mean_diff"] <= 2e-2 * max(1.0, rep["logit_scale"])
-    assert rep["mask_disagree"] <= 2e-3
+    assert rep["score_max_diff"] <= 2e-2
+    assert rep["logit_max_diff"] <= 2e-2 * max(1.0, rep["logit_scale"])
+    assert rep["mask_disagree_off_boundary"] <= 1e-4
 
 
 def test_anchor_1024_end_to_end_matches_oracle():
@@ -106,8 +116,9 @@ def test_anchor_1024_end_to_end_matches_oracle():
     rep = _anchor_case("base", 1024, False, 3, "anchor_vitb_1024")
     assert rep["n_gpu"] > 0 and rep["n_ref"] > 0
     assert rep["matched"] >= 0.8 * max(rep["n_gpu"], rep["n_ref"])
-    assert rep["logit_mean_diff"] <= 2e-2 * max(1.0, rep["logit_scale"])
-    assert rep["mask_disagree"] <= 2e-3
+    assert rep["score_max_diff"] <= 2e-2
+    assert rep["logit_max_diff"] <= 2e-2 * max(1.0, rep["logit_scale"])
+    assert rep["mask_disagree_off_boundary"] <= 1e-4
 
 
 def test_query_1024_end_to_end_matches_oracle():
