@@ -214,8 +214,9 @@ int rsp_sin_fold(const float* in, float* out, long long n_out, void* stream);
 
 /* ---- RSPrompter-query head (M:274-715) ---- */
 
-/* GroupNorm(G) over channels-last bf16 [B,H,W,C] (C/G = 4), fp32 statistics in stats_ws (fp32 [B,G,2], zeroed by
- * the call); optional `up` bf16 [B,H/2,W/2,C] is bilinearly x2-upsampled (align_corners=False) and added after the
+/* GroupNorm(G) over channels-last bf16 [B,H,W,C] (C/G = 4).  stats_ws: 16-byte aligned fp32 workspace of
+ * B*G*2 * (1 + ceil(H*W/256)) floats: (mean, rstd) [B,G,2] followed by the per-256-pixel-block (sum, sumsq) partials,
+ * which are folded in fp64 without atomics (bit-reproducible, no E[x^2]-mean^2 cancellation in fp32); optional `up` bf16 [B,H/2,W/2,C] is bilinearly x2-upsampled (align_corners=False) and added after the
  * affine, optional ReLU last: the ConvModule(norm=GN) tails and the FPN top-down add of MSDeformAttnPixelDecoder
  * (msdeformattn_pixel_decoder.py:94-109, 230-240). */
 int rsp_groupnorm_nhwc(const void* x, float* stats_ws, const float* gamma, const float* beta, const void* up,

@@ -147,6 +147,21 @@ def image_wide_positional_embedding(gauss: torch.Tensor, size: int) -> torch.Ten
     return pe.permute(2, 0, 1)[None]
 
 
+def embed_boxes(gauss: torch.Tensor, point_embed_2: torch.Tensor, point_embed_3: torch.Tensor, boxes: torch.Tensor,
+                image_size: int) -> torch.Tensor:
+    """SamPromptEncoder._embed_boxes (HF:636-645) + SamPositionalEmbedding.forward (HF:552-566): boxes [B, nb, 4]
+    (image-space xyxy) -> sparse prompt embeddings [B, nb, 2, C]."""
+    coords = (boxes + 0.5).reshape(boxes.shape[0], boxes.shape[1], 2, 2).clone()
+    coords[..., 0] = coords[..., 0] / image_size
+    coords[..., 1] = coords[..., 1] / image_size
+    c = (2 * coords - 1) @ gauss
+    c = 2 * math.pi * c
+    emb = torch.cat([torch.sin(c), torch.cos(c)], dim=-1)
+    emb[:, :, 0, :] += point_embed_2.reshape(-1)
+    emb[:, :, 1, :] += point_embed_3.reshape(-1)
+    return emb
+
+
 def sam_mask_embedding(sd: dict, masks: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
     """SamMaskEmbedding.forward (HF:583-593): conv2x2s2 -> LN -> GELU -> conv2x2s2 -> LN -> GELU -> conv1x1."""
     p = "mask_embed."

@@ -11,4 +11,4 @@ from . import sam_encoder  # noqa: F401
 
 __version__ = "0.1.0"
 from . import sam_decoder  # noqa: F401,E402
-from . import necks, anchor_heads, query_heads, preprocess, detectors  # noqa: F401,E402
+from . import necks, anchor_heads, query_heads, preprocess, detectors, sam_model  # noqa: F401,E402

@@ -139,9 +139,17 @@ def _stream() -> int:
 
 
 def _require_cuda(*ts: torch.Tensor | None) -> None:
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RspError("rsprompter_b200 kernels take CUDA tensors only (there is no CPU path)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:   # launches go to the current device's current stream
+            raise RspError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: "
+                           "wrap the call in torch.cuda.device(...) (one process per GPU is the supported layout)")
 
 
 def _host_f4(v):
@@ -599,19 +607,24 @@ def mask_paste(logits: torch.Tensor, size: tuple, thr: float, mode: int) -> torc
     return out.view(torch.bool)
 
 
-def mask_paste_rescale(logits: torch.Tensor, batch_hw: tuple, crop_hw: tuple, ori_hw: tuple, thr: float) -> torch.Tensor:
+def mask_paste_rescale(logits: torch.Tensor, batch_hw: tuple, crop_hw: tuple, ori_hw: tuple, thr: float,
+                       raw: bool = False) -> torch.Tensor:
     """M:1763-1777 for a resized / padded image: sigmoid -> bilinear to batch_hw -> crop -> bilinear to ori_hw -> >= thr.
+    raw=True: no sigmoid, > thr on the resized logits (SAMDet, M:1133-1152).
     logits fp32 [n, hm, wm] -> bool [n, ori_h, ori_w]."""
     global launch_count
     _require_cuda(logits)
     n, hm, wm = logits.shape
     assert logits.dtype == torch.float32 and logits.is_contiguous() and n > 0
-    act = torch.empty_like(logits)
-    _check(_lib.rsp_sigmoid_f32(_ptr(logits), _ptr(act), logits.numel(), _stream()), "rsp_sigmoid_f32")
+    act = logits
+    if not raw:
+        act = torch.empty_like(logits)
+        _check(_lib.rsp_sigmoid_f32(_ptr(logits), _ptr(act), logits.numel(), _stream()), "rsp_sigmoid_f32")
+        launch_count += 1
     out = torch.empty(n, ori_hw[0], ori_hw[1], device=logits.device, dtype=torch.uint8)
     _check(_lib.rsp_mask_paste_rescale(_ptr(act), _ptr(out), n, hm, wm, batch_hw[0], batch_hw[1], crop_hw[0], crop_hw[1],
-                                       ori_hw[0], ori_hw[1], float(thr), 2, _stream()), "rsp_mask_paste_rescale")
-    launch_count += 2
+                                       ori_hw[0], ori_hw[1], float(thr), 1 if raw else 2, _stream()), "rsp_mask_paste_rescale")
+    launch_count += 1
     return out.view(torch.bool)
 
 
@@ -676,11 +689,11 @@ def groupnorm_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, gro
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and gamma.dtype == torch.float32 and beta.dtype == torch.float32
     if up is not None:
         assert up.dtype == torch.bfloat16 and up.is_contiguous() and up.shape == (B, H // 2, W // 2, C)
-    stats = torch.empty(B * groups * 2, device=x.device, dtype=torch.float32)
+    stats = torch.empty(B * groups * 2 * (1 + (H * W + 255) // 256), device=x.device, dtype=torch.float32)
     out = torch.empty_like(x)
     _check(_lib.rsp_groupnorm_nhwc(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(up), _ptr(out), B, H, W, C,
                                    groups, float(eps), int(relu), _stream()), "rsp_groupnorm_nhwc")
-    launch_count += 2
+    launch_count += 3
     return out
 
 

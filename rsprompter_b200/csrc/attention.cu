@@ -467,7 +467,8 @@ static int launch_att(const AttentionArgs& a, cudaStream_t stream) {
   p.scale2 = (1.0f / sqrtf(static_cast<float>(HD))) * LOG2E;
   p.out_row_map = a.out_row_map;
   auto kern = vit_attention_kernel<HD, GS>;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};   // the attribute is per device (one flag per ordinal)
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     RSP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));

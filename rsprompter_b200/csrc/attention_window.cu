@@ -337,7 +337,8 @@ static int launch(const AttentionArgs& a, cudaStream_t stream) {
   p.scale2 = (1.0f / sqrtf(static_cast<float>(HD))) * LOG2E;
   p.out_row_map = a.out_row_map;
   auto kern = vit_window_attention_kernel<HD>;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};   // the attribute is per device (one flag per ordinal)
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     RSP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;

@@ -294,7 +294,8 @@ int t2i_attention(const void* q, const void* K, const void* V, int ldkv, const i
   RSP_CHECK_ARG(ldkv >= 128 && ldkv % 8 == 0 && (reinterpret_cast<uintptr_t>(K) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(V) & 15) == 0, "t2i_attention: K / V row stride / alignment");
   const int smem = 2 * T2I_STAGE;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};   // the attribute is per device (one flag per ordinal)
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     RSP_CHECK_CUDA(cudaFuncSetAttribute(t2i_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;

@@ -125,7 +125,8 @@ __device__ __forceinline__ void store32(const GemmDev& p, const float (&v)[32], 
 // layer_norm4 fused into cross_attn_image_to_token.out_proj (HF:341-347).
 template <int BN>
 __device__ __forceinline__ void epilogue_ln_row(const GemmDev& p, uint32_t t_row, int orow, int rrow) {
-  float sum = 0.f, sq = 0.f;
+  // shifted sums (pivot = the row's first value): no E[x^2] - E[x]^2 cancellation for rows with a large mean
+  float sum = 0.f, sq = 0.f, piv = 0.f;
   const int nch = p.N / 32;
   for (int c = 0; c < nch; ++c) {
     uint32_t r[32];
@@ -136,11 +137,13 @@ __device__ __forceinline__ void epilogue_ln_row(const GemmDev& p, uint32_t t_row
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
     add_bias_residual32(p, v, rrow, c * 32);
+    if (c == 0) piv = v[0];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { sum += v[i]; sq += v[i] * v[i]; }
+    for (int i = 0; i < 32; ++i) { const float d = v[i] - piv; sum += d; sq += d * d; }
   }
-  const float mean = sum / p.N;
-  const float rstd = rsqrtf(fmaxf(sq / p.N - mean * mean, 0.f) + p.ln_eps);
+  const float dmean = sum / p.N;
+  const float mean = piv + dmean;
+  const float rstd = rsqrtf(fmaxf(sq / p.N - dmean * dmean, 0.f) + p.ln_eps);
   for (int c = 0; c < nch; ++c) {
     uint32_t r[32];
     tmem_ld_32x32b_x32(t_row + c * 32, r);
@@ -492,7 +495,8 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.num_n_blocks = (a.N + BN - 1) / BN;
   p.num_tiles = num_m_blocks * p.num_n_blocks;
   auto kern = gemm_bf16_tcgen05_kernel<BN, B_MN>;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};   // the attribute is per device (one flag per ordinal)
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     RSP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));

@@ -250,7 +250,7 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
         const uint32_t sbuf = smem_u32(stg_all) + e * 4096;
         const uint32_t srow = sbuf + lane * 128;
         const int sw = lane & 7;
-        float2* xchg = reinterpret_cast<float2*>(stg_all + 8 * 4096);   // [2][128] (sum, sumsq)
+        float2* xchg = reinterpret_cast<float2*>(stg_all + 8 * 4096);   // [2][128] (mean, M2) of each half row
         const bool valid = row0 < p.M;
         const uint32_t rbar = smem_u32(&bar_res[e]);
         int rrow0 = row0;
@@ -268,7 +268,10 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
         if (valid) issue_res(col_warp);
         mbar_wait(smem_u32(&bar_tmem_full[as]), (it >> 1) & 1);
         tc_fence_after();
-        float sum = 0.f, sumsq = 0.f;
+        // shifted sums: d = v - pivot with the pivot = this half row's first value, so a large common offset of the
+        // row (keys with a big mean) does not cancel in E[d^2] - E[d]^2; the halves are merged with Chan's formula
+        float sum = 0.f, sumsq = 0.f, piv = 0.f;
+        bool have_piv = false;
         if (valid) {
 #pragma unroll 1
           for (int ps = 0; ps < 2; ++ps) {
@@ -296,10 +299,12 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
                 v[5] = __uint_as_float(r[8 * j + 5]) + bb.y + __uint_as_float(w2 & 0xffff0000u);
                 v[6] = __uint_as_float(r[8 * j + 6]) + bb.z + __uint_as_float(w3 << 16);
                 v[7] = __uint_as_float(r[8 * j + 7]) + bb.w + __uint_as_float(w3 & 0xffff0000u);
+                if (!have_piv) { piv = v[0]; have_piv = true; }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                  sum += v[k];
-                  sumsq = fmaf(v[k], v[k], sumsq);
+                  const float d = v[k] - piv;
+                  sum += d;
+                  sumsq = fmaf(d, d, sumsq);
                   r[8 * j + k] = __float_as_uint(v[k]);
                 }
               }
@@ -310,11 +315,14 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
           }
           tmem_st_wait();
         }
-        xchg[hf * 128 + q * 32 + lane] = make_float2(sum, sumsq);
+        const float mean_h = piv + sum * (1.0f / 128.0f);
+        const float m2_h = fmaxf(sumsq - sum * sum * (1.0f / 128.0f), 0.f);
+        xchg[hf * 128 + q * 32 + lane] = make_float2(mean_h, m2_h);
         asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
         const float2 ot = xchg[(hf ^ 1) * 128 + q * 32 + lane];
-        const float mean = (sum + ot.x) * (1.0f / 256.0f);
-        const float var = fmaxf((sumsq + ot.y) * (1.0f / 256.0f) - mean * mean, 0.f);
+        const float mean = 0.5f * (mean_h + ot.x);
+        const float dm = mean_h - ot.x;
+        const float var = (m2_h + ot.y + dm * dm * 64.0f) * (1.0f / 256.0f);     // n0 n1 / (n0 + n1) = 64
         const float rstd = rsqrtf(var + p.ln_eps);
         asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // xchg may be rewritten by the next tile
         if (valid) {
@@ -807,7 +815,8 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
   p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
   p.hyper = a.hyper; p.mask_out = a.mask_out; p.grid_h = a.grid_h; p.grid_w = a.grid_w;
   auto kern = gemm_bf16_tcgen05_v2_kernel<BN, EPI>;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};   // the attribute is per device (one flag per ordinal)
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     RSP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;

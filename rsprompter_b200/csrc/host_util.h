@@ -61,6 +61,9 @@ inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, 
   return make_tmap_bf16(out, base, 2, dims, strides, box);
 }
 
-int num_sms();
+int num_sms();   // of the current device
+
+constexpr int kMaxDevices = 64;
+int current_device();   // cudaGetDevice, clamped to [0, kMaxDevices)
 
 }  // namespace rsp

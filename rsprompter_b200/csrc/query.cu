@@ -33,15 +33,16 @@ __device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------------------------ GroupNorm
-// stats[b][g] = (sum, sumsq) over H*W*(C/G) values; C = 128, G = 32 -> 4 channels per group.
-__global__ void groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats, int HW,
+// Two-level, atomic-free (bit-reproducible) statistics: part[b][blk][g] = (sum, sumsq) of one 256-pixel block in
+// fp32, then one thread per (b, g) folds the block partials in fp64 and emits (mean, rstd): the E[x^2] - mean^2
+// cancellation happens in double precision, so large-mean inputs keep their variance.  C/G = 4 channels per group.
+__global__ void groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part, int HW,
                                        int C, int G, int pix_per_block) {
   const int b = blockIdx.y;
   const int lanes_c = C / 8;                       // threads across channels (8 channels each)
   const int tc = threadIdx.x % lanes_c, tp = threadIdx.x / lanes_c;
   const int rows = blockDim.x / lanes_c;
   const int p0 = blockIdx.x * pix_per_block;
-  const int cpg = C / G;                           // 4
   float s[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};      // 8 channels = 2 groups of 4
   for (int p = p0 + tp; p < min(p0 + pix_per_block, HW); p += rows) {
     float f[8];
@@ -49,7 +50,6 @@ __global__ void groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x, floa
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j / 4] += f[j]; q[j / 4] += f[j] * f[j]; }
   }
-  (void)cpg;
   __shared__ float red[256 * 4];
   red[threadIdx.x * 4 + 0] = s[0]; red[threadIdx.x * 4 + 1] = q[0];
   red[threadIdx.x * 4 + 2] = s[1]; red[threadIdx.x * 4 + 3] = q[1];
@@ -59,9 +59,25 @@ __global__ void groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x, floa
     for (int r = 0; r < rows; ++r)
 #pragma unroll
       for (int k = 0; k < 4; ++k) a[k] += red[(r * lanes_c + tc) * 4 + k];
-    float* st = stats + (static_cast<size_t>(b) * G + tc * 2) * 2;
-    atomicAdd(st + 0, a[0]); atomicAdd(st + 1, a[1]); atomicAdd(st + 2, a[2]); atomicAdd(st + 3, a[3]);
+    float* st = part + ((static_cast<size_t>(b) * gridDim.x + blockIdx.x) * G + tc * 2) * 2;
+    st[0] = a[0]; st[1] = a[1]; st[2] = a[2]; st[3] = a[3];
   }
+}
+
+__global__ void groupnorm_finalize_kernel(const float* __restrict__ part, float* __restrict__ stats, int B, int G,
+                                          int nblk, double n, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * G) return;
+  const int b = i / G, g = i - b * G;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < nblk; ++k) {
+    const float* st = part + ((static_cast<size_t>(b) * nblk + k) * G + g) * 2;
+    s += st[0]; q += st[1];
+  }
+  const double mean = s / n;
+  const double var = fmax(q / n - mean * mean, 0.0);
+  stats[2 * i] = static_cast<float>(mean);
+  stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
 }
 
 // y = GN(x) (+ bilinear x2 upsample of `up` [B, H/2, W/2, C]) (ReLU)
@@ -79,14 +95,17 @@ __global__ void groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, cons
   const int y = rem / W, xx = rem - y * W;
   float f[8];
   unpack8f(*reinterpret_cast<const uint4*>(x + pix * C + tc * 8), f);
-  const float n = static_cast<float>(H) * W * (C / G);
+  // (mean, rstd) of this thread's two groups (4 channels each): one 16-byte load
+  const float4 mr = __ldg(reinterpret_cast<const float4*>(stats + (static_cast<size_t>(b) * G + tc * 2) * 2));
+  const float4 ga0 = __ldg(reinterpret_cast<const float4*>(gamma + tc * 8)), ga1 = __ldg(reinterpret_cast<const float4*>(gamma + tc * 8 + 4));
+  const float4 be0 = __ldg(reinterpret_cast<const float4*>(beta + tc * 8)), be1 = __ldg(reinterpret_cast<const float4*>(beta + tc * 8 + 4));
+  const float gam[8] = {ga0.x, ga0.y, ga0.z, ga0.w, ga1.x, ga1.y, ga1.z, ga1.w};
+  const float bet[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
   float o[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int g = (tc * 8 + j) / (C / G);
-    const float mean = stats[(static_cast<size_t>(b) * G + g) * 2] / n;
-    const float var = fmaxf(stats[(static_cast<size_t>(b) * G + g) * 2 + 1] / n - mean * mean, 0.f);
-    o[j] = (f[j] - mean) * rsqrtf(var + eps) * gamma[tc * 8 + j] + beta[tc * 8 + j];
+    const float mean = j < 4 ? mr.x : mr.z, rstd = j < 4 ? mr.y : mr.w;
+    o[j] = (f[j] - mean) * rstd * gam[j] + bet[j];
   }
   if (up) {
     const int h2 = H / 2, w2 = W / 2;
@@ -116,11 +135,16 @@ int groupnorm_nhwc(const void* x, float* stats_ws, const float* gamma, const flo
                    int B, int H, int W, int C, int G, float eps, int relu, cudaStream_t stream) {
   RSP_CHECK_ARG(x && stats_ws && gamma && beta && out, "groupnorm: null pointer");
   RSP_CHECK_ARG(C % 8 == 0 && C / G == 4 && C / 8 <= 32 && 256 % (C / 8) == 0, "groupnorm: C=%d G=%d unsupported", C, G);
-  RSP_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * B * G * 2, stream));
+  RSP_CHECK_ARG((reinterpret_cast<uintptr_t>(stats_ws) & 15) == 0, "groupnorm: stats_ws must be 16-byte aligned");
   const int HW = H * W;
   const int ppb = 256;
-  dim3 grid((HW + ppb - 1) / ppb, B);
-  groupnorm_stats_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), stats_ws, HW, C, G, ppb);
+  const int nblk = (HW + ppb - 1) / ppb;
+  dim3 grid(nblk, B);
+  float* part = stats_ws + static_cast<size_t>(B) * G * 2;       // [B, nblk, G, 2] block partials behind the stats
+  groupnorm_stats_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), part, HW, C, G, ppb);
+  RSP_CHECK_LAUNCH();
+  groupnorm_finalize_kernel<<<(B * G + 127) / 128, 128, 0, stream>>>(part, stats_ws, B, G, nblk,
+                                                                   static_cast<double>(HW) * (C / G), eps);
   RSP_CHECK_LAUNCH();
   const long long total = static_cast<long long>(B) * HW * (C / 8);
   groupnorm_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(

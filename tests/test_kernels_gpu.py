@@ -172,3 +172,24 @@ def test_conv3x3_geometry_gate():
     assert not _lib.conv3x3_ok(1, 14, 14, 256)       # 14 x 14 RoI maps do not tile into 128-pixel boxes
     assert not _lib.conv3x3_ok(1, 48, 48, 64)
     assert _lib.conv3x3_ok(8, 256, 256, 256) and _lib.conv3x3_ok(8, 16, 16, 128)
+
+
+@pytest.mark.parametrize("M,offset", [(4096, 0.0), (4096, 300.0), (37, 300.0)])
+def test_gemm_fused_row_layernorm_large_mean(M, offset):
+    """LN(acc + bias + residual) fused into the GEMM epilogue (mask decoder layer_norm4 / token norms, HF:346-347) on
+    rows whose mean dwarfs their spread: the statistics must not lose the variance to E[x^2] - E[x]^2 cancellation."""
+    import torch.nn.functional as F
+    from rsprompter_b200 import _lib
+    g = torch.Generator().manual_seed(7)
+    K, N = 128, 256
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g) * 0.1
+    res = (torch.randn(M, N, generator=g) + offset).to(torch.bfloat16)
+    gamma, beta = 1 + 0.1 * torch.randn(N, generator=g), 0.1 * torch.randn(N, generator=g)
+    ref = F.layer_norm(a.float() @ w.float().t() + bias + res.float(), (N,), gamma, beta, 1e-6)
+    for out_dtype in ((torch.bfloat16, torch.float32) if M < 128 else (torch.bfloat16,)):
+        out = _lib.gemm(a.cuda(), w.cuda(), bias.cuda(), residual=res.cuda(), ln=(gamma.cuda(), beta.cuda(), 1e-6),
+                        out_dtype=out_dtype)
+        torch.cuda.synchronize()
+        assert (out.float().cpu() - ref).abs().max().item() < 4e-2, (M, offset, out_dtype)

@@ -223,3 +223,30 @@ def test_init_cfg_pretrained_picks_submodule_by_prefix(tmp_path, fmt):
     assert all(torch.equal(got[k], v) for k, v in dec.items())
     assert torch.equal(e.prompt_encoder.mask_embed.conv3.weight, pe["mask_embed.conv3.weight"])
     assert torch.equal(s.shared_image_embedding.positional_embedding, pos["positional_embedding"])
+
+
+def test_rssammodel_state_dict_names_match_hf_sammodel():
+    """RSSamModel.sam_model (SURVEY 8(f4), M:718-741) carries HF SamModel's parameter names and shapes (ViT-B)."""
+    import torch
+    from transformers import SamConfig, SamModel
+    with torch.device("meta"):
+        hf = SamModel(SamConfig())
+    m = MODELS.build(dict(type="RSSamModel", hf_pretrain_name="facebook/sam-vit-base"))
+    ours = {k: tuple(v.shape) for k, v in m.sam_model.state_dict().items()}
+    ref = {k: tuple(v.shape) for k, v in hf.state_dict().items()}
+    assert ours == ref
+
+
+def test_oracle_embed_boxes_matches_hf_prompt_encoder():
+    import torch
+    from transformers import SamConfig
+    from transformers.models.sam.modeling_sam import SamPromptEncoder
+    from oracle import restate
+    torch.manual_seed(0)
+    pe = SamPromptEncoder(SamConfig()).eval()
+    boxes = torch.rand(2, 3, 4) * 1000
+    with torch.no_grad():
+        ref = pe._embed_boxes(boxes.clone())
+        got = restate.embed_boxes(pe.shared_embedding.positional_embedding, pe.point_embed[2].weight,
+                                  pe.point_embed[3].weight, boxes, 1024)
+    assert torch.allclose(got, ref, atol=1e-5)
