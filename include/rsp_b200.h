@@ -270,6 +270,18 @@ int rsp_query_postprocess_rescale(const float* logits, const int32_t* sel, const
 int rsp_query_postprocess(const float* logits, const int32_t* sel, const float* cls_scores, int n_inst, int hm, int wm,
                           int H, int W, uint8_t* masks, float* part_ws, float* scores, float* boxes, void* stream);
 
+/* ---- global attention on grids the flash kernel does not specialise (S = 48 / 80: 768^2 / 1280^2 inputs, VS:570-602):
+ * three passes per (image, head) with the two contractions on rsp_gemm_bf16:
+ *   scores = Q K^T (fp32 [T, T]),  tab = Q [Rh; Rw]^T (fp32 [T, 2*NT], NT >= 2S-1 zero-padded table rows)
+ *   P = softmax_k(scale * scores[q, k] + tab[q, qh-kh+S-1] + tab[q, NT + qw-kw+S-1])   (this entry point, bf16 out)
+ *   out = P V with V^T from rsp_transpose_cols.
+ * Replaces HF:803-831 + HF:760-801 / VS:202-221 + VS:117-157 for those grids. ---- */
+int rsp_attn_softmax_bias(const float* scores, int lds, const float* tab, int ldt, int NT, void* P, int ldp, int T,
+                          int S, float scale, void* stream);
+
+/* bf16 [n_seq*T, ld] columns [col0, col0+C) -> bf16 [n_seq, C, T] (per-head V as the K-contiguous operand of P V). */
+int rsp_transpose_cols(const void* in, int ld, int col0, int C, int n_seq, int T, void* out, void* stream);
+
 /* ---- result record payload: masks leave the device bit-packed.  Bit layout everywhere: a mask
  * row of W pixels is ceil(W/8) bytes, pixel x = bit (x % 8) of byte x / 8 (numpy.packbits(bitorder='little')).  This
  * is the device-side stand-in for encode_mask_results + collect_results (coco_metric.py:346-400, :365). ---- */

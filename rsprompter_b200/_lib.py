@@ -86,6 +86,8 @@ _SIGNATURES = {
     "rsp_mask_embed_src": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp], _i),
     "rsp_query_postprocess": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "rsp_sin_fold": ([_vp, _vp, ctypes.c_longlong, _vp], _i),
+    "rsp_attn_softmax_bias": ([_vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _f, _vp], _i),
+    "rsp_transpose_cols": ([_vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "rsp_query_postprocess_bits": ([_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "rsp_mask_paste_bits": ([_vp, _vp, _i, _i, _i, _f, _i, _vp], _i),
     "rsp_pack_mask_bits": ([_vp, _vp, ctypes.c_longlong, _i, _vp], _i),
@@ -359,6 +361,8 @@ def vit_attention(qkv: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor, n
     _require_cuda(qkv, rel_h, rel_w, out)
     T = S * S
     D = H * hd
+    if not simt and out_row_map is None and S not in (14, 32, 64) and T % 8 == 0:
+        return vit_attention_generic(qkv, rel_h, rel_w, n_seq, S, H, hd, out=out)
     if not simt and S in (14, 32, 64):     # QK^T + PV on the tensor cores (rel-pos prologue not counted)
         _log("attention_window" if S == 14 else "attention_global", 4.0 * n_seq * H * T * T * hd)
     assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (n_seq * T, 3 * D)
@@ -383,6 +387,43 @@ def vit_attention(qkv: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor, n
            "rsp_vit_attention")
     launch_count += 1
     return out
+
+
+def vit_attention_generic(qkv: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor, n_seq: int, S: int, H: int,
+                          hd: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Global attention on any grid (S = 48 / 80 for 768^2 / 1280^2 inputs): per (image, head) two tcgen05 GEMMs
+    (Q K^T, Q [Rh; Rw]^T), the softmax + decomposed rel-pos row kernel, and the P V GEMM against the transposed V.
+    Intermediates: fp32 [T, T] scores and bf16 [T, T] probabilities, reused across heads."""
+    global launch_count
+    _require_cuda(qkv, rel_h, rel_w, out)
+    T, D = S * S, H * hd
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (n_seq * T, 3 * D)
+    dev = qkv.device
+    if out is None:
+        out = torch.empty((n_seq * T, D), device=dev, dtype=torch.bfloat16)
+    NT = (2 * S - 1 + 15) // 16 * 16
+    tabs = torch.zeros(2 * NT, hd, device=dev, dtype=torch.bfloat16)      # [Rh; Rw], zero rows as padding
+    tabs[:2 * S - 1] = rel_h
+    tabs[NT:NT + 2 * S - 1] = rel_w
+    vt = torch.empty(n_seq, D, T, device=dev, dtype=torch.bfloat16)
+    _check(_lib.rsp_transpose_cols(_ptr(qkv), 3 * D, 2 * D, D, n_seq, T, _ptr(vt), _stream()), "rsp_transpose_cols")
+    launch_count += 1
+    scores = torch.empty(T, T, device=dev, dtype=torch.float32)
+    tab = torch.empty(T, 2 * NT, device=dev, dtype=torch.float32)
+    P = torch.empty(T, T, device=dev, dtype=torch.bfloat16)
+    scale = float(hd) ** -0.5
+    for b in range(n_seq):
+        rows = qkv[b * T:(b + 1) * T]
+        for h in range(H):
+            q = rows[:, h * hd:(h + 1) * hd]
+            k = rows[:, D + h * hd:D + (h + 1) * hd]
+            gemm(q, k, out=scores)
+            gemm(q, tabs, out=tab)
+            _check(_lib.rsp_attn_softmax_bias(_ptr(scores), T, _ptr(tab), 2 * NT, NT, _ptr(P), T, T, S, scale, _stream()),
+                   "rsp_attn_softmax_bias")
+            launch_count += 1
+            gemm(P, vt[b, h * hd:(h + 1) * hd], out=out[b * T:(b + 1) * T, h * hd:(h + 1) * hd])
+    return out      # (its GEMM launches are in the launch log as kind "gemm")
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *,

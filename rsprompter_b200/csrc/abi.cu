@@ -75,6 +75,15 @@ int rsp_vit_attention_simt(const void* qkv, const void* rel_h, const void* rel_w
   return vit_attention_simt(make_att_args(qkv, rel_h, rel_w, out, n_seq, T, Sg, H, hd), S(stream));
 }
 
+int rsp_attn_softmax_bias(const float* scores, int lds, const float* tab, int ldt, int NT, void* P, int ldp, int T,
+                          int Sg, float scale, void* stream) {
+  return attn_softmax_bias(scores, lds, tab, ldt, NT, P, ldp, T, Sg, scale, S(stream));
+}
+
+int rsp_transpose_cols(const void* in, int ld, int col0, int C, int n_seq, int T, void* out, void* stream) {
+  return transpose_cols(in, ld, col0, C, n_seq, T, out, S(stream));
+}
+
 int rsp_layernorm(const void* in, int in_fp32, int ld_in, void* out, int out_fp32, int ld_out,
                   const float* gamma, const float* beta, const int32_t* src_map, int rows_out, int C,
                   float eps, int act, void* stream) {
