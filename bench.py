@@ -311,6 +311,16 @@ def _roofline(model_step, trace_fn, inst_steps: int, step_ms: float, peaks: dict
                                                 tflops=fl / (ms * 1e-3) if ms > 0 else 0.0,
                                                 frac=fl / (ms * 1e-3) / peaks["tflops"] if ms > 0 else 0.0)
         groups[gname] = g
+    import collections
+    import re
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for n, t in kernels:
+        short = re.sub(r"^void |rsp::|v2::|win::", "", n)
+        short = re.sub(r"\(.*", "", short)[:70]
+        agg[short][0] += 1
+        agg[short][1] += t
+    out["top_kernels"] = [dict(kernel=k, launches_per_step=v[0] / inst_steps, ms_per_step=v[1] / inst_steps)
+                          for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]]
     gm = groups["gemm"]
     out.update(achieved=gm["tflops"], frac=gm["frac"], launches_per_step=gm["launches_per_step"],
                gemm_ms_per_step=gm["ms_per_step"], algorithmic_tflop_per_step=gm["tflop_per_step"], groups=groups)

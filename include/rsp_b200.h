@@ -271,16 +271,29 @@ int rsp_query_postprocess(const float* logits, const int32_t* sel, const float* 
                           int H, int W, uint8_t* masks, float* part_ws, float* scores, float* boxes, void* stream);
 
 /* ---- global attention on grids the flash kernel does not specialise (S = 48 / 80: 768^2 / 1280^2 inputs, VS:570-602):
- * three passes per (image, head) with the two contractions on rsp_gemm_bf16:
- *   scores = Q K^T (fp32 [T, T]),  tab = Q [Rh; Rw]^T (fp32 [T, 2*NT], NT >= 2S-1 zero-padded table rows)
- *   P = softmax_k(scale * scores[q, k] + tab[q, qh-kh+S-1] + tab[q, NT + qw-kw+S-1])   (this entry point, bf16 out)
- *   out = P V with V^T from rsp_transpose_cols.
+ * three passes per image, all heads batched (rows stacked [H*T]), the two contractions on the tcgen05 GEMM:
+ *   Qh, Kh = rsp_split_heads(qkv)  (bf16 [H*T, hd] each),  Vt = rsp_transpose_cols(qkv)  (bf16 [H*hd, T])
+ *   scores = rsp_gemm_bf16_grouped(Qh, Kh)            fp32 [H*T, T]    (group h: Q_h K_h^T)
+ *   tab    = rsp_gemm_bf16(Qh, [Rh; Rw])              fp32 [H*T, 2*NT] (NT >= 2S-1 zero-padded table rows)
+ *   P      = rsp_attn_softmax_bias(scores, tab)       bf16 [H*T, T]
+ *            softmax_k(scale * scores[q, k] + tab[q, qh-kh+S-1] + tab[q, NT + qw-kw+S-1])
+ *   out    = rsp_gemm_bf16_grouped(P, Vt, row_map)    bf16 [T, H*hd]   (row_map scatters (h, t) to token t, head h)
  * Replaces HF:803-831 + HF:760-801 / VS:202-221 + VS:117-157 for those grids. ---- */
-int rsp_attn_softmax_bias(const float* scores, int lds, const float* tab, int ldt, int NT, void* P, int ldp, int T,
-                          int S, float scale, void* stream);
+int rsp_attn_softmax_bias(const float* scores, int lds, const float* tab, int ldt, int NT, void* P, int ldp, int n_rows,
+                          int T, int S, float scale, void* stream);
 
 /* bf16 [n_seq*T, ld] columns [col0, col0+C) -> bf16 [n_seq, C, T] (per-head V as the K-contiguous operand of P V). */
 int rsp_transpose_cols(const void* in, int ld, int col0, int C, int n_seq, int T, void* out, void* stream);
+
+/* bf16 [n_seq*T, ld] columns [col0 + h*hd, +hd) -> bf16 [n_seq, H, T, hd] (hd % 8 == 0): contiguous per-head operands. */
+int rsp_split_heads(const void* in, int ld, int col0, int H, int hd, int n_seq, int T, void* out, void* stream);
+
+/* rsp_gemm_bf16 with one weight matrix per row group: rows [g*m_group_rows, +m_group_rows) of A (m_group_rows % 128
+ * == 0, M % m_group_rows == 0) are multiplied with W rows [g*w_group_rows, +N):
+ *   out[row_map[m], n] = sum_k A[m, k] * W[(m / m_group_rows) * w_group_rows + n, k]
+ * (batched Q K^T / P V; also the per-image  mask_embed x mask_feature  products of the query head, M:352). */
+int rsp_gemm_bf16_grouped(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
+                          int m_group_rows, int w_group_rows, const int32_t* row_map, int out_fp32, void* stream);
 
 /* ---- result record payload: masks leave the device bit-packed.  Bit layout everywhere: a mask
  * row of W pixels is ceil(W/8) bytes, pixel x = bit (x % 8) of byte x / 8 (numpy.packbits(bitorder='little')).  This

@@ -86,8 +86,10 @@ _SIGNATURES = {
     "rsp_mask_embed_src": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp], _i),
     "rsp_query_postprocess": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "rsp_sin_fold": ([_vp, _vp, ctypes.c_longlong, _vp], _i),
-    "rsp_attn_softmax_bias": ([_vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _f, _vp], _i),
+    "rsp_attn_softmax_bias": ([_vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _f, _vp], _i),
     "rsp_transpose_cols": ([_vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
+    "rsp_split_heads": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp], _i),
+    "rsp_gemm_bf16_grouped": ([_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp], _i),
     "rsp_query_postprocess_bits": ([_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "rsp_mask_paste_bits": ([_vp, _vp, _i, _i, _i, _f, _i, _vp], _i),
     "rsp_pack_mask_bits": ([_vp, _vp, ctypes.c_longlong, _i, _vp], _i),
@@ -361,7 +363,7 @@ def vit_attention(qkv: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor, n
     _require_cuda(qkv, rel_h, rel_w, out)
     T = S * S
     D = H * hd
-    if not simt and out_row_map is None and S not in (14, 32, 64) and T % 8 == 0:
+    if not simt and out_row_map is None and S not in (14, 32, 64) and T % 128 == 0 and S % 4 == 0:
         return vit_attention_generic(qkv, rel_h, rel_w, n_seq, S, H, hd, out=out)
     if not simt and S in (14, 32, 64):     # QK^T + PV on the tensor cores (rel-pos prologue not counted)
         _log("attention_window" if S == 14 else "attention_global", 4.0 * n_seq * H * T * T * hd)
@@ -389,40 +391,74 @@ def vit_attention(qkv: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor, n
     return out
 
 
+def gemm_grouped(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, N: int, m_group_rows: int, w_group_rows: int,
+                 row_map: torch.Tensor | None = None) -> torch.Tensor:
+    """out[row_map[m], n] = sum_k a[m, k] * w[(m // m_group_rows) * w_group_rows + n, k]: one [N, K] weight per row
+    group of a (m_group_rows % 128 == 0).  a bf16 [M, K]; w bf16 [groups * w_group_rows (+ slack), K]."""
+    global launch_count
+    _require_cuda(a, w, out, row_map)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+    assert a.stride(1) == 1 and w.stride(1) == 1 and out.dim() == 2 and out.stride(1) == 1
+    M, K = a.shape
+    assert w.shape[1] == K and M % m_group_rows == 0 and m_group_rows % 128 == 0
+    assert w.shape[0] >= (M // m_group_rows - 1) * w_group_rows + N and out.shape[1] >= N
+    assert out.dtype in (torch.bfloat16, torch.float32)
+    if row_map is not None:
+        assert row_map.dtype == torch.int32 and row_map.numel() == M and row_map.is_contiguous()
+    _check(_lib.rsp_gemm_bf16_grouped(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K,
+                                      m_group_rows, w_group_rows, _ptr(row_map), int(out.dtype == torch.float32),
+                                      _stream()), "rsp_gemm_bf16_grouped")
+    launch_count += 1
+    _log("gemm", 2.0 * M * N * K)
+    return out
+
+
+_head_scatter_maps: dict = {}
+
+
 def vit_attention_generic(qkv: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor, n_seq: int, S: int, H: int,
                           hd: int, out: torch.Tensor | None = None) -> torch.Tensor:
-    """Global attention on any grid (S = 48 / 80 for 768^2 / 1280^2 inputs): per (image, head) two tcgen05 GEMMs
-    (Q K^T, Q [Rh; Rw]^T), the softmax + decomposed rel-pos row kernel, and the P V GEMM against the transposed V.
-    Intermediates: fp32 [T, T] scores and bf16 [T, T] probabilities, reused across heads."""
+    """Global attention on any grid with S % 4 == 0 and T % 128 == 0 (S = 48 / 80 for 768^2 / 1280^2 inputs): per
+    image, all heads batched along the rows - grouped tcgen05 GEMMs for Q K^T and P V, one GEMM for Q [Rh; Rw]^T, the
+    softmax + decomposed rel-pos row kernel in between.  Intermediates per image: fp32 [H*T, T] scores, bf16 [H*T, T]
+    probabilities (2.6 + 1.3 GB for ViT-H at 1280^2), reused across images."""
     global launch_count
     _require_cuda(qkv, rel_h, rel_w, out)
     T, D = S * S, H * hd
     assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (n_seq * T, 3 * D)
+    assert T % 128 == 0 and S % 4 == 0 and hd % 8 == 0, "generic attention path: T % 128 == 0, S % 4 == 0"
     dev = qkv.device
     if out is None:
         out = torch.empty((n_seq * T, D), device=dev, dtype=torch.bfloat16)
+    assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.shape == (n_seq * T, D)
     NT = (2 * S - 1 + 15) // 16 * 16
     tabs = torch.zeros(2 * NT, hd, device=dev, dtype=torch.bfloat16)      # [Rh; Rw], zero rows as padding
     tabs[:2 * S - 1] = rel_h
     tabs[NT:NT + 2 * S - 1] = rel_w
+    qh = torch.empty(n_seq, H * T, hd, device=dev, dtype=torch.bfloat16)
+    kh = torch.empty(n_seq, H * T, hd, device=dev, dtype=torch.bfloat16)
     vt = torch.empty(n_seq, D, T, device=dev, dtype=torch.bfloat16)
+    _check(_lib.rsp_split_heads(_ptr(qkv), 3 * D, 0, H, hd, n_seq, T, _ptr(qh), _stream()), "rsp_split_heads")
+    _check(_lib.rsp_split_heads(_ptr(qkv), 3 * D, D, H, hd, n_seq, T, _ptr(kh), _stream()), "rsp_split_heads")
     _check(_lib.rsp_transpose_cols(_ptr(qkv), 3 * D, 2 * D, D, n_seq, T, _ptr(vt), _stream()), "rsp_transpose_cols")
-    launch_count += 1
-    scores = torch.empty(T, T, device=dev, dtype=torch.float32)
-    tab = torch.empty(T, 2 * NT, device=dev, dtype=torch.float32)
-    P = torch.empty(T, T, device=dev, dtype=torch.bfloat16)
+    launch_count += 3
+    key = (T, H, dev)
+    if key not in _head_scatter_maps:        # stacked row (h, t) -> row t * H + h of the image's [T * H, hd] view
+        t = torch.arange(T, device=dev, dtype=torch.int32)
+        h = torch.arange(H, device=dev, dtype=torch.int32)
+        _head_scatter_maps[key] = (t.view(1, T) * H + h.view(H, 1)).reshape(-1).contiguous()
+    rmap = _head_scatter_maps[key]
+    scores = torch.empty(H * T, T, device=dev, dtype=torch.float32)
+    tab = torch.empty(H * T, 2 * NT, device=dev, dtype=torch.float32)
+    P = torch.empty(H * T, T, device=dev, dtype=torch.bfloat16)
     scale = float(hd) ** -0.5
     for b in range(n_seq):
-        rows = qkv[b * T:(b + 1) * T]
-        for h in range(H):
-            q = rows[:, h * hd:(h + 1) * hd]
-            k = rows[:, D + h * hd:D + (h + 1) * hd]
-            gemm(q, k, out=scores)
-            gemm(q, tabs, out=tab)
-            _check(_lib.rsp_attn_softmax_bias(_ptr(scores), T, _ptr(tab), 2 * NT, NT, _ptr(P), T, T, S, scale, _stream()),
-                   "rsp_attn_softmax_bias")
-            launch_count += 1
-            gemm(P, vt[b, h * hd:(h + 1) * hd], out=out[b * T:(b + 1) * T, h * hd:(h + 1) * hd])
+        gemm_grouped(qh[b], kh[b], scores, T, T, T)
+        gemm(qh[b], tabs, out=tab)
+        _check(_lib.rsp_attn_softmax_bias(_ptr(scores), T, _ptr(tab), 2 * NT, NT, _ptr(P), T, H * T, T, S, scale,
+                                          _stream()), "rsp_attn_softmax_bias")
+        launch_count += 1
+        gemm_grouped(P, vt[b], out[b * T:(b + 1) * T].view(T * H, hd), hd, T, hd, row_map=rmap)
     return out      # (its GEMM launches are in the launch log as kind "gemm")
 
 

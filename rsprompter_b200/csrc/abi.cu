@@ -34,6 +34,13 @@ int rsp_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int
                                   res_mod, row_map, act, out_fp32), S(stream));
 }
 
+int rsp_gemm_bf16_grouped(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
+                          int m_group_rows, int w_group_rows, const int32_t* row_map, int out_fp32, void* stream) {
+  GemmArgs a = make_gemm_args(A, lda, W, ldw, out, ldo, M, N, K, nullptr, nullptr, 0, 1, 0, row_map, 0, out_fp32);
+  a.m_group_rows = m_group_rows; a.w_group_rows = w_group_rows;
+  return gemm_bf16(a, S(stream));
+}
+
 int rsp_conv3x3_nhwc_bf16(const void* x, int B, int H, int W, int C, const void* Wt, int ldw, void* out, int ldo,
                           int N, const float* bias, const void* residual, int ldr, int res_fp32, int act,
                           int out_fp32, void* stream) {
@@ -75,13 +82,17 @@ int rsp_vit_attention_simt(const void* qkv, const void* rel_h, const void* rel_w
   return vit_attention_simt(make_att_args(qkv, rel_h, rel_w, out, n_seq, T, Sg, H, hd), S(stream));
 }
 
-int rsp_attn_softmax_bias(const float* scores, int lds, const float* tab, int ldt, int NT, void* P, int ldp, int T,
-                          int Sg, float scale, void* stream) {
-  return attn_softmax_bias(scores, lds, tab, ldt, NT, P, ldp, T, Sg, scale, S(stream));
+int rsp_attn_softmax_bias(const float* scores, int lds, const float* tab, int ldt, int NT, void* P, int ldp, int n_rows,
+                          int T, int Sg, float scale, void* stream) {
+  return attn_softmax_bias(scores, lds, tab, ldt, NT, P, ldp, n_rows, T, Sg, scale, S(stream));
 }
 
 int rsp_transpose_cols(const void* in, int ld, int col0, int C, int n_seq, int T, void* out, void* stream) {
   return transpose_cols(in, ld, col0, C, n_seq, T, out, S(stream));
+}
+
+int rsp_split_heads(const void* in, int ld, int col0, int H, int hd, int n_seq, int T, void* out, void* stream) {
+  return split_heads(in, ld, col0, H, hd, n_seq, T, out, S(stream));
 }
 
 int rsp_layernorm(const void* in, int in_fp32, int ld_in, void* out, int out_fp32, int ld_out,

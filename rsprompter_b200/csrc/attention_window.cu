@@ -3,8 +3,9 @@
 // latencies, so throughput comes from how many CTAs an SM can overlap, not from per-CTA pipelining.  This kernel is
 // therefore as small as the problem allows:
 //   * 192 threads: warps 0-3 softmax (thread = query row, no exchange of any kind), warp 4 TMA, warp 5 MMA;
-//   * TMEM: one S tile of KT keys + one accumulator = 128 columns (hd 64: KT = 64; hd 80: KT = 32), i.e. 4 CTAs / SM
-//     by TMEM; shared memory 54 KB (hd 64, 4 CTAs / SM) / 64 KB (hd 80, 3 CTAs / SM);
+//   * TMEM: one S tile of KT keys + one accumulator = 128 columns (hd 64: KT = 64; hd 80: KT = 48 -> 5 key rounds
+//     instead of the 7 of a 32-key tile: every round is a serial TMA -> MMA -> softmax -> MMA chain), i.e. 4 CTAs / SM
+//     by TMEM; shared memory 54 KB (hd 64, 4 CTAs / SM) / 73 KB (hd 80, 3 CTAs / SM);
 //   * P is written in place over the scores in TMEM and P V is a TS-form MMA, Q K_{j+1}^T is issued right behind
 //     P V_j (same issuing thread: in order on the tensor pipe);
 //   * rel-pos: prologue MMA Q x table^T (27 rows each), gathered per row through a scratch buffer into 14 + 14
@@ -37,8 +38,8 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 template <int HD>
 struct Cfg {
   static constexpr int NA = (HD + 63) / 64;
-  static constexpr int KT = (HD <= 64) ? 64 : 32;       // keys per tile
-  static constexpr int NKT = (T + KT - 1) / KT;         // 4 / 7
+  static constexpr int KT = (HD <= 64) ? 64 : 48;       // keys per tile (S tile + accumulator = 128 TMEM columns)
+  static constexpr int NKT = (T + KT - 1) / KT;         // 4 / 5
   static constexpr int Q_BYTES = NA * 16384;
   static constexpr int TAB_BYTES = NA * NREL * 128;     // one table: 32 rows x NA x 128 B
   static constexpr int KV_BYTES = NA * KT * 128;        // one K or V tile
@@ -257,30 +258,27 @@ vit_window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
       }
       float ls4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < KT / 32; ++c) {       // 32 keys -> 16 packed columns, written over the scores just read
-        uint32_t pk[16];
+      for (int g = 0; g < KT / 16; ++g) {       // 16 keys -> 8 packed columns, written over scores already consumed
+        uint32_t pk[8];
+        const int kb = j * KT + g * 16;         // compile-time after unrolling
+        if (kb >= T) {
 #pragma unroll
-        for (int h16 = 0; h16 < 2; ++h16) {
-          const int kb = j * KT + c * 32 + h16 * 16;     // compile-time after unrolling
-          if (kb >= T) {
+          for (int i = 0; i < 8; ++i) pk[i] = 0u;
+        } else {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tS + lane_off + g * 16, v);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) pk[h16 * 8 + i] = 0u;
-          } else {
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(tS + lane_off + c * 32 + h16 * 16, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int k0 = kb + 2 * i, k1 = k0 + 1;
-              const int kh0 = k0 / 14, kw0 = k0 - kh0 * 14, kh1 = k1 / 14, kw1 = k1 - kh1 * 14;
-              const float e0 = (k0 < T) ? ex2(fmaf(__uint_as_float(v[2 * i]), scale2, relh[kh0 < 14 ? kh0 : 0] - m_run) + relw[kw0]) : 0.f;
-              const float e1 = (k1 < T) ? ex2(fmaf(__uint_as_float(v[2 * i + 1]), scale2, relh[kh1 < 14 ? kh1 : 0] - m_run) + relw[kw1]) : 0.f;
-              ls4[i & 3] += e0 + e1;
-              pk[h16 * 8 + i] = pack_bf16x2(e0, e1);
-            }
+          for (int i = 0; i < 8; ++i) {
+            const int k0 = kb + 2 * i, k1 = k0 + 1;
+            const int kh0 = k0 / 14, kw0 = k0 - kh0 * 14, kh1 = k1 / 14, kw1 = k1 - kh1 * 14;
+            const float e0 = (k0 < T) ? ex2(fmaf(__uint_as_float(v[2 * i]), scale2, relh[kh0 < 14 ? kh0 : 0] - m_run) + relw[kw0]) : 0.f;
+            const float e1 = (k1 < T) ? ex2(fmaf(__uint_as_float(v[2 * i + 1]), scale2, relh[kh1 < 14 ? kh1 : 0] - m_run) + relw[kw1]) : 0.f;
+            ls4[i & 3] += e0 + e1;
+            pk[i] = pack_bf16x2(e0, e1);
           }
         }
-        tmem_st_32x32b_x16(tS + lane_off + c * 16, pk);
+        tmem_st_32x32b_x8(tS + lane_off + g * 8, pk);
       }
       l_run += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
       tmem_st_wait();

@@ -543,6 +543,9 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
     return launch_gemm<128, false>(a, stream);
   }
   RSP_CHECK_ARG(a.epi_mode == EPI_STD, "gemm: epi_mode %d", a.epi_mode);
+  if (a.m_group_rows > 0)
+    RSP_CHECK_ARG(a.m_group_rows % BM == 0 && a.M % a.m_group_rows == 0 && a.w_group_rows > 0 && !a.w_is_kn &&
+                  a.conv_c == 0 && gemm_v2_eligible(a), "gemm: grouped weights need m_group_rows %% 128 == 0 and the v2 kernel");
   if (a.w_is_kn) {
     RSP_CHECK_ARG(a.N % 64 == 0, "gemm: [K,N] weights need N %% 64 == 0");
     if (a.N % 128 == 0) return launch_gemm<128, true>(a, stream);
@@ -563,7 +566,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   }
   {
     static const bool force_v1 = getenv("RSP_GEMM_V1") != nullptr;
-    if (!force_v1 && gemm_v2_eligible(a)) return gemm_bf16_v2(a, bn, stream);
+    if ((!force_v1 || a.m_group_rows > 0) && gemm_v2_eligible(a)) return gemm_bf16_v2(a, bn, stream);
   }
   switch (bn) {
     case 256: return launch_gemm<256, false>(a, stream);

@@ -34,6 +34,9 @@ struct GemmArgs {
   // implicit 3x3 / stride 1 / pad 1 convolution: A = bf16 NHWC [conv_b, conv_h, conv_w, conv_c], M = b*h*w,
   // K = 9 * conv_c, W = [N, (ky, kx, c)]; the im2col matrix is never built (TMA zero-fills the halo)
   int conv_b = 0, conv_h = 0, conv_w = 0, conv_c = 0;
+  // grouped weights: rows [g * m_group_rows, (g+1) * m_group_rows) of A multiply W rows [g * w_group_rows, +N)
+  // (every group has its own [N, K] operand; batched Q K^T / P V of the three-pass attention).  m_group_rows % 128 == 0.
+  int m_group_rows = 0, w_group_rows = 0;
 };
 
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream);

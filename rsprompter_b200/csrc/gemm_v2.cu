@@ -62,6 +62,7 @@ struct Dev {
   float* mask_out;
   int grid_h, grid_w;
   int conv_kb, conv_h, conv_w;   // conv_kb = Cin / 64 k-blocks per tap (0 = plain GEMM)
+  int mblk_per_group, w_group_rows;   // grouped weights (0 = one W for every row)
   int tma_store;                 // output leaves through tma_c (no scatter, BN >= 64)
   int tma_res;                   // residual slabs arrive through tma_r into the staging buffer (added in place)
 };
@@ -126,6 +127,7 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile % p.num_n_blocks;
       int cb = 0, cy = 0, cx = 0, tap = 0, ckb = 0;
+      const int w_row0 = p.mblk_per_group > 0 ? (m_blk / p.mblk_per_group) * p.w_group_rows : 0;
       if (p.conv_kb > 0) {   // the tile's 128 output pixels are a (images x rows x cols) box of the NHWC map
         const int hw = p.conv_h * p.conv_w, p0 = m_blk * BM;
         cb = p0 / hw;
@@ -145,7 +147,7 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
         } else {
           tma_load_2d(sa, &tma_a, full, kb * BK, m_blk * BM);
         }
-        tma_load_2d(sa + A_BYTES, &tma_b, full, kb * BK, n_blk * BN);
+        tma_load_2d(sa + A_BYTES, &tma_b, full, kb * BK, n_blk * BN + w_row0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -768,7 +770,9 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
   } else {
     RSP_TRY(make_tmap_bf16_2d(&ta, a.A, a.M, a.K, static_cast<uint64_t>(a.lda) * 2, BM, BK));
   }
-  RSP_TRY(make_tmap_bf16_2d(&tb, a.W, a.N, a.K, static_cast<uint64_t>(a.ldw) * 2, BN, BK));
+  const int n_groups = a.m_group_rows > 0 ? (a.M + a.m_group_rows - 1) / a.m_group_rows : 1;
+  const uint64_t w_rows = a.m_group_rows > 0 ? static_cast<uint64_t>(n_groups - 1) * a.w_group_rows + a.N : a.N;
+  RSP_TRY(make_tmap_bf16_2d(&tb, a.W, w_rows, a.K, static_cast<uint64_t>(a.ldw) * 2, BN, BK));
   CUtensorMap tc = tb, tr = tb;
   p.tma_store = 0;
   p.tma_res = 0;
@@ -810,6 +814,8 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
   p.res_block_map = a.res_block_map; p.res_block_rows = a.res_block_rows;
   p.res_mod = a.res_mod; p.ldo = a.ldo; p.ldr = a.ldr; p.act = a.act;
   p.out_fp32 = a.out_fp32; p.res_fp32 = a.res_fp32;
+  p.mblk_per_group = a.m_group_rows > 0 ? a.m_group_rows / BM : 0;
+  p.w_group_rows = a.w_group_rows;
   p.num_n_blocks = (a.N + BN - 1) / BN;
   p.num_tiles = ((a.M + BM - 1) / BM) * p.num_n_blocks;
   p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;

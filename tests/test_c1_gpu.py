@@ -26,8 +26,9 @@ def test_global_attention_on_32x32_grid():
 
 @pytest.mark.parametrize("S,n_seq,H,hd", [(48, 2, 2, 64), (80, 1, 2, 80), (48, 1, 3, 80)])
 def test_other_grids_run_the_three_pass_tensor_core_path(S, n_seq, H, hd):
-    """768^2 / 1280^2 inputs (S = 48 / 80): Q K^T, Q [Rh; Rw]^T and P V on the tcgen05 GEMM with the softmax +
-    decomposed rel-pos row kernel in between (rsp_attn_softmax_bias); also checked against the CUDA-core kernel."""
+    """768^2 / 1280^2 inputs (S = 48 / 80): Q K^T and P V as grouped tcgen05 GEMMs over all heads of an image,
+    Q [Rh; Rw]^T as a plain GEMM, the softmax + decomposed rel-pos row kernel in between (rsp_attn_softmax_bias);
+    also checked against the CUDA-core kernel."""
     from oracle import restate
     from rsprompter_b200 import _lib
     g = torch.Generator().manual_seed(S + hd)
@@ -40,7 +41,7 @@ def test_other_grids_run_the_three_pass_tensor_core_path(S, n_seq, H, hd):
     ref = ref.reshape(n_seq, H, T, hd).permute(0, 2, 1, 3).reshape(n_seq * T, D)
     n0 = _lib.launch_count
     out = _lib.vit_attention(qkv.cuda(), rh.cuda(), rw.cuda(), n_seq, S, H, hd)
-    assert _lib.launch_count - n0 == 1 + 4 * n_seq * H          # transpose + (2 GEMMs, softmax, GEMM) per (image, head)
+    assert _lib.launch_count - n0 == 3 + 4 * n_seq              # head split x2 + transpose, then 4 launches per image
     simt = _lib.vit_attention(qkv.cuda(), rh.cuda(), rw.cuda(), n_seq, S, H, hd, simt=True)
     torch.cuda.synchronize()
     assert (out.float().cpu() - ref).abs().max().item() / ref.abs().max().item() < 1.5e-2

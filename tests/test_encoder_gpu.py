@@ -45,6 +45,48 @@ def test_vit_base_matches_oracle():
     _check(*_run(VISION_ARCHS["base"], 1, 12), tol=2e-2)
 
 
+@pytest.mark.parametrize("heads,hd", [(4, 64), (4, 80)])
+def test_vit_with_outlier_channels_matches_oracle(heads, hd):
+    """Real SAM checkpoints carry a few residual-stream channels that are orders of magnitude larger than the rest and
+    non-trivial LayerNorm gains; the seeded randn * 0.02 weights do not.  Inject both (three channels offset by +-25
+    through the patch-embed bias and re-fed by every lin2 bias, LayerNorm gains in [0.5, 2], attention logits scaled up
+    through the q/k weights) and require the same range-relative tolerance."""
+    from oracle import restate
+    from rsprompter_b200 import synthetic
+    from rsprompter_b200.sam_config import SamVisionArch
+    from rsprompter_b200.sam_encoder import SamVisionEncoderB200
+    D = heads * hd
+    arch = SamVisionArch("outlier", hidden_size=D, num_layers=4, num_heads=heads, mlp_dim=4 * D,
+                         global_attn_indexes=(3,), image_size=1024)
+    sd = synthetic.vision_encoder_state_dict(arch, seed=21)
+    g = torch.Generator().manual_seed(22)
+    big = [5, D // 2 + 3, D - 7]
+    sd["patch_embed.projection.bias"][big] += torch.tensor([25.0, -25.0, 18.0])
+    for i in range(arch.num_layers):
+        p = f"layers.{i}."
+        sd[p + "mlp.lin2.bias"][big] += torch.tensor([4.0, -4.0, 3.0])
+        sd[p + "layer_norm1.weight"] = 0.5 + 1.5 * torch.rand(D, generator=g)
+        sd[p + "layer_norm2.weight"] = 0.5 + 1.5 * torch.rand(D, generator=g)
+        sd[p + "attn.qkv.weight"][:2 * D] *= 3.0          # sharper attention
+    torch.manual_seed(23)
+    x = torch.randn(1, 3, 1024, 1024)
+    with torch.no_grad():
+        emb_ref, hid_ref = restate.vit_encoder(sd, arch, x)
+    enc = SamVisionEncoderB200(arch)
+    enc.load_state_dict(sd)
+    enc = enc.cuda()
+    emb, hid, _ = enc.encode(x.cuda())
+    torch.cuda.synchronize()
+    assert hid_ref[-1].abs().max().item() > 25.0        # the outliers really are there
+    small = [c for c in range(D) if c not in big]
+    for i, (a, b) in enumerate(zip(hid, hid_ref)):
+        d = (a.cpu() - b).abs()
+        # ordinary channels are judged on their own range (not hidden behind the outliers'), outliers on theirs
+        assert d[..., small].max().item() <= 2e-2 * max(1.0, b[..., small].abs().max().item()), f"hidden {i} (ordinary channels)"
+        assert d[..., big].max().item() <= 2e-2 * b[..., big].abs().max().item(), f"hidden {i} (outlier channels)"
+    assert (emb.cpu() - emb_ref).abs().max().item() <= 2e-2 * max(1.0, emb_ref.abs().max().item())
+
+
 def test_output_contract():
     """forward() returns what extract_feat unpacks (M:97-106)."""
     import dataclasses
