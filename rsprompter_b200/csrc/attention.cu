@@ -18,6 +18,15 @@
 //   warp 8     TMA producer (Q once; K_j / V_j tiles; the two rel-pos tables) + TMEM alloc
 //   warp 9     tcgen05.mma issuer: S_j = Q K_j^T (128x128x hd), O_h += P_j V_j over the key steps of half h,
 //              V consumed straight from the qkv matrix as an MN-major operand
+// hd 80 (ViT-H) cannot afford two 80-column accumulators next to two score tiles in the 256 TMEM columns a CTA gets
+// at 2 CTAs / SM, and with a single score tile every key tile is a serial  Q K^T -> softmax -> P V  chain (ncu: 46 %
+// of all warp samples sat on the "S ready" barrier).  For HD > 64 the two key halves of a row therefore share ONE
+// accumulator and one running reference: the pair exchanges its chunk bounds through shared memory once per tile
+// (one bar.sync of the two warps of a lane quarter), both threads take the same rescale decision and each rescales
+// its share of the accumulator's columns.  That frees the columns for a second score tile: Q K_{j+1}^T runs while the
+// softmax warps work on tile j, as in the hd 64 pipeline.  K is double-buffered in shared memory (the second stage
+// lives in the half of the rel_w table region that relh_s does not use), V stays single-buffered (its load hides
+// behind the softmax of the same tile).
 // The decomposed relative-position bias is never materialised as a T x T tensor: a
 // prologue MMA computes Q (unscaled) x table^T for both tables (the reference's two
 // einsums), each thread gathers the values its row / key half needs, and the bias is added
@@ -46,20 +55,21 @@ __device__ __forceinline__ float fast_exp2(float x) {
 template <int HD>
 struct AttCfg {
   static constexpr int NA = (HD + 63) / 64;           // 64-wide swizzle atoms per head
-  static constexpr bool SB = HD > 64;                 // single-buffered S / K / V (hd 80): fits 2 CTAs per SM
-  static constexpr int NBUF = SB ? 1 : 2;
+  static constexpr bool ONE_ACC = HD > 64;            // hd 80: one shared accumulator, pair-exchanged running max
+  static constexpr int VBUF = ONE_ACC ? 1 : 2;        // V stages in shared memory (K and S always have 2)
   static constexpr int Q_BYTES = NA * 16384;          // 128 rows x NA x 128 B
   static constexpr int KV_BYTES = NA * 8192;          // one 64-key stage of K or V
   static constexpr int TAB_BYTES = NA * 16384;        // a rel-pos table in the prologue (<= 128 rows x NA x 128 B)
   static constexpr int SCRATCH_BYTES = 32768;         // prologue gather scratch: [kw <= 64][128] fp32
   static constexpr int RELH_BYTES = 64 * 128 * 2;     // global: [kh][row] fp16
   // hd 64: [Q | K x2 (rel_h table) | V x2 (rel_w table) | scratch | relh_s]
-  // hd 80: [Q | A: rel_h table -> scratch -> K, V | B: rel_w table -> relh_s]   (K / V loads wait for the gather)
-  static constexpr int SMEM_BYTES = SB ? Q_BYTES + 2 * TAB_BYTES + 1024
-                                       : Q_BYTES + 4 * KV_BYTES + SCRATCH_BYTES + RELH_BYTES + 1024;
-  static constexpr int O_STRIDE = (HD <= 64) ? 64 : 96;   // column distance between the two accumulators
-  static constexpr int O_COL = SB ? 64 : 128;         // hd 64: S_0 [0,64) S_1 [64,128) O_0 [128,192) O_1 [192,256)
-  static constexpr int TMEM_COLS = 256;               // hd 80: S [0,64) O_0 [64,144) O_1 [160,240)
+  // hd 80: [Q | A: rel_h table -> scratch -> K_0, V | B: rel_w table -> relh_s, K_1]   (K / V loads wait for the gather)
+  static constexpr int SMEM_BYTES = ONE_ACC ? Q_BYTES + 2 * TAB_BYTES + 1024
+                                            : Q_BYTES + 4 * KV_BYTES + SCRATCH_BYTES + RELH_BYTES + 1024;
+  static constexpr int O_STRIDE = 64;                 // hd 64: column distance between the two accumulators
+  static constexpr int O_COL = 128;                   // S_0 [0,64) S_1 [64,128) | hd 64: O_0 [128,192) O_1 [192,256)
+  static constexpr int TMEM_COLS = 256;               //                          | hd 80: O [128,208)
+  static_assert(!ONE_ACC || (KV_BYTES * 2 <= TAB_BYTES && RELH_BYTES + KV_BYTES <= TAB_BYTES), "hd 80 smem aliasing");
 };
 
 struct AttDev {
@@ -90,22 +100,27 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[B_COUNT];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float2 xchg[2][128];            // (m, l) of each key half, exchanged once at the end
+  __shared__ float2 xchg[2][128];            // hd 64: (m, l) of each key half, exchanged once at the end;
+                                             // hd 80: per-tile chunk bounds [tile parity][row] (.x / .y = key half 0 / 1)
 
-  constexpr bool SB = Cfg::SB;
-  constexpr int NBUF = Cfg::NBUF;
+  constexpr bool ONE_ACC = Cfg::ONE_ACC;
+  constexpr int VBUF = Cfg::VBUF;
   const uint32_t sQ = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sTabH = sQ + Cfg::Q_BYTES;                               // rel_h table (prologue)
-  const uint32_t sTabW = sTabH + (SB ? Cfg::TAB_BYTES : 2 * Cfg::KV_BYTES);   // rel_w table (prologue)
-  const uint32_t sK = sTabH;                                             // K stage(s)
-  const uint32_t sV = SB ? sTabH + Cfg::KV_BYTES : sTabW;                // V stage(s)
-  const uint32_t sScr = SB ? sTabH : sTabW + 2 * Cfg::KV_BYTES;          // gather scratch
-  const uint32_t sRH = SB ? sTabW : sScr + Cfg::SCRATCH_BYTES;           // relh_s
+  const uint32_t sTabW = sTabH + (ONE_ACC ? Cfg::TAB_BYTES : 2 * Cfg::KV_BYTES);   // rel_w table (prologue)
+  const uint32_t sK0 = sTabH;                                            // K stage 0
+  const uint32_t sK1 = ONE_ACC ? sTabW + Cfg::RELH_BYTES : sTabH + Cfg::KV_BYTES;   // K stage 1
+  const uint32_t sV = ONE_ACC ? sTabH + Cfg::KV_BYTES : sTabW;           // V stage(s)
+  const uint32_t sScr = ONE_ACC ? sTabH : sTabW + 2 * Cfg::KV_BYTES;     // gather scratch
+  const uint32_t sRH = ONE_ACC ? sTabW : sScr + Cfg::SCRATCH_BYTES;      // relh_s
   uint8_t* gP = smem_raw + (sScr - smem_u32(smem_raw));
   uint8_t* gRH = smem_raw + (sRH - smem_u32(smem_raw));
-  // ring slot / mbarrier phase of tile t (two slots for hd 64, one for hd 80)
-  auto slot = [](int t) { return SB ? 0 : (t & 1); };
-  auto phase = [](int t) -> uint32_t { return SB ? (t & 1) : ((t >> 1) & 1); };
+  // two-slot rings (K, S, P): slot = t & 1, phase of use n of a slot = (n >> 1) & 1; the V ring has VBUF slots
+  auto slot = [](int t) { return t & 1; };
+  auto phase = [](int t) -> uint32_t { return (t >> 1) & 1; };
+  auto vslot = [](int t) { return VBUF == 1 ? 0 : (t & 1); };
+  auto vphase = [](int t) -> uint32_t { return VBUF == 1 ? (t & 1) : ((t >> 1) & 1); };
+  auto sK = [&](int sl) { return sl ? sK1 : sK0; };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -138,8 +153,8 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t tS = tmem_base;                             // S_0 | S_1 (and the rel_h prologue product)
   const uint32_t tOpro = tmem_base + 128;                    // rel_w prologue product
-  const uint32_t tO = tmem_base + Cfg::O_COL;                // accumulator of key half 0
-  const uint32_t tO1 = tO + Cfg::O_STRIDE;                   // accumulator of key half 1
+  const uint32_t tO = tmem_base + Cfg::O_COL;                // accumulator (hd 64: of key half 0)
+  const uint32_t tO1 = ONE_ACC ? tO : tO + Cfg::O_STRIDE;    // hd 64: accumulator of key half 1
   const int n_kt = GLOBAL ? p.n_kt : 4;
 
   if (warp == 8 && lane == 0) {
@@ -151,20 +166,19 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       tma_load_2d(sTabH + a * 16384, &tm_relh, bar(B_Q), a * 64, 0);
       tma_load_2d(sTabW + a * 16384, &tm_relw, bar(B_Q), a * 64, 0);
     }
-    if (SB) mbar_wait(bar(B_RELC), 0);        // the gather scratch / relh_s live where K / V land
+    if (ONE_ACC) mbar_wait(bar(B_RELC), 0);   // the gather scratch / dead tables live where K / V land
     for (int j = 0; j < n_kt; ++j) {
-      const int s = slot(j);
-      const uint32_t ph = phase(j);
-      mbar_wait(bar(B_KE + s), ph);           // phase 0 of the "empty" slots completes with the prologue MMAs
+      const int s = slot(j), vs = vslot(j);
+      mbar_wait(bar(B_KE + s), phase(j));     // phase 0 of the "empty" slots completes with the prologue MMAs
       mbar_expect_tx(bar(B_KF + s), Cfg::KV_BYTES);
 #pragma unroll
       for (int a = 0; a < NA; ++a)
-        tma_load_2d(sK + s * Cfg::KV_BYTES + a * 8192, &tm_kv, bar(B_KF + s), colk + a * 64, row0 + j * 64);
-      mbar_wait(bar(B_VE + s), ph);
-      mbar_expect_tx(bar(B_VF + s), Cfg::KV_BYTES);
+        tma_load_2d(sK(s) + a * 8192, &tm_kv, bar(B_KF + s), colk + a * 64, row0 + j * 64);
+      mbar_wait(bar(B_VE + vs), vphase(j));
+      mbar_expect_tx(bar(B_VF + vs), Cfg::KV_BYTES);
 #pragma unroll
       for (int a = 0; a < NA; ++a)
-        tma_load_2d(sV + s * Cfg::KV_BYTES + a * 8192, &tm_kv, bar(B_VF + s), colv + a * 64, row0 + j * 64);
+        tma_load_2d(sV + vs * Cfg::KV_BYTES + a * 8192, &tm_kv, bar(B_VF + vs), colv + a * 64, row0 + j * 64);
     }
   } else if (warp == 9 && lane == 0) {
     // ------------------------------------------------------------ MMA issuer (own warp: sharing the producer's
@@ -194,35 +208,34 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     auto issue_qk = [&](int t) {   // S_slot(t) = Q K_t^T
       const int s = slot(t);
       mbar_wait(bar(B_KF + s), phase(t));
-      if (t >= NBUF) mbar_wait(bar(B_PV + s), phase(t - NBUF));   // P V of the previous user has consumed S_s / P_s
+      if (t >= 2) mbar_wait(bar(B_PV + s), phase(t - 2));   // P V of the previous user has consumed S_s / P_s
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < HD / 16; ++ks) {
         const uint32_t qoff = (ks >> 2) * 16384 + (ks & 3) * 32;
-        const uint32_t koff = s * Cfg::KV_BYTES + (ks >> 2) * 8192 + (ks & 3) * 32;
-        umma_ss(tS + s * 64, make_sdesc(sQ + qoff, 0, 1024), make_sdesc(sK + koff, 0, 1024), idesc_s, ks != 0);
+        const uint32_t koff = (ks >> 2) * 8192 + (ks & 3) * 32;
+        umma_ss(tS + s * 64, make_sdesc(sQ + qoff, 0, 1024), make_sdesc(sK(s) + koff, 0, 1024), idesc_s, ks != 0);
       }
       umma_commit(bar(B_SF + s));
       umma_commit(bar(B_KE + s));
     };
     issue_qk(0);
     for (int j = 0; j < n_kt; ++j) {
-      if (!SB && j + 1 < n_kt) issue_qk(j + 1);      // runs while the softmax warps work on tile j
-      const int s = slot(j);
-      const uint32_t ph = phase(j);
-      mbar_wait(bar(B_PF + s), ph);
-      mbar_wait(bar(B_VF + s), ph);
+      if (j + 1 < n_kt) issue_qk(j + 1);      // runs while the softmax warps work on tile j
+      const int s = slot(j), vs = vslot(j);
+      mbar_wait(bar(B_PF + s), phase(j));
+      mbar_wait(bar(B_VF + vs), vphase(j));
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {   // 16 keys per step; 32-key chunk ks >> 1 belongs to key half ks >> 1
         // A = P straight from TMEM: 8 packed bf16x2 columns per step, written in place over the chunk's scores
         const uint32_t a_tmem = tS + s * 64 + (ks >> 1) * 32 + (ks & 1) * 8;
-        const uint64_t bdesc = make_sdesc(sV + s * Cfg::KV_BYTES + ks * 2048, 8192, 1024);
-        umma_ts((ks >> 1) ? tO1 : tO, a_tmem, bdesc, idesc_pv, (j | (ks & 1)) != 0);
+        const uint64_t bdesc = make_sdesc(sV + vs * Cfg::KV_BYTES + ks * 2048, 8192, 1024);
+        if (ONE_ACC) umma_ts(tO, a_tmem, bdesc, idesc_pv, (j | ks) != 0);
+        else umma_ts((ks >> 1) ? tO1 : tO, a_tmem, bdesc, idesc_pv, (j | (ks & 1)) != 0);
       }
       umma_commit(bar(B_PV + s));
-      umma_commit(bar(B_VE + s));
-      if (SB && j + 1 < n_kt) issue_qk(j + 1);       // single S: the next scores follow P V
+      umma_commit(bar(B_VE + vs));
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------ softmax / correction / output
@@ -321,6 +334,9 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       for (int i = 0; i < 14; ++i) { a = fmaxf(a, relh[i]); b = fmaxf(b, relw[i]); }
       bias_max = a + b;
     }
+    // hd 80: the accumulator's 16-column chunks this thread rescales / stores (its share of the shared accumulator)
+    constexpr int NC0 = (HD / 16 + 1) / 2;     // chunks of half 0 (hd 80: 3 of 5; hd 64: 2 of 4)
+    const int c_lo = hf ? NC0 : 0, c_hi = hf ? HD / 16 : NC0;
 
 #pragma unroll(GLOBAL ? 1 : 4)
     for (int j = 0; j < n_kt; ++j) {
@@ -344,24 +360,43 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 #pragma unroll
         for (int i = 0; i < 8; ++i) mx4[i & 3] = max3(mx4[i & 3], __uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
       }
-      const float bound = fmaf(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])), scale2, rh + bias_max);
+      float bound = fmaf(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])), scale2, rh + bias_max);
+      if (ONE_ACC) {
+        // one reference per ROW: the two threads of a row see both chunk bounds and take the same decision
+        float* xb = reinterpret_cast<float*>(&xchg[j & 1][r]);
+        xb[hf] = bound;
+        pair_sync();
+        bound = fmaxf(bound, xb[hf ^ 1]);
+      }
       const bool need = bound > m_run + 8.0f;
       if (__any_sync(0xffffffffu, need)) {
-        // the reference moves up (always on the first tile, rarely later): O_h / l_h are rescaled
+        // the reference moves up (always on the first tile, rarely later): the accumulator / l are rescaled
         const float alpha = need ? fast_exp2(m_run - bound) : 1.0f;
         l_run *= alpha;
         m_run = need ? bound : m_run;
         if (j > 0) {
-          mbar_wait(bar(B_PV + slot(j - 1)), phase(j - 1));     // P V of tile j-1 has landed in O_h
+          mbar_wait(bar(B_PV + slot(j - 1)), phase(j - 1));     // P V of tile j-1 has landed in the accumulator
           tc_fence_after();
+          if (ONE_ACC) {
+#pragma unroll 1
+            for (int c = c_lo; c < c_hi; ++c) {                 // my share of the shared accumulator's columns
+              uint32_t o[16];
+              tmem_ld_32x32b_x16(tO + lane_off + c * 16, o);
+              tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < HD / 16; ++c) {
-            uint32_t o[16];
-            tmem_ld_32x32b_x16(tOme + lane_off + c * 16, o);
-            tmem_ld_wait();
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x32b_x16(tO + lane_off + c * 16, o);
+            }
+          } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32b_x16(tOme + lane_off + c * 16, o);
+            for (int c = 0; c < HD / 16; ++c) {
+              uint32_t o[16];
+              tmem_ld_32x32b_x16(tOme + lane_off + c * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x32b_x16(tOme + lane_off + c * 16, o);
+            }
           }
           tmem_st_wait();
         }
@@ -403,33 +438,39 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       mbar_arrive(bar(B_PF + s));
     }
 
-    // ---- epilogue: merge the two key halves, O / l -> out[token, head*HD .. ]
+    // ---- epilogue: O / l -> out[token, head*HD .. ]  (hd 64: merge the two key halves first)
     mbar_wait(bar(B_PV + slot(n_kt - 1)), phase(n_kt - 1));
     tc_fence_after();
+    pair_sync();                               // hd 80: the last tile's bound exchange has been read by both threads
     xchg[hf][r] = make_float2(m_run, l_run);
     pair_sync();
     const float2 other = xchg[hf ^ 1][r];
-    const float m_all = fmaxf(m_run, other.x);
-    const float a_me = fast_exp2(m_run - m_all), a_ot = fast_exp2(other.x - m_all);
-    const float inv = 1.0f / (l_run * a_me + other.y * a_ot);
-    const float w_me = a_me * inv, w_ot = a_ot * inv;
+    float w_me, w_ot;
+    if (ONE_ACC) {                             // same reference in both halves: the sums simply add
+      w_me = 1.0f / (l_run + other.y);
+      w_ot = 0.f;
+    } else {
+      const float m_all = fmaxf(m_run, other.x);
+      const float a_me = fast_exp2(m_run - m_all), a_ot = fast_exp2(other.x - m_all);
+      const float inv = 1.0f / (l_run * a_me + other.y * a_ot);
+      w_me = a_me * inv; w_ot = a_ot * inv;
+    }
     const uint32_t tOot = hf ? tO : tO1;
     int dst_row = row0 + tq;
     if (p.out_row_map && tq < T) dst_row = __ldg(p.out_row_map + dst_row);
     const bool store = tq < T && dst_row >= 0;
     __nv_bfloat16* orow = p.out + static_cast<size_t>(store ? dst_row : 0) * p.D + colq;
-    constexpr int NC0 = (HD / 16 + 1) / 2;     // 16-column output chunks written by half 0
-    const int c_lo = hf ? NC0 : 0, c_hi = hf ? HD / 16 : NC0;
 #pragma unroll 1
     for (int c = c_lo; c < c_hi; ++c) {
       uint32_t o[16], o2[16];
       tmem_ld_32x32b_x16(tOme + lane_off + c * 16, o);
-      tmem_ld_32x32b_x16(tOot + lane_off + c * 16, o2);
+      if (!ONE_ACC) tmem_ld_32x32b_x16(tOot + lane_off + c * 16, o2);
       tmem_ld_wait();
       if (store) {
         float f[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(o[i]) * w_me + __uint_as_float(o2[i]) * w_ot;
+        for (int i = 0; i < 16; ++i)
+          f[i] = ONE_ACC ? __uint_as_float(o[i]) * w_me : __uint_as_float(o[i]) * w_me + __uint_as_float(o2[i]) * w_ot;
         uint4 w0 = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
                               pack_bf16x2(f[6], f[7]));
         uint4 w1 = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
