@@ -167,18 +167,32 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       tma_load_2d(sTabW + a * 16384, &tm_relw, bar(B_Q), a * 64, 0);
     }
     if (ONE_ACC) mbar_wait(bar(B_RELC), 0);   // the gather scratch / dead tables live where K / V land
-    for (int j = 0; j < n_kt; ++j) {
-      const int s = slot(j), vs = vslot(j);
-      mbar_wait(bar(B_KE + s), phase(j));     // phase 0 of the "empty" slots completes with the prologue MMAs
+    auto load_k = [&](int t) {
+      const int s = slot(t);
+      mbar_wait(bar(B_KE + s), phase(t));     // phase 0 of the "empty" slots completes with the prologue MMAs
       mbar_expect_tx(bar(B_KF + s), Cfg::KV_BYTES);
 #pragma unroll
       for (int a = 0; a < NA; ++a)
-        tma_load_2d(sK(s) + a * 8192, &tm_kv, bar(B_KF + s), colk + a * 64, row0 + j * 64);
-      mbar_wait(bar(B_VE + vs), vphase(j));
+        tma_load_2d(sK(s) + a * 8192, &tm_kv, bar(B_KF + s), colk + a * 64, row0 + t * 64);
+    };
+    auto load_v = [&](int t) {
+      const int vs = vslot(t);
+      mbar_wait(bar(B_VE + vs), vphase(t));
       mbar_expect_tx(bar(B_VF + vs), Cfg::KV_BYTES);
 #pragma unroll
       for (int a = 0; a < NA; ++a)
-        tma_load_2d(sV + vs * Cfg::KV_BYTES + a * 8192, &tm_kv, bar(B_VF + vs), colv + a * 64, row0 + j * 64);
+        tma_load_2d(sV + vs * Cfg::KV_BYTES + a * 8192, &tm_kv, bar(B_VF + vs), colv + a * 64, row0 + t * 64);
+    };
+    if (ONE_ACC) {
+      // single V stage: V_j can only be fetched once P V_{j-1} has drained it, so K runs one tile ahead of that wait
+      // (otherwise Q K_{j+1}^T - which only needs K - would sit behind V_j's wait and the second S tile buys nothing)
+      load_k(0);
+      for (int j = 0; j < n_kt; ++j) {
+        if (j + 1 < n_kt) load_k(j + 1);
+        load_v(j);
+      }
+    } else {
+      for (int j = 0; j < n_kt; ++j) { load_k(j); load_v(j); }
     }
   } else if (warp == 9 && lane == 0) {
     // ------------------------------------------------------------ MMA issuer (own warp: sharing the producer's
