@@ -223,10 +223,18 @@ vit_window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
 
     float m_run = -INFINITY, l_run = 0.f;
     const float scale2 = p.scale2;
+    // a warp whose 32 rows all lie past the sequence (rows 224..255 of the second query tile) has nothing to compute:
+    // it only keeps the barrier protocol going (its TMEM lanes hold whatever Q K^T left there; they are never stored)
+    const bool dead_warp = q0 + warp * 32 >= T;
 #pragma unroll
     for (int j = 0; j < NKT; ++j) {
       mbar_wait(bar(B_SF), j & 1);
       tc_fence_after();
+      if (dead_warp) {
+        tc_fence_before();
+        mbar_arrive(bar(B_PF));
+        continue;
+      }
       // upper bound of the tile's scores from the raw accumulator maximum (scale2 > 0)
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
