@@ -83,11 +83,13 @@ int rsp_vit_attention_simt(const void* qkv, const void* rel_h, const void* rel_w
 /* LayerNorm over the last dim of [rows, C] (+ optional GELU), fp32 statistics.
  * src_map (int32 [rows_out], NULL = identity): out row i is LN(in[src_map[i]]), or zeros when
  * src_map[i] < 0 -- window_partition's zero padding after LN1 (HF:959-962, HF:900-922).
+ * copy_out (bf16 [rows_in, ld_copy] or NULL, fp32 input only): every source row read is also written back as bf16 -
+ * the hidden states RSFeatureAggregator consumes (M:1046-1050) leave the encoder without a separate cast pass.
  * Replaces nn.LayerNorm (HF:894-896), SamLayerNorm channels_first (HF:147-170), mmpretrain
  * LayerNorm2d (norm.py:64-89) and LN2d (M:33-50) on channels-last data. */
 int rsp_layernorm(const void* in, int in_fp32, int ld_in, void* out, int out_fp32, int ld_out,
                   const float* gamma, const float* beta, const int32_t* src_map, int rows_out, int C,
-                  float eps, int act, void* stream);
+                  float eps, int act, void* copy_out, int ld_copy, void* stream);
 
 /* out = LayerNorm(x + residual) over bf16 rows of C <= 256 channels (fp32 statistics): x bf16 [rows, C];
  * residual fp32 or bf16 [*, C], optionally block-mapped as in rsp_gemm_bf16_ex.  The

@@ -53,7 +53,7 @@ _SIGNATURES = {
     "rsp_vit_attention": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "rsp_vit_attention_scatter": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "rsp_vit_attention_simt": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
-    "rsp_layernorm": ([_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _f, _i, _vp], _i),
+    "rsp_layernorm": ([_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _i, _vp], _i),
     "rsp_patchify16": ([_vp, _vp, _i, _i, _i, _vp], _i),
     "rsp_layernorm_add": ([_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, ctypes.c_longlong, _i, _f, _vp], _i),
     "rsp_im2col_nhwc": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
@@ -464,10 +464,15 @@ def vit_attention_generic(qkv: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.T
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *,
               out: torch.Tensor | None = None, out_dtype: torch.dtype = torch.bfloat16,
-              src_map: torch.Tensor | None = None, gelu: bool = False) -> torch.Tensor:
-    """Row LayerNorm of x [rows, C] (fp32 or bf16); optional gather map (-1 -> zero row)."""
+              src_map: torch.Tensor | None = None, gelu: bool = False,
+              copy_out: torch.Tensor | None = None) -> torch.Tensor:
+    """Row LayerNorm of x [rows, C] (fp32 or bf16); optional gather map (-1 -> zero row); copy_out (bf16, same shape
+    as x, fp32 x only) also receives a bf16 copy of every source row read."""
     global launch_count
-    _require_cuda(x, gamma, beta, out, src_map)
+    _require_cuda(x, gamma, beta, out, src_map, copy_out)
+    if copy_out is not None:
+        assert x.dtype == torch.float32 and copy_out.dtype == torch.bfloat16 and copy_out.shape == x.shape
+        assert copy_out.stride(1) == 1
     assert x.dim() == 2 and x.stride(1) == 1 and x.dtype in (torch.float32, torch.bfloat16)
     C = x.shape[1]
     assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
@@ -480,7 +485,8 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     assert out.shape == (rows_out, C) and out.stride(1) == 1
     _check(_lib.rsp_layernorm(_ptr(x), int(x.dtype == torch.float32), x.stride(0), _ptr(out),
                               int(out.dtype == torch.float32), out.stride(0), _ptr(gamma), _ptr(beta),
-                              _ptr(src_map), rows_out, C, float(eps), int(gelu), _stream()),
+                              _ptr(src_map), rows_out, C, float(eps), int(gelu), _ptr(copy_out),
+                              copy_out.stride(0) if copy_out is not None else 0, _stream()),
            "rsp_layernorm")
     launch_count += 1
     return out

@@ -97,8 +97,9 @@ int rsp_split_heads(const void* in, int ld, int col0, int H, int hd, int n_seq, 
 
 int rsp_layernorm(const void* in, int in_fp32, int ld_in, void* out, int out_fp32, int ld_out,
                   const float* gamma, const float* beta, const int32_t* src_map, int rows_out, int C,
-                  float eps, int act, void* stream) {
+                  float eps, int act, void* copy_out, int ld_copy, void* stream) {
   LayerNormArgs a;
+  a.copy_out = copy_out; a.ld_copy = ld_copy;
   a.in = in; a.in_fp32 = in_fp32; a.ld_in = ld_in; a.out = out; a.out_fp32 = out_fp32;
   a.ld_out = ld_out; a.gamma = gamma; a.beta = beta; a.src_map = src_map; a.rows_out = rows_out;
   a.C = C; a.eps = eps; a.act = act;

@@ -29,7 +29,8 @@ __global__ void layernorm_rows_kernel(const TIn* __restrict__ in, TOut* __restri
                                       const float* __restrict__ gamma,
                                       const float* __restrict__ beta,
                                       const int* __restrict__ src_map, int rows_out, int C,
-                                      int ld_in, int ld_out, float eps, int act) {
+                                      int ld_in, int ld_out, float eps, int act,
+                                      __nv_bfloat16* __restrict__ copy_out, int ld_copy) {
   const int warps_per_block = blockDim.x >> 5;
   const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -53,6 +54,9 @@ __global__ void layernorm_rows_kernel(const TIn* __restrict__ in, TOut* __restri
       if (sizeof(TIn) == 4) {
         const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + c);
         v[i][0] = f.x; v[i][1] = f.y; v[i][2] = f.z; v[i][3] = f.w;
+        if (copy_out)      // bf16 copy of the un-normalised source row (every source row occurs once in a window map)
+          *reinterpret_cast<uint2*>(copy_out + static_cast<size_t>(src) * ld_copy + c) =
+              make_uint2(pack_bf16x2(f.x, f.y), pack_bf16x2(f.z, f.w));
       } else {
         const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + c);
         const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
@@ -110,15 +114,15 @@ static int launch_ln(const LayerNormArgs& a, cudaStream_t stream) {
   if (a.C <= 32 * 4 * 2) {
     layernorm_rows_kernel<TIn, TOut, 2><<<blocks, warps * 32, 0, stream>>>(
         static_cast<const TIn*>(a.in), static_cast<TOut*>(a.out), a.gamma, a.beta, a.src_map,
-        a.rows_out, a.C, a.ld_in, a.ld_out, a.eps, a.act);
+        a.rows_out, a.C, a.ld_in, a.ld_out, a.eps, a.act, static_cast<__nv_bfloat16*>(a.copy_out), a.ld_copy);
   } else if (a.C <= 32 * 4 * 6) {
     layernorm_rows_kernel<TIn, TOut, 6><<<blocks, warps * 32, 0, stream>>>(
         static_cast<const TIn*>(a.in), static_cast<TOut*>(a.out), a.gamma, a.beta, a.src_map,
-        a.rows_out, a.C, a.ld_in, a.ld_out, a.eps, a.act);
+        a.rows_out, a.C, a.ld_in, a.ld_out, a.eps, a.act, static_cast<__nv_bfloat16*>(a.copy_out), a.ld_copy);
   } else {
     layernorm_rows_kernel<TIn, TOut, 10><<<blocks, warps * 32, 0, stream>>>(
         static_cast<const TIn*>(a.in), static_cast<TOut*>(a.out), a.gamma, a.beta, a.src_map,
-        a.rows_out, a.C, a.ld_in, a.ld_out, a.eps, a.act);
+        a.rows_out, a.C, a.ld_in, a.ld_out, a.eps, a.act, static_cast<__nv_bfloat16*>(a.copy_out), a.ld_copy);
   }
   RSP_CHECK_LAUNCH();
   return RSP_OK;
@@ -128,6 +132,7 @@ int layernorm_rows(const LayerNormArgs& a, cudaStream_t stream) {
   RSP_CHECK_ARG(a.in && a.out && a.gamma && a.beta, "layernorm: null pointer");
   RSP_CHECK_ARG(a.rows_out > 0 && a.C > 0 && a.C % 4 == 0 && a.C <= 1280, "layernorm: C=%d", a.C);
   RSP_CHECK_ARG(a.ld_in % 4 == 0 && a.ld_out % 4 == 0, "layernorm: ld must be multiple of 4");
+  RSP_CHECK_ARG(!a.copy_out || (a.in_fp32 && a.ld_copy % 4 == 0 && a.ld_copy >= a.C), "layernorm: copy_out needs fp32 input");
   if (a.in_fp32 && !a.out_fp32) return launch_ln<float, __nv_bfloat16>(a, stream);
   if (a.in_fp32 && a.out_fp32) return launch_ln<float, float>(a, stream);
   if (!a.in_fp32 && !a.out_fp32) return launch_ln<__nv_bfloat16, __nv_bfloat16>(a, stream);

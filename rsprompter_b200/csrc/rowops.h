@@ -13,6 +13,8 @@ struct LayerNormArgs {
   float eps = 1e-6f;
   int act = 0;                  // 1 = GELU(erf) after the affine
   int in_fp32 = 1, out_fp32 = 0;
+  void* copy_out = nullptr;     // optional bf16 [rows_in, ld_copy]: bf16 copy of every source row read (fp32 input only)
+  int ld_copy = 0;
 };
 
 int layernorm_rows(const LayerNormArgs& a, cudaStream_t stream);

@@ -75,7 +75,12 @@ class _SamDetectorBase(BaseModule):
         """-> (emb_rows fp32 [B*g*g, C], pos_rows fp32 [g*g, C], (g, g), emb_nhwc_bf16 | None, hidden | None)."""
         enc = self.backbone.vision_encoder
         want_hidden = not isinstance(self.backbone, MMPretrainSamVisionEncoder)
-        emb, hidden, emb_nhwc = enc.encode(batch_inputs, want_hidden=want_hidden)
+        # hidden states the aggregator reads leave the encoder as bf16 side outputs of the next layer's LN1
+        sel = getattr(getattr(self.neck, "feature_aggregator", None), "select_layers", None)
+        copies = {int(i): None for i in sel if int(i) < enc.arch.num_layers} if (want_hidden and sel is not None) else None
+        emb, hidden, emb_nhwc = enc.encode(batch_inputs, want_hidden=want_hidden, bf16_copies=copies)
+        if copies:
+            hidden = tuple(copies.get(i, h) if copies.get(i) is not None else h for i, h in enumerate(hidden))
         B, g = emb_nhwc.shape[0], emb_nhwc.shape[1]
         pos_rows = self.shared_image_embedding.shared_image_embedding.image_wide_rows(g)
         return emb_nhwc.reshape(B * g * g, -1), pos_rows, (g, g), emb_nhwc, hidden

@@ -202,8 +202,10 @@ class SamVisionEncoderB200(nn.Module):
 
     # ---------------------------------------------------------------- forward
     @torch.no_grad()
-    def encode(self, pixel_values: torch.Tensor, want_hidden: bool = True):
-        """Returns (embeddings fp32 [B,C,g,g], [hidden_states fp32 [B,g,g,D]] * (L+1))."""
+    def encode(self, pixel_values: torch.Tensor, want_hidden: bool = True, bf16_copies: dict | None = None):
+        """Returns (embeddings fp32 [B,C,g,g], [hidden_states fp32 [B,g,g,D]] * (L+1), embeddings NHWC).
+        bf16_copies: dict whose keys are hidden-state indices i < L; on return bf16_copies[i] is a bf16 [B,g,g,D] copy
+        of hidden_states[i], written by layer i's LN1 kernel while it reads that state (no separate cast pass)."""
         a = self.arch
         if pixel_values.dim() != 4 or pixel_values.shape[1] != 3:
             raise ValueError("Make sure that the channel dimension of the pixel values match with the "
@@ -233,13 +235,17 @@ class SamVisionEncoderB200(nn.Module):
         ws = a.window_size
         for i, lw in enumerate(p["layers"]):
             is_global = i in a.global_attn_indexes
+            cp = None
+            if bf16_copies is not None and i in bf16_copies:
+                cp = torch.empty(M, D, device=x.device, dtype=torch.bfloat16)
+                bf16_copies[i] = cp.view(B, g, g, D)
             if is_global:
-                xn = _lib.layernorm(h, lw["ln1_w"], lw["ln1_b"], a.layer_norm_eps)
+                xn = _lib.layernorm(h, lw["ln1_w"], lw["ln1_b"], a.layer_norm_eps, copy_out=cp)
                 qkv = _lib.gemm(xn, lw["qkv_w"], lw["qkv_b"])
                 att = _lib.vit_attention(qkv, lw["rel_h"], lw["rel_w"], B, g, H, hd)
                 x1 = _lib.gemm(att, lw["proj_w"], lw["proj_b"], residual=h, out_dtype=torch.float32)
             else:
-                xn = _lib.layernorm(h, lw["ln1_w"], lw["ln1_b"], a.layer_norm_eps, src_map=wmap)
+                xn = _lib.layernorm(h, lw["ln1_w"], lw["ln1_b"], a.layer_norm_eps, src_map=wmap, copy_out=cp)
                 qkv = _lib.gemm(xn, lw["qkv_w"], lw["qkv_b"])
                 # window_unpartition + crop happen in the attention store: the projection is a plain GEMM
                 att = _lib.vit_attention(qkv, lw["rel_h"], lw["rel_w"], B * n_win, ws, H, hd, out_row_map=wmap,
