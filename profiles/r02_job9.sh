@@ -1,0 +1,8 @@
+set -x
+mkdir -p gpurun_out
+timeout 2400 python -m pytest tests/ -q -m gpu 2>&1 | tail -30 > gpurun_out/r02_j9_pytest.log
+tail -6 gpurun_out/r02_j9_pytest.log
+RSP_BENCH_SKIP_CPU=1 timeout 900 python bench.py 2> gpurun_out/r02_j9_bench_n1.err | tail -1 > gpurun_out/r02_j9_bench_query_vith_n1.json
+RSP_BENCH_SKIP_CPU=1 timeout 600 python bench.py --config anchor_vitb 2> gpurun_out/r02_j9_bench_anchor.err | tail -1 > gpurun_out/r02_j9_bench_anchor_vitb_n1.json
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_j9_smoke.log 2>&1; tail -2 gpurun_out/r02_j9_smoke.log
+for f in gpurun_out/r02_j9_bench_*.json; do echo $f; cut -c1-200 $f; echo; done
