@@ -54,9 +54,6 @@ __global__ void layernorm_rows_kernel(const TIn* __restrict__ in, TOut* __restri
       if (sizeof(TIn) == 4) {
         const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + c);
         v[i][0] = f.x; v[i][1] = f.y; v[i][2] = f.z; v[i][3] = f.w;
-        if (copy_out)      // bf16 copy of the un-normalised source row (every source row occurs once in a window map)
-          *reinterpret_cast<uint2*>(copy_out + static_cast<size_t>(src) * ld_copy + c) =
-              make_uint2(pack_bf16x2(f.x, f.y), pack_bf16x2(f.z, f.w));
       } else {
         const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + c);
         const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
@@ -65,6 +62,16 @@ __global__ void layernorm_rows_kernel(const TIn* __restrict__ in, TOut* __restri
         v[i][2] = __bfloat162float(b.x); v[i][3] = __bfloat162float(b.y);
       }
       sum += v[i][0] + v[i][1] + v[i][2] + v[i][3];
+    }
+  }
+  if (sizeof(TIn) == 4 && copy_out) {
+    // bf16 copy of the un-normalised source row (every source row occurs once in a window map); after ALL loads
+    // have been issued, so the stores do not break up the batch of outstanding loads
+    __nv_bfloat16* cp = copy_out + static_cast<size_t>(src) * ld_copy;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < C) *reinterpret_cast<uint2*>(cp + c) = make_uint2(pack_bf16x2(v[i][0], v[i][1]), pack_bf16x2(v[i][2], v[i][3]));
     }
   }
 #pragma unroll
