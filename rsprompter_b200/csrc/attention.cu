@@ -543,9 +543,8 @@ int vit_attention(const AttentionArgs& a, cudaStream_t stream) {
   if (a.S != 14 && a.S != 32 && a.S != 64)   // other grids (768^2 / 1280^2 inputs): CUDA-core kernel
     return vit_attention_simt(a, stream);
   if (a.S == 14 && (a.hd == 64 || a.hd == 80)) {
-    static const bool old_path = getenv("RSP_ATT_WINDOW_GENERIC") != nullptr;   // A/B switches for the self-test
-    static const bool rounds = getenv("RSP_ATT_WINDOW_ROUNDS") != nullptr;      // first window kernel (key rounds)
-    if (!old_path) return rounds ? vit_window_attention(a, stream) : vit_window_attention2(a, stream);
+    static const bool old_path = getenv("RSP_ATT_WINDOW_GENERIC") != nullptr;   // A/B switch for the self-test
+    if (!old_path) return vit_window_attention(a, stream);
   }
   if (a.hd == 64) {
     if (a.S == 64) return launch_att<64, 64>(a, stream);
