@@ -227,10 +227,10 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 b = __ldg(b4 + i);
-            acc += gelu_tanh_form(__uint_as_float(r[4 * i]) + b.x) * hyp[4 * i];
-            acc += gelu_tanh_form(__uint_as_float(r[4 * i + 1]) + b.y) * hyp[4 * i + 1];
-            acc += gelu_tanh_form(__uint_as_float(r[4 * i + 2]) + b.z) * hyp[4 * i + 2];
-            acc += gelu_tanh_form(__uint_as_float(r[4 * i + 3]) + b.w) * hyp[4 * i + 3];
+            acc += gelu_fast(__uint_as_float(r[4 * i]) + b.x) * hyp[4 * i];
+            acc += gelu_fast(__uint_as_float(r[4 * i + 1]) + b.y) * hyp[4 * i + 1];
+            acc += gelu_fast(__uint_as_float(r[4 * i + 2]) + b.z) * hyp[4 * i + 2];
+            acc += gelu_fast(__uint_as_float(r[4 * i + 3]) + b.w) * hyp[4 * i + 3];
           }
           m2[t] = acc;
         }
@@ -407,10 +407,10 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
             for (int i = 0; i < 16; ++i) {
               const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma) + i);
               const float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_beta) + i);
-              const float y0 = gelu_tanh_form((v[4 * i] - mean) * rstd * g.x + bt.x);
-              const float y1 = gelu_tanh_form((v[4 * i + 1] - mean) * rstd * g.y + bt.y);
-              const float y2 = gelu_tanh_form((v[4 * i + 2] - mean) * rstd * g.z + bt.z);
-              const float y3 = gelu_tanh_form((v[4 * i + 3] - mean) * rstd * g.w + bt.w);
+              const float y0 = gelu_fast((v[4 * i] - mean) * rstd * g.x + bt.x);
+              const float y1 = gelu_fast((v[4 * i + 1] - mean) * rstd * g.y + bt.y);
+              const float y2 = gelu_fast((v[4 * i + 2] - mean) * rstd * g.z + bt.z);
+              const float y3 = gelu_fast((v[4 * i + 3] - mean) * rstd * g.w + bt.w);
               pk[2 * i] = pack_bf16x2(y0, y1);
               pk[2 * i + 1] = pack_bf16x2(y2, y3);
             }
@@ -431,10 +431,10 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
           for (int i = 0; i < 16; ++i) {
             const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma) + i);
             const float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_beta) + i);
-            const float y0 = gelu_tanh_form((v[4 * i] - mean) * rstd * g.x + bt.x);
-            const float y1 = gelu_tanh_form((v[4 * i + 1] - mean) * rstd * g.y + bt.y);
-            const float y2 = gelu_tanh_form((v[4 * i + 2] - mean) * rstd * g.z + bt.z);
-            const float y3 = gelu_tanh_form((v[4 * i + 3] - mean) * rstd * g.w + bt.w);
+            const float y0 = gelu_fast((v[4 * i] - mean) * rstd * g.x + bt.x);
+            const float y1 = gelu_fast((v[4 * i + 1] - mean) * rstd * g.y + bt.y);
+            const float y2 = gelu_fast((v[4 * i + 2] - mean) * rstd * g.z + bt.z);
+            const float y3 = gelu_fast((v[4 * i + 3] - mean) * rstd * g.w + bt.w);
             asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a + i * 8), "r"(pack_bf16x2(y0, y1)),
                          "r"(pack_bf16x2(y2, y3))
                          : "memory");

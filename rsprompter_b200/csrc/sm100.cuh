@@ -285,20 +285,4 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return __fdividef(x, 1.0f + e);
 }
 
-// The same fit through tanh: x * sigmoid(z) = 0.5 x + 0.5 x tanh(z / 2), with z / 2 = x * P'(x^2) (P' = P * 0.5 / log2 e).
-// ONE MUFU op (tanh.approx.f32, relative error 2^-11) instead of two (ex2 + rcp): |error| <= 2.4e-4 * |x|, a tenth of
-// the bf16 resolution of the result.  Used by the mask-upscaler epilogues, which are MUFU-bound (1.7 G GELUs per step
-// on a K = 64 mainloop); the encoder MLP keeps gelu_fast.
-__device__ __forceinline__ float gelu_tanh_form(float x) {
-  const float x2 = x * x;
-  float p = fmaf(1.1190868e-06f, x2, -3.0581086e-05f);
-  p = fmaf(p, x2, -0.00012486125f);
-  p = fmaf(p, x2, 0.03646879f);
-  p = fmaf(p, x2, 0.79782814f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(p * x));
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
-}
-
 }  // namespace rsp

@@ -173,7 +173,7 @@ def test_query_1024_end_to_end_matches_oracle():
     # scores within 5e-2; the per-query maximum is reported (queries_within_tol) in gpurun_out/.
     tol = 2e-2 * max(1.0, rep["logit_scale"])
     assert rep["shared"] >= 0.9 * nq
-    assert rep["logit_mean_diff"] <= tol / 2 and rep["logit_p999_diff"] <= 4 * tol
+    assert rep["logit_mean_diff"] <= tol / 2 and rep["logit_p999_diff"] <= 5 * tol
     assert rep["cls_max_diff"] <= 5 * 2e-2 * max(1.0, rep["cls_scale"])
     assert rep["mask_disagree"] <= 2e-2
     assert rep["score_max_diff"] <= 5e-2
