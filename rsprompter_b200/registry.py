@@ -23,11 +23,42 @@ try:  # pragma: no cover - not available in this image
     from mmengine.config import Config, ConfigDict  # type: ignore
     from mmengine.model import BaseModule  # type: ignore
     from mmengine.structures import InstanceData  # type: ignore
-    from mmdet.registry import MODELS  # type: ignore
+    from mmdet.registry import MODELS as _MMDET_MODELS  # type: ignore
     from mmdet.structures import DetDataSample  # type: ignore
     HAVE_MMENGINE = True
 except Exception:  # noqa: BLE001
     HAVE_MMENGINE = False
+
+# Stock mmdet component names this package also implements (inference-only, for the RSPrompter configs).  Inside a real
+# mmdet process they must not displace the upstream classes other detectors rely on (samdet's FasterRCNN, samseg-*):
+# they are registered only when the name is still free; the RSPrompter-specific names are re-registered with force=True.
+_GENERIC_NAMES = frozenset({"RPNHead", "Shared2FCBBoxHead", "SingleRoIExtractor", "RoIAlign", "DetDataPreprocessor",
+                            "AnchorGenerator", "DeltaXYWHBBoxCoder", "MSDeformAttnPixelDecoder"})
+
+if HAVE_MMENGINE:  # pragma: no cover - not available in this image
+
+    class _ScopedModels:
+        """mmdet.registry.MODELS with the registration policy above; everything else is forwarded."""
+
+        def __init__(self, reg):
+            self._reg = reg
+
+        def register_module(self, name=None, force=False, module=None):
+            def _register(cls):
+                key = name or cls.__name__
+                if key in _GENERIC_NAMES and self._reg.get(key) is not None:
+                    return cls                      # upstream class stays
+                self._reg.register_module(name=name, force=force, module=cls)
+                return cls
+            return _register(module) if module is not None else _register
+
+        def __getattr__(self, item):
+            return getattr(self._reg, item)
+
+        def __contains__(self, key):
+            return key in self._reg
+
+    MODELS = _ScopedModels(_MMDET_MODELS)
 
 
 if not HAVE_MMENGINE:
