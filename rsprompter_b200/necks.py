@@ -78,11 +78,16 @@ def fold_bn(w: torch.Tensor, b: torch.Tensor | None, bn: _BN | None):
     return w, b
 
 
-def prep_conv(w: torch.Tensor, b: torch.Tensor | None, bn: _BN | None = None, pad_out: int = 0):
-    """[Cout, Cin, kh, kw] -> bf16 [Cout(+pad), kh*kw*Cin] (tap-major to match im2col) + fp32 bias."""
+def prep_conv(w: torch.Tensor, b: torch.Tensor | None, bn: _BN | None = None, pad_out: int = 0, pad_in: int = 0):
+    """[Cout, Cin, kh, kw] -> bf16 [Cout(+pad), kh*kw*Cin(+pad)] (tap-major to match im2col) + fp32 bias.
+    pad_in / pad_out: zero input / output channels up to that count (the padded output channels stay exactly 0 through
+    bias-free ReLU stacks, which lets 32-channel maps ride in 64-channel buffers = one TMA swizzle atom)."""
     w, b = fold_bn(w, b, bn)
     co = w.shape[0]
-    wg = w.permute(0, 2, 3, 1).reshape(co, -1)
+    wp = w.permute(0, 2, 3, 1)                               # [co, kh, kw, ci]
+    if pad_in > wp.shape[3]:
+        wp = torch.cat([wp, wp.new_zeros(*wp.shape[:3], pad_in - wp.shape[3])], dim=3)
+    wg = wp.reshape(co, -1)
     if pad_out > co:
         wg = torch.cat([wg, wg.new_zeros(pad_out - co, wg.shape[1])])
         b = torch.cat([b, b.new_zeros(pad_out - co)])
@@ -200,13 +205,18 @@ class RSFeatureAggregator(_PrepMixin, BaseModule):
 
     @torch.no_grad()
     def _prepare(self):
+        # the 32 hidden channels ride in 64-channel maps (upper half exactly zero): 64 bf16 = one 128-byte swizzle atom,
+        # so the 3x3 convs take the implicit-GEMM path (4-D TMA taps) instead of im2col + GEMM
+        hc = self.downconvs[0][3].weight.shape[0]
+        hp = (hc + 63) // 64 * 64
         p = {"down": [], "hid": []}
         for d in self.downconvs:
-            p["down"].append((prep_conv(d[0].weight, d[0].bias, d[1]), prep_conv(d[3].weight, d[3].bias, d[4])))
+            p["down"].append((prep_conv(d[0].weight, d[0].bias, d[1], pad_out=hp),
+                              prep_conv(d[3].weight, d[3].bias, d[4], pad_out=hp, pad_in=hp)))
         for h in self.hidden_convs:
-            p["hid"].append(prep_conv(h[0].weight, h[0].bias, h[1]))
+            p["hid"].append(prep_conv(h[0].weight, h[0].bias, h[1], pad_out=hp, pad_in=hp))
         f = self.fusion_conv
-        p["fus"] = (prep_conv(f[0].weight, f[0].bias, f[1]), prep_conv(f[3].weight, f[3].bias, f[4]),
+        p["fus"] = (prep_conv(f[0].weight, f[0].bias, f[1], pad_in=hp), prep_conv(f[3].weight, f[3].bias, f[4]),
                     prep_conv(f[6].weight, f[6].bias, None))
         self._prep = p
         return p

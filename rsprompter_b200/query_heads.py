@@ -304,11 +304,26 @@ class RSMask2FormerHead(_PrepMixin, BaseModule):
             self._const[key] = out
         return self._const[key]
 
-    def _mlp(self, x_bf: torch.Tensor, layers: list, out_dtype=torch.bfloat16) -> torch.Tensor:
+    def _mlp(self, x_bf: torch.Tensor, layers: list, out_dtype=torch.bfloat16, out=None, row_map=None) -> torch.Tensor:
         h = x_bf
         for w, b in layers[:-1]:
             h = _lib.gemm(h, w, b, act="relu")
+        if out is not None:
+            return _lib.gemm(h, *layers[-1], out=out, row_map=row_map)
         return _lib.gemm(h, *layers[-1], out_dtype=out_dtype)
+
+    def _padded_queries(self, B: int, nq: int, C: int, device):
+        """Per-image 128-row blocks for the grouped  mask_embed x mask_feature  products (one launch for all images):
+        -> (zero-initialised bf16 [B*128, C] buffer, scatter map compact row -> padded row, map padded -> compact / -1)."""
+        key = ("mepad", B, nq, C, str(device))
+        if key not in self._const:
+            q = torch.arange(nq, device=device, dtype=torch.int32)
+            b = torch.arange(B, device=device, dtype=torch.int32)
+            scat = (b.view(B, 1) * 128 + q.view(1, nq)).reshape(-1).contiguous()
+            back = torch.full((B, 128), -1, device=device, dtype=torch.int32)
+            back[:, :nq] = b.view(B, 1) * nq + q.view(1, nq)
+            self._const[key] = (torch.zeros(B * 128, C, device=device, dtype=torch.bfloat16), scat, back.reshape(-1).contiguous())
+        return self._const[key]
 
     @torch.no_grad()
     def forward_nhwc(self, feats: list, emb_rows: torch.Tensor, pos_rows: torch.Tensor, emb_hw: tuple,
@@ -328,17 +343,30 @@ class RSMask2FormerHead(_PrepMixin, BaseModule):
         # the intermediate layers only ever need level-sized logits, never the H0 x W0 maps (M:386-392)
         mf_lvl = [_lib.resize_bilinear_nhwc(mask_feature, s).view(B, s[0] * s[1], -1) for s in shapes]
 
+        grouped = nq <= 128
+        if grouped:
+            me_pad, scat, back = self._padded_queries(B, nq, self.out_channels, mask_feature.device)
+
         def head(qf32: torch.Tensor, lvl: int, final: bool):
             x = _lib.layernorm(qf32, *p["post"], 1e-5)                                    # post_norm -> bf16
-            me = self._mlp(x, p["mask"])                                                  # [B*nq, 256]
+            if grouped:      # mask_embed rows of image b land in rows [128 b, 128 b + nq) of a zero-padded buffer
+                self._mlp(x, p["mask"], out=me_pad, row_map=scat)
+                me_of = lambda b: me_pad[b * 128:b * 128 + nq]  # noqa: E731
+            else:
+                me = self._mlp(x, p["mask"])                                              # [B*nq, 256]
+                me_of = lambda b: me[b * nq:(b + 1) * nq]  # noqa: E731
             if not final:
-                logits = torch.empty(B * nq, mf_lvl[lvl].shape[1], device=x.device, dtype=torch.float32)
-                for b in range(B):
-                    _lib.gemm(me[b * nq:(b + 1) * nq], mf_lvl[lvl][b], None, out=logits[b * nq:(b + 1) * nq])
+                hw_l = mf_lvl[lvl].shape[1]
+                logits = torch.empty(B * nq, hw_l, device=x.device, dtype=torch.float32)
+                if grouped:  # one grouped GEMM for all images: row block b multiplies its own image's features
+                    _lib.gemm_grouped(me_pad, mf_lvl[lvl].reshape(B * hw_l, -1), logits, hw_l, 128, hw_l, row_map=back)
+                else:
+                    for b in range(B):
+                        _lib.gemm(me_of(b), mf_lvl[lvl][b], None, out=logits[b * nq:(b + 1) * nq])
                 return _lib.attn_mask_bits(logits), None, None, None
             mpp = torch.empty(B, nq, H0 * W0, device=x.device, dtype=torch.float32)
             for b in range(B):                                                            # einsum 'bqc,bchw->bqhw'
-                _lib.gemm(me[b * nq:(b + 1) * nq], mf_rows[b], None, out=mpp[b])
+                _lib.gemm(me_of(b), mf_rows[b], None, out=mpp[b])
             cls = self._mlp(x, p["cls"], out_dtype=torch.float32)
             pts = self._mlp(x, p["pts"], out_dtype=torch.float32).view(B * nq, self.per_pointset_point, -1)
             sparse = _lib.sin_fold(pts.contiguous()) if self.with_sincos else pts
