@@ -75,3 +75,23 @@ def test_reference_query_configs_build(name, enc_cls, nq):
     sd = synthetic.query_detector_state_dict(arch, 10, 0 if pseudo else 6, nq=nq, seed=0, pseudo_neck=pseudo)
     assert set(model.state_dict()) == set(sd)
     model.load_state_dict(sd, strict=True)
+
+
+def test_reference_samdet_config_builds_the_segmentor():
+    """configs/rsprompter/samdet-nwpu.py: type SAMDet with a stock mmdet FasterRCNN detector (outside this package) and
+    an RSSamModel segmentor (SURVEY 8(f4), M:718-741, 1060-1215): the segmentor entry builds the B200 SamModel
+    (ViT-B: samdet-nwpu.py:25 points at sam_vit_base) with HF SamModel's parameter names; SAMDet is in the registry."""
+    from rsprompter_b200.registry import MODELS, Config
+    cfg = Config.fromfile(os.path.join(REF_CFG, "samdet-nwpu.py"))
+    m = cfg.to_dict()["model"]
+    assert m["type"] == "SAMDet" and MODELS.get("SAMDet") is not None
+    assert m["segmentor"]["type"] == "RSSamModel" and m["detector"]["type"] == "FasterRCNN"
+    seg = MODELS.build(_strip_init(dict(m["segmentor"])))
+    sam = seg.sam_model
+    assert sam.varch.name == "base" and sam.varch.num_layers == 12
+    keys = set(sam.state_dict())
+    for k in ("vision_encoder.layers.11.attn.qkv.weight", "prompt_encoder.point_embed.3.weight",
+              "prompt_encoder.shared_embedding.positional_embedding", "shared_image_embedding.positional_embedding",
+              "mask_decoder.transformer.layers.1.cross_attn_image_to_token.out_proj.weight",
+              "mask_decoder.output_hypernetworks_mlps.3.proj_out.weight"):
+        assert k in keys, k
