@@ -8,6 +8,7 @@ Configs (BASELINE.json `configs`):
     query_vith   (default) configs[2] / [3]: RSPrompter-query ViT-H bf16, bs 8 per GPU, 1024^2, 100 queries
     anchor_vitb            configs[1]:       RSPrompter-anchor ViT-B bf16, bs 8 per GPU, 1024^2
     anchor_vith, query_vitb                  the other two pairings
+    maskrcnn_vitb          SAMSegMaskRCNN ViT-B (SAM encoder + RSFPN + stock Mask R-CNN heads), bs 8 per GPU, 1024^2
     encoder_vith           configs[4]:       SAM ViT-H encoder only at --size {512,768,1024,1280}
 
 A step is one full pass of one batch: uint8 images -> DetDataPreprocessor (fused into the patch-embed loader) -> SAM
@@ -49,6 +50,8 @@ CONFIGS = {
                         workload=f"RSPrompter-anchor ViT-H bf16, bs={BATCH}/GPU, {SIZE}x{SIZE} synthetic"),
     "query_vitb": dict(variant="query", arch="base",
                        workload=f"RSPrompter-query ViT-B bf16, bs={BATCH}/GPU, {SIZE}x{SIZE} synthetic, {NQ} queries"),
+    "maskrcnn_vitb": dict(variant="maskrcnn", arch="base",
+                          workload=f"SAM-seg Mask R-CNN ViT-B bf16 (SAMSegMaskRCNN), bs={BATCH}/GPU, {SIZE}x{SIZE} synthetic"),
     "encoder_vith": dict(variant="encoder", arch="huge",
                          workload="SAM-seg ViT-H encoder only (MMPretrainSamVisionEncoder), bs=%d/GPU, {S}x{S} synthetic "
                                   "(BASELINE.json configs[4])" % BATCH),
@@ -179,6 +182,10 @@ def _oracle_setup(args):
         from oracle import restate_anchor as ra
         sd = synthetic.anchor_detector_state_dict(arch, NUM_CLASSES, len(sel), seed=0)
         return lambda x: ra.anchor_predict(sd, arch, darch, x, NUM_CLASSES, sel)
+    if c["variant"] == "maskrcnn":
+        from oracle import restate_anchor as ra
+        sd = synthetic.maskrcnn_detector_state_dict(arch, NUM_CLASSES, len(sel), seed=0)
+        return lambda x: ra.maskrcnn_predict(sd, arch, x, NUM_CLASSES, sel)
     if c["variant"] == "query":
         from oracle import restate_query as rq
         sd = synthetic.query_detector_state_dict(arch, NUM_CLASSES, len(sel), nq=NQ, seed=0)
@@ -378,6 +385,9 @@ def run_ours(args) -> None:
         if variant == "anchor":
             cfg = model_configs.anchor_model_cfg(arch_name, NUM_CLASSES)
             sd = synthetic.anchor_detector_state_dict(arch, NUM_CLASSES, n_sel, seed=0)
+        elif variant == "maskrcnn":
+            cfg = model_configs.maskrcnn_model_cfg(arch_name, NUM_CLASSES)
+            sd = synthetic.maskrcnn_detector_state_dict(arch, NUM_CLASSES, n_sel, seed=0)
         else:
             cfg = model_configs.query_model_cfg(arch_name, NUM_CLASSES, prompt_shape=(NQ, 5))
             sd = synthetic.query_detector_state_dict(arch, NUM_CLASSES, n_sel, nq=NQ, seed=0)

@@ -310,6 +310,13 @@ int rsp_query_postprocess_bits(const float* logits, const int32_t* sel, const fl
  * (anchor variant, M:1758-1780 when ori_shape == batch shape). */
 int rsp_mask_paste_bits(const float* maps, uint8_t* bits, int n, int hm, int wm, float thr, int mode, void* stream);
 
+/* FCNMaskHead mask paste (SAMSegMaskRCNN; fcn_mask_head.py:_do_paste_mask + threshold :388-392): activated RoI masks
+ * probs fp32 [n, hm, wm] are sampled with F.grid_sample(bilinear, align_corners=False, zero padding) semantics at the
+ * image pixel centres mapped into boxes fp32 [n, 4] (x1, y1, x2, y2) -> out uint8 [n, H, W] = (value >= thr); packed != 0 (W % 16 == 0): the
+ * result-record layout uint8 [n, H, W/8], pixel x = bit x % 8 of byte x / 8. */
+int rsp_mask_paste_boxes(const float* probs, const float* boxes, uint8_t* out, int n, int hm, int wm, int H, int W,
+                         float thr, int packed, void* stream);
+
 /* Generic pack / unpack between uint8 {0,1} masks [rows, W] and the payload [rows, ceil(W/8)] (masks produced by the
  * *_rescale entry points; unpack is for consumers that want torch.bool masks back). */
 int rsp_pack_mask_bits(const uint8_t* masks, uint8_t* bits, long long rows, int W, void* stream);

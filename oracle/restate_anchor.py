@@ -395,6 +395,101 @@ def anchor_predict(sd: dict, vision_arch, decoder_arch, images: torch.Tensor, nu
     return results
 
 
+# ------------------------------------------------------------------------------ stock Mask R-CNN mask branch (SAMSegMaskRCNN)
+def fcn_mask_head(sd: dict, roi_feats: torch.Tensor, prefix: str = "roi_head.mask_head.") -> torch.Tensor:
+    """FCNMaskHead.forward (fcn_mask_head.py:128-147): convs (conv3x3 + ReLU) -> deconv k2 s2 + ReLU -> 1x1 logits.
+    roi_feats fp32 [n, C, 14, 14] -> [n, num_classes, 28, 28]."""
+    x = roi_feats
+    i = 0
+    while f"{prefix}convs.{i}.conv.weight" in sd:
+        x = F.relu(F.conv2d(x, sd[f"{prefix}convs.{i}.conv.weight"], sd[f"{prefix}convs.{i}.conv.bias"], padding=1))
+        i += 1
+    x = F.relu(F.conv_transpose2d(x, sd[prefix + "upsample.weight"], sd[prefix + "upsample.bias"], stride=2))
+    return F.conv2d(x, sd[prefix + "conv_logits.weight"], sd[prefix + "conv_logits.bias"])
+
+
+def paste_masks_in_boxes(probs: torch.Tensor, boxes: torch.Tensor, img_h: int, img_w: int) -> torch.Tensor:
+    """_do_paste_mask (fcn_mask_head.py:395-458, skip_empty=False) written out: every image pixel centre is mapped into
+    the box's [-1, 1] frame and the RoI mask is sampled bilinearly with F.grid_sample's align_corners=False / zero
+    padding rule (pixel index = ((g + 1) * size - 1) / 2; taps outside the grid contribute 0).
+    probs fp32 [n, hm, wm], boxes fp32 [n, 4] -> fp32 [n, img_h, img_w]."""
+    n, hm, wm = probs.shape
+    x0, y0, x1, y1 = boxes[:, 0:1], boxes[:, 1:2], boxes[:, 2:3], boxes[:, 3:4]
+    ys = torch.arange(img_h, dtype=torch.float32) + 0.5
+    xs = torch.arange(img_w, dtype=torch.float32) + 0.5
+    gy = (ys[None] - y0) / (y1 - y0) * 2 - 1          # [n, H]
+    gx = (xs[None] - x0) / (x1 - x0) * 2 - 1          # [n, W]
+    gy = torch.where(torch.isinf(gy), torch.zeros_like(gy), gy)
+    gx = torch.where(torch.isinf(gx), torch.zeros_like(gx), gx)
+    iy = ((gy + 1) * hm - 1) / 2
+    ix = ((gx + 1) * wm - 1) / 2
+    fy, fx = torch.floor(iy), torch.floor(ix)
+    out = torch.zeros(n, img_h, img_w)
+    ar = torch.arange(n)[:, None, None]
+    for dy in (0, 1):
+        yy = fy + dy
+        wy = ((fy + 1) - iy) if dy == 0 else (iy - fy)
+        vy = (yy >= 0) & (yy < hm)
+        for dx in (0, 1):
+            xx = fx + dx
+            wx = ((fx + 1) - ix) if dx == 0 else (ix - fx)
+            vx = (xx >= 0) & (xx < wm)
+            tap = probs[ar, yy.clamp(0, hm - 1).long()[:, :, None], xx.clamp(0, wm - 1).long()[:, None, :]]
+            out += tap * (wy[:, :, None] * wx[:, None, :]) * (vy[:, :, None] & vx[:, None, :])
+    return out
+
+
+def fcn_mask_predict_single(mask_logits: torch.Tensor, bboxes: torch.Tensor, labels: torch.Tensor, ori_hw,
+                            scale_factor=(1.0, 1.0), rescale: bool = True, thr: float = 0.5):
+    """FCNMaskHead._predict_by_feat_single (fcn_mask_head.py:278-393): sigmoid, boxes to the output frame, the label's
+    channel, paste, >= thr.  -> (bool masks [n, h, w], boxes in the output frame)."""
+    probs = torch.sigmoid(mask_logits)
+    sf = bboxes.new_tensor(scale_factor).repeat(2)
+    img_h, img_w = int(ori_hw[0]), int(ori_hw[1])
+    if rescale:
+        bboxes = bboxes / sf
+    else:
+        img_h, img_w = int(round(img_h * float(sf[1]))), int(round(img_w * float(sf[0])))
+    n = probs.shape[0]
+    if n == 0:
+        return torch.zeros(0, img_h, img_w, dtype=torch.bool), bboxes
+    sel = probs[torch.arange(n), labels]
+    return paste_masks_in_boxes(sel, bboxes, img_h, img_w) >= thr, bboxes
+
+
+def maskrcnn_predict(sd: dict, vision_arch, images: torch.Tensor, num_classes: int, select_layers,
+                     strides=(4, 8, 16, 32, 64), scales=(8,), ratios=(0.5, 1.0, 2.0), extra_boxes: list | None = None):
+    """SAMSegMaskRCNN.predict (M:1218-1244 + two_stage.py:196-243) for img_shape == ori_shape == batch shape, scale 1:
+    per-image dicts(bboxes, scores, labels, masks, mask_logits [n, num_classes, 28, 28]).
+    extra_boxes / extra_labels: see anchor_predict - the mask branch evaluated on given detections."""
+    B, _, H, W = images.shape
+    emb, hidden = restate.vit_encoder(_sub(sd, "backbone.vision_encoder."), vision_arch, images)
+    agg = feature_aggregator(_sub(sd, "neck.feature_aggregator."), hidden, list(select_layers))
+    feats = simple_fpn(_sub(sd, "neck.feature_spliter."), agg)
+    heads = rpn_forward(_sub(sd, "rpn_head."), feats, prefix="")
+    priors = [grid_anchors(f.shape[-2:], s, base_anchors(s, scales, ratios)) for f, s in zip(feats, strides)]
+    props = [rpn_predict_single([c[b] for c, _ in heads], [r[b] for _, r in heads], priors, (H, W))[0] for b in range(B)]
+    rois = torch.cat([torch.cat([pb.new_full((pb.shape[0], 1), b), pb], dim=1) for b, pb in enumerate(props)])
+    cls, reg = bbox_head_forward(_sub(sd, "roi_head.bbox_head."), roi_extract(feats[:4], rois, 7), prefix="")
+    results, off = [], 0
+    msd = _sub(sd, "roi_head.mask_head.")
+    for b, pb in enumerate(props):
+        n = pb.shape[0]
+        db, ds, dl = bbox_predict_single(rois[off:off + n], cls[off:off + n], reg[off:off + n], (H, W), num_classes)
+        off += n
+        r = dict(bboxes=db, scores=ds, labels=dl, proposals=pb)
+        if db.shape[0] > 0:
+            mrois = torch.cat([db.new_full((db.shape[0], 1), b), db], dim=1)
+            r["mask_logits"] = fcn_mask_head(msd, roi_extract(feats[:4], mrois, 14), prefix="")
+            r["masks"], _ = fcn_mask_predict_single(r["mask_logits"], db, dl, (H, W))
+        if extra_boxes is not None and extra_boxes[b].shape[0] > 0:
+            xb = extra_boxes[b]
+            xr = torch.cat([xb.new_full((xb.shape[0], 1), b), xb], dim=1)
+            r["extra_mask_logits"] = fcn_mask_head(msd, roi_extract(feats[:4], xr, 14), prefix="")
+        results.append(r)
+    return results
+
+
 def mask2bbox(masks: torch.Tensor) -> torch.Tensor:
     """Tight boxes of boolean masks (mmdet/structures/mask/utils.py:56-77)."""
     n = masks.shape[0]

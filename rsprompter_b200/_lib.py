@@ -74,6 +74,7 @@ _SIGNATURES = {
     "rsp_mask_paste": ([_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp], _i),
     "rsp_pool2_nhwc": ([_vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "rsp_sigmoid_f32": ([_vp, _vp, ctypes.c_longlong, _vp], _i),
+    "rsp_mask_paste_boxes": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp], _i),
     "rsp_groupnorm_nhwc": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp], _i),
     "rsp_ms_deform_attn_sample": ([_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
     "rsp_mha_small": ([_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp], _i),
@@ -688,6 +689,41 @@ def mask_paste(logits: torch.Tensor, size: tuple, thr: float, mode: int) -> torc
                "rsp_mask_paste")
         launch_count += 1
     return out.view(torch.bool)
+
+
+def sigmoid_f32(x: torch.Tensor) -> torch.Tensor:
+    """fp32 sigmoid (numel % 4 == 0), the activation FCNMaskHead / the paste kernels apply once per low-res pixel."""
+    global launch_count
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() % 4 == 0
+    out = torch.empty_like(x)
+    if x.numel():
+        _check(_lib.rsp_sigmoid_f32(_ptr(x), _ptr(out), x.numel(), _stream()), "rsp_sigmoid_f32")
+        launch_count += 1
+    return out
+
+
+def mask_paste_boxes(probs: torch.Tensor, boxes: torch.Tensor, size: tuple, thr: float,
+                     bits: torch.Tensor | None = None) -> torch.Tensor:
+    """FCNMaskHead paste (fcn_mask_head.py:_do_paste_mask + :388-392): probs fp32 [n, hm, wm] sampled into boxes fp32
+    [n, 4] on a size = (H, W) canvas, >= thr -> bool [n, H, W]; with ``bits`` (uint8, n * H * W/8 bytes) the result is
+    written bit-packed into it (result-record layout) instead."""
+    global launch_count
+    _require_cuda(probs)
+    n, hm, wm = probs.shape
+    assert probs.dtype == torch.float32 and probs.is_contiguous() and boxes.dtype == torch.float32
+    assert boxes.is_contiguous() and boxes.shape == (n, 4)
+    if bits is not None:
+        assert bits.dtype == torch.uint8 and bits.is_contiguous() and size[1] % 16 == 0
+        assert bits.numel() == n * size[0] * size[1] // 8
+        out = bits
+    else:
+        out = torch.empty(n, size[0], size[1], device=probs.device, dtype=torch.uint8)
+    if n > 0:
+        _check(_lib.rsp_mask_paste_boxes(_ptr(probs), _ptr(boxes), _ptr(out), n, hm, wm, size[0], size[1], float(thr),
+                                         0 if bits is None else 1, _stream()), "rsp_mask_paste_boxes")
+        launch_count += 1
+    return out if bits is not None else out.view(torch.bool)
 
 
 def mask_paste_rescale(logits: torch.Tensor, batch_hw: tuple, crop_hw: tuple, ori_hw: tuple, thr: float,

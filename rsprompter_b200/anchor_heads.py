@@ -24,7 +24,8 @@ import torch
 from torch import nn
 
 from . import _lib
-from .necks import _BN, _PrepMixin, _Slot, _conv, conv1x1, conv3x3, prep_conv, to_nhwc_bf16
+from .necks import (_BN, _ConvT, _PrepMixin, _Slot, _conv, conv1x1, conv3x3, convT2x2, prep_conv, prep_convT,
+                    to_nhwc_bf16)
 from .registry import MODELS, BaseModule, ConfigDict, InstanceData
 from .sam_encoder import _Affine
 
@@ -297,6 +298,42 @@ class RSPrompterAnchorMaskHead(_PrepMixin, BaseModule):
 
 
 # ------------------------------------------------------------------------------ RoI head
+def _predict_bboxes(head, feats: list, proposals: torch.Tensor, prop_counts: torch.Tensor, img_hw: tuple,
+                    pes: list | None = None, capture: dict | None = None):
+    """StandardRoIHead.predict_bbox (standard_roi_head.py:292-345) + BBoxHead._predict_by_feat_single
+    (bbox_head.py:505-571) + multiclass_nms (bbox_nms.py:13-105), batched over the B images.
+    -> detections bboxes fp32 [B, M, 4], scores [B, M], labels int64 [B, M], counts int32 [B]."""
+    cfg = head.test_cfg
+    B, K, _ = proposals.shape
+    dev = proposals.device
+    bidx = torch.arange(B, device=dev, dtype=torch.float32).view(B, 1, 1).expand(B, K, 1)
+    rois = torch.cat([bidx, proposals], dim=2).reshape(B * K, 5).contiguous()
+    valid = (torch.arange(K, device=dev).view(1, K) < prop_counts.view(B, 1)).reshape(-1).to(torch.uint8)
+    feats7 = head.bbox_roi_extractor.extract(feats, rois, pes)
+    cls, reg = head.bbox_head.forward_rows(feats7)
+    if capture is not None:
+        capture.update(roi_feats7=feats7, cls=cls, reg=reg, rois=rois)
+    C = head.bbox_head.num_classes
+    s, b, lab = _lib.bbox_cls_decode(cls, reg, rois, valid.contiguous(), C, img_hw, float(cfg.get("score_thr", 0.05)),
+                                     stds=head.bbox_head.bbox_coder.stds)
+    n = K * C
+    s, b, lab = s.view(B, n), b.view(B, n, 4), lab.view(B, n)
+    s_sorted, order = torch.sort(s, dim=1, descending=True, stable=True)
+    b_sorted = torch.gather(b, 1, order[:, :, None].expand(-1, -1, 4)).contiguous()
+    l_sorted = torch.gather(lab, 1, order).contiguous()
+    nvalid = (s_sorted >= 0).sum(dim=1).to(torch.int32)
+    keep = _lib.nms_batched(b_sorted, l_sorted, nvalid, float(cfg.nms.get("iou_threshold", 0.5)))
+    M = int(cfg.get("max_per_img", 100))
+    db, ds, dl, _, cnt = _lib.compact_keep(keep, b_sorted, s_sorted.contiguous(), l_sorted, M)
+    return db, ds, dl, cnt
+
+
+def _detection_rois(db: torch.Tensor) -> torch.Tensor:
+    B, M, _ = db.shape
+    bidx = torch.arange(B, device=db.device, dtype=torch.float32).view(B, 1, 1).expand(B, M, 1)
+    return torch.cat([bidx, db], dim=2).reshape(B * M, 5).contiguous()
+
+
 def sine_pe_rows(h: int, w: int, num_feats: int, device, temperature: int = 10000,
                  scale: float = 2 * math.pi, eps: float = 1e-6) -> torch.Tensor:
     """SinePositionalEncoding(normalize=True) on an all-valid h x w mask -> fp32 [1, 2F, h, w]
@@ -353,36 +390,16 @@ class RSPrompterAnchorRoIPromptHead(BaseModule):
                      emb_rows: torch.Tensor, pos_rows: torch.Tensor, emb_hw: tuple, capture: dict | None = None):
         """proposals fp32 [B, K, 4] (zero padded), prop_counts int32 [B].
         -> dict(bboxes [B, M, 4], scores [B, M], labels [B, M], counts int32 [B], mask_logits [B*M, 1, 4h, 4w])."""
-        cfg = self.test_cfg
-        B, K, _ = proposals.shape
-        dev = proposals.device
+        B, dev = proposals.shape[0], proposals.device
         pes = self._extra_pe(feats)
         if pes is not None:       # x = [xi + pe_i] once per level (M:1566-1574); both extractors then read bf16 only
             n_lvl = max(self.bbox_roi_extractor.num_inputs, self.mask_roi_extractor.num_inputs)
             feats = [_lib.add_table_bf16(f, t) for f, t in zip(feats[:n_lvl], pes[:n_lvl])] + list(feats[n_lvl:])
             pes = None
-        bidx = torch.arange(B, device=dev, dtype=torch.float32).view(B, 1, 1).expand(B, K, 1)
-        rois = torch.cat([bidx, proposals], dim=2).reshape(B * K, 5).contiguous()
-        valid = (torch.arange(K, device=dev).view(1, K) < prop_counts.view(B, 1)).reshape(-1).to(torch.uint8)
-        feats7 = self.bbox_roi_extractor.extract(feats, rois, pes)
-        cls, reg = self.bbox_head.forward_rows(feats7)
-        if capture is not None:
-            capture.update(roi_feats7=feats7, cls=cls, reg=reg, rois=rois)
-        C = self.bbox_head.num_classes
-        s, b, lab = _lib.bbox_cls_decode(cls, reg, rois, valid.contiguous(), C, img_hw, float(cfg.get("score_thr", 0.05)),
-                                         stds=self.bbox_head.bbox_coder.stds)
-        n = K * C
-        s, b, lab = s.view(B, n), b.view(B, n, 4), lab.view(B, n)
-        s_sorted, order = torch.sort(s, dim=1, descending=True, stable=True)
-        b_sorted = torch.gather(b, 1, order[:, :, None].expand(-1, -1, 4)).contiguous()
-        l_sorted = torch.gather(lab, 1, order).contiguous()
-        nvalid = (s_sorted >= 0).sum(dim=1).to(torch.int32)
-        keep = _lib.nms_batched(b_sorted, l_sorted, nvalid, float(cfg.nms.get("iou_threshold", 0.5)))
-        M = int(cfg.get("max_per_img", 100))
-        db, ds, dl, _, cnt = _lib.compact_keep(keep, b_sorted, s_sorted.contiguous(), l_sorted, M)
+        db, ds, dl, cnt = _predict_bboxes(self, feats, proposals, prop_counts, img_hw, pes, capture)
+        M = db.shape[1]
         # mask branch (M:1511-1550): RoIs = detections
-        bidx = torch.arange(B, device=dev, dtype=torch.float32).view(B, 1, 1).expand(B, M, 1)
-        mrois = torch.cat([bidx, db], dim=2).reshape(B * M, 5).contiguous()
+        mrois = _detection_rois(db)
         feats14 = self.mask_roi_extractor.extract(feats, mrois, pes)
         if capture is not None:
             capture.update(roi_feats14=feats14, mask_rois=mrois)
@@ -391,5 +408,109 @@ class RSPrompterAnchorRoIPromptHead(BaseModule):
         return dict(bboxes=db, scores=ds, labels=dl, counts=cnt, mask_logits=logits, iou=iou)
 
 
-__all__ = ["AnchorGenerator", "DeltaXYWHBBoxCoder", "RoIAlign", "SingleRoIExtractor", "RPNHead",
+# ------------------------------------------------------------------------------ stock Mask R-CNN heads (SAMSegMaskRCNN)
+class _ConvOnly(nn.Module):
+    """mmcv ConvModule(norm_cfg=None): conv (+ ReLU); parameters live under ``.conv``."""
+
+    def __init__(self, cin: int, cout: int, k: int = 3):
+        super().__init__()
+        self.conv = _conv(cout, cin, k)
+
+
+@MODELS.register_module(force=True)
+class FCNMaskHead(_PrepMixin, BaseModule):
+    """mmdet/models/roi_heads/mask_heads/fcn_mask_head.py (inference half): num_convs x (conv3x3 + ReLU) ->
+    ConvTranspose2d(k2, s2) + ReLU -> 1x1 conv_logits (:31-126 build, :128-147 forward); the per-class channel is picked
+    by the detection label (:377-379)."""
+
+    def __init__(self, num_convs=4, roi_feat_size=14, in_channels=256, conv_kernel_size=3, conv_out_channels=256,
+                 num_classes=80, class_agnostic=False, upsample_cfg=None, conv_cfg=None, norm_cfg=None,
+                 predictor_cfg=None, loss_mask=None, init_cfg=None, **kwargs):
+        BaseModule.__init__(self, init_cfg=None)
+        up = dict(upsample_cfg or dict(type="deconv", scale_factor=2))
+        assert up.get("type") == "deconv" and up.get("scale_factor", 2) == 2 and conv_kernel_size == 3 and norm_cfg is None, \
+            "FCNMaskHead is built as the RSPrompter configs use it (deconv x2, 3x3 convs, no norm)"
+        self.num_convs, self.roi_feat_size, self.in_channels = num_convs, roi_feat_size, in_channels
+        self.conv_out_channels, self.num_classes, self.class_agnostic = conv_out_channels, num_classes, class_agnostic
+        self.convs = nn.ModuleList(
+            _ConvOnly(in_channels if i == 0 else conv_out_channels, conv_out_channels) for i in range(num_convs))
+        c_up = conv_out_channels if num_convs > 0 else in_channels
+        self.upsample = _ConvT(c_up, conv_out_channels)
+        self.conv_logits = _conv(1 if class_agnostic else num_classes, conv_out_channels, 1)
+        self._init_prep()
+
+    def init_weights(self):
+        pass
+
+    @torch.no_grad()
+    def _prepare(self):
+        f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
+        wl = self.conv_logits.weight.detach().reshape(self.conv_logits.weight.shape[0], -1)
+        pad = ((wl.shape[0] + 31) // 32) * 32 - wl.shape[0]
+        wl = torch.cat([wl, wl.new_zeros(pad, wl.shape[1])]).to(torch.bfloat16).contiguous()
+        bl = torch.cat([f32(self.conv_logits.bias), self.conv_logits.bias.new_zeros(pad).float()])
+        self._prep = dict(convs=[prep_conv(c.conv.weight, c.conv.bias) for c in self.convs],
+                          up=prep_convT(self.upsample.weight, self.upsample.bias), logits=(wl, bl))
+        return self._prep
+
+    @torch.no_grad()
+    def forward_rows(self, roi_feats: torch.Tensor) -> torch.Tensor:
+        """roi_feats bf16 [N, R*R*C] in (ph, pw, c) order -> mask logits fp32 [N, 2R, 2R, n_cls (padded to 32)]."""
+        p = self._prep or self._prepare()
+        N, R = roi_feats.shape[0], self.roi_feat_size
+        x = roi_feats.view(N, R, R, self.in_channels)
+        for w, b in p["convs"]:
+            x = conv3x3(x, w, b, act="relu")
+        x = convT2x2(x, *p["up"], act="relu")
+        y = _lib.gemm(x.reshape(N * 4 * R * R, -1), *p["logits"], out_dtype=torch.float32)
+        return y.view(N, 2 * R, 2 * R, -1)
+
+    @torch.no_grad()
+    def select(self, logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """logits fp32 [N, h, w, C_pad], labels int64 [N] -> the label's channel fp32 [N, h, w] (:377-379)."""
+        N, h, w, _ = logits.shape
+        if self.class_agnostic:
+            return logits[..., 0].contiguous()
+        idx = labels.clamp(0, self.num_classes - 1).view(N, 1, 1, 1).expand(N, h, w, 1)
+        return torch.gather(logits, 3, idx)[..., 0].contiguous()
+
+
+@MODELS.register_module(force=True)
+class StandardRoIHead(BaseModule):
+    """mmdet/models/roi_heads/standard_roi_head.py (inference half): predict_bbox :292-345, predict_mask :347-419."""
+
+    def __init__(self, bbox_roi_extractor=None, bbox_head=None, mask_roi_extractor=None, mask_head=None,
+                 shared_head=None, train_cfg=None, test_cfg=None, init_cfg=None, **kwargs):
+        BaseModule.__init__(self, init_cfg=None)
+        assert shared_head is None
+        self.bbox_roi_extractor = MODELS.build(bbox_roi_extractor)
+        self.bbox_head = MODELS.build(bbox_head)
+        self.with_mask = mask_head is not None
+        if self.with_mask:
+            self.mask_roi_extractor = MODELS.build(mask_roi_extractor) if mask_roi_extractor is not None else None
+            self.mask_head = MODELS.build(mask_head)
+        self.test_cfg = _cfg(test_cfg)
+
+    def init_weights(self):
+        pass
+
+    @torch.no_grad()
+    def predict_nhwc(self, feats: list, proposals: torch.Tensor, prop_counts: torch.Tensor, img_hw: tuple,
+                     capture: dict | None = None):
+        """-> dict(bboxes [B, M, 4], scores [B, M], labels [B, M], counts int32 [B],
+        mask_probs fp32 [B*M, 2R, 2R] = sigmoid of the label's mask channel (fcn_mask_head.py:358 / :377-379))."""
+        db, ds, dl, cnt = _predict_bboxes(self, feats, proposals, prop_counts, img_hw, None, capture)
+        out = dict(bboxes=db, scores=ds, labels=dl, counts=cnt)
+        if self.with_mask:
+            mrois = _detection_rois(db)
+            ext = self.mask_roi_extractor or self.bbox_roi_extractor     # share_roi_extractor (:56-63)
+            feats14 = ext.extract(feats, mrois, None)
+            logits = self.mask_head.forward_rows(feats14)
+            if capture is not None:
+                capture.update(roi_feats14=feats14, mask_rois=mrois, mask_logits_all=logits)
+            out["mask_probs"] = _lib.sigmoid_f32(self.mask_head.select(logits, dl.reshape(-1)))
+        return out
+
+
+__all__ = ["FCNMaskHead", "StandardRoIHead", "AnchorGenerator", "DeltaXYWHBBoxCoder", "RoIAlign", "SingleRoIExtractor", "RPNHead",
            "Shared2FCBBoxHead", "RSPrompterAnchorMaskHead", "RSPrompterAnchorRoIPromptHead", "sine_pe_rows"]

@@ -287,6 +287,11 @@ int rsp_query_postprocess_bits(const float* logits, const int32_t* sel, const fl
   return query_postprocess_bits(logits, sel, cls_scores, n_inst, hm, wm, bits, part_ws, scores, boxes, S(stream));
 }
 
+int rsp_mask_paste_boxes(const float* probs, const float* boxes, uint8_t* out, int n, int hm, int wm, int H, int W,
+                         float thr, int packed, void* stream) {
+  return mask_paste_boxes(probs, boxes, out, n, hm, wm, H, W, thr, packed, S(stream));
+}
+
 int rsp_mask_paste_bits(const float* maps, uint8_t* bits, int n, int hm, int wm, float thr, int mode, void* stream) {
   return mask_paste_bits(maps, bits, n, hm, wm, thr, mode, S(stream));
 }

@@ -216,7 +216,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     umma_commit(bar(B_KE));
     umma_commit(bar(B_KE + 1));
     umma_commit(bar(B_VE));
-    umma_commit(bar(B_VE + 1));
+    if (Cfg::VBUF == 2) umma_commit(bar(B_VE + 1));
     mbar_wait(bar(B_RELC), 0);
     tc_fence_after();
     auto issue_qk = [&](int t) {   // S_slot(t) = Q K_t^T
@@ -231,7 +231,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         umma_ss(tS + s * 64, make_sdesc(sQ + qoff, 0, 1024), make_sdesc(sK(s) + koff, 0, 1024), idesc_s, ks != 0);
       }
       umma_commit(bar(B_SF + s));
-      umma_commit(bar(B_KE + s));
+      if (t + 2 < n_kt) umma_commit(bar(B_KE + s));   // "empty" is only signalled when load_k(t + 2) will wait for it
     };
     issue_qk(0);
     for (int j = 0; j < n_kt; ++j) {
@@ -249,7 +249,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         else umma_ts((ks >> 1) ? tO1 : tO, a_tmem, bdesc, idesc_pv, (j | (ks & 1)) != 0);
       }
       umma_commit(bar(B_PV + s));
-      umma_commit(bar(B_VE + vs));
+      if (j + Cfg::VBUF < n_kt) umma_commit(bar(B_VE + vs));
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------ softmax / correction / output

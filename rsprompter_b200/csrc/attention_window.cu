@@ -158,7 +158,7 @@ vit_window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
         umma_ss(tS, make_sdesc(sQ + qoff, 0, 1024), make_sdesc(sK + koff, 0, 1024), idesc_s, ks != 0);
       }
       umma_commit(bar(B_SF));
-      umma_commit(bar(B_KE));
+      if (t + 1 < NKT) umma_commit(bar(B_KE));   // only signalled when the producer will wait for it (synccheck-clean exit)
     };
     issue_qk(0);
 #pragma unroll 1
@@ -172,8 +172,9 @@ vit_window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
         const uint64_t bdesc = make_sdesc(sV + ks * 2048, KT * 128, 1024);   // MN-major: 16 keys x 128 B per step
         umma_ts(tO, tS + ks * 8, bdesc, idesc_pv, (j | ks) != 0);
       }
-      umma_commit(bar(B_PV));
-      umma_commit(bar(B_VE));
+      if (j + 1 == NKT) umma_commit(bar(B_PV));   // only the epilogue waits for P V (intermediate tiles are ordered by
+                                                  // the in-order MMA pipe), so only the last tile signals it
+      if (j + 1 < NKT) umma_commit(bar(B_VE));
       if (j + 1 < NKT) issue_qk(j + 1);    // same thread, in order behind P V_j: S / P may be overwritten
     }
   } else if (warp < 4) {
@@ -295,7 +296,7 @@ vit_window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
     }
 
     // ---- O / l -> out[token, head * HD ..]
-    mbar_wait(bar(B_PV), (NKT - 1) & 1);
+    mbar_wait(bar(B_PV), 0);
     tc_fence_after();
     const float inv = 1.0f / l_run;
     int dst_row = row0 + tq;

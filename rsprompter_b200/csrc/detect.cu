@@ -541,6 +541,75 @@ int mask_paste_rescale(const float* maps, unsigned char* out, int n, int hm, int
   return RSP_OK;
 }
 
+// FCNMaskHead paste (fcn_mask_head.py:_do_paste_mask + the threshold of _predict_by_feat_single :388-392): the
+// activated RoI mask probs fp32 [n, hm, wm] of detection i are sampled bilinearly (F.grid_sample, align_corners=False,
+// zero padding) at every image pixel centre mapped into its box, then compared with thr.  thread = 16 output pixels of
+// one row (one 16-byte store); rows / columns whose taps all fall outside the RoI grid write zeros without loads.
+__global__ void mask_paste_boxes_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
+                                        unsigned char* __restrict__ out, int n, int hm, int wm, int H, int W, float thr,
+                                        int packed) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int w16 = (W + 15) / 16;
+  if (idx >= static_cast<long long>(n) * H * w16) return;
+  const int xb = static_cast<int>(idx % w16);
+  long long t = idx / w16;
+  const int y = static_cast<int>(t % H);
+  const int m = static_cast<int>(t / H);
+  const float x0 = boxes[m * 4], y0 = boxes[m * 4 + 1], x1 = boxes[m * 4 + 2], y1 = boxes[m * 4 + 3];
+  // normalised grid coordinate in [-1, 1] (inf from a degenerate box becomes 0, as the reference does)
+  float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(y + 0.5f, y0), __fsub_rn(y1, y0)), 2.f), 1.f);
+  if (isinf(gy)) gy = 0.f;
+  const float iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), static_cast<float>(hm)), 1.f), 0.5f);
+  const float fy = floorf(iy);
+  const int yi0 = static_cast<int>(fy), yi1 = yi0 + 1;
+  const bool vy0 = yi0 >= 0 && yi0 < hm, vy1 = yi1 >= 0 && yi1 < hm;
+  const float* p = probs + static_cast<size_t>(m) * hm * wm;
+  uint32_t pk[4] = {0u, 0u, 0u, 0u};
+  if (vy0 || vy1) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int x = xb * 16 + k;
+      float gx = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x + 0.5f, x0), __fsub_rn(x1, x0)), 2.f), 1.f);
+      if (isinf(gx)) gx = 0.f;
+      const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), static_cast<float>(wm)), 1.f), 0.5f);
+      const float fx = floorf(ix);
+      const int xi0 = static_cast<int>(fx), xi1 = xi0 + 1;
+      const bool vx0 = xi0 >= 0 && xi0 < wm, vx1 = xi1 >= 0 && xi1 < wm;
+      const float v00 = (vy0 && vx0) ? __ldg(p + yi0 * wm + xi0) : 0.f, v01 = (vy0 && vx1) ? __ldg(p + yi0 * wm + xi1) : 0.f;
+      const float v10 = (vy1 && vx0) ? __ldg(p + yi1 * wm + xi0) : 0.f, v11 = (vy1 && vx1) ? __ldg(p + yi1 * wm + xi1) : 0.f;
+      // grid_sample weights in ATen's form: (x_se - ix)(y_se - iy), (ix - x_nw)(y_se - iy), (x_se - ix)(iy - y_nw), ...
+      const float wx0 = (fx + 1.f) - ix, wx1 = ix - fx, wy0 = (fy + 1.f) - iy, wy1 = iy - fy;
+      const float v = v00 * (wx0 * wy0) + v01 * (wx1 * wy0) + v10 * (wx0 * wy1) + v11 * (wx1 * wy1);
+      pk[k >> 2] |= (v >= thr ? 1u : 0u) << ((k & 3) * 8);
+    }
+  }
+  if (packed) {   // result-record layout: pixel x = bit x % 8 of byte x / 8 (W % 16 == 0)
+    uint32_t bits = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) bits |= ((pk[k >> 2] >> ((k & 3) * 8)) & 1u) << k;
+    *reinterpret_cast<unsigned short*>(out + (static_cast<size_t>(m) * H + y) * (W / 8) + xb * 2) =
+        static_cast<unsigned short>(bits);
+    return;
+  }
+  unsigned char* dst = out + (static_cast<size_t>(m) * H + y) * W + xb * 16;
+  if ((W & 15) == 0) {
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  } else {   // original-image canvases of any width: byte stores
+    for (int k = 0; k < 16 && xb * 16 + k < W; ++k) dst[k] = static_cast<unsigned char>((pk[k >> 2] >> ((k & 3) * 8)) & 1u);
+  }
+}
+
+int mask_paste_boxes(const float* probs, const float* boxes, unsigned char* out, int n, int hm, int wm, int H, int W,
+                     float thr, int packed, cudaStream_t stream) {
+  RSP_CHECK_ARG(probs && boxes && out && n > 0 && hm > 0 && wm > 0 && H > 0 && W > 0, "mask_paste_boxes: bad arguments");
+  RSP_CHECK_ARG(!packed || W % 16 == 0, "mask_paste_boxes: bit-packed output needs W % 16 == 0");
+  const long long total = static_cast<long long>(n) * H * ((W + 15) / 16);
+  mask_paste_boxes_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(probs, boxes, out, n, hm, wm, H, W,
+                                                                                         thr, packed);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
 __global__ void sigmoid_f32_kernel(const float4* __restrict__ in, float4* __restrict__ out, long long n4) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;

@@ -23,6 +23,8 @@ int mask_paste(const float* logits, unsigned char* out, int n, int hm, int wm, i
                int mode, cudaStream_t stream);
 int mask_paste_bits(const float* maps, unsigned char* bits, int n, int hm, int wm, float thr, int mode,
                     cudaStream_t stream);
+int mask_paste_boxes(const float* probs, const float* boxes, unsigned char* out, int n, int hm, int wm, int H, int W,
+                     float thr, int packed, cudaStream_t stream);
 int sigmoid_f32(const float* in, float* out, long long n, cudaStream_t stream);
 int pool2_nhwc(const void* in, void* out, int B, int H, int W, int C, int mode, cudaStream_t stream);
 int sin_fold(const float* in, float* out, long long n_out, cudaStream_t stream);

@@ -308,6 +308,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    for (int i = 0; i < STAGES; ++i) {   // tail: leave no "empty" completion without a waiter (see gemm_v2.cu)
+      mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, B_MN_MAJOR ? 1 : 0);

@@ -151,6 +151,12 @@ gemm_bf16_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    // tail: consume the ring's last "empty" completions, so that no tcgen05.commit arrive is left without a waiter when
+    // the CTA retires (compute-sanitizer synccheck "missing wait"); never-used slots pass at once
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);

@@ -82,7 +82,8 @@ class _SamDetectorBase(BaseModule):
         if copies:
             hidden = tuple(copies.get(i, h) if copies.get(i) is not None else h for i, h in enumerate(hidden))
         B, g = emb_nhwc.shape[0], emb_nhwc.shape[1]
-        pos_rows = self.shared_image_embedding.shared_image_embedding.image_wide_rows(g)
+        sie = getattr(self, "shared_image_embedding", None)        # SAMSegMaskRCNN has no SAM decoder, hence no PE
+        pos_rows = sie.shared_image_embedding.image_wide_rows(g) if sie is not None else None
         return emb_nhwc.reshape(B * g * g, -1), pos_rows, (g, g), emb_nhwc, hidden
 
     def extract_feat(self, batch_inputs: torch.Tensor):
@@ -304,4 +305,107 @@ class RSPrompterQuery(_SamDetectorBase):
         return self.predict(data["inputs"], data.get("data_samples"))
 
 
-__all__ = ["RSPrompterAnchor", "RSPrompterQuery"]
+@MODELS.register_module(force=True)
+class SAMSegMaskRCNN(_SamDetectorBase):
+    """M:1218-1244 over mmdet MaskRCNN / TwoStageDetector.predict (detectors/two_stage.py:196-243): the SAM encoder +
+    RSFPN feed the stock RPNHead -> StandardRoIHead (Shared2FCBBoxHead + FCNMaskHead); the masks are the 28x28 RoI
+    masks pasted into their boxes (fcn_mask_head.py:278-418), not SAM decoder outputs."""
+
+    def __init__(self, backbone=None, neck=None, rpn_head=None, roi_head=None, train_cfg=None, test_cfg=None,
+                 data_preprocessor=None, init_cfg=None, **kwargs):
+        BaseModule.__init__(self, init_cfg=None)
+        test_cfg = _cfg(test_cfg)
+        self.backbone = MODELS.build(backbone)
+        self.neck = MODELS.build(neck)
+        rpn = dict(rpn_head)
+        rpn.update(train_cfg=None, test_cfg=test_cfg.get("rpn"))
+        rpn.setdefault("num_classes", 1)
+        self.rpn_head = MODELS.build(rpn)
+        roi = dict(roi_head)
+        roi.update(train_cfg=None, test_cfg=test_cfg.get("rcnn"))
+        self.roi_head = MODELS.build(roi)
+        self.test_cfg = test_cfg
+        self.data_preprocessor_cfg = data_preprocessor
+        self.data_preprocessor = MODELS.build(dict(data_preprocessor)) if data_preprocessor else None
+        self.eval()
+
+    def extract_feat(self, batch_inputs: torch.Tensor):
+        """M:1233-1244: the neck outputs only (NCHW tuple)."""
+        vision_outputs = self.backbone(batch_inputs)
+        if isinstance(vision_outputs, SamVisionEncoderOutput):
+            hidden = vision_outputs[1]
+        elif isinstance(vision_outputs, tuple):
+            hidden = vision_outputs
+        else:
+            raise NotImplementedError
+        return self.neck(hidden)
+
+    @torch.no_grad()
+    def predict_raw(self, batch_inputs: torch.Tensor, capture: dict | None = None):
+        """Device-resident results: dict(bboxes [B,M,4], scores, labels, counts, mask_probs fp32 [B*M, 28, 28])."""
+        img_hw = tuple(batch_inputs.shape[-2:])
+        _, _, _, emb_nhwc, hidden = self._encode(batch_inputs)
+        if isinstance(getattr(self.neck, "feature_aggregator", None), PseudoFeatureAggregator):
+            feats = self.neck.forward_nhwc(None, _lib.cast_bf16(emb_nhwc.contiguous()))
+        else:
+            feats = self.neck.forward_nhwc(hidden)
+        props, _, pcnt = self.rpn_head.predict_nhwc(feats, img_hw)
+        if capture is not None:
+            capture.update(feats=feats, proposals=props, prop_counts=pcnt)
+        return self.roi_head.predict_nhwc(feats, props, pcnt, img_hw, capture=capture)
+
+    @torch.no_grad()
+    def predict(self, batch_inputs: torch.Tensor, batch_data_samples=None, rescale: bool = True):
+        if batch_data_samples is None:
+            batch_data_samples = make_data_samples(batch_inputs.shape[0], tuple(batch_inputs.shape[-2:]))
+        hw, metas = self._metas(batch_data_samples, batch_inputs)
+        r = self._raw(batch_inputs)
+        if getattr(self, "_graphs", None) is not None:     # graph buffers are overwritten by the next replay
+            r = {k: v.clone() for k, v in r.items()}
+        thr = float(self.test_cfg.rcnn.get("mask_thr_binary", 0.5))
+        B, M = r["scores"].shape
+        probs = r["mask_probs"]
+        fast = all(m is None for m in metas)
+        masks = _lib.mask_paste_boxes(probs, r["bboxes"].reshape(B * M, 4), hw, thr).view(B, M, *hw) if fast else None
+        counts = r["counts"].cpu().tolist()          # the only device->host read
+        for b, ds in enumerate(batch_data_samples):
+            n, m = counts[b], metas[b]
+            boxes = r["bboxes"][b, :n]
+            if m is None:
+                mk = masks[b, :n]
+            else:   # fcn_mask_head.py:333-343: boxes to the original image (rescale) or canvas = round(ori * scale)
+                sf, size = m["scale_factor"], m["ori_hw"]
+                if rescale:
+                    boxes = boxes / boxes.new_tensor(sf).repeat(2)
+                else:
+                    size = (int(round(size[0] * sf[1])), int(round(size[1] * sf[0])))
+                pb = torch.zeros(max(n, 1), 4, device=boxes.device)
+                pb[:n] = boxes
+                mk = _lib.mask_paste_boxes(probs[b * M:b * M + max(n, 1)].contiguous(), pb, size, thr)[:n]
+            ds.pred_instances = InstanceData(bboxes=boxes, scores=r["scores"][b, :n], labels=r["labels"][b, :n], masks=mk)
+        return batch_data_samples
+
+    @torch.no_grad()
+    def predict_records(self, batch_inputs: torch.Tensor, record: ResultRecord | None = None) -> ResultRecord:
+        """predict() for images at the batch shape, left on the device as one ResultRecord."""
+        r = self._raw(batch_inputs)
+        hw = tuple(int(v) for v in batch_inputs.shape[-2:])
+        B, M = r["scores"].shape
+        rec = record or self._new_record(B, M, hw, r["scores"].device)
+        thr = float(self.test_cfg.rcnn.get("mask_thr_binary", 0.5))
+        _lib.mask_paste_boxes(r["mask_probs"], r["bboxes"].reshape(B * M, 4), hw, thr, bits=rec.mask_bits)
+        torch.cat([r["bboxes"], r["scores"][..., None], r["labels"].to(torch.float32)[..., None]], dim=2, out=rec.rows)
+        rec.counts.copy_(r["counts"])
+        return rec
+
+    def forward(self, inputs, data_samples=None, mode: str = "predict"):
+        if mode == "predict":
+            return self.predict(inputs, data_samples)
+        raise NotImplementedError("rsprompter_b200 implements the inference path only (mode='predict')")
+
+    def test_step(self, data):
+        data = self._preprocess(data)
+        return self.predict(data["inputs"], data.get("data_samples"))
+
+
+__all__ = ["RSPrompterAnchor", "RSPrompterQuery", "SAMSegMaskRCNN"]

@@ -104,3 +104,36 @@ def query_model_cfg(arch: str = "base", num_classes: int = 10, prompt_shape: tup
                                   num_stuff_classes=0, loss_panoptic=None, init_cfg=None),
         test_cfg=dict(panoptic_on=False, semantic_on=False, instance_on=True, max_per_image=prompt_shape[0],
                       iou_thr=0.8, filter_low_score=True))
+
+
+def maskrcnn_model_cfg(arch: str = "base", num_classes: int = 10) -> dict:
+    """configs/rsprompter/_base_/samseg-maskrcnn.py:57-184 + samseg-maskrcnn-nwpu.py overrides."""
+    name, backbone, neck = _backbone_neck(arch, None)
+    return dict(
+        type="SAMSegMaskRCNN",
+        backbone=backbone,
+        neck=neck,
+        rpn_head=dict(type="RPNHead", in_channels=256, feat_channels=256,
+                      anchor_generator=dict(type="AnchorGenerator", scales=[8], ratios=[0.5, 1.0, 2.0],
+                                            strides=[4, 8, 16, 32, 64]),
+                      bbox_coder=dict(type="DeltaXYWHBBoxCoder", target_means=[0., 0., 0., 0.],
+                                      target_stds=[1.0, 1.0, 1.0, 1.0])),
+        roi_head=dict(
+            type="StandardRoIHead",
+            bbox_roi_extractor=dict(type="SingleRoIExtractor",
+                                    roi_layer=dict(type="RoIAlign", output_size=7, sampling_ratio=0),
+                                    out_channels=256, featmap_strides=[4, 8, 16, 32]),
+            bbox_head=dict(type="Shared2FCBBoxHead", in_channels=256, fc_out_channels=1024, roi_feat_size=7,
+                           num_classes=num_classes,
+                           bbox_coder=dict(type="DeltaXYWHBBoxCoder", target_means=[0., 0., 0., 0.],
+                                           target_stds=[0.1, 0.1, 0.2, 0.2]),
+                           reg_class_agnostic=False),
+            mask_roi_extractor=dict(type="SingleRoIExtractor",
+                                    roi_layer=dict(type="RoIAlign", output_size=14, sampling_ratio=0),
+                                    out_channels=256, featmap_strides=[4, 8, 16, 32]),
+            mask_head=dict(type="FCNMaskHead", num_convs=4, in_channels=256, conv_out_channels=256,
+                           num_classes=num_classes)),
+        test_cfg=dict(rpn=dict(nms_pre=1000, max_per_img=1000, nms=dict(type="nms", iou_threshold=0.7),
+                               min_bbox_size=0),
+                      rcnn=dict(score_thr=0.05, nms=dict(type="nms", iou_threshold=0.5), max_per_img=100,
+                                mask_thr_binary=0.5)))

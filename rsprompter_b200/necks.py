@@ -142,13 +142,13 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None, act=None, 
     return y.view(B, Ho, Wo, -1)
 
 
-def convT2x2(x: torch.Tensor, taps: list, b: torch.Tensor) -> torch.Tensor:
+def convT2x2(x: torch.Tensor, taps: list, b: torch.Tensor, act=None) -> torch.Tensor:
     B, H, W, C = x.shape
     co = taps[0].shape[0]
     out = torch.empty(B * 2 * H * 2 * W, co, device=x.device, dtype=torch.bfloat16)
     rows = x.reshape(B * H * W, C)
     for t, rm in enumerate(tap_maps(B, H, W, x.device)):
-        _lib.gemm(rows, taps[t], b, out=out, row_map=rm)
+        _lib.gemm(rows, taps[t], b, out=out, row_map=rm, act=act)
     return out.view(B, 2 * H, 2 * W, co)
 
 

@@ -33,7 +33,8 @@ except Exception:  # noqa: BLE001
 # mmdet process they must not displace the upstream classes other detectors rely on (samdet's FasterRCNN, samseg-*):
 # they are registered only when the name is still free; the RSPrompter-specific names are re-registered with force=True.
 _GENERIC_NAMES = frozenset({"RPNHead", "Shared2FCBBoxHead", "SingleRoIExtractor", "RoIAlign", "DetDataPreprocessor",
-                            "AnchorGenerator", "DeltaXYWHBBoxCoder", "MSDeformAttnPixelDecoder"})
+                            "AnchorGenerator", "DeltaXYWHBBoxCoder", "MSDeformAttnPixelDecoder", "StandardRoIHead",
+                            "FCNMaskHead"})
 
 if HAVE_MMENGINE:  # pragma: no cover - not available in this image
 

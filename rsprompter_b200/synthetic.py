@@ -255,6 +255,31 @@ def anchor_detector_state_dict(arch: SamVisionArch, num_classes: int, n_select: 
     return sd
 
 
+def fcn_mask_head_state_dict(num_classes: int, c: int = 256, num_convs: int = 4, seed: int = 16):
+    """FCNMaskHead (fcn_mask_head.py:68-126): convs.{i}.conv, upsample (ConvTranspose2d), conv_logits."""
+    gen = torch.Generator().manual_seed(seed)
+    sd: dict[str, torch.Tensor] = {}
+    for i in range(num_convs):
+        _conv_sd(sd, gen, f"convs.{i}.conv", c, c, 3, gain=1.4)
+    sd["upsample.weight"] = _randn(gen, c, c, 2, 2, std=1.4 / math.sqrt(c))
+    sd["upsample.bias"] = _randn(gen, c, std=0.05)
+    _conv_sd(sd, gen, "conv_logits", num_classes, c, 1, gain=4.0)
+    return sd
+
+
+def maskrcnn_detector_state_dict(arch: SamVisionArch, num_classes: int, n_select: int, seed: int = 0) -> dict:
+    """Full SAMSegMaskRCNN state dict with the reference's key names (M:1218-1244 + _base_/samseg-maskrcnn.py)."""
+    sd: dict[str, torch.Tensor] = {}
+    sd.update(_prefixed("backbone.vision_encoder.", vision_encoder_state_dict(arch, seed)))
+    sd.update(_prefixed("neck.feature_aggregator.",
+                        feature_aggregator_state_dict(arch.hidden_size, n_select, seed=seed + 10)))
+    sd.update(_prefixed("neck.feature_spliter.", simple_fpn_state_dict(seed=seed + 12)))
+    sd.update(_prefixed("rpn_head.", rpn_head_state_dict(num_anchors=3, seed=seed + 13)))
+    sd.update(_prefixed("roi_head.bbox_head.", bbox_head_state_dict(num_classes, seed=seed + 14)))
+    sd.update(_prefixed("roi_head.mask_head.", fcn_mask_head_state_dict(num_classes, seed=seed + 16)))
+    return sd
+
+
 # ================================================================================================
 # RSPrompter-query head (reference module tree, M:274-330 + configs/rsprompter/_base_/rsprompter_query.py)
 # ================================================================================================

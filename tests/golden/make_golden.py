@@ -174,7 +174,45 @@ def main():
     print("wrote", OUT, {k: list(v.keys()) for k, v in fx.items()})
 
 
+def main_maskrcnn():
+    """tests/golden/reference_maskrcnn.pt: FCNMaskHead's paste path (SAMSegMaskRCNN), a file of its own so that the
+    first fixture file stays byte-identical."""
+    g = torch.Generator().manual_seed(4321)
+    fx = {}
+    rel = "mmdet/models/roi_heads/mask_heads/fcn_mask_head.py"
+    pm = load_defs(rel, ["_do_paste_mask"])
+    n, hm, H, W = 9, 28, 72, 100
+    probs = torch.rand(n, 1, hm, hm, generator=g)
+    boxes = torch.rand(n, 4, generator=g) * torch.tensor([60., 40., 60., 40.])
+    boxes[:, 2:] = boxes[:, :2] + torch.rand(n, 2, generator=g) * 50 + 0.5
+    boxes[0] = torch.tensor([-8.0, -3.5, 30.0, 90.0])          # sticks out of the canvas
+    boxes[1] = torch.tensor([40.0, 10.0, 40.0, 30.0])          # zero width: inf -> 0 rule
+    boxes[2] = torch.tensor([0.0, 0.0, float(W), float(H)])    # the whole canvas
+    out, _ = pm["_do_paste_mask"](probs, boxes, H, W, skip_empty=False)
+    fx["do_paste_mask"] = dict(probs=probs, boxes=boxes, hw=(H, W), out=out)
+
+    mh = load_defs(rel, ["_predict_by_feat_single"], cls="FCNMaskHead")
+    mh["_predict_by_feat_single"].__globals__.update(_do_paste_mask=pm["_do_paste_mask"], BYTES_PER_FLOAT=4,
+                                                     GPU_MEM_LIMIT=1024 ** 3)
+    C = 3
+    logits = torch.randn(n, C, hm, hm, generator=g) * 3
+    labels = torch.randint(0, C, (n,), generator=g)
+    self_ = SimpleNamespace(class_agnostic=False)
+    for name, rescale in (("fcn_predict_rescale", True), ("fcn_predict_norescale", False)):
+        meta = dict(ori_shape=(60, 84), scale_factor=(1.25, 1.2))
+        b_in = boxes.clone()
+        im = mh["_predict_by_feat_single"](self_, logits.clone(), b_in, labels, meta,
+                                           SimpleNamespace(mask_thr_binary=0.5), rescale=rescale)
+        fx[name] = dict(logits=logits, boxes=boxes, labels=labels, meta=meta, rescale=rescale, masks=im, boxes_out=b_in)
+    out_path = os.path.join(os.path.dirname(OUT), "reference_maskrcnn.pt")
+    torch.save(fx, out_path)
+    print("wrote", out_path, {k: list(v.keys()) for k, v in fx.items()})
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("/root/reference not mounted")
-    main()
+    if "maskrcnn" in sys.argv[1:]:
+        main_maskrcnn()
+    else:
+        main()

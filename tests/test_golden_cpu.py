@@ -133,3 +133,32 @@ def test_checkpoint_tables_resize_like_mmpretrain():
     assert torch.allclose(enc.pos_embed, f["pos_embed_out"], rtol=1e-6, atol=1e-6)
     assert torch.allclose(enc.layers[0].attn.rel_pos_h, f["rel_pos_out"], rtol=1e-6, atol=1e-6)
     assert torch.equal(enc.layers[1].attn.rel_pos_w, f["rel_win_out"])        # same length: untouched
+
+
+# ---- SAMSegMaskRCNN mask branch (tests/golden/reference_maskrcnn.pt; make_golden.py maskrcnn)
+FXM = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_maskrcnn.pt"), weights_only=False)
+
+
+def test_paste_masks_in_boxes_matches_reference():
+    f = FXM["do_paste_mask"]
+    got = ra.paste_masks_in_boxes(f["probs"][:, 0], f["boxes"], *f["hw"])
+    torch.testing.assert_close(got, f["out"], rtol=0, atol=2e-6)
+    assert ((got >= 0.5) != (f["out"] >= 0.5)).sum().item() == 0
+
+
+@pytest.mark.parametrize("key", ["fcn_predict_rescale", "fcn_predict_norescale"])
+def test_fcn_mask_predict_single_matches_reference(key):
+    f = FXM[key]
+    masks, boxes = ra.fcn_mask_predict_single(f["logits"], f["boxes"], f["labels"], f["meta"]["ori_shape"],
+                                              f["meta"]["scale_factor"], rescale=f["rescale"])
+    assert masks.shape == f["masks"].shape and masks.dtype == torch.bool
+    # box 1 has zero width.  The fixture ran the reference on the CPU, where _predict_by_feat_single pastes with
+    # skip_empty=True (fcn_mask_head.py:383) and only fills the box's own column band; on a GPU (skip_empty=False, the
+    # branch restated here and in the CUDA kernel) the inf -> 0 rule samples the RoI's centre column for the whole row.
+    diff = masks != f["masks"]
+    x0 = int(boxes[1, 0].floor().item()) - 1
+    x1 = int(boxes[1, 2].ceil().item()) + 1
+    assert diff[1, :, x0:x1].sum().item() == 0
+    diff[1] = False
+    assert diff.sum().item() <= 2          # fp ties at the 0.5 threshold
+    torch.testing.assert_close(boxes, f["boxes_out"], rtol=0, atol=1e-5)

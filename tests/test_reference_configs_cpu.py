@@ -95,3 +95,24 @@ def test_reference_samdet_config_builds_the_segmentor():
               "mask_decoder.transformer.layers.1.cross_attn_image_to_token.out_proj.weight",
               "mask_decoder.output_hypernetworks_mlps.3.proj_out.weight"):
         assert k in keys, k
+
+
+def test_reference_samseg_maskrcnn_config_builds():
+    """configs/rsprompter/samseg-maskrcnn-nwpu.py (M:1218-1244): SAMSegMaskRCNN with the stock
+    StandardRoIHead / Shared2FCBBoxHead / FCNMaskHead builds from the reference's own config file and takes a state dict
+    with mmdet's parameter names (fcn_mask_head.py:68-126: convs.N.conv, upsample, conv_logits)."""
+    from rsprompter_b200 import synthetic
+    from rsprompter_b200.registry import MODELS, Config
+    cfg = Config.fromfile(os.path.join(REF_CFG, "samseg-maskrcnn-nwpu.py"))
+    model = MODELS.build(_strip_init(cfg.to_dict()["model"]))
+    assert type(model).__name__ == "SAMSegMaskRCNN" and type(model.roi_head).__name__ == "StandardRoIHead"
+    assert type(model.roi_head.mask_head).__name__ == "FCNMaskHead" and model.roi_head.mask_head.num_classes == 10
+    assert model.rpn_head.prior_generator.num_base_priors[0] == 3            # scales=[8] x 3 ratios
+    arch = model.backbone.vision_encoder.arch
+    assert arch.name == "base"
+    sd = synthetic.maskrcnn_detector_state_dict(arch, 10, 6, seed=0)
+    assert set(model.state_dict()) == set(sd)
+    model.load_state_dict(sd, strict=True)
+    assert sd["roi_head.mask_head.upsample.weight"].shape == (256, 256, 2, 2)
+    assert sd["roi_head.mask_head.conv_logits.weight"].shape == (10, 256, 1, 1)
+    assert model.test_cfg.rcnn.mask_thr_binary == 0.5 and not hasattr(model, "shared_image_embedding")
