@@ -9,6 +9,7 @@ Configs (BASELINE.json `configs`):
     anchor_vitb            configs[1]:       RSPrompter-anchor ViT-B bf16, bs 8 per GPU, 1024^2
     anchor_vith, query_vitb                  the other two pairings
     maskrcnn_vitb          SAMSegMaskRCNN ViT-B (SAM encoder + RSFPN + stock Mask R-CNN heads), bs 8 per GPU, 1024^2
+    mask2former_vitb       SAMSegMask2Former ViT-B (SAM encoder + RSFPN + stock Mask2Former head), bs 8 per GPU, 1024^2
     encoder_vith           configs[4]:       SAM ViT-H encoder only at --size {512,768,1024,1280}
 
 A step is one full pass of one batch: uint8 images -> DetDataPreprocessor (fused into the patch-embed loader) -> SAM
@@ -52,6 +53,8 @@ CONFIGS = {
                        workload=f"RSPrompter-query ViT-B bf16, bs={BATCH}/GPU, {SIZE}x{SIZE} synthetic, {NQ} queries"),
     "maskrcnn_vitb": dict(variant="maskrcnn", arch="base",
                           workload=f"SAM-seg Mask R-CNN ViT-B bf16 (SAMSegMaskRCNN), bs={BATCH}/GPU, {SIZE}x{SIZE} synthetic"),
+    "mask2former_vitb": dict(variant="mask2former", arch="base",
+                             workload=f"SAM-seg Mask2Former ViT-B bf16 (SAMSegMask2Former), bs={BATCH}/GPU, {SIZE}x{SIZE} synthetic, {NQ} queries"),
     "encoder_vith": dict(variant="encoder", arch="huge",
                          workload="SAM-seg ViT-H encoder only (MMPretrainSamVisionEncoder), bs=%d/GPU, {S}x{S} synthetic "
                                   "(BASELINE.json configs[4])" % BATCH),
@@ -186,6 +189,10 @@ def _oracle_setup(args):
         from oracle import restate_anchor as ra
         sd = synthetic.maskrcnn_detector_state_dict(arch, NUM_CLASSES, len(sel), seed=0)
         return lambda x: ra.maskrcnn_predict(sd, arch, x, NUM_CLASSES, sel)
+    if c["variant"] == "mask2former":
+        from oracle import restate_query as rq
+        sd = synthetic.mask2former_detector_state_dict(arch, NUM_CLASSES, len(sel), nq=NQ, seed=0)
+        return lambda x: rq.samseg_mask2former_predict(sd, arch, x, NUM_CLASSES, sel, max_per_image=NQ)
     if c["variant"] == "query":
         from oracle import restate_query as rq
         sd = synthetic.query_detector_state_dict(arch, NUM_CLASSES, len(sel), nq=NQ, seed=0)
@@ -388,6 +395,9 @@ def run_ours(args) -> None:
         elif variant == "maskrcnn":
             cfg = model_configs.maskrcnn_model_cfg(arch_name, NUM_CLASSES)
             sd = synthetic.maskrcnn_detector_state_dict(arch, NUM_CLASSES, n_sel, seed=0)
+        elif variant == "mask2former":
+            cfg = model_configs.mask2former_model_cfg(arch_name, NUM_CLASSES, num_queries=NQ)
+            sd = synthetic.mask2former_detector_state_dict(arch, NUM_CLASSES, n_sel, nq=NQ, seed=0)
         else:
             cfg = model_configs.query_model_cfg(arch_name, NUM_CLASSES, prompt_shape=(NQ, 5))
             sd = synthetic.query_detector_state_dict(arch, NUM_CLASSES, n_sel, nq=NQ, seed=0)
@@ -403,7 +413,7 @@ def run_ours(args) -> None:
     # resident arm: what the data preprocessor hands the detector (the uint8 batch with the normalisation attached)
     resident = [prep(dict(inputs=h.to(dev)), False, fuse_patch_embed=True)["inputs"] for h in host]
     side = torch.cuda.Stream()
-    M = NQ if variant == "query" else 100
+    M = NQ if variant in ("query", "mask2former") else 100
 
     enc_graphs = {}
 

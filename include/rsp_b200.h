@@ -230,6 +230,10 @@ int rsp_groupnorm_nhwc(const void* x, float* stats_ws, const float* gamma, const
  * the query's own cell centre, bilinear zero-padded sampling as grid_sample(align_corners=False).  out bf16. */
 int rsp_ms_deform_attn_sample(const void* value, const float* ow, int ld_ow, const int32_t* hs, const int32_t* ws,
                               int L, int P, int B, int NQ, void* out, void* stream);
+/* ... with channels = 8 heads x 16 (128, as above) or 8 heads x 32 (256: the stock Mask2FormerHead's pixel decoder,
+ * configs/rsprompter/_base_/samseg-mask2former.py:104-112). */
+int rsp_ms_deform_attn_sample_c(const void* value, const float* ow, int ld_ow, const int32_t* hs, const int32_t* ws,
+                                int L, int P, int B, int NQ, void* out, int channels, void* stream);
 
 /* nn.MultiheadAttention core, 8 heads x 16 (mma.sync flash form): Q bf16 [B,nq,ldq], K / V bf16 [B,nk,ld*],
  * mask_bits uint64 [B*nq, ceil(nk/64)] (bit k%64 of word k/64 set = key k masked, shared by the heads) or NULL;
@@ -237,6 +241,10 @@ int rsp_ms_deform_attn_sample(const void* value, const float* ow, int ld_ow, con
  * (mask2former_layers.py:113-135). */
 int rsp_mha_small(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const uint64_t* mask_bits,
                   int B, int nq, int nk, void* out, void* stream);
+/* ... with head_dim 16 (as above) or 32 (8 heads x 32 = 256 channels, out bf16 [B,nq,256]: the stock
+ * Mask2FormerTransformerDecoder of samseg-mask2former.py:120-140; 1/sqrt(32) multiplies the fp32 scores). */
+int rsp_mha_small_hd(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const uint64_t* mask_bits,
+                     int B, int nq, int nk, void* out, int head_dim, void* stream);
 
 /* attn_mask = sigmoid(x) < 0.5 (= x < 0) per row of level-sized mask logits fp32 [rows, ld >= nk]; a row whose keys
  * are all masked is cleared (M:386-392, M:439-442).  The logits are mask_embed x (bilinearly resized

@@ -245,3 +245,66 @@ def query_predict(sd: dict, vision_arch, decoder_arch, images: torch.Tensor, num
     if timings is not None:
         timings.update(encoder=t1 - t0, neck=t2 - t1, head=t3 - t2, post=t4 - t3)
     return out
+
+
+# ------------------------------------------------------------------------------ stock Mask2FormerHead (SAMSegMask2Former)
+def stock_forward_head(sd: dict, decoder_out, mask_feature, target_size, heads=8, prefix=""):
+    """Mask2FormerHead._forward_head (dense_heads/mask2former_head.py:340-380)."""
+    p = prefix
+    x = _ln(sd, p + "transformer_decoder.post_norm.", decoder_out)
+    cls_pred = F.linear(x, sd[p + "cls_embed.weight"], sd[p + "cls_embed.bias"])
+    mask_embed = _mlp(sd, p + "mask_embed.", [0, 2, 4], x)
+    mask_pred = torch.einsum("bqc,bchw->bqhw", mask_embed, mask_feature)
+    am = F.interpolate(mask_pred, target_size, mode="bilinear", align_corners=False)
+    am = am.flatten(2).unsqueeze(1).repeat(1, heads, 1, 1).flatten(0, 1)
+    return cls_pred, mask_pred, am.sigmoid() < 0.5
+
+
+def stock_mask2former_head(sd: dict, feats, levels=3, heads=8, prefix=""):
+    """Mask2FormerHead.forward (mask2former_head.py:382-460) -> the last layer's (cls_pred, mask_pred)."""
+    p = prefix
+    B = feats[0].shape[0]
+    mask_feature, memories = pixel_decoder(sd, feats, p + "pixel_decoder.", heads=heads)
+    E = memories[0].shape[1]
+    dec_in, dec_pos = [], []
+    for i in range(levels):
+        m = memories[i]
+        dec_in.append(m.flatten(2).permute(0, 2, 1) + sd[p + "level_embed.weight"][i].view(1, 1, -1))
+        dec_pos.append(sine_positional_encoding(B, m.shape[-2], m.shape[-1], E // 2).flatten(2).permute(0, 2, 1))
+    qf = sd[p + "query_feat.weight"].unsqueeze(0).repeat(B, 1, 1)
+    qe = sd[p + "query_embed.weight"].unsqueeze(0).repeat(B, 1, 1)
+    cls, mp, am = stock_forward_head(sd, qf, mask_feature, memories[0].shape[-2:], heads, p)
+    i = 0
+    while f"{p}transformer_decoder.layers.{i}.norms.0.weight" in sd:
+        lvl = i % levels
+        am = am & (am.sum(-1) != am.shape[-1]).unsqueeze(-1)
+        lp = f"{p}transformer_decoder.layers.{i}."
+        qf = _mha(sd, lp + "cross_attn.", qf, dec_in[lvl], dec_in[lvl], qe, dec_pos[lvl], am, heads)
+        qf = _ln(sd, lp + "norms.0.", qf)
+        qf = _mha(sd, lp + "self_attn.", qf, qf, qf, qe, qe, None, heads)
+        qf = _ln(sd, lp + "norms.1.", qf)
+        qf = _ffn(sd, lp + "ffn.", qf)
+        qf = _ln(sd, lp + "norms.2.", qf)
+        cls, mp, am = stock_forward_head(sd, qf, mask_feature, memories[(i + 1) % levels].shape[-2:], heads, p)
+        i += 1
+    return cls, mp
+
+
+def samseg_mask2former_predict(sd: dict, vision_arch, images: torch.Tensor, num_classes: int, select_layers,
+                               max_per_image: int = 100):
+    """SAMSegMask2Former.predict (M:1247-1274 + detectors/maskformer.py:95-140) for img_shape == ori_shape == batch
+    shape, scale 1: extract_feat -> Mask2FormerHead.predict (maskformer_head.py:569-604: last layer, bilinear to the
+    batch shape) -> MaskFormerFusionHead.predict (instance_on) -> per-image dicts as query_predict returns."""
+    from . import restate, restate_anchor
+    B, _, H, W = images.shape
+    emb, hidden = restate.vit_encoder(_sub(sd, "backbone.vision_encoder."), vision_arch, images)
+    agg = restate_anchor.feature_aggregator(_sub(sd, "neck.feature_aggregator."), hidden, list(select_layers))
+    feats = restate_anchor.simple_fpn(_sub(sd, "neck.feature_spliter."), agg)
+    cls, mp = stock_mask2former_head(_sub(sd, "panoptic_head."), feats)
+    up = F.interpolate(mp, size=(H, W), mode="bilinear", align_corners=False)
+    out = []
+    for b in range(B):
+        r = instance_postprocess(cls[b], up[b], num_classes, max_per_image)
+        r.update(mask_logits=mp[b], cls=cls[b])
+        out.append(r)
+    return out

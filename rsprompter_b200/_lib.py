@@ -78,6 +78,8 @@ _SIGNATURES = {
     "rsp_groupnorm_nhwc": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp], _i),
     "rsp_ms_deform_attn_sample": ([_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
     "rsp_mha_small": ([_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp], _i),
+    "rsp_ms_deform_attn_sample_c": ([_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp], _i),
+    "rsp_mha_small_hd": ([_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp], _i),
     "rsp_conv3x3_nhwc_bf16": ([_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "rsp_conv3x3_geometry_ok": ([_i, _i, _i, _i], _i),
     "rsp_mask_paste_rescale": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, ctypes.c_float, _i, _vp], _i),
@@ -817,35 +819,37 @@ def groupnorm_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, gro
 
 
 def ms_deform_attn_sample(value: torch.Tensor, ow: torch.Tensor, shapes: list, points: int) -> torch.Tensor:
-    """value bf16 [B, NQ, 128]; ow fp32 [B*NQ, >= 8*L*P*3]; shapes [(h, w)] low -> high res -> bf16 [B*NQ, 128]."""
+    """value bf16 [B, NQ, E] (E = 8 heads x 16 or x 32); ow fp32 [B*NQ, >= 8*L*P*3]; shapes [(h, w)] low -> high res
+    -> bf16 [B*NQ, E]."""
     global launch_count
     _require_cuda(value, ow)
     B, NQ, E = value.shape
     L = len(shapes)
-    assert E == 128 and value.dtype == torch.bfloat16 and value.is_contiguous()
+    assert E in (128, 256) and value.dtype == torch.bfloat16 and value.is_contiguous()
     assert ow.dtype == torch.float32 and ow.stride(1) == 1 and ow.shape[0] == B * NQ and ow.shape[1] >= 8 * L * points * 3
     hs = (ctypes.c_int32 * L)(*[s[0] for s in shapes])
     ws = (ctypes.c_int32 * L)(*[s[1] for s in shapes])
-    out = torch.empty(B * NQ, 128, device=value.device, dtype=torch.bfloat16)
-    _check(_lib.rsp_ms_deform_attn_sample(_ptr(value), _ptr(ow), ow.stride(0), ctypes.cast(hs, _vp), ctypes.cast(ws, _vp),
-                                          L, points, B, NQ, _ptr(out), _stream()), "rsp_ms_deform_attn_sample")
+    out = torch.empty(B * NQ, E, device=value.device, dtype=torch.bfloat16)
+    _check(_lib.rsp_ms_deform_attn_sample_c(_ptr(value), _ptr(ow), ow.stride(0), ctypes.cast(hs, _vp), ctypes.cast(ws, _vp),
+                                            L, points, B, NQ, _ptr(out), E, _stream()), "rsp_ms_deform_attn_sample_c")
     launch_count += 1
     return out
 
 
 def mha_small(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, nq: int, nk: int,
-              mask: torch.Tensor | None = None) -> torch.Tensor:
-    """q [B*nq, >=128], k / v [B*nk, >=128] bf16 row views (row stride = leading dim); mask = bit words
-    int64 [B*nq, ceil(nk/64)] from attn_mask_bits -> bf16 [B*nq, 128]."""
+              mask: torch.Tensor | None = None, head_dim: int = 16) -> torch.Tensor:
+    """q [B*nq, >=E], k / v [B*nk, >=E] bf16 row views (row stride = leading dim), E = 8 * head_dim (16 or 32);
+    mask = bit words int64 [B*nq, ceil(nk/64)] from attn_mask_bits -> bf16 [B*nq, E]."""
     global launch_count
     _require_cuda(q, k, v, mask)
     for t in (q, k, v):
         assert t.dtype == torch.bfloat16 and t.stride(1) == 1
     if mask is not None:
         assert mask.dtype == torch.int64 and mask.is_contiguous() and mask.shape == (B * nq, (nk + 63) // 64)
-    out = torch.empty(B * nq, 128, device=q.device, dtype=torch.bfloat16)
-    _check(_lib.rsp_mha_small(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(mask), B, nq, nk,
-                              _ptr(out), _stream()), "rsp_mha_small")
+    assert head_dim in (16, 32)
+    out = torch.empty(B * nq, 8 * head_dim, device=q.device, dtype=torch.bfloat16)
+    _check(_lib.rsp_mha_small_hd(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(mask), B, nq, nk,
+                                 _ptr(out), head_dim, _stream()), "rsp_mha_small_hd")
     launch_count += 1
     return out
 

@@ -243,13 +243,24 @@ int rsp_groupnorm_nhwc(const void* x, float* stats_ws, const float* gamma, const
 
 int rsp_ms_deform_attn_sample(const void* value, const float* ow, int ld_ow, const int32_t* hs, const int32_t* ws,
                               int L, int P, int B, int NQ, void* out, void* stream) {
-  return ms_deform_attn_sample(value, ow, ld_ow, hs, ws, L, P, B, NQ, out, S(stream));
+  return ms_deform_attn_sample(value, ow, ld_ow, hs, ws, L, P, B, NQ, out, 128, S(stream));
+}
+
+int rsp_ms_deform_attn_sample_c(const void* value, const float* ow, int ld_ow, const int32_t* hs, const int32_t* ws,
+                                int L, int P, int B, int NQ, void* out, int channels, void* stream) {
+  return ms_deform_attn_sample(value, ow, ld_ow, hs, ws, L, P, B, NQ, out, channels, S(stream));
 }
 
 int rsp_mha_small(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const uint64_t* mask_bits,
                   int B, int nq, int nk, void* out, void* stream) {
-  return mha_small(Q, ldq, K, ldk, V, ldv, reinterpret_cast<const unsigned long long*>(mask_bits), B, nq, nk, out,
+  return mha_small(Q, ldq, K, ldk, V, ldv, reinterpret_cast<const unsigned long long*>(mask_bits), B, nq, nk, out, 16,
                    S(stream));
+}
+
+int rsp_mha_small_hd(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const uint64_t* mask_bits,
+                     int B, int nq, int nk, void* out, int head_dim, void* stream) {
+  return mha_small(Q, ldq, K, ldk, V, ldv, reinterpret_cast<const unsigned long long*>(mask_bits), B, nq, nk, out,
+                   head_dim, S(stream));
 }
 
 int rsp_attn_mask_bits(const float* logits, int ld, int rows, int nk, uint64_t* mask_bits, void* stream) {

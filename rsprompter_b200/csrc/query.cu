@@ -35,7 +35,9 @@ __device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
 // ------------------------------------------------------------------------------------ GroupNorm
 // Two-level, atomic-free (bit-reproducible) statistics: part[b][blk][g] = (sum, sumsq) of one 256-pixel block in
 // fp32, then one thread per (b, g) folds the block partials in fp64 and emits (mean, rstd): the E[x^2] - mean^2
-// cancellation happens in double precision, so large-mean inputs keep their variance.  C/G = 4 channels per group.
+// cancellation happens in double precision, so large-mean inputs keep their variance.  CPG = C/G channels per group:
+// 4 (E = 128, the RSPrompter-query head) or 8 (E = 256, the stock Mask2Former head).
+template <int CPG>
 __global__ void groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part, int HW,
                                        int C, int G, int pix_per_block) {
   const int b = blockIdx.y;
@@ -43,12 +45,13 @@ __global__ void groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x, floa
   const int tc = threadIdx.x % lanes_c, tp = threadIdx.x / lanes_c;
   const int rows = blockDim.x / lanes_c;
   const int p0 = blockIdx.x * pix_per_block;
-  float s[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};      // 8 channels = 2 groups of 4
+  constexpr int GPT = 8 / CPG;                     // groups per thread (a thread owns 8 channels)
+  float s[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};
   for (int p = p0 + tp; p < min(p0 + pix_per_block, HW); p += rows) {
     float f[8];
     unpack8f(*reinterpret_cast<const uint4*>(x + (static_cast<size_t>(b) * HW + p) * C + tc * 8), f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s[j / 4] += f[j]; q[j / 4] += f[j] * f[j]; }
+    for (int j = 0; j < 8; ++j) { s[j / CPG] += f[j]; q[j / CPG] += f[j] * f[j]; }
   }
   __shared__ float red[256 * 4];
   red[threadIdx.x * 4 + 0] = s[0]; red[threadIdx.x * 4 + 1] = q[0];
@@ -59,8 +62,9 @@ __global__ void groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x, floa
     for (int r = 0; r < rows; ++r)
 #pragma unroll
       for (int k = 0; k < 4; ++k) a[k] += red[(r * lanes_c + tc) * 4 + k];
-    float* st = part + ((static_cast<size_t>(b) * gridDim.x + blockIdx.x) * G + tc * 2) * 2;
-    st[0] = a[0]; st[1] = a[1]; st[2] = a[2]; st[3] = a[3];
+    float* st = part + ((static_cast<size_t>(b) * gridDim.x + blockIdx.x) * G + tc * GPT) * 2;
+    st[0] = a[0]; st[1] = a[1];
+    if (GPT == 2) { st[2] = a[2]; st[3] = a[3]; }
   }
 }
 
@@ -81,6 +85,7 @@ __global__ void groupnorm_finalize_kernel(const float* __restrict__ part, float*
 }
 
 // y = GN(x) (+ bilinear x2 upsample of `up` [B, H/2, W/2, C]) (ReLU)
+template <int CPG>
 __global__ void groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                        const __nv_bfloat16* __restrict__ up, __nv_bfloat16* __restrict__ out, int B,
@@ -95,8 +100,14 @@ __global__ void groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, cons
   const int y = rem / W, xx = rem - y * W;
   float f[8];
   unpack8f(*reinterpret_cast<const uint4*>(x + pix * C + tc * 8), f);
-  // (mean, rstd) of this thread's two groups (4 channels each): one 16-byte load
-  const float4 mr = __ldg(reinterpret_cast<const float4*>(stats + (static_cast<size_t>(b) * G + tc * 2) * 2));
+  // (mean, rstd) of this thread's group(s): two groups of 4 channels (one 16-byte load) or one group of 8
+  float4 mr;
+  if (CPG == 4) {
+    mr = __ldg(reinterpret_cast<const float4*>(stats + (static_cast<size_t>(b) * G + tc * 2) * 2));
+  } else {
+    const float2 m2 = __ldg(reinterpret_cast<const float2*>(stats + (static_cast<size_t>(b) * G + tc) * 2));
+    mr = make_float4(m2.x, m2.y, m2.x, m2.y);
+  }
   const float4 ga0 = __ldg(reinterpret_cast<const float4*>(gamma + tc * 8)), ga1 = __ldg(reinterpret_cast<const float4*>(gamma + tc * 8 + 4));
   const float4 be0 = __ldg(reinterpret_cast<const float4*>(beta + tc * 8)), be1 = __ldg(reinterpret_cast<const float4*>(beta + tc * 8 + 4));
   const float gam[8] = {ga0.x, ga0.y, ga0.z, ga0.w, ga1.x, ga1.y, ga1.z, ga1.w};
@@ -134,22 +145,30 @@ __global__ void groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, cons
 int groupnorm_nhwc(const void* x, float* stats_ws, const float* gamma, const float* beta, const void* up, void* out,
                    int B, int H, int W, int C, int G, float eps, int relu, cudaStream_t stream) {
   RSP_CHECK_ARG(x && stats_ws && gamma && beta && out, "groupnorm: null pointer");
-  RSP_CHECK_ARG(C % 8 == 0 && C / G == 4 && C / 8 <= 32 && 256 % (C / 8) == 0, "groupnorm: C=%d G=%d unsupported", C, G);
+  RSP_CHECK_ARG(C % 8 == 0 && C % G == 0 && (C / G == 4 || C / G == 8) && C / 8 <= 32 && 256 % (C / 8) == 0,
+                "groupnorm: C=%d G=%d unsupported", C, G);
+  const bool cpg8 = C / G == 8;
   RSP_CHECK_ARG((reinterpret_cast<uintptr_t>(stats_ws) & 15) == 0, "groupnorm: stats_ws must be 16-byte aligned");
   const int HW = H * W;
   const int ppb = 256;
   const int nblk = (HW + ppb - 1) / ppb;
   dim3 grid(nblk, B);
   float* part = stats_ws + static_cast<size_t>(B) * G * 2;       // [B, nblk, G, 2] block partials behind the stats
-  groupnorm_stats_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), part, HW, C, G, ppb);
+  if (cpg8) groupnorm_stats_kernel<8><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), part, HW, C, G, ppb);
+  else groupnorm_stats_kernel<4><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), part, HW, C, G, ppb);
   RSP_CHECK_LAUNCH();
   groupnorm_finalize_kernel<<<(B * G + 127) / 128, 128, 0, stream>>>(part, stats_ws, B, G, nblk,
                                                                    static_cast<double>(HW) * (C / G), eps);
   RSP_CHECK_LAUNCH();
   const long long total = static_cast<long long>(B) * HW * (C / 8);
-  groupnorm_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(x), stats_ws, gamma, beta, static_cast<const __nv_bfloat16*>(up),
-      static_cast<__nv_bfloat16*>(out), B, H, W, C, G, eps, relu);
+  if (cpg8)
+    groupnorm_apply_kernel<8><<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), stats_ws, gamma, beta, static_cast<const __nv_bfloat16*>(up),
+        static_cast<__nv_bfloat16*>(out), B, H, W, C, G, eps, relu);
+  else
+    groupnorm_apply_kernel<4><<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), stats_ws, gamma, beta, static_cast<const __nv_bfloat16*>(up),
+        static_cast<__nv_bfloat16*>(out), B, H, W, C, G, eps, relu);
   RSP_CHECK_LAUNCH();
   return RSP_OK;
 }
@@ -157,15 +176,17 @@ int groupnorm_nhwc(const void* x, float* stats_ws, const float* gamma, const flo
 // ------------------------------------------------------------------------------------ MSDeformAttn
 struct DeformLevels { int h[4], w[4], start[4]; };
 
-// thread = 8 channels of one (batch, query, head); embed 128 = 8 heads x 16
-__global__ void ms_deform_attn_kernel(const __nv_bfloat16* __restrict__ value,   // [B, NQ, 128]
+// thread = 8 channels of one (batch, query, head); embed C = 8 heads x HD (HD = 16: RSPrompter-query, 32: Mask2Former)
+template <int HD>
+__global__ void ms_deform_attn_kernel(const __nv_bfloat16* __restrict__ value,   // [B, NQ, C]
                                       const float* __restrict__ ow, int ld_ow,    // [B*NQ, >= H*L*P*3]: offsets | logits
                                       DeformLevels lv, int B, int NQ, int L, int P,
-                                      __nv_bfloat16* __restrict__ out) {          // [B*NQ, 128]
+                                      __nv_bfloat16* __restrict__ out) {          // [B*NQ, C]
+  constexpr int PARTS = HD / 8, C = 8 * HD;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<long long>(B) * NQ * 16) return;
-  const int half = static_cast<int>(idx & 1), h = static_cast<int>((idx >> 1) & 7);
-  const long long bq = idx >> 4;
+  if (idx >= static_cast<long long>(B) * NQ * 8 * PARTS) return;
+  const int half = static_cast<int>(idx % PARTS), h = static_cast<int>((idx / PARTS) & 7);
+  const long long bq = idx / (8 * PARTS);
   const int b = static_cast<int>(bq / NQ), q = static_cast<int>(bq - static_cast<long long>(b) * NQ);
   // reference point: centre of the query's own cell, normalised
   int ql = 0;
@@ -184,7 +205,7 @@ __global__ void ms_deform_attn_kernel(const __nv_bfloat16* __restrict__ value,  
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   for (int l = 0; l < L; ++l) {
     const int H = lv.h[l], W = lv.w[l];
-    const __nv_bfloat16* vb = value + (static_cast<size_t>(b) * NQ + lv.start[l]) * 128 + h * 16 + half * 8;
+    const __nv_bfloat16* vb = value + (static_cast<size_t>(b) * NQ + lv.start[l]) * C + h * HD + half * 8;
     for (int pt = 0; pt < P; ++pt) {
       const float wgt = expf(logit[l * P + pt] - mx) / den;
       const float lx = rx + offs[(l * P + pt) * 2] / W, ly = ry + offs[(l * P + pt) * 2 + 1] / H;
@@ -200,20 +221,21 @@ __global__ void ms_deform_attn_kernel(const __nv_bfloat16* __restrict__ value,  
           if (xi < 0 || xi >= W || yi < 0 || yi >= H) continue;   // zero padding
           const float cw = (cx ? ax : 1.f - ax) * (cy ? ay : 1.f - ay) * wgt;
           float f[8];
-          unpack8f(*reinterpret_cast<const uint4*>(vb + (static_cast<size_t>(yi) * W + xi) * 128), f);
+          unpack8f(*reinterpret_cast<const uint4*>(vb + (static_cast<size_t>(yi) * W + xi) * C), f);
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] += cw * f[j];
         }
     }
   }
-  *reinterpret_cast<uint4*>(out + bq * 128 + h * 16 + half * 8) =
+  *reinterpret_cast<uint4*>(out + bq * C + h * HD + half * 8) =
       make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
                  pack_bf16x2(acc[6], acc[7]));
 }
 
 int ms_deform_attn_sample(const void* value, const float* ow, int ld_ow, const int* hs, const int* ws, int L, int P,
-                          int B, int NQ, void* out, cudaStream_t stream) {
+                          int B, int NQ, void* out, int channels, cudaStream_t stream) {
   RSP_CHECK_ARG(value && ow && hs && ws && out && L >= 1 && L <= 4 && P >= 1, "ms_deform_attn: bad args");
+  RSP_CHECK_ARG(channels == 128 || channels == 256, "ms_deform_attn: channels %d (8 heads x 16 or 32 supported)", channels);
   DeformLevels lv;
   int start = 0;
   for (int l = 0; l < 4; ++l) {
@@ -221,9 +243,13 @@ int ms_deform_attn_sample(const void* value, const float* ow, int ld_ow, const i
     if (l < L) start += hs[l] * ws[l];
   }
   RSP_CHECK_ARG(start == NQ, "ms_deform_attn: sum of level sizes %d != NQ %d", start, NQ);
-  const long long total = static_cast<long long>(B) * NQ * 16;
-  ms_deform_attn_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(value), ow, ld_ow, lv, B, NQ, L, P, static_cast<__nv_bfloat16*>(out));
+  const long long total = static_cast<long long>(B) * NQ * (channels / 8);
+  if (channels == 128)
+    ms_deform_attn_kernel<16><<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(value), ow, ld_ow, lv, B, NQ, L, P, static_cast<__nv_bfloat16*>(out));
+  else
+    ms_deform_attn_kernel<32><<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(value), ow, ld_ow, lv, B, NQ, L, P, static_cast<__nv_bfloat16*>(out));
   RSP_CHECK_LAUNCH();
   return RSP_OK;
 }
@@ -244,44 +270,56 @@ __device__ __forceinline__ void cp_async16q(uint32_t dst, const void* src) {
 }
 
 constexpr int MHA_KC = 64;     // keys per chunk
-constexpr int MHA_ROWB = 48;   // bytes per staged key row (16 bf16 + 16 B pad: conflict-free fragment reads)
 constexpr int MHA_WARPS = 4;
 
+// HD = head channels (16: RSPrompter-query E = 128; 32: stock Mask2Former E = 256), 8 heads.  A staged key row is
+// HD bf16 + 16 B pad (48 / 80 bytes: conflict-free fragment reads).
+template <int HD>
 __global__ void __launch_bounds__(MHA_WARPS * 32)
-mha16_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* __restrict__ K, int ldk,
-             const __nv_bfloat16* __restrict__ V, int ldv, const unsigned long long* __restrict__ mask, int mask_words,
-             int nq, int nk, __nv_bfloat16* __restrict__ out) {
-  __shared__ __align__(16) unsigned char sK[2][MHA_KC * MHA_ROWB];
-  __shared__ __align__(16) unsigned char sV[2][MHA_KC * MHA_ROWB];
+mha_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* __restrict__ K, int ldk,
+           const __nv_bfloat16* __restrict__ V, int ldv, const unsigned long long* __restrict__ mask, int mask_words,
+           int nq, int nk, __nv_bfloat16* __restrict__ out) {
+  constexpr int KS = HD / 16;            // k-steps of Q K^T
+  constexpr int PARTS = HD / 8;          // 16-byte pieces per staged row
+  constexpr int ROWB = HD * 2 + 16;
+  constexpr int E = 8 * HD;
+  __shared__ __align__(16) unsigned char sK[2][MHA_KC * ROWB];
+  __shared__ __align__(16) unsigned char sV[2][MHA_KC * ROWB];
   const int b = blockIdx.x >> 3, h = blockIdx.x & 7;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int q0 = (blockIdx.y * MHA_WARPS + warp) * 16;
   const bool active = q0 < nq;
   const int r0 = min(q0 + g, nq - 1), r1 = min(q0 + g + 8, nq - 1);
 
-  uint32_t qa[4];
+  // 1/sqrt(16) is exact in bf16 and is folded into Q; 1/sqrt(32) is not: it multiplies the fp32 scores instead
+  constexpr float POST_SCALE = HD == 16 ? 1.0f : 0.17677669529663687f;
+  uint32_t qa[KS][4];
   {
-    const __nv_bfloat162 sc = __float2bfloat162_rn(0.25f);   // 1/sqrt(16), exact in bf16
-    const __nv_bfloat16* p0 = Q + (static_cast<size_t>(b) * nq + r0) * ldq + h * 16 + 2 * t;
-    const __nv_bfloat16* p1 = Q + (static_cast<size_t>(b) * nq + r1) * ldq + h * 16 + 2 * t;
-    __nv_bfloat162 v;
-    v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(p0), sc);     qa[0] = *reinterpret_cast<uint32_t*>(&v);
-    v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(p1), sc);     qa[1] = *reinterpret_cast<uint32_t*>(&v);
-    v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(p0 + 8), sc); qa[2] = *reinterpret_cast<uint32_t*>(&v);
-    v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(p1 + 8), sc); qa[3] = *reinterpret_cast<uint32_t*>(&v);
+    const __nv_bfloat162 sc = __float2bfloat162_rn(HD == 16 ? 0.25f : 1.0f);
+    const __nv_bfloat16* p0 = Q + (static_cast<size_t>(b) * nq + r0) * ldq + h * HD + 2 * t;
+    const __nv_bfloat16* p1 = Q + (static_cast<size_t>(b) * nq + r1) * ldq + h * HD + 2 * t;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      __nv_bfloat162 v;
+      v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(p0 + ks * 16), sc);     qa[ks][0] = *reinterpret_cast<uint32_t*>(&v);
+      v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(p1 + ks * 16), sc);     qa[ks][1] = *reinterpret_cast<uint32_t*>(&v);
+      v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(p0 + ks * 16 + 8), sc); qa[ks][2] = *reinterpret_cast<uint32_t*>(&v);
+      v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(p1 + ks * 16 + 8), sc); qa[ks][3] = *reinterpret_cast<uint32_t*>(&v);
+    }
   }
   const uint32_t sK0 = smem_u32(&sK[0][0]), sV0 = smem_u32(&sV[0][0]);
-  constexpr uint32_t BUF = MHA_KC * MHA_ROWB;
+  constexpr uint32_t BUF = MHA_KC * ROWB;
   const int nchunks = (nk + MHA_KC - 1) / MHA_KC;
   auto issue = [&](int c, int buf) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int piece = threadIdx.x + i * MHA_WARPS * 32;       // 256 pieces of 16 B: K rows then V rows
-      const int which = piece >> 7, row = (piece & 127) >> 1, half = piece & 1;
+    for (int i = 0; i < PARTS; ++i) {
+      const int piece = threadIdx.x + i * MHA_WARPS * 32;       // 2 * 64 * PARTS pieces of 16 B: K rows then V rows
+      const int which = piece / (MHA_KC * PARTS), rem = piece % (MHA_KC * PARTS);
+      const int row = rem / PARTS, part = rem % PARTS;
       const int key = min(c * MHA_KC + row, nk - 1);
       const __nv_bfloat16* src = (which ? V + (static_cast<size_t>(b) * nk + key) * ldv
-                                        : K + (static_cast<size_t>(b) * nk + key) * ldk) + h * 16 + half * 8;
-      cp_async16q((which ? sV0 : sK0) + buf * BUF + row * MHA_ROWB + half * 16, src);
+                                        : K + (static_cast<size_t>(b) * nk + key) * ldk) + h * HD + part * 8;
+      cp_async16q((which ? sV0 : sK0) + buf * BUF + row * ROWB + part * 16, src);
     }
     asm volatile("cp.async.commit_group;\n" ::);
   };
@@ -292,7 +330,9 @@ mha16_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* 
 
   constexpr float L2E = 1.4426950408889634f, NEG = -1e30f;
   float m0 = NEG, m1 = NEG, l0 = 0.f, l1 = 0.f;
-  float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float o[HD / 8][4];
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
   for (int c = 0; c < nchunks; ++c) {
     const int buf = c & 1;
     asm volatile("cp.async.wait_all;\n" ::);
@@ -305,9 +345,11 @@ mha16_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* 
     const unsigned char* kb = sK[buf];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const uint32_t* kr = reinterpret_cast<const uint32_t*>(kb + (8 * j + g) * MHA_ROWB);
+      const uint32_t* kr = reinterpret_cast<const uint32_t*>(kb + (8 * j + g) * ROWB);
       s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-      mma_bf16_16816q(s[j], qa, kr[t], kr[t + 4]);
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) mma_bf16_16816q(s[j], qa[ks], kr[ks * 8 + t], kr[ks * 8 + t + 4]);
+      if (HD != 16) { s[j][0] *= POST_SCALE; s[j][1] *= POST_SCALE; s[j][2] *= POST_SCALE; s[j][3] *= POST_SCALE; }
     }
     const int kbase = c * MHA_KC;
     float mx0 = NEG, mx1 = NEG;
@@ -337,7 +379,7 @@ mha16_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* 
     }
     l0 = l0 * a0 + rs0; l1 = l1 * a1 + rs1;
 #pragma unroll
-    for (int n = 0; n < 2; ++n) { o[n][0] *= a0; o[n][1] *= a0; o[n][2] *= a1; o[n][3] *= a1; }
+    for (int n = 0; n < HD / 8; ++n) { o[n][0] *= a0; o[n][1] *= a0; o[n][2] *= a1; o[n][3] *= a1; }
     const uint32_t vb = sV0 + buf * BUF;
     const int mi = lane >> 3, rr = lane & 7;
 #pragma unroll
@@ -347,12 +389,15 @@ mha16_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* 
       pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
       pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
       pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-      uint32_t v0, v1, v2, v3;
-      const uint32_t addr = vb + (16 * kk + (mi & 1) * 8 + rr) * MHA_ROWB + (mi >> 1) * 16;
-      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                   : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(addr));
-      mma_bf16_16816q(o[0], pa, v0, v1);
-      mma_bf16_16816q(o[1], pa, v2, v3);
+#pragma unroll
+      for (int np = 0; np < KS; ++np) {        // 16 output channels per ldmatrix.x4.trans
+        uint32_t v0, v1, v2, v3;
+        const uint32_t addr = vb + (16 * kk + (mi & 1) * 8 + rr) * ROWB + (mi >> 1) * 16 + np * 32;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                     : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(addr));
+        mma_bf16_16816q(o[2 * np], pa, v0, v1);
+        mma_bf16_16816q(o[2 * np + 1], pa, v2, v3);
+      }
     }
   }
   if (!active) return;
@@ -360,24 +405,30 @@ mha16_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* 
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const float i0 = 1.0f / l0, i1 = 1.0f / l1;
 #pragma unroll
-  for (int n = 0; n < 2; ++n) {
+  for (int n = 0; n < HD / 8; ++n) {
     if (q0 + g < nq)
-      *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * nq + q0 + g) * 128 + h * 16 + 8 * n + 2 * t) =
+      *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * nq + q0 + g) * E + h * HD + 8 * n + 2 * t) =
           pack_bf16x2(o[n][0] * i0, o[n][1] * i0);
     if (q0 + g + 8 < nq)
-      *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * nq + q0 + g + 8) * 128 + h * 16 + 8 * n + 2 * t) =
+      *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * nq + q0 + g + 8) * E + h * HD + 8 * n + 2 * t) =
           pack_bf16x2(o[n][2] * i1, o[n][3] * i1);
   }
 }
 
 int mha_small(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const unsigned long long* mask,
-              int B, int nq, int nk, void* out, cudaStream_t stream) {
+              int B, int nq, int nk, void* out, int head_dim, cudaStream_t stream) {
   RSP_CHECK_ARG(Q && K && V && out && B > 0 && nq > 0 && nk > 0, "mha_small: bad args");
   RSP_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0, "mha_small: leading dims must be multiples of 8");
+  RSP_CHECK_ARG(head_dim == 16 || head_dim == 32, "mha_small: head_dim %d (16 or 32 supported)", head_dim);
   dim3 grid(B * 8, (nq + MHA_WARPS * 16 - 1) / (MHA_WARPS * 16));
-  mha16_kernel<<<grid, MHA_WARPS * 32, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(Q), ldq, static_cast<const __nv_bfloat16*>(K), ldk,
-      static_cast<const __nv_bfloat16*>(V), ldv, mask, (nk + 63) / 64, nq, nk, static_cast<__nv_bfloat16*>(out));
+  if (head_dim == 16)
+    mha_kernel<16><<<grid, MHA_WARPS * 32, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(Q), ldq, static_cast<const __nv_bfloat16*>(K), ldk,
+        static_cast<const __nv_bfloat16*>(V), ldv, mask, (nk + 63) / 64, nq, nk, static_cast<__nv_bfloat16*>(out));
+  else
+    mha_kernel<32><<<grid, MHA_WARPS * 32, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(Q), ldq, static_cast<const __nv_bfloat16*>(K), ldk,
+        static_cast<const __nv_bfloat16*>(V), ldv, mask, (nk + 63) / 64, nq, nk, static_cast<__nv_bfloat16*>(out));
   RSP_CHECK_LAUNCH();
   return RSP_OK;
 }

@@ -6,9 +6,9 @@ namespace rsp {
 int groupnorm_nhwc(const void* x, float* stats_ws, const float* gamma, const float* beta, const void* up, void* out,
                    int B, int H, int W, int C, int G, float eps, int relu, cudaStream_t stream);
 int ms_deform_attn_sample(const void* value, const float* ow, int ld_ow, const int* hs, const int* ws, int L, int P,
-                          int B, int NQ, void* out, cudaStream_t stream);
+                          int B, int NQ, void* out, int channels, cudaStream_t stream);   // channels = 8 heads x {16, 32}
 int mha_small(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const unsigned long long* mask,
-              int B, int nq, int nk, void* out, cudaStream_t stream);
+              int B, int nq, int nk, void* out, int head_dim, cudaStream_t stream);        // 8 heads x head_dim {16, 32}
 int attn_mask_bits(const float* logits, int ld, int rows, int nk, unsigned long long* out, cudaStream_t stream);
 int resize_bilinear_nhwc(const void* x, int B, int H, int W, int C, int h, int w, void* out, cudaStream_t stream);
 int mask_embed_src(const float* mpp, const float* const* wts, const float* emb, const float* pos, int N, int n_per_img,

@@ -408,4 +408,47 @@ class SAMSegMaskRCNN(_SamDetectorBase):
         return self.predict(data["inputs"], data.get("data_samples"))
 
 
-__all__ = ["RSPrompterAnchor", "RSPrompterQuery", "SAMSegMaskRCNN"]
+@MODELS.register_module(force=True)
+class SAMSegMask2Former(_SamDetectorBase):
+    """M:1247-1274 over mmdet Mask2Former / MaskFormer.predict (detectors/maskformer.py:95-140): SAM encoder + RSFPN
+    feed the stock Mask2FormerHead; MaskFormerFusionHead turns the last layer's (cls, masks) into instances."""
+
+    def __init__(self, backbone=None, neck=None, panoptic_head=None, panoptic_fusion_head=None, train_cfg=None,
+                 test_cfg=None, data_preprocessor=None, init_cfg=None, **kwargs):
+        BaseModule.__init__(self, init_cfg=None)
+        test_cfg = _cfg(test_cfg)
+        self.backbone = MODELS.build(backbone)
+        self.neck = MODELS.build(neck)
+        ph = dict(panoptic_head)
+        ph.update(train_cfg=None, test_cfg=test_cfg)
+        self.panoptic_head = MODELS.build(ph)
+        pf = dict(panoptic_fusion_head)
+        pf.update(test_cfg=test_cfg)
+        self.panoptic_fusion_head = MODELS.build(pf)
+        self.test_cfg = test_cfg
+        self.data_preprocessor_cfg = data_preprocessor
+        self.data_preprocessor = MODELS.build(dict(data_preprocessor)) if data_preprocessor else None
+        self.eval()
+
+    extract_feat = SAMSegMaskRCNN.extract_feat
+
+    @torch.no_grad()
+    def predict_raw(self, batch_inputs: torch.Tensor, capture: dict | None = None):
+        """-> dict(cls fp32 [B, nq, C+1], mask_logits fp32 [B*nq, H/4, W/4])."""
+        _, _, _, emb_nhwc, hidden = self._encode(batch_inputs)
+        if isinstance(getattr(self.neck, "feature_aggregator", None), PseudoFeatureAggregator):
+            feats = self.neck.forward_nhwc(None, _lib.cast_bf16(emb_nhwc.contiguous()))
+        else:
+            feats = self.neck.forward_nhwc(hidden)
+        if capture is not None:
+            capture.update(feats=feats)
+        cls, masks = self.panoptic_head.forward_nhwc(feats, capture=capture)
+        return dict(cls=cls, mask_logits=masks)
+
+    predict = RSPrompterQuery.predict
+    predict_records = RSPrompterQuery.predict_records
+    forward = RSPrompterQuery.forward
+    test_step = RSPrompterQuery.test_step
+
+
+__all__ = ["RSPrompterAnchor", "RSPrompterQuery", "SAMSegMaskRCNN", "SAMSegMask2Former"]

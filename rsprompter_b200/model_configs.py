@@ -137,3 +137,36 @@ def maskrcnn_model_cfg(arch: str = "base", num_classes: int = 10) -> dict:
                                min_bbox_size=0),
                       rcnn=dict(score_thr=0.05, nms=dict(type="nms", iou_threshold=0.5), max_per_img=100,
                                 mask_thr_binary=0.5)))
+
+
+def mask2former_model_cfg(arch: str = "base", num_classes: int = 10, num_queries: int = 100) -> dict:
+    """configs/rsprompter/_base_/samseg-mask2former.py:60-191 + samseg-mask2former-nwpu.py overrides."""
+    name, backbone, neck = _backbone_neck(arch, None)
+    attn = dict(embed_dims=256, num_heads=8, dropout=0.0, batch_first=True)
+    return dict(
+        type="SAMSegMask2Former",
+        backbone=backbone,
+        neck=neck,
+        panoptic_head=dict(
+            type="Mask2FormerHead", in_channels=[256, 256, 256, 256, 256], feat_channels=256, out_channels=256,
+            num_things_classes=num_classes, num_stuff_classes=0, num_queries=num_queries, num_transformer_feat_level=3,
+            pixel_decoder=dict(
+                type="MSDeformAttnPixelDecoder", strides=[4, 8, 16, 32, 64], num_outs=3,
+                norm_cfg=dict(type="GN", num_groups=32), act_cfg=dict(type="ReLU"),
+                encoder=dict(num_layers=3, layer_cfg=dict(
+                    self_attn_cfg=dict(embed_dims=256, num_heads=8, num_levels=3, num_points=4, dropout=0.0,
+                                       batch_first=True),
+                    ffn_cfg=dict(embed_dims=256, feedforward_channels=1024, num_fcs=2, ffn_drop=0.0,
+                                 act_cfg=dict(type="ReLU", inplace=True)))),
+                positional_encoding=dict(num_feats=128, normalize=True)),
+            enforce_decoder_input_project=False,
+            positional_encoding=dict(num_feats=128, normalize=True),
+            transformer_decoder=dict(return_intermediate=True, num_layers=9,
+                                     layer_cfg=dict(self_attn_cfg=attn, cross_attn_cfg=attn,
+                                                    ffn_cfg=dict(embed_dims=256, feedforward_channels=2048, num_fcs=2,
+                                                                 ffn_drop=0.0, act_cfg=dict(type="ReLU", inplace=True))),
+                                     init_cfg=None)),
+        panoptic_fusion_head=dict(type="MaskFormerFusionHead", num_things_classes=num_classes, num_stuff_classes=0,
+                                  loss_panoptic=None, init_cfg=None),
+        test_cfg=dict(panoptic_on=False, semantic_on=False, instance_on=True, max_per_image=100, iou_thr=0.8,
+                      filter_low_score=True))

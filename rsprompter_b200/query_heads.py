@@ -120,7 +120,7 @@ class MSDeformAttnPixelDecoder(_PrepMixin, BaseModule):
         BaseModule.__init__(self, init_cfg=None)
         enc = _cfg(encoder)
         sa = enc.layer_cfg.self_attn_cfg
-        assert norm_cfg is not None and norm_cfg.get("type") == "GN" and feat_channels == 128 and sa.num_heads == 8
+        assert norm_cfg is not None and norm_cfg.get("type") == "GN" and feat_channels in (128, 256) and sa.num_heads == 8
         self.num_input_levels, self.num_encoder_levels = len(in_channels), sa.num_levels
         self.num_points, self.num_outs, self.E = sa.num_points, num_outs, feat_channels
         self.groups = norm_cfg.get("num_groups", 32)
@@ -462,4 +462,141 @@ class RSMaskFormerFusionHead(BaseModule):
         rec.counts.fill_(K)
 
 
-__all__ = ["MSDeformAttnPixelDecoder", "RSMask2FormerHead", "RSMaskFormerFusionHead"]
+@MODELS.register_module(force=True)
+class Mask2FormerHead(_PrepMixin, BaseModule):
+    """The stock mmdet Mask2FormerHead (dense_heads/mask2former_head.py:24-156 build, :340-380 _forward_head, :382-460
+    forward; inference half) as SAMSegMask2Former uses it (configs/rsprompter/_base_/samseg-mask2former.py:86-160):
+    feat_channels 256 (8 heads x 32), 9 decoder layers, cls_embed = one Linear, masks = mask_embed x mask_feature.
+    Same kernels and the same constant-folding of the positional terms as RSMask2FormerHead; the attention masks of the
+    intermediate layers are formed at the level size from bilinearly resized mask features (F.interpolate is linear),
+    so only the last layer materialises the H/4 x W/4 mask logits."""
+
+    def __init__(self, in_channels=None, feat_channels=256, out_channels=256, num_things_classes=80,
+                 num_stuff_classes=0, num_queries=100, num_transformer_feat_level=3, pixel_decoder=None,
+                 enforce_decoder_input_project=False, transformer_decoder=None, positional_encoding=None, loss_cls=None,
+                 loss_mask=None, loss_dice=None, train_cfg=None, test_cfg=None, init_cfg=None, **kwargs):
+        BaseModule.__init__(self, init_cfg=None)
+        td = _cfg(transformer_decoder)
+        assert not enforce_decoder_input_project and feat_channels in (128, 256)
+        assert td.layer_cfg.cross_attn_cfg.num_heads == 8 and td.layer_cfg.cross_attn_cfg.embed_dims == feat_channels
+        self.num_classes = num_things_classes + num_stuff_classes
+        self.num_queries, self.num_levels = num_queries, num_transformer_feat_level
+        self.feat_channels, self.out_channels = feat_channels, out_channels
+        self.num_layers = td.num_layers
+        E = feat_channels
+        pd = dict(pixel_decoder)
+        pd.update(in_channels=in_channels, feat_channels=feat_channels, out_channels=out_channels)
+        self.pixel_decoder = MODELS.build(pd)
+        self.transformer_decoder = _Decoder(td.num_layers, E, td.layer_cfg.ffn_cfg.feedforward_channels)
+        self.query_embed, self.query_feat = _Emb(num_queries, E), _Emb(num_queries, E)
+        self.level_embed = _Emb(num_transformer_feat_level, E)
+        self.cls_embed = _Affine((self.num_classes + 1, E))
+        self.mask_embed = nn.Sequential(_Affine((E, E)), nn.Identity(), _Affine((E, E)), nn.Identity(),
+                                        _Affine((out_channels, E)))
+        self._init_prep()
+        self._const: dict = {}
+
+    def init_weights(self):
+        pass
+
+    _level_consts = RSMask2FormerHead._level_consts
+    _mlp = RSMask2FormerHead._mlp
+    _padded_queries = RSMask2FormerHead._padded_queries
+
+    @torch.no_grad()
+    def _prepare(self):
+        E = self.feat_channels
+        lin = lambda m: (_bf(m.weight), _f32(m.bias))  # noqa: E731
+        layers = []
+        for l in self.transformer_decoder.layers:
+            d = {}
+            for name, mod in (("ca", l.cross_attn.attn), ("sa", l.self_attn.attn)):
+                W, b = mod.in_proj_weight, mod.in_proj_bias
+                d[name] = dict(wq=_bf(W[:E]), bq=_f32(b[:E]), wk=_bf(W[E:2 * E]), bk=_f32(b[E:2 * E]), wv=_bf(W[2 * E:]),
+                               bv=_f32(b[2 * E:]), wqk=_bf(W[:2 * E]), bqk=_f32(b[:2 * E]), w32=_f32(W),
+                               wo=_bf(mod.out_proj.weight), bo=_f32(mod.out_proj.bias))
+            d["norms"] = [(_f32(n.weight), _f32(n.bias)) for n in l.norms]
+            d["w1"], d["b1"] = lin(l.ffn.layers[0][0])
+            d["w2"], d["b2"] = lin(l.ffn.layers[1])
+            layers.append(d)
+        self._prep = dict(
+            layers=layers, post=(_f32(self.transformer_decoder.post_norm.weight), _f32(self.transformer_decoder.post_norm.bias)),
+            cls=[lin(self.cls_embed)], mask=[lin(self.mask_embed[i]) for i in (0, 2, 4)],
+            qe=_f32(self.query_embed.weight), qf=_f32(self.query_feat.weight), le=_f32(self.level_embed.weight))
+        self._const = {}
+        return self._prep
+
+    @torch.no_grad()
+    def forward_nhwc(self, feats: list, capture: dict | None = None):
+        """feats: the 5 bf16 NHWC neck levels -> cls fp32 [B, nq, C+1], mask logits fp32 [B*nq, H/4, W/4] (last layer)."""
+        p = self._prep or self._prepare()
+        E, nq, B = self.feat_channels, self.num_queries, feats[0].shape[0]
+        hd = E // 8
+        mask_feature, mems = self.pixel_decoder.forward_nhwc(feats)
+        H0, W0 = mask_feature.shape[1], mask_feature.shape[2]
+        shapes = [(m.shape[1], m.shape[2]) for m in mems[:self.num_levels]]
+        consts = self._level_consts(shapes, mask_feature.device)
+        mem_rows = [m.reshape(B * m.shape[1] * m.shape[2], E) for m in mems[:self.num_levels]]
+        mf_rows = mask_feature.view(B, H0 * W0, -1)
+        qf = p["qf"].unsqueeze(0).expand(B, -1, -1).reshape(B * nq, E).contiguous()      # fp32 query stream
+        mf_lvl = [_lib.resize_bilinear_nhwc(mask_feature, s).view(B, s[0] * s[1], -1) for s in shapes]
+        grouped = nq <= 128
+        if grouped:
+            me_pad, scat, back = self._padded_queries(B, nq, self.out_channels, mask_feature.device)
+
+        def head(qf32: torch.Tensor, lvl: int, final: bool):
+            x = _lib.layernorm(qf32, *p["post"], 1e-5)                                    # post_norm -> bf16
+            if grouped:
+                self._mlp(x, p["mask"], out=me_pad, row_map=scat)
+                me_of = lambda b: me_pad[b * 128:b * 128 + nq]  # noqa: E731
+            else:
+                me = self._mlp(x, p["mask"])
+                me_of = lambda b: me[b * nq:(b + 1) * nq]  # noqa: E731
+            if not final:
+                hw_l = mf_lvl[lvl].shape[1]
+                logits = torch.empty(B * nq, hw_l, device=x.device, dtype=torch.float32)
+                if grouped:
+                    _lib.gemm_grouped(me_pad, mf_lvl[lvl].reshape(B * hw_l, -1), logits, hw_l, 128, hw_l, row_map=back)
+                else:
+                    for b in range(B):
+                        _lib.gemm(me_of(b), mf_lvl[lvl][b], None, out=logits[b * nq:(b + 1) * nq])
+                return _lib.attn_mask_bits(logits), None, None
+            mp = torch.empty(B, nq, H0 * W0, device=x.device, dtype=torch.float32)
+            for b in range(B):                                                            # einsum 'bqc,bchw->bqhw'
+                _lib.gemm(me_of(b), mf_rows[b], None, out=mp[b])
+            cls = self._mlp(x, p["cls"], out_dtype=torch.float32)
+            return None, mp.view(B * nq, H0, W0), cls
+
+        attn_mask, mp, cls = head(qf, 0, final=self.num_layers == 0)
+        for i, d in enumerate(p["layers"]):
+            lvl = i % self.num_levels
+            hw = shapes[lvl][0] * shapes[lvl][1]
+            c = consts[i]
+            ca, sa = d["ca"], d["sa"]
+            qb = _lib.cast_bf16(qf)
+            Q = _lib.gemm(qb, ca["wq"], ca["bq"], residual=c["qe_q"], res_mod=nq)
+            K = _lib.gemm(mem_rows[lvl], ca["wk"], ca["bk"], residual=c["pk"], res_mod=hw)
+            V = _lib.gemm(mem_rows[lvl], ca["wv"], c["bv"])
+            att = _lib.mha_small(Q, K, V, B, nq, hw, mask=attn_mask, head_dim=hd)
+            qf = _lib.gemm(att, ca["wo"], ca["bo"], residual=qf, out_dtype=torch.float32, ln=(*d["norms"][0], 1e-5))
+            qb = _lib.cast_bf16(qf)
+            QK = _lib.gemm(qb, sa["wqk"], sa["bqk"], residual=c["qe_qk"], res_mod=nq)      # [B*nq, 2E]
+            Vs = _lib.gemm(qb, sa["wv"], sa["bv"])
+            att = _lib.mha_small(QK[:, :E], QK[:, E:], Vs, B, nq, nq, head_dim=hd)
+            qf = _lib.gemm(att, sa["wo"], sa["bo"], residual=qf, out_dtype=torch.float32, ln=(*d["norms"][1], 1e-5))
+            hdn = _lib.gemm(_lib.cast_bf16(qf), d["w1"], d["b1"], act="relu")
+            qf = _lib.gemm(hdn, d["w2"], d["b2"], residual=qf, out_dtype=torch.float32, ln=(*d["norms"][2], 1e-5))
+            attn_mask, mp, cls = head(qf, (i + 1) % self.num_levels, final=i == self.num_layers - 1)
+        if capture is not None:
+            capture.update(mask_feature=mask_feature, memories=mems)
+        return cls.view(B, nq, -1), mp
+
+
+@MODELS.register_module(force=True)
+class MaskFormerFusionHead(RSMaskFormerFusionHead):
+    """seg_heads/panoptic_fusion_heads/maskformer_fusion_head.py (this repository's copy crops with the scaled original
+    size exactly as M:679-691 does, :239-252): instance_on post-processing shared with RSMaskFormerFusionHead."""
+
+
+__all__ = ["MSDeformAttnPixelDecoder", "RSMask2FormerHead", "RSMaskFormerFusionHead", "Mask2FormerHead",
+           "MaskFormerFusionHead"]

@@ -34,7 +34,7 @@ except Exception:  # noqa: BLE001
 # they are registered only when the name is still free; the RSPrompter-specific names are re-registered with force=True.
 _GENERIC_NAMES = frozenset({"RPNHead", "Shared2FCBBoxHead", "SingleRoIExtractor", "RoIAlign", "DetDataPreprocessor",
                             "AnchorGenerator", "DeltaXYWHBBoxCoder", "MSDeformAttnPixelDecoder", "StandardRoIHead",
-                            "FCNMaskHead"})
+                            "FCNMaskHead", "Mask2FormerHead", "MaskFormerFusionHead"})
 
 if HAVE_MMENGINE:  # pragma: no cover - not available in this image
 

@@ -359,3 +359,36 @@ def query_detector_state_dict(arch: SamVisionArch, num_classes: int, n_select: i
     sd.update(_prefixed("shared_image_embedding.shared_image_embedding.",
                         positional_embedding_state_dict(arch, seed + 3)))
     return sd
+
+
+def mask2former_head_state_dict(num_classes: int, nq: int = 100, E: int = 256, C: int = 256, F_enc: int = 1024,
+                                F_dec: int = 2048, in_levels: int = 5, enc_levels: int = 3, enc_layers: int = 3,
+                                enc_points: int = 4, dec_layers: int = 9, heads: int = 8, seed: int = 30) -> dict:
+    """Stock Mask2FormerHead parameters (dense_heads/mask2former_head.py:100-141; _base_/samseg-mask2former.py:86-140)."""
+    sd = query_head_state_dict(num_classes, nq, points=1, E=E, C=C, F=F_enc, in_levels=in_levels, enc_levels=enc_levels,
+                               enc_layers=enc_layers, enc_points=enc_points, dec_layers=0, heads=heads, seed=seed)
+    for k in [k for k in sd if k.startswith(("cls_embed.", "point_emb."))]:
+        del sd[k]
+    gen = torch.Generator().manual_seed(seed + 1)
+    for i in range(dec_layers):
+        p = f"transformer_decoder.layers.{i}."
+        for a in ("cross_attn", "self_attn"):
+            sd[f"{p}{a}.attn.in_proj_weight"] = _randn(gen, 3 * E, E, std=1.3 / math.sqrt(E))
+            sd[f"{p}{a}.attn.in_proj_bias"] = _randn(gen, 3 * E, std=0.02)
+            _linear(sd, gen, f"{p}{a}.attn.out_proj", E, E)
+        _ffn_sd(sd, gen, p + "ffn", E, F_dec)
+        for n in range(3):
+            _norm(sd, gen, f"{p}norms.{n}", E)
+    _linear(sd, gen, "cls_embed", num_classes + 1, E, std=2.0 / math.sqrt(E))
+    return sd
+
+
+def mask2former_detector_state_dict(arch: SamVisionArch, num_classes: int, n_select: int, nq: int = 100, seed: int = 0) -> dict:
+    """Full SAMSegMask2Former state dict with the reference's key names (M:1247-1274)."""
+    sd: dict[str, torch.Tensor] = {}
+    sd.update(_prefixed("backbone.vision_encoder.", vision_encoder_state_dict(arch, seed)))
+    sd.update(_prefixed("neck.feature_aggregator.",
+                        feature_aggregator_state_dict(arch.hidden_size, n_select, seed=seed + 10)))
+    sd.update(_prefixed("neck.feature_spliter.", simple_fpn_state_dict(seed=seed + 12)))
+    sd.update(_prefixed("panoptic_head.", mask2former_head_state_dict(num_classes, nq, seed=seed + 30)))
+    return sd

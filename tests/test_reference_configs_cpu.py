@@ -116,3 +116,26 @@ def test_reference_samseg_maskrcnn_config_builds():
     assert sd["roi_head.mask_head.upsample.weight"].shape == (256, 256, 2, 2)
     assert sd["roi_head.mask_head.conv_logits.weight"].shape == (10, 256, 1, 1)
     assert model.test_cfg.rcnn.mask_thr_binary == 0.5 and not hasattr(model, "shared_image_embedding")
+
+
+def test_reference_samseg_mask2former_config_builds():
+    """configs/rsprompter/samseg-mask2former-nwpu.py (M:1247-1274): SAMSegMask2Former with the stock
+    Mask2FormerHead (feat_channels 256, 9 decoder layers, FFN 2048) / MaskFormerFusionHead builds from the reference's
+    own config file and takes a state dict with mmdet's parameter names."""
+    from rsprompter_b200 import synthetic
+    from rsprompter_b200.registry import MODELS, Config
+    cfg = Config.fromfile(os.path.join(REF_CFG, "samseg-mask2former-nwpu.py"))
+    model = MODELS.build(_strip_init(cfg.to_dict()["model"]))
+    assert type(model).__name__ == "SAMSegMask2Former" and type(model.panoptic_head).__name__ == "Mask2FormerHead"
+    assert type(model.panoptic_fusion_head).__name__ == "MaskFormerFusionHead"
+    head = model.panoptic_head
+    assert head.feat_channels == 256 and head.num_layers == 9 and head.num_queries == 70 and head.num_classes == 10
+    assert head.pixel_decoder.E == 256 and head.pixel_decoder.num_encoder_levels == 3
+    arch = model.backbone.vision_encoder.arch
+    sd = synthetic.mask2former_detector_state_dict(arch, 10, 6, nq=70, seed=0)          # nwpu: num_queries = 70
+    assert set(model.state_dict()) == set(sd)
+    model.load_state_dict(sd, strict=True)
+    assert sd["panoptic_head.cls_embed.weight"].shape == (11, 256)
+    assert sd["panoptic_head.transformer_decoder.layers.8.ffn.layers.0.0.weight"].shape == (2048, 256)
+    assert sd["panoptic_head.pixel_decoder.encoder.layers.2.ffn.layers.1.weight"].shape == (256, 1024)
+    assert model.test_cfg.instance_on and not model.test_cfg.panoptic_on
