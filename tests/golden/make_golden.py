@@ -209,10 +209,112 @@ def main_maskrcnn():
     print("wrote", out_path, {k: list(v.keys()) for k, v in fx.items()})
 
 
+def _exec_class(relpath, name, ns):
+    """Execute one top-level class definition of a reference file (decorators and annotations stripped) in `ns`."""
+    tree = ast.parse(open(os.path.join(REF, relpath)).read())
+    node = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == name)
+    node.decorator_list = []
+    for sub in ast.walk(node):
+        if isinstance(sub, ast.FunctionDef):
+            sub.returns = None
+            for a in sub.args.args + sub.args.kwonlyargs:
+                a.annotation = None
+    exec(compile(ast.fix_missing_locations(ast.Module(body=[node], type_ignores=[])), relpath, "exec"), ns)
+    return ns[name]
+
+
+def _self_assign(relpath, cls, attr, self_ns, ns):
+    """Evaluate the right-hand side of `self.<attr> = ...` (last occurrence) inside `cls.__init__` of a reference file
+    with `self` bound to `self_ns`; for constructors whose base classes (mmdet / mmcv) cannot be instantiated here."""
+    tree = ast.parse(open(os.path.join(REF, relpath)).read())
+    cnode = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls)
+    init = next(n for n in cnode.body if isinstance(n, ast.FunctionDef) and n.name == "__init__")
+    rhs = None
+    for n in ast.walk(init):
+        if isinstance(n, ast.Assign) and len(n.targets) == 1 and isinstance(n.targets[0], ast.Attribute) \
+                and n.targets[0].attr == attr and getattr(n.targets[0].value, "id", None) == "self":
+            rhs = n.value
+    assert rhs is not None, (cls, attr)
+    return eval(compile(ast.fix_missing_locations(ast.Expression(body=rhs)), relpath, "eval"), dict(ns, self=self_ns))
+
+
+def main_state_keys():
+    """tests/golden/reference_state_keys.json: parameter / buffer names and shapes produced by the reference's OWN
+    constructors for the RSPrompter-specific modules (mmdet/rsprompter/models.py), executed here with torch only.
+    mmengine's BaseModule is replaced by nn.Module; mmcv's ConvModule / build_norm_layer cannot be imported (mmcv is
+    neither in the image nor under /root/reference), so sub-modules built through them (RSSimpleFPN's lateral / fpn
+    convs and its LN2d) are recorded from a 12-line stand-in that follows mmcv's documented naming (conv under `.conv`,
+    the norm under infer_abbr(LN2d) = `norm_layer`): those entries are marked "stub": true."""
+    import json
+    from torch import nn
+    rel = "mmdet/rsprompter/models.py"
+
+    class BaseModule(nn.Module):
+        def __init__(self, init_cfg=None):
+            super().__init__()
+
+    ln_ns = dict(torch=torch, nn=nn, F=F)
+    LayerNorm2d = _exec_class("mmpretrain/models/utils/norm.py", "LayerNorm2d", dict(ln_ns))
+    ns = dict(torch=torch, nn=nn, F=F, BaseModule=BaseModule, LayerNorm2d=LayerNorm2d, List=list, Tensor=torch.Tensor)
+    LN2d = _exec_class(rel, "LN2d", ns)
+
+    def build_norm_layer(cfg, num_features, postfix=""):
+        assert cfg["type"] == "LN2d"
+        return "norm_layer" + str(postfix), LN2d(num_features, **{k: v for k, v in cfg.items() if k not in ("type", "requires_grad")})
+
+    class ConvModule(nn.Module):      # stand-in, see the docstring
+        def __init__(self, cin, cout, k, padding=0, conv_cfg=None, norm_cfg=None, act_cfg=None, inplace=False):
+            super().__init__()
+            self.conv = nn.Conv2d(cin, cout, k, padding=padding, bias=norm_cfg is None)
+            if norm_cfg is not None:
+                name, layer = build_norm_layer(norm_cfg, cout)
+                self.add_module(name, layer)
+
+    ns.update(build_norm_layer=build_norm_layer, ConvModule=ConvModule)
+    out = {}
+
+    def record(name, module, stub_prefixes=()):
+        out[name] = {k: dict(shape=list(v.shape), **({"stub": True} if k.startswith(tuple(stub_prefixes)) and stub_prefixes else {}))
+                     for k, v in module.state_dict().items()}
+
+    agg = _exec_class(rel, "RSFeatureAggregator", ns)
+    record("RSFeatureAggregator[base,hidden32,range(1,13,2)]",
+           agg("work_dirs/sam_cache/sam_vit_base", hidden_channels=32, out_channels=256, select_layers=range(1, 13, 2)))
+    record("RSFeatureAggregator[huge,hidden32,range(1,33,2)]",
+           agg("facebook/sam-vit-huge", hidden_channels=32, out_channels=256, select_layers=range(1, 33, 2)))
+    pagg = _exec_class(rel, "PseudoFeatureAggregator", ns)
+    record("PseudoFeatureAggregator[256,512,256]", pagg(256, hidden_channels=512, out_channels=256))
+    fpn = _exec_class(rel, "RSSimpleFPN", ns)
+    record("RSSimpleFPN[256,[64,128,256,256],256,5,LN2d]",
+           fpn(256, [64, 128, 256, 256], 256, 5, norm_cfg=dict(type="LN2d", requires_grad=True)),
+           stub_prefixes=("lateral_convs.", "fpn_convs."))
+    # statements of constructors whose bases are mmdet classes
+    pe = _self_assign(rel, "RSPrompterAnchorMaskHead", "point_emb", SimpleNamespace(),
+                      dict(nn=nn, in_channels=256, roi_feat_size=14, num_sincos=2, per_pointset_point=5))
+    record("RSPrompterAnchorMaskHead.point_emb[256,14,sincos,5]", pe)
+    self_q = SimpleNamespace(feat_channels=128, out_channels=256, num_classes=10)
+    record("RSMask2FormerHead.point_emb[128,256,sincos,5]",
+           _self_assign(rel, "RSMask2FormerHead", "point_emb", self_q, dict(nn=nn, num_sincos=2, per_pointset_point=5)))
+    record("RSMask2FormerHead.cls_embed[128,10]", _self_assign(rel, "RSMask2FormerHead", "cls_embed", self_q, dict(nn=nn)))
+    # stock heads used by the SAM-seg detectors (plain torch statements of their constructors)
+    m2f = "mmdet/models/dense_heads/mask2former_head.py"
+    self_m = SimpleNamespace(num_classes=10, num_queries=100, num_transformer_feat_level=3)
+    record("Mask2FormerHead.mask_embed[256,256]",
+           _self_assign(m2f, "Mask2FormerHead", "mask_embed", self_m, dict(nn=nn, feat_channels=256, out_channels=256)))
+    record("Mask2FormerHead.cls_embed[256,10]",
+           _self_assign(m2f, "Mask2FormerHead", "cls_embed", self_m, dict(nn=nn, feat_channels=256)))
+    path = os.path.join(os.path.dirname(OUT), "reference_state_keys.json")
+    with open(path, "w") as f:
+        json.dump(out, f, indent=0, sort_keys=True)
+    print("wrote", path, {k: len(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("/root/reference not mounted")
     if "maskrcnn" in sys.argv[1:]:
         main_maskrcnn()
+    elif "state_keys" in sys.argv[1:]:
+        main_state_keys()
     else:
         main()

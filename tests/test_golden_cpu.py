@@ -162,3 +162,59 @@ def test_fcn_mask_predict_single_matches_reference(key):
     diff[1] = False
     assert diff.sum().item() <= 2          # fp ties at the 0.5 threshold
     torch.testing.assert_close(boxes, f["boxes_out"], rtol=0, atol=1e-5)
+
+
+# ---- checkpoint compatibility: names / shapes produced by the reference's OWN constructors
+#      (tests/golden/reference_state_keys.json; make_golden.py state_keys)
+def _ref_sd(name):
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_state_keys.json")) as f:
+        fx = json.load(f)[name]
+    return {k: torch.zeros(v["shape"], dtype=torch.long if k.endswith("num_batches_tracked") else torch.float32)
+            for k, v in fx.items()}
+
+
+@pytest.mark.parametrize("fixture,cfg", [
+    ("RSFeatureAggregator[base,hidden32,range(1,13,2)]",
+     dict(type="RSFeatureAggregator", in_channels="work_dirs/sam_cache/sam_vit_base", hidden_channels=32, out_channels=256,
+          select_layers=range(1, 13, 2))),
+    ("RSFeatureAggregator[huge,hidden32,range(1,33,2)]",
+     dict(type="RSFeatureAggregator", in_channels="facebook/sam-vit-huge", hidden_channels=32, out_channels=256,
+          select_layers=range(1, 33, 2))),
+    ("PseudoFeatureAggregator[256,512,256]",
+     dict(type="PseudoFeatureAggregator", in_channels=256, hidden_channels=512, out_channels=256)),
+    ("RSSimpleFPN[256,[64,128,256,256],256,5,LN2d]",
+     dict(type="RSSimpleFPN", backbone_channel=256, in_channels=[64, 128, 256, 256], out_channels=256, num_outs=5,
+          norm_cfg=dict(type="LN2d", requires_grad=True))),
+])
+def test_neck_modules_take_reference_constructor_state_dicts(fixture, cfg):
+    """A state dict with exactly the names and shapes the reference constructor produces loads strictly."""
+    from rsprompter_b200.registry import MODELS
+    m = MODELS.build(cfg)
+    sd = _ref_sd(fixture)
+    m.load_state_dict(sd, strict=True)
+    own = m.state_dict()
+    assert len(own) == len(sd)
+    for k, v in sd.items():
+        k2 = k.replace(".norm_layer.", ".ln.")
+        assert k2 in own and tuple(own[k2].shape) == tuple(v.shape), k
+
+
+def test_head_submodules_take_reference_constructor_state_dicts():
+    from rsprompter_b200 import model_configs
+    from rsprompter_b200.registry import MODELS
+    acfg = model_configs.anchor_model_cfg("base", 10)["roi_head"]["mask_head"]
+    mh = MODELS.build(acfg)
+    mh.point_emb.load_state_dict(_ref_sd("RSPrompterAnchorMaskHead.point_emb[256,14,sincos,5]"), strict=True)
+    qcfg = model_configs.query_model_cfg("base", 10, prompt_shape=(100, 5))
+    ph = dict(qcfg["panoptic_head"])
+    ph.update(test_cfg=qcfg["test_cfg"])
+    qh = MODELS.build(ph)
+    qh.point_emb.load_state_dict(_ref_sd("RSMask2FormerHead.point_emb[128,256,sincos,5]"), strict=True)
+    qh.cls_embed.load_state_dict(_ref_sd("RSMask2FormerHead.cls_embed[128,10]"), strict=True)
+    mcfg = model_configs.mask2former_model_cfg("base", 10)
+    ph = dict(mcfg["panoptic_head"])
+    ph.update(test_cfg=mcfg["test_cfg"])
+    sh = MODELS.build(ph)
+    sh.mask_embed.load_state_dict(_ref_sd("Mask2FormerHead.mask_embed[256,256]"), strict=True)
+    sh.cls_embed.load_state_dict(_ref_sd("Mask2FormerHead.cls_embed[256,10]"), strict=True)
