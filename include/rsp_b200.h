@@ -164,6 +164,11 @@ int rsp_i2t_attention(const void* Q, const int32_t* q_block, const void* ktok, c
 int rsp_rpn_decode(const float* head_out, int ld, const int64_t* topk_idx, int K, int B, int H, int W,
                    int A, int stride, const float* base_anchors, const float* stds4, float img_h, float img_w,
                    float min_size, int out_off, int out_ld, float* boxes, float* scores, void* stream);
+/* ... clipping every image to its own img_meta['img_shape'] (rpn_head.py:208-215): img_shapes = DEVICE fp32 [B, 2]
+ * (h, w) per image - batches whose images were padded to a common shape by DetDataPreprocessor. */
+int rsp_rpn_decode_shapes(const float* head_out, int ld, const int64_t* topk_idx, int K, int B, int H, int W, int A,
+                          int stride, const float* base_anchors, const float* stds4, const float* img_shapes,
+                          float min_size, int out_off, int out_ld, float* boxes, float* scores, void* stream);
 
 /* RoI bbox head post-processing before NMS: softmax over C+1 logits, per-class delta2bbox with the
  * coder's target_stds (stds4: HOST array of 4 floats), score_thr filter; rois fp32 [n, 5], roi_valid uint8 [n] or NULL.  Outputs
@@ -173,6 +178,10 @@ int rsp_rpn_decode(const float* head_out, int ld, const int64_t* topk_idx, int K
 int rsp_bbox_cls_decode(const float* cls, int ld_cls, const float* reg, int ld_reg, const float* rois,
                         const uint8_t* roi_valid, int n, int C, const float* stds4, float img_h, float img_w,
                         float score_thr, float* scores, float* boxes, int64_t* labels, void* stream);
+/* ... clipping to the per-image img_shape (bbox_head.py:545-548): img_shapes DEVICE fp32 [B, 2], indexed by rois[:, 0]. */
+int rsp_bbox_cls_decode_shapes(const float* cls, int ld_cls, const float* reg, int ld_reg, const float* rois,
+                               const uint8_t* roi_valid, int n, int C, const float* stds4, const float* img_shapes,
+                               float score_thr, float* scores, float* boxes, int64_t* labels, void* stream);
 
 /* mmcv.ops.batched_nms semantics on score-sorted candidates: boxes fp32 [B, n, 4], ids int64 [B, n]
  * (level or class; boxes are offset by id * (max_coord + 1) exactly as mmcv does), nvalid int32 [B]

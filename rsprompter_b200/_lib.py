@@ -68,6 +68,8 @@ _SIGNATURES = {
     "rsp_i2t_attention": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
     "rsp_rpn_decode": ([_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _f, _f, _i, _i, _vp, _vp, _vp], _i),
     "rsp_bbox_cls_decode": ([_vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _f, _f, _f, _vp, _vp, _vp, _vp], _i),
+    "rsp_rpn_decode_shapes": ([_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp], _i),
+    "rsp_bbox_cls_decode_shapes": ([_vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp], _i),
     "rsp_nms_batched": ([_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp], _i),
     "rsp_compact_keep": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "rsp_roi_align_nhwc": ([_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _f, _vp, _vp], _i),
@@ -572,14 +574,24 @@ def add_table_bf16(x: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------ detection ops
 def rpn_decode(head_out: torch.Tensor, topk_idx: torch.Tensor, B: int, H: int, W: int, A: int, stride: int,
                base_anchors: torch.Tensor, img_hw: tuple, min_size: float, boxes: torch.Tensor,
-               scores: torch.Tensor, out_off: int, stds=(1.0, 1.0, 1.0, 1.0)) -> None:
-    """Decode the K top anchors of one level into boxes[B, n, 4] / scores[B, n] at column out_off."""
+               scores: torch.Tensor, out_off: int, stds=(1.0, 1.0, 1.0, 1.0),
+               img_shapes: torch.Tensor | None = None) -> None:
+    """Decode the K top anchors of one level into boxes[B, n, 4] / scores[B, n] at column out_off.
+    img_shapes: device fp32 [B, 2] (h, w) = every image's own img_shape to clip to (default: img_hw for all)."""
     global launch_count
     _require_cuda(head_out, topk_idx, base_anchors, boxes, scores)
     assert head_out.dtype == torch.float32 and head_out.dim() == 2 and head_out.stride(1) == 1
     assert topk_idx.dtype == torch.int64 and topk_idx.is_contiguous() and topk_idx.shape[0] == B
     assert boxes.is_contiguous() and scores.is_contiguous() and boxes.dtype == torch.float32
     K = topk_idx.shape[1]
+    if img_shapes is not None:
+        _require_cuda(img_shapes)
+        assert img_shapes.dtype == torch.float32 and img_shapes.is_contiguous() and img_shapes.shape == (B, 2)
+        _check(_lib.rsp_rpn_decode_shapes(_ptr(head_out), head_out.stride(0), _ptr(topk_idx), K, B, H, W, A, stride,
+                                          _ptr(base_anchors), _host_f4(stds), _ptr(img_shapes), float(min_size), out_off,
+                                          scores.shape[1], _ptr(boxes), _ptr(scores), _stream()), "rsp_rpn_decode_shapes")
+        launch_count += 1
+        return
     _check(_lib.rsp_rpn_decode(_ptr(head_out), head_out.stride(0), _ptr(topk_idx), K, B, H, W, A, stride,
                                _ptr(base_anchors), _host_f4(stds), float(img_hw[0]), float(img_hw[1]), float(min_size),
                                out_off, scores.shape[1], _ptr(boxes), _ptr(scores), _stream()), "rsp_rpn_decode")
@@ -587,8 +599,10 @@ def rpn_decode(head_out: torch.Tensor, topk_idx: torch.Tensor, B: int, H: int, W
 
 
 def bbox_cls_decode(cls: torch.Tensor, reg: torch.Tensor, rois: torch.Tensor, roi_valid: torch.Tensor | None,
-                    C: int, img_hw: tuple, score_thr: float, stds=(0.1, 0.1, 0.2, 0.2)):
-    """-> scores fp32 [n*C] (-1 filtered), boxes fp32 [n*C, 4], labels int64 [n*C]."""
+                    C: int, img_hw: tuple, score_thr: float, stds=(0.1, 0.1, 0.2, 0.2),
+                    img_shapes: torch.Tensor | None = None):
+    """-> scores fp32 [n*C] (-1 filtered), boxes fp32 [n*C, 4], labels int64 [n*C].
+    img_shapes: device fp32 [B, 2] (h, w), indexed by rois[:, 0]: per-image clipping (default: img_hw for all)."""
     global launch_count
     _require_cuda(cls, reg, rois, roi_valid)
     n = rois.shape[0]
@@ -599,10 +613,18 @@ def bbox_cls_decode(cls: torch.Tensor, reg: torch.Tensor, rois: torch.Tensor, ro
     labels = torch.empty(n * C, device=cls.device, dtype=torch.int64)
     if roi_valid is not None:
         assert roi_valid.dtype == torch.uint8 and roi_valid.numel() == n
-    _check(_lib.rsp_bbox_cls_decode(_ptr(cls), cls.stride(0), _ptr(reg), reg.stride(0), _ptr(rois),
-                                    _ptr(roi_valid), n, C, _host_f4(stds), float(img_hw[0]), float(img_hw[1]),
-                                    float(score_thr), _ptr(scores), _ptr(boxes), _ptr(labels), _stream()),
-           "rsp_bbox_cls_decode")
+    if img_shapes is not None:
+        _require_cuda(img_shapes)
+        assert img_shapes.dtype == torch.float32 and img_shapes.is_contiguous() and img_shapes.shape[1] == 2
+        _check(_lib.rsp_bbox_cls_decode_shapes(_ptr(cls), cls.stride(0), _ptr(reg), reg.stride(0), _ptr(rois),
+                                               _ptr(roi_valid), n, C, _host_f4(stds), _ptr(img_shapes), float(score_thr),
+                                               _ptr(scores), _ptr(boxes), _ptr(labels), _stream()),
+               "rsp_bbox_cls_decode_shapes")
+    else:
+        _check(_lib.rsp_bbox_cls_decode(_ptr(cls), cls.stride(0), _ptr(reg), reg.stride(0), _ptr(rois),
+                                        _ptr(roi_valid), n, C, _host_f4(stds), float(img_hw[0]), float(img_hw[1]),
+                                        float(score_thr), _ptr(scores), _ptr(boxes), _ptr(labels), _stream()),
+               "rsp_bbox_cls_decode")
     launch_count += 1
     return scores, boxes, labels
 

@@ -133,8 +133,11 @@ class RPNHead(_PrepMixin, BaseModule):
         return self._prep
 
     @torch.no_grad()
-    def predict_nhwc(self, feats: list, img_hw: tuple, capture: dict | None = None):
+    def predict_nhwc(self, feats: list, img_hw: tuple, capture: dict | None = None,
+                     img_shapes: torch.Tensor | None = None):
         """feats: bf16 NHWC levels -> proposals fp32 [B, K, 4], scores [B, K], counts int32 [B].
+        img_shapes: device fp32 [B, 2] per-image (h, w) the boxes are clipped to (img_meta['img_shape'],
+        rpn_head.py:208-215); None = the batch shape img_hw for every image.
         capture (tests): receives the raw per-level head outputs."""
         p = self._prep or self._prepare()
         cfg = self.test_cfg
@@ -163,7 +166,7 @@ class RPNHead(_PrepMixin, BaseModule):
             _, idx = torch.topk(logits, k, dim=1, largest=True, sorted=True)
             _lib.rpn_decode(out, idx.contiguous(), B, H, W, A, self.prior_generator.strides[l],
                             p["anchors"][l], img_hw, float(cfg.get("min_bbox_size", 0)), boxes, scores, off,
-                            stds=self.bbox_coder.stds)
+                            stds=self.bbox_coder.stds, img_shapes=img_shapes)
             ids[:, off:off + k] = l
             off += k
         # batched_nms sorts by score internally; filtered boxes (score -1) sink to the end
@@ -299,7 +302,7 @@ class RSPrompterAnchorMaskHead(_PrepMixin, BaseModule):
 
 # ------------------------------------------------------------------------------ RoI head
 def _predict_bboxes(head, feats: list, proposals: torch.Tensor, prop_counts: torch.Tensor, img_hw: tuple,
-                    pes: list | None = None, capture: dict | None = None):
+                    pes: list | None = None, capture: dict | None = None, img_shapes: torch.Tensor | None = None):
     """StandardRoIHead.predict_bbox (standard_roi_head.py:292-345) + BBoxHead._predict_by_feat_single
     (bbox_head.py:505-571) + multiclass_nms (bbox_nms.py:13-105), batched over the B images.
     -> detections bboxes fp32 [B, M, 4], scores [B, M], labels int64 [B, M], counts int32 [B]."""
@@ -315,7 +318,7 @@ def _predict_bboxes(head, feats: list, proposals: torch.Tensor, prop_counts: tor
         capture.update(roi_feats7=feats7, cls=cls, reg=reg, rois=rois)
     C = head.bbox_head.num_classes
     s, b, lab = _lib.bbox_cls_decode(cls, reg, rois, valid.contiguous(), C, img_hw, float(cfg.get("score_thr", 0.05)),
-                                     stds=head.bbox_head.bbox_coder.stds)
+                                     stds=head.bbox_head.bbox_coder.stds, img_shapes=img_shapes)
     n = K * C
     s, b, lab = s.view(B, n), b.view(B, n, 4), lab.view(B, n)
     s_sorted, order = torch.sort(s, dim=1, descending=True, stable=True)
@@ -387,7 +390,8 @@ class RSPrompterAnchorRoIPromptHead(BaseModule):
 
     @torch.no_grad()
     def predict_nhwc(self, feats: list, proposals: torch.Tensor, prop_counts: torch.Tensor, img_hw: tuple,
-                     emb_rows: torch.Tensor, pos_rows: torch.Tensor, emb_hw: tuple, capture: dict | None = None):
+                     emb_rows: torch.Tensor, pos_rows: torch.Tensor, emb_hw: tuple, capture: dict | None = None,
+                     img_shapes: torch.Tensor | None = None):
         """proposals fp32 [B, K, 4] (zero padded), prop_counts int32 [B].
         -> dict(bboxes [B, M, 4], scores [B, M], labels [B, M], counts int32 [B], mask_logits [B*M, 1, 4h, 4w])."""
         B, dev = proposals.shape[0], proposals.device
@@ -396,7 +400,7 @@ class RSPrompterAnchorRoIPromptHead(BaseModule):
             n_lvl = max(self.bbox_roi_extractor.num_inputs, self.mask_roi_extractor.num_inputs)
             feats = [_lib.add_table_bf16(f, t) for f, t in zip(feats[:n_lvl], pes[:n_lvl])] + list(feats[n_lvl:])
             pes = None
-        db, ds, dl, cnt = _predict_bboxes(self, feats, proposals, prop_counts, img_hw, pes, capture)
+        db, ds, dl, cnt = _predict_bboxes(self, feats, proposals, prop_counts, img_hw, pes, capture, img_shapes)
         M = db.shape[1]
         # mask branch (M:1511-1550): RoIs = detections
         mrois = _detection_rois(db)
@@ -496,10 +500,10 @@ class StandardRoIHead(BaseModule):
 
     @torch.no_grad()
     def predict_nhwc(self, feats: list, proposals: torch.Tensor, prop_counts: torch.Tensor, img_hw: tuple,
-                     capture: dict | None = None):
+                     capture: dict | None = None, img_shapes: torch.Tensor | None = None):
         """-> dict(bboxes [B, M, 4], scores [B, M], labels [B, M], counts int32 [B],
         mask_probs fp32 [B*M, 2R, 2R] = sigmoid of the label's mask channel (fcn_mask_head.py:358 / :377-379))."""
-        db, ds, dl, cnt = _predict_bboxes(self, feats, proposals, prop_counts, img_hw, None, capture)
+        db, ds, dl, cnt = _predict_bboxes(self, feats, proposals, prop_counts, img_hw, None, capture, img_shapes)
         out = dict(bboxes=db, scores=ds, labels=dl, counts=cnt)
         if self.with_mask:
             mrois = _detection_rois(db)

@@ -184,14 +184,30 @@ int rsp_rpn_decode(const float* head_out, int ld, const int64_t* topk_idx, int K
                    int A, int stride, const float* base_anchors, const float* stds4, float img_h, float img_w,
                    float min_size, int out_off, int out_ld, float* boxes, float* scores, void* stream) {
   return rpn_decode(head_out, ld, reinterpret_cast<const long long*>(topk_idx), K, B, H, W, A, stride,
-                    base_anchors, stds4, img_h, img_w, min_size, out_off, out_ld, boxes, scores, S(stream));
+                    base_anchors, stds4, img_h, img_w, nullptr, min_size, out_off, out_ld, boxes, scores, S(stream));
+}
+
+int rsp_rpn_decode_shapes(const float* head_out, int ld, const int64_t* topk_idx, int K, int B, int H, int W, int A,
+                          int stride, const float* base_anchors, const float* stds4, const float* img_shapes,
+                          float min_size, int out_off, int out_ld, float* boxes, float* scores, void* stream) {
+  RSP_CHECK_ARG(img_shapes, "rpn_decode_shapes: img_shapes is null");
+  return rpn_decode(head_out, ld, reinterpret_cast<const long long*>(topk_idx), K, B, H, W, A, stride,
+                    base_anchors, stds4, 0.f, 0.f, img_shapes, min_size, out_off, out_ld, boxes, scores, S(stream));
 }
 
 int rsp_bbox_cls_decode(const float* cls, int ld_cls, const float* reg, int ld_reg, const float* rois,
                         const uint8_t* roi_valid, int n, int C, const float* stds4, float img_h, float img_w,
                         float score_thr, float* scores, float* boxes, int64_t* labels, void* stream) {
-  return bbox_cls_decode(cls, ld_cls, reg, ld_reg, rois, roi_valid, n, C, stds4, img_h, img_w, score_thr, scores,
-                         boxes, reinterpret_cast<long long*>(labels), S(stream));
+  return bbox_cls_decode(cls, ld_cls, reg, ld_reg, rois, roi_valid, n, C, stds4, img_h, img_w, nullptr, score_thr,
+                         scores, boxes, reinterpret_cast<long long*>(labels), S(stream));
+}
+
+int rsp_bbox_cls_decode_shapes(const float* cls, int ld_cls, const float* reg, int ld_reg, const float* rois,
+                               const uint8_t* roi_valid, int n, int C, const float* stds4, const float* img_shapes,
+                               float score_thr, float* scores, float* boxes, int64_t* labels, void* stream) {
+  RSP_CHECK_ARG(img_shapes, "bbox_cls_decode_shapes: img_shapes is null");
+  return bbox_cls_decode(cls, ld_cls, reg, ld_reg, rois, roi_valid, n, C, stds4, 0.f, 0.f, img_shapes, score_thr,
+                         scores, boxes, reinterpret_cast<long long*>(labels), S(stream));
 }
 
 int rsp_nms_batched(const float* boxes, const int64_t* ids, const int32_t* nvalid, int B, int n, float thr,

@@ -49,11 +49,12 @@ __device__ __forceinline__ void delta2bbox_one(const float r[4], const float d[4
 __global__ void rpn_decode_kernel(const float* __restrict__ head_out, int ld,
                                   const long long* __restrict__ topk_idx, int K, int B, int H, int W,
                                   int A, int stride, const float* __restrict__ base_anchors, Stds4 sd,
-                                  float img_h, float img_w, float min_size, int out_off, int out_ld,
-                                  float* __restrict__ boxes, float* __restrict__ scores) {
+                                  float img_h, float img_w, const float* __restrict__ img_shapes, float min_size,
+                                  int out_off, int out_ld, float* __restrict__ boxes, float* __restrict__ scores) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * K) return;
   const int b = i / K, k = i - b * K;
+  if (img_shapes) { img_h = img_shapes[2 * b]; img_w = img_shapes[2 * b + 1]; }   // per-image img_meta['img_shape']
   const long long idx = topk_idx[i];
   const int a = static_cast<int>(idx % A);
   const long long pix = idx / A;
@@ -76,14 +77,15 @@ __global__ void rpn_decode_kernel(const float* __restrict__ head_out, int ld,
 
 int rpn_decode(const float* head_out, int ld, const long long* topk_idx, int K, int B, int H, int W,
                int A, int stride, const float* base_anchors, const float* stds4, float img_h, float img_w,
-               float min_size, int out_off, int out_ld, float* boxes, float* scores, cudaStream_t stream) {
+               const float* img_shapes, float min_size, int out_off, int out_ld, float* boxes, float* scores,
+               cudaStream_t stream) {
   RSP_CHECK_ARG(head_out && topk_idx && base_anchors && stds4 && boxes && scores && B > 0 && K > 0,
                 "rpn_decode: bad args");
   const int n = B * K;
   Stds4 sd{{stds4[0], stds4[1], stds4[2], stds4[3]}};
   rpn_decode_kernel<<<(n + 127) / 128, 128, 0, stream>>>(head_out, ld, topk_idx, K, B, H, W, A, stride,
-                                                         base_anchors, sd, img_h, img_w, min_size, out_off,
-                                                         out_ld, boxes, scores);
+                                                         base_anchors, sd, img_h, img_w, img_shapes, min_size,
+                                                         out_off, out_ld, boxes, scores);
   RSP_CHECK_LAUNCH();
   return RSP_OK;
 }
@@ -94,7 +96,8 @@ int rpn_decode(const float* head_out, int ld, const long long* topk_idx, int K, 
 __global__ void bbox_cls_decode_kernel(const float* __restrict__ cls, int ld_cls,
                                        const float* __restrict__ reg, int ld_reg,
                                        const float* __restrict__ rois, const unsigned char* __restrict__ roi_valid,
-                                       int n, int C, Stds4 sd, float img_h, float img_w, float score_thr,
+                                       int n, int C, Stds4 sd, float img_h, float img_w,
+                                       const float* __restrict__ img_shapes, float score_thr,
                                        float* __restrict__ scores, float* __restrict__ boxes,
                                        long long* __restrict__ labels) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,6 +111,10 @@ __global__ void bbox_cls_decode_kernel(const float* __restrict__ cls, int ld_cls
   float s = expf(cr[c] - mx) / sum;
   const float* rr = rois + static_cast<size_t>(r) * 5;
   const float roi[4] = {rr[1], rr[2], rr[3], rr[4]};
+  if (img_shapes) {   // per-image img_meta['img_shape'] (bbox_head.py:545-548); the RoI carries its image index
+    const int b = static_cast<int>(rr[0]);
+    img_h = img_shapes[2 * b]; img_w = img_shapes[2 * b + 1];
+  }
   const float* dp = reg + static_cast<size_t>(r) * ld_reg + c * 4;
   const float d[4] = {dp[0], dp[1], dp[2], dp[3]};
   const float stds[4] = {sd.v[0], sd.v[1], sd.v[2], sd.v[3]};
@@ -122,12 +129,14 @@ __global__ void bbox_cls_decode_kernel(const float* __restrict__ cls, int ld_cls
 
 int bbox_cls_decode(const float* cls, int ld_cls, const float* reg, int ld_reg, const float* rois,
                     const unsigned char* roi_valid, int n, int C, const float* stds4, float img_h, float img_w,
-                    float score_thr, float* scores, float* boxes, long long* labels, cudaStream_t stream) {
+                    const float* img_shapes, float score_thr, float* scores, float* boxes, long long* labels,
+                    cudaStream_t stream) {
   RSP_CHECK_ARG(cls && reg && rois && stds4 && scores && boxes && labels && n > 0 && C > 0, "bbox_cls_decode: bad args");
   const int t = n * C;
   Stds4 sd{{stds4[0], stds4[1], stds4[2], stds4[3]}};
   bbox_cls_decode_kernel<<<(t + 127) / 128, 128, 0, stream>>>(cls, ld_cls, reg, ld_reg, rois, roi_valid, n, C, sd,
-                                                              img_h, img_w, score_thr, scores, boxes, labels);
+                                                              img_h, img_w, img_shapes, score_thr, scores, boxes,
+                                                              labels);
   RSP_CHECK_LAUNCH();
   return RSP_OK;
 }

@@ -5,10 +5,12 @@ namespace rsp {
 
 int rpn_decode(const float* head_out, int ld, const long long* topk_idx, int K, int B, int H, int W,
                int A, int stride, const float* base_anchors, const float* stds4, float img_h, float img_w,
-               float min_size, int out_off, int out_ld, float* boxes, float* scores, cudaStream_t stream);
+               const float* img_shapes, float min_size, int out_off, int out_ld, float* boxes, float* scores,
+               cudaStream_t stream);   // img_shapes: device fp32 [B, 2] (h, w) per image, or null = (img_h, img_w)
 int bbox_cls_decode(const float* cls, int ld_cls, const float* reg, int ld_reg, const float* rois,
                     const unsigned char* roi_valid, int n, int C, const float* stds4, float img_h, float img_w,
-                    float score_thr, float* scores, float* boxes, long long* labels, cudaStream_t stream);
+                    const float* img_shapes, float score_thr, float* scores, float* boxes, long long* labels,
+                    cudaStream_t stream);
 int nms_batched(const float* boxes, const long long* ids, const int* nvalid, int B, int n, float thr,
                 unsigned long long* mask_ws, float* max_coord_ws, unsigned char* keep, cudaStream_t stream);
 int compact_keep(const unsigned char* keep, const float* boxes, const float* scores, const long long* labels,

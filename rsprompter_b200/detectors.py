@@ -48,12 +48,15 @@ class _SamDetectorBase(BaseModule):
         graphs = getattr(self, "_graphs", None)
         if graphs is None:
             return self.predict_raw(batch_inputs)
+        shapes = getattr(batch_inputs, "rsp_img_shapes", None)
         key = (tuple(batch_inputs.shape), batch_inputs.dtype, tuple(batch_inputs.stride()),
-               getattr(batch_inputs, "rsp_norm", None))
+               getattr(batch_inputs, "rsp_norm", None), shapes is not None)
         if key not in graphs:
             static_in = batch_inputs.to(next(self.parameters()).device, copy=True)   # also accepts a pinned host batch
             if hasattr(batch_inputs, "rsp_norm"):      # uint8 batch: normalisation rides along (DetDataPreprocessor)
                 static_in.rsp_norm = batch_inputs.rsp_norm
+            if shapes is not None:                     # per-image clip shapes: a static buffer refreshed per call
+                static_in.rsp_img_shapes = shapes.clone()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):          # warm-up: one-time attribute calls, caches, constant tables
@@ -67,6 +70,8 @@ class _SamDetectorBase(BaseModule):
             graphs[key] = (g, static_in, out, _lib.launch_count - n0)
         g, static_in, out, n_launch = graphs[key]
         static_in.copy_(batch_inputs, non_blocking=True)
+        if shapes is not None:
+            static_in.rsp_img_shapes.copy_(shapes, non_blocking=True)
         g.replay()
         _lib.launch_count += n_launch      # the replay launches the library's kernels again
         return out      # static output buffers: valid until the next call with this shape
@@ -120,6 +125,22 @@ class _SamDetectorBase(BaseModule):
         return slot["recs"][slot["i"]]
 
     @staticmethod
+    def _attach_img_shapes(batch_data_samples, batch_inputs):
+        """img_meta['img_shape'] of every image as a device fp32 [B, 2] tensor riding on the batch tensor
+        (``rsp_img_shapes``) when any image is smaller than the batch shape (DetDataPreprocessor padding): the RPN and
+        bbox-head decoders clip to it per image (rpn_head.py:208-215, bbox_head.py:545-548).  Nothing is attached when
+        every img_shape equals the batch shape (the shipped Resize + Pad pipelines)."""
+        hw = tuple(int(v) for v in batch_inputs.shape[-2:])
+        shapes = [tuple(int(v) for v in tuple(ds.metainfo.get("img_shape", hw))[:2]) for ds in batch_data_samples]
+        if all(s == hw for s in shapes):
+            if hasattr(batch_inputs, "rsp_img_shapes"):      # the same tensor object went through a padded batch before
+                del batch_inputs.rsp_img_shapes
+            return batch_inputs
+        t = torch.tensor(shapes, dtype=torch.float32).to(batch_inputs.device, non_blocking=True)
+        batch_inputs.rsp_img_shapes = t
+        return batch_inputs
+
+    @staticmethod
     def _metas(batch_data_samples, batch_inputs):
         """-> (batch hw, per-image list of None (ori_shape == img_shape == batch shape, scale_factor 1: the fast
         batched post-process applies) or dict(ori_hw, crop_hw, scale_factor) for resized / padded images)."""
@@ -171,14 +192,16 @@ class RSPrompterAnchor(_SamDetectorBase):
             feats = self.neck.forward_nhwc(None, _lib.cast_bf16(emb_nhwc.contiguous()))
         else:
             feats = self.neck.forward_nhwc(hidden)
-        props, _, pcnt = self.rpn_head.predict_nhwc(feats, img_hw)
-        return self.roi_head.predict_nhwc(feats, props, pcnt, img_hw, emb_rows, pos_rows, ghw)
+        shapes = getattr(batch_inputs, "rsp_img_shapes", None)
+        props, _, pcnt = self.rpn_head.predict_nhwc(feats, img_hw, img_shapes=shapes)
+        return self.roi_head.predict_nhwc(feats, props, pcnt, img_hw, emb_rows, pos_rows, ghw, img_shapes=shapes)
 
     @torch.no_grad()
     def predict(self, batch_inputs: torch.Tensor, batch_data_samples=None, rescale: bool = True):
         if batch_data_samples is None:
             batch_data_samples = make_data_samples(batch_inputs.shape[0], tuple(batch_inputs.shape[-2:]))
         hw, metas = self._metas(batch_data_samples, batch_inputs)
+        batch_inputs = self._attach_img_shapes(batch_data_samples, batch_inputs)
         r = self._raw(batch_inputs)
         if getattr(self, "_graphs", None) is not None:     # graph buffers are overwritten by the next replay
             r = dict(r, bboxes=r["bboxes"].clone(), scores=r["scores"].clone(), labels=r["labels"].clone())
@@ -349,16 +372,18 @@ class SAMSegMaskRCNN(_SamDetectorBase):
             feats = self.neck.forward_nhwc(None, _lib.cast_bf16(emb_nhwc.contiguous()))
         else:
             feats = self.neck.forward_nhwc(hidden)
-        props, _, pcnt = self.rpn_head.predict_nhwc(feats, img_hw)
+        shapes = getattr(batch_inputs, "rsp_img_shapes", None)
+        props, _, pcnt = self.rpn_head.predict_nhwc(feats, img_hw, img_shapes=shapes)
         if capture is not None:
             capture.update(feats=feats, proposals=props, prop_counts=pcnt)
-        return self.roi_head.predict_nhwc(feats, props, pcnt, img_hw, capture=capture)
+        return self.roi_head.predict_nhwc(feats, props, pcnt, img_hw, capture=capture, img_shapes=shapes)
 
     @torch.no_grad()
     def predict(self, batch_inputs: torch.Tensor, batch_data_samples=None, rescale: bool = True):
         if batch_data_samples is None:
             batch_data_samples = make_data_samples(batch_inputs.shape[0], tuple(batch_inputs.shape[-2:]))
         hw, metas = self._metas(batch_data_samples, batch_inputs)
+        batch_inputs = self._attach_img_shapes(batch_data_samples, batch_inputs)
         r = self._raw(batch_inputs)
         if getattr(self, "_graphs", None) is not None:     # graph buffers are overwritten by the next replay
             r = {k: v.clone() for k, v in r.items()}

@@ -214,7 +214,9 @@ def test_predict_rescales_to_original_image(model_and_sd):
     m, _ = model_and_sd
     torch.manual_seed(5)
     x = torch.randn(2, 3, 1024, 1024).cuda()
-    base = m.predict(x)
+    base_samples = make_data_samples(2, (1024, 1024))
+    base_samples[1].set_metainfo(dict(img_shape=(768, 1024)))              # same per-image clip, no rescale
+    base = m.predict(x, base_samples)
     samples = make_data_samples(2, (1024, 1024))
     samples[1].set_metainfo(dict(ori_shape=(600, 800), img_shape=(768, 1024), scale_factor=(1.28, 1.28),
                                  batch_input_shape=(1024, 1024)))
@@ -243,5 +245,86 @@ def test_cuda_graph_replay_equals_eager(model_and_sd):
                 for d, (b, s, k) in zip(out, ref):
                     assert torch.equal(d.pred_instances.bboxes, b) and torch.equal(d.pred_instances.scores, s)
                     assert torch.equal(d.pred_instances.masks, k)
+    finally:
+        m.enable_cuda_graphs(False)
+
+
+def test_per_image_img_shape_clipping(model_and_sd):
+    """Batches whose images were padded to a common shape: the RPN (rpn_head.py:208-215) and the bbox head
+    (bbox_head.py:545-548) clip every image's boxes to its own img_meta['img_shape'], carried as a device [B, 2]
+    tensor; exact against the oracle's post-processing of the same logits with the per-image shapes."""
+    from oracle import restate_anchor as ra
+    m, sd = model_and_sd
+    g = torch.Generator().manual_seed(16)
+    B, K = 2, 150
+    shapes = [(1024, 1024), (800, 904)]
+    sh = torch.tensor(shapes, dtype=torch.float32).cuda()
+    sizes = [256, 128, 64, 32, 16]
+    feats = [torch.randn(B, 256, s, s, generator=g).to(torch.bfloat16).float() for s in sizes]
+    nh = [_nhwc_bf16(f) for f in feats]
+    cap = {}
+    props, scores, cnt = m.rpn_head.predict_nhwc(nh, (1024, 1024), capture=cap, img_shapes=sh)
+    strides, A = [4, 8, 16, 32, 64], 6
+    for b in range(B):
+        cls_l, reg_l, pri_l = [], [], []
+        for lvl, s in enumerate(sizes):
+            out = cap["head_out"][lvl][b].cpu()
+            cls_l.append(out[..., :A].permute(2, 0, 1))
+            reg_l.append(out[..., A:5 * A].permute(2, 0, 1))
+            pri_l.append(ra.grid_anchors((s, s), strides[lvl], ra.base_anchors(strides[lvl], [4, 8], [0.5, 1.0, 2.0])))
+        pb, ps = ra.rpn_predict_single(cls_l, reg_l, pri_l, shapes[b])
+        n = cnt[b].item()
+        assert n == pb.shape[0]
+        _assert_same_detections(props[b, :n].cpu(), scores[b, :n].cpu(), pb, ps)
+        assert props[b, :n, 0::2].max().item() <= shapes[b][1] and props[b, :n, 1::2].max().item() <= shapes[b][0]
+    assert props[1, :, 0::2].max().item() > 890            # the clip is the image's, not a tighter one
+    # bbox head on random proposals
+    ctr = torch.rand(B, K, 2, generator=g) * 1024
+    wh = torch.exp(torch.rand(B, K, 2, generator=g) * 5.0 + 1.5)
+    rp = torch.cat([(ctr - wh / 2).clamp(0, 1024), (ctr + wh / 2).clamp(0, 1024)], dim=2)
+    pcnt = torch.tensor([K, K], dtype=torch.int32)
+    emb_rows = torch.randn(B * 4096, 256, generator=g).cuda()
+    pos_rows = torch.randn(4096, 256, generator=g).cuda()
+    cap = {}
+    r = m.roi_head.predict_nhwc(nh, rp.cuda(), pcnt.cuda(), (1024, 1024), emb_rows, pos_rows, (64, 64), capture=cap,
+                                img_shapes=sh)
+    torch.cuda.synchronize()
+    rois = cap["rois"].cpu()
+    for b in range(B):
+        sl = slice(b * K, (b + 1) * K)
+        db, ds, dl = ra.bbox_predict_single(rois[sl], cap["cls"][sl].cpu(), cap["reg"][sl].cpu(), shapes[b], NUM_CLASSES)
+        n = r["counts"][b].item()
+        assert n == db.shape[0]
+        _assert_same_detections(r["bboxes"][b, :n].cpu(), r["scores"][b, :n].cpu(), db, ds, r["labels"][b, :n].cpu(), dl)
+        assert r["bboxes"][b, :n, 0::2].max().item() <= shapes[b][1] and r["bboxes"][b, :n, 1::2].max().item() <= shapes[b][0]
+
+
+def test_predict_attaches_per_image_shapes(model_and_sd):
+    """predict() with data samples whose img_shape is smaller than the batch shape: detections stay inside the image
+    (eager and graph mode); an image whose img_shape equals the batch shape is unaffected."""
+    from rsprompter_b200.registry import make_data_samples
+    m, _ = model_and_sd
+    torch.manual_seed(17)
+    x = torch.randn(2, 3, 1024, 1024).cuda()
+    base = m.predict(x, make_data_samples(2, 1024))
+    ds = make_data_samples(2, 1024)
+    ds[1].set_metainfo(dict(img_shape=(640, 768)))
+    out = m.predict(x, ds)
+    p0, p1 = out[0].pred_instances, out[1].pred_instances
+    assert torch.equal(p0.bboxes, base[0].pred_instances.bboxes) and torch.equal(p0.masks, base[0].pred_instances.masks)
+    assert len(p1) > 0 and p1.bboxes[:, 0::2].max().item() <= 768 and p1.bboxes[:, 1::2].max().item() <= 640
+    assert base[1].pred_instances.bboxes[:, 0::2].max().item() > 768        # the un-clipped run does reach the padding
+    m.enable_cuda_graphs()
+    try:
+        ds2 = make_data_samples(2, 1024)
+        ds2[1].set_metainfo(dict(img_shape=(640, 768)))
+        g1 = m.predict(x, ds2)
+        ds3 = make_data_samples(2, 1024)
+        ds3[1].set_metainfo(dict(img_shape=(512, 1000)))                      # same graph, refreshed shape buffer
+        g2 = m.predict(x, ds3)
+        torch.cuda.synchronize()
+        assert torch.equal(g1[1].pred_instances.bboxes, p1.bboxes) and torch.equal(g1[1].pred_instances.scores, p1.scores)
+        b2 = g2[1].pred_instances.bboxes
+        assert b2[:, 1::2].max().item() <= 512 and b2[:, 0::2].max().item() <= 1000 and b2[:, 0::2].max().item() > 768
     finally:
         m.enable_cuda_graphs(False)

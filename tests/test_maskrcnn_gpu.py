@@ -181,11 +181,12 @@ def test_samseg_maskrcnn_rescale_and_record():
     ds = make_data_samples(1, (1024, 1024))
     ds[0].set_metainfo(dict(ori_shape=(700, 811), img_shape=(884, 1024), scale_factor=(1024 / 811, 884 / 700)))
     cap: dict = {}
-    raw = m.predict_raw(x, capture=cap)
+    raw = m.predict_raw(m._attach_img_shapes(ds, x), capture=cap)          # boxes clipped to img_shape, as predict() does
     out = m.predict(x, ds, rescale=True)[0].pred_instances
     torch.cuda.synchronize()
     n = len(out)
-    assert n == len(base) and out.masks.shape == (n, 700, 811)
+    assert n == int(raw["counts"][0]) and out.masks.shape == (n, 700, 811)
+    assert raw["bboxes"][0, :n, 1::2].max().item() <= 884
     logits = cap["mask_logits_all"][:n, :, :, :NUM_CLASSES].permute(0, 3, 1, 2).cpu()
     masks, boxes = ra.fcn_mask_predict_single(logits, raw["bboxes"][0, :n].cpu(), out.labels.cpu(), (700, 811),
                                               (1024 / 811, 884 / 700), rescale=True)

@@ -80,3 +80,60 @@ def test_mask_embedding_matches_hf():
         ref = mod(x)
     got = restate.sam_mask_embedding(sd, x)
     torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
+
+
+# ---- query-path bricks whose mmcv originals are absent: pinned to independent implementations of the same operators
+@pytest.mark.parametrize("E", [128, 256])
+def test_ms_deform_attn_restatement_matches_hf_module(E):
+    """oracle.restate_query.ms_deform_attn (mmcv MultiScaleDeformableAttention, batch_first, identity residual) against
+    transformers' Mask2FormerPixelDecoderEncoderMultiscaleDeformableAttention - a separate port of the Deformable-DETR
+    operator with the same parameter names - on seeded weights."""
+    from transformers.models.mask2former.modeling_mask2former import (
+        Mask2FormerPixelDecoderEncoderMultiscaleDeformableAttention as HFAttn)
+    from oracle import restate_query as rq
+    torch.manual_seed(E)
+    heads, L, P, B = 8, 3, 4, 2
+    shapes = [(6, 5), (12, 10), (24, 20)]
+    nq = sum(h * w for h, w in shapes)
+    mod = HFAttn(E, heads, L, P).eval()
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.05)
+        mod.sampling_offsets.bias.normal_(0, 1.5)
+        mod.attention_weights.weight.normal_(0, 0.1)
+        mod.attention_weights.bias.normal_(0, 0.5)
+    sd = {"a." + k: v.detach() for k, v in mod.state_dict().items()}
+    x, pos = torch.randn(B, nq, E), torch.randn(B, nq, E)
+    refs = []
+    for h, w in shapes:
+        ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+        refs.append(torch.stack([(xs.reshape(-1) + 0.5) / w, (ys.reshape(-1) + 0.5) / h], dim=-1))
+    ref = torch.cat(refs)[None, :, None].repeat(B, 1, L, 1)
+    with torch.no_grad():
+        want, _ = mod(x, encoder_hidden_states=x, position_embeddings=pos, reference_points=ref, spatial_shapes_list=shapes)
+        got = rq.ms_deform_attn(sd, "a.", x, pos, ref, shapes, heads, P)
+    torch.testing.assert_close(got - x, want, rtol=1e-4, atol=1e-4)          # the restatement adds the identity
+
+
+@pytest.mark.parametrize("E,masked", [(128, True), (256, True), (256, False)])
+def test_mha_restatement_matches_torch_multihead_attention(E, masked):
+    """oracle.restate_query._mha (mmcv MultiheadAttention wrapper: q + query_pos, k + key_pos, identity + out) against
+    torch.nn.MultiheadAttention(batch_first=True) with a boolean attn_mask [B*heads, nq, nk]."""
+    from oracle import restate_query as rq
+    torch.manual_seed(E + masked)
+    heads, B, nq, nk = 8, 2, 7, 33
+    mha = torch.nn.MultiheadAttention(E, heads, batch_first=True).eval()
+    with torch.no_grad():
+        mha.in_proj_bias.normal_(0, 0.1)
+        mha.out_proj.bias.normal_(0, 0.1)
+    sd = {"m.attn." + k: v.detach() for k, v in mha.state_dict().items()}
+    q, qp = torch.randn(B, nq, E), torch.randn(B, nq, E)
+    k, kp = torch.randn(B, nk, E), torch.randn(B, nk, E)
+    am = None
+    if masked:
+        am = torch.rand(B, 1, nq, nk) < 0.5
+        am[:, :, :, 0] = False                                            # no fully masked row
+        am = am.repeat(1, heads, 1, 1).flatten(0, 1)
+    with torch.no_grad():
+        want = q + mha(q + qp, k + kp, k, attn_mask=am, need_weights=False)[0]
+        got = rq._mha(sd, "m.", q, k, k, qp, kp, am, heads)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
