@@ -1,5 +1,5 @@
 """A few whole-pipeline steps of one detector variant, for ncu launch lists / traffic captures and quick timings:
-    python profiles/run_step.py --variant anchor|query [--arch base] [--batch 8] [--size 1024] [--steps 2]
+    python profiles/run_step.py --variant anchor|query|maskrcnn|mask2former [--arch base] [--batch 8] [--size 1024] [--steps 2]
 Prints the CUDA-event time per step (meaningless under ncu) and the number of library launches."""
 import argparse
 import json
@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--variant", default="anchor", choices=["anchor", "query"])
+    ap.add_argument("--variant", default="anchor", choices=["anchor", "query", "maskrcnn", "mask2former"])
     ap.add_argument("--arch", default="base")
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--size", type=int, default=1024)
@@ -30,6 +30,12 @@ def main():
     if a.variant == "anchor":
         model = MODELS.build(model_configs.anchor_model_cfg(a.arch, a.classes))
         model.load_state_dict(synthetic.anchor_detector_state_dict(arch, a.classes, nsel, seed=0))
+    elif a.variant == "maskrcnn":
+        model = MODELS.build(model_configs.maskrcnn_model_cfg(a.arch, a.classes))
+        model.load_state_dict(synthetic.maskrcnn_detector_state_dict(arch, a.classes, nsel, seed=0))
+    elif a.variant == "mask2former":
+        model = MODELS.build(model_configs.mask2former_model_cfg(a.arch, a.classes))
+        model.load_state_dict(synthetic.mask2former_detector_state_dict(arch, a.classes, nsel, seed=0))
     else:
         model = MODELS.build(model_configs.query_model_cfg(a.arch, a.classes))
         model.load_state_dict(synthetic.query_detector_state_dict(arch, a.classes, nsel, seed=0))
@@ -46,6 +52,7 @@ def main():
         model.predict(x)
     e1.record()
     torch.cuda.synchronize()
+    launches = (_lib.launch_count - l0) // a.steps
     # host-side issue time of one step (no synchronisation inside): tells whether the step is launch-bound
     import time
     cpu_ms = []
@@ -57,7 +64,7 @@ def main():
         torch.cuda.synchronize()
     print(json.dumps(dict(host_issue_ms_per_step=cpu_ms)))
     print(json.dumps(dict(variant=a.variant, arch=a.arch, batch=a.batch, size=a.size, steps=a.steps,
-                          ms_per_step=e0.elapsed_time(e1) / a.steps, launches_per_step=(_lib.launch_count - l0) // a.steps,
+                          ms_per_step=e0.elapsed_time(e1) / a.steps, launches_per_step=launches,
                           images_per_s=a.batch * a.steps / (e0.elapsed_time(e1) * 1e-3))))
 
 

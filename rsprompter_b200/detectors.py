@@ -396,14 +396,16 @@ class SAMSegMaskRCNN(_SamDetectorBase):
         for b, ds in enumerate(batch_data_samples):
             n, m = counts[b], metas[b]
             boxes = r["bboxes"][b, :n]
-            if m is None:
+            if fast:
                 mk = masks[b, :n]
             else:   # fcn_mask_head.py:333-343: boxes to the original image (rescale) or canvas = round(ori * scale)
-                sf, size = m["scale_factor"], m["ori_hw"]
-                if rescale:
-                    boxes = boxes / boxes.new_tensor(sf).repeat(2)
-                else:
-                    size = (int(round(size[0] * sf[1])), int(round(size[1] * sf[0])))
+                size = hw
+                if m is not None:
+                    sf, size = m["scale_factor"], m["ori_hw"]
+                    if rescale:
+                        boxes = boxes / boxes.new_tensor(sf).repeat(2)
+                    else:
+                        size = (int(round(size[0] * sf[1])), int(round(size[1] * sf[0])))
                 pb = torch.zeros(max(n, 1), 4, device=boxes.device)
                 pb[:n] = boxes
                 mk = _lib.mask_paste_boxes(probs[b * M:b * M + max(n, 1)].contiguous(), pb, size, thr)[:n]
