@@ -190,6 +190,10 @@ int rsp_bbox_cls_decode_shapes(const float* cls, int ld_cls, const float* reg, i
  * Replaces mmcv.ops.batched_nms / nms (rpn_head.py:285, bbox_nms.py:95). */
 int rsp_nms_batched(const float* boxes, const int64_t* ids, const int32_t* nvalid, int B, int n, float thr,
                     void* mask_ws, float* max_coord_ws, uint8_t* keep, void* stream);
+/* ... for callers that only read the first max_keep kept candidates (batched_nms(...)[:max_per_img], rpn_head.py:285-291,
+ * bbox_nms.py:95-103): the greedy scan stops once max_keep candidates are kept, later keep flags are 0. */
+int rsp_nms_batched_topk(const float* boxes, const int64_t* ids, const int32_t* nvalid, int B, int n, float thr,
+                         void* mask_ws, float* max_coord_ws, uint8_t* keep, int max_keep, void* stream);
 
 /* First K kept candidates per image, in order, zero padded; counts int32 [B].  labels / out_labels /
  * out_index may be NULL.  Replaces results[keep][:max_per_img] (rpn_head.py:289, bbox_nms.py:97-99). */

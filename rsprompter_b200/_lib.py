@@ -69,6 +69,7 @@ _SIGNATURES = {
     "rsp_rpn_decode": ([_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _f, _f, _i, _i, _vp, _vp, _vp], _i),
     "rsp_bbox_cls_decode": ([_vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _f, _f, _f, _vp, _vp, _vp, _vp], _i),
     "rsp_rpn_decode_shapes": ([_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp], _i),
+    "rsp_nms_batched_topk": ([_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _i, _vp], _i),
     "rsp_bbox_cls_decode_shapes": ([_vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp], _i),
     "rsp_nms_batched": ([_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp], _i),
     "rsp_compact_keep": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
@@ -629,8 +630,10 @@ def bbox_cls_decode(cls: torch.Tensor, reg: torch.Tensor, rois: torch.Tensor, ro
     return scores, boxes, labels
 
 
-def nms_batched(boxes: torch.Tensor, ids: torch.Tensor, nvalid: torch.Tensor, iou_thr: float) -> torch.Tensor:
-    """boxes fp32 [B, n, 4] sorted by descending score, ids int64 [B, n], nvalid int32 [B] -> keep uint8 [B, n]."""
+def nms_batched(boxes: torch.Tensor, ids: torch.Tensor, nvalid: torch.Tensor, iou_thr: float,
+                max_keep: int = 0) -> torch.Tensor:
+    """boxes fp32 [B, n, 4] sorted by descending score, ids int64 [B, n], nvalid int32 [B] -> keep uint8 [B, n].
+    max_keep > 0: the caller takes only the first max_keep kept candidates; the scan stops once they exist."""
     global launch_count
     _require_cuda(boxes, ids, nvalid)
     B, n, _ = boxes.shape
@@ -641,8 +644,8 @@ def nms_batched(boxes: torch.Tensor, ids: torch.Tensor, nvalid: torch.Tensor, io
     mask_ws = torch.empty(B * n * words, device=boxes.device, dtype=torch.int64)
     mx = torch.empty(B, device=boxes.device, dtype=torch.float32)
     keep = torch.empty(B, n, device=boxes.device, dtype=torch.uint8)
-    _check(_lib.rsp_nms_batched(_ptr(boxes), _ptr(ids), _ptr(nvalid), B, n, float(iou_thr), _ptr(mask_ws),
-                                _ptr(mx), _ptr(keep), _stream()), "rsp_nms_batched")
+    _check(_lib.rsp_nms_batched_topk(_ptr(boxes), _ptr(ids), _ptr(nvalid), B, n, float(iou_thr), _ptr(mask_ws),
+                                     _ptr(mx), _ptr(keep), int(max_keep), _stream()), "rsp_nms_batched_topk")
     launch_count += 3
     return keep
 

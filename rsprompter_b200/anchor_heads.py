@@ -174,7 +174,7 @@ class RPNHead(_PrepMixin, BaseModule):
         b_sorted = torch.gather(boxes, 1, order[:, :, None].expand(-1, -1, 4)).contiguous()
         i_sorted = torch.gather(ids, 1, order).contiguous()
         nvalid = (s_sorted >= 0).sum(dim=1).to(torch.int32)
-        keep = _lib.nms_batched(b_sorted, i_sorted, nvalid, float(cfg.nms.get("iou_threshold", 0.7)))
+        keep = _lib.nms_batched(b_sorted, i_sorted, nvalid, float(cfg.nms.get("iou_threshold", 0.7)), max_keep=K)
         pb, ps, _, _, cnt = _lib.compact_keep(keep, b_sorted, s_sorted.contiguous(), None, K)
         return pb, ps, cnt
 
@@ -325,8 +325,8 @@ def _predict_bboxes(head, feats: list, proposals: torch.Tensor, prop_counts: tor
     b_sorted = torch.gather(b, 1, order[:, :, None].expand(-1, -1, 4)).contiguous()
     l_sorted = torch.gather(lab, 1, order).contiguous()
     nvalid = (s_sorted >= 0).sum(dim=1).to(torch.int32)
-    keep = _lib.nms_batched(b_sorted, l_sorted, nvalid, float(cfg.nms.get("iou_threshold", 0.5)))
     M = int(cfg.get("max_per_img", 100))
+    keep = _lib.nms_batched(b_sorted, l_sorted, nvalid, float(cfg.nms.get("iou_threshold", 0.5)), max_keep=M)
     db, ds, dl, _, cnt = _lib.compact_keep(keep, b_sorted, s_sorted.contiguous(), l_sorted, M)
     return db, ds, dl, cnt
 

@@ -213,7 +213,13 @@ int rsp_bbox_cls_decode_shapes(const float* cls, int ld_cls, const float* reg, i
 int rsp_nms_batched(const float* boxes, const int64_t* ids, const int32_t* nvalid, int B, int n, float thr,
                     void* mask_ws, float* max_coord_ws, uint8_t* keep, void* stream) {
   return nms_batched(boxes, reinterpret_cast<const long long*>(ids), nvalid, B, n, thr,
-                     static_cast<unsigned long long*>(mask_ws), max_coord_ws, keep, S(stream));
+                     static_cast<unsigned long long*>(mask_ws), max_coord_ws, keep, 0, S(stream));
+}
+
+int rsp_nms_batched_topk(const float* boxes, const int64_t* ids, const int32_t* nvalid, int B, int n, float thr,
+                         void* mask_ws, float* max_coord_ws, uint8_t* keep, int max_keep, void* stream) {
+  return nms_batched(boxes, reinterpret_cast<const long long*>(ids), nvalid, B, n, thr,
+                     static_cast<unsigned long long*>(mask_ws), max_coord_ws, keep, max_keep, S(stream));
 }
 
 int rsp_compact_keep(const uint8_t* keep, const float* boxes, const float* scores, const int64_t* labels,

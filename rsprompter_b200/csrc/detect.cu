@@ -209,7 +209,7 @@ __global__ void nms_mask_kernel(const float* __restrict__ boxes, const long long
 // shuffle); then all 128 threads OR the kept rows' remaining words into the suppression bitmap,
 // eight independent loads in flight per thread (the mask is L2-resident).
 __global__ void __launch_bounds__(128)
-nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ nvalid, int n,
+nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ nvalid, int n, int max_keep,
                 unsigned char* __restrict__ keep) {
   extern __shared__ unsigned long long remv[];
   __shared__ unsigned long long kept_s;
@@ -221,9 +221,10 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
   for (int w = tid; w < words; w += blockDim.x) remv[w] = 0ull;
   __syncthreads();
   const unsigned long long* mbase = mask + static_cast<size_t>(b) * n * words;
+  int kept_total = 0;     // the caller reads only the first max_keep kept candidates (compact_keep): stop once they exist
   for (int blk = 0; blk < words; ++blk) {
     const int i0 = blk * 64;
-    if (blk < nvw) {
+    if (blk < nvw && !(max_keep > 0 && kept_total >= max_keep)) {
       if (tid < 32) {
         const int r0 = i0 + lane, r1 = i0 + 32 + lane;
         const unsigned long long d0 = (r0 < nv) ? mbase[static_cast<size_t>(r0) * words + blk] : 0ull;
@@ -240,6 +241,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
       }
       __syncthreads();
       const unsigned long long keptbits = kept_s;
+      kept_total += __popcll(keptbits);
       for (int w = blk + 1 + tid; w < nvw; w += blockDim.x) {
         unsigned long long acc = remv[w];
         unsigned long long kb = keptbits;
@@ -270,7 +272,8 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
 }
 
 int nms_batched(const float* boxes, const long long* ids, const int* nvalid, int B, int n, float thr,
-                unsigned long long* mask_ws, float* max_coord_ws, unsigned char* keep, cudaStream_t stream) {
+                unsigned long long* mask_ws, float* max_coord_ws, unsigned char* keep, int max_keep,
+                cudaStream_t stream) {
   RSP_CHECK_ARG(boxes && ids && nvalid && mask_ws && max_coord_ws && keep && B > 0 && n > 0, "nms: bad args");
   const int words = (n + 63) / 64;
   RSP_CHECK_ARG(words * 8 <= 48 * 1024, "nms: at most %d candidates per image", 48 * 1024 / 8 * 64);
@@ -279,7 +282,7 @@ int nms_batched(const float* boxes, const long long* ids, const int* nvalid, int
   dim3 grid(words, words, B);
   nms_mask_kernel<<<grid, 64, 0, stream>>>(boxes, ids, nvalid, max_coord_ws, n, thr, mask_ws);
   RSP_CHECK_LAUNCH();
-  nms_scan_kernel<<<B, 128, words * 8, stream>>>(mask_ws, nvalid, n, keep);
+  nms_scan_kernel<<<B, 128, words * 8, stream>>>(mask_ws, nvalid, n, max_keep, keep);
   RSP_CHECK_LAUNCH();
   return RSP_OK;
 }

@@ -12,7 +12,8 @@ int bbox_cls_decode(const float* cls, int ld_cls, const float* reg, int ld_reg, 
                     const float* img_shapes, float score_thr, float* scores, float* boxes, long long* labels,
                     cudaStream_t stream);
 int nms_batched(const float* boxes, const long long* ids, const int* nvalid, int B, int n, float thr,
-                unsigned long long* mask_ws, float* max_coord_ws, unsigned char* keep, cudaStream_t stream);
+                unsigned long long* mask_ws, float* max_coord_ws, unsigned char* keep, int max_keep,
+                cudaStream_t stream);   // max_keep > 0: flags past the first max_keep kept candidates may be 0
 int compact_keep(const unsigned char* keep, const float* boxes, const float* scores, const long long* labels,
                  int B, int n, int K, float* out_boxes, float* out_scores, long long* out_labels,
                  int* out_index, int* counts, cudaStream_t stream);

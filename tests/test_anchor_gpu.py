@@ -328,3 +328,26 @@ def test_predict_attaches_per_image_shapes(model_and_sd):
         assert b2[:, 1::2].max().item() <= 512 and b2[:, 0::2].max().item() <= 1000 and b2[:, 0::2].max().item() > 768
     finally:
         m.enable_cuda_graphs(False)
+
+
+@pytest.mark.parametrize("n,K", [(3000, 50), (700, 1000), (64, 1)])
+def test_nms_early_stop_keeps_the_same_first_k(n, K):
+    """rsp_nms_batched_topk: stopping the greedy scan after max_keep kept candidates leaves the first K kept ones (all a
+    caller of batched_nms(...)[:max_per_img] reads) unchanged."""
+    from rsprompter_b200 import _lib
+    g = torch.Generator().manual_seed(n + K)
+    B = 3
+    ctr = torch.rand(B, n, 2, generator=g) * 600
+    wh = torch.rand(B, n, 2, generator=g) * 120 + 4
+    boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], dim=2).cuda().contiguous()
+    scores = torch.sort(torch.rand(B, n, generator=g), dim=1, descending=True).values.cuda().contiguous()
+    ids = torch.randint(0, 4, (B, n), generator=g).cuda()
+    nvalid = torch.tensor([n, n - 17, max(n // 2, 1)], dtype=torch.int32).cuda()
+    full = _lib.nms_batched(boxes, ids, nvalid, 0.5)
+    part = _lib.nms_batched(boxes, ids, nvalid, 0.5, max_keep=K)
+    a = _lib.compact_keep(full, boxes, scores, ids, K)
+    b = _lib.compact_keep(part, boxes, scores, ids, K)
+    torch.cuda.synchronize()
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    assert (part <= full).all()
