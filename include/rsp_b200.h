@@ -224,6 +224,11 @@ int rsp_sigmoid_f32(const float* in, float* out, long long n, void* stream);
 /* bf16 NHWC pooling: mode 0 = MaxPool2d(2, 2) (M:1307), mode 1 = max_pool2d(k=1, stride=2) (M:1362). */
 int rsp_pool2_nhwc(const void* in, void* out, int B, int H, int W, int C, int mode, void* stream);
 
+/* Zero the 1-pixel border of bf16 NHWC maps [N, H, W, C] in place (C % 8 == 0).  FCNMaskHead's 3x3 convolutions
+ * (fcn_mask_head.py:84-98) run on 14x14 RoI maps embedded in 16x16 canvases so that the implicit-GEMM convolution
+ * (rsp_conv3x3_nhwc) applies; the border is the convolutions' zero padding and is restored after every layer. */
+int rsp_zero_border_nhwc(void* x, int N, int H, int W, int C, void* stream);
+
 /* out[i] = sin(in[2i]) + in[2i+1]: the sin/identity fold of the point embeddings (M:348, M:1672). */
 int rsp_sin_fold(const float* in, float* out, long long n_out, void* stream);
 

@@ -76,6 +76,7 @@ _SIGNATURES = {
     "rsp_roi_align_nhwc": ([_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _f, _vp, _vp], _i),
     "rsp_mask_paste": ([_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp], _i),
     "rsp_pool2_nhwc": ([_vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    "rsp_zero_border_nhwc": ([_vp, _i, _i, _i, _i, _vp], _i),
     "rsp_sigmoid_f32": ([_vp, _vp, ctypes.c_longlong, _vp], _i),
     "rsp_mask_paste_boxes": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp], _i),
     "rsp_groupnorm_nhwc": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp], _i),
@@ -772,6 +773,17 @@ def mask_paste_rescale(logits: torch.Tensor, batch_hw: tuple, crop_hw: tuple, or
                                        ori_hw[0], ori_hw[1], float(thr), 1 if raw else 2, _stream()), "rsp_mask_paste_rescale")
     launch_count += 1
     return out.view(torch.bool)
+
+
+def zero_border_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """Zero the 1-pixel border of bf16 NHWC maps [N, H, W, C] in place."""
+    global launch_count
+    _require_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4 and x.shape[3] % 8 == 0
+    N, H, W, C = x.shape
+    _check(_lib.rsp_zero_border_nhwc(_ptr(x), N, H, W, C, _stream()), "rsp_zero_border_nhwc")
+    launch_count += 1
+    return x
 
 
 def pool2_nhwc(x: torch.Tensor, mode: int) -> torch.Tensor:

@@ -248,6 +248,10 @@ int rsp_pool2_nhwc(const void* in, void* out, int B, int H, int W, int C, int mo
   return pool2_nhwc(in, out, B, H, W, C, mode, S(stream));
 }
 
+int rsp_zero_border_nhwc(void* x, int N, int H, int W, int C, void* stream) {
+  return zero_border_nhwc(x, N, H, W, C, S(stream));
+}
+
 int rsp_sin_fold(const float* in, float* out, long long n_out, void* stream) {
   return sin_fold(in, out, n_out, S(stream));
 }

@@ -708,6 +708,32 @@ int pool2_nhwc(const void* in, void* out, int B, int H, int W, int C, int mode, 
   return RSP_OK;
 }
 
+// Zero the 1-pixel border of bf16 NHWC maps in place.  FCNMaskHead runs its 3x3 convolutions on 14x14 RoI maps embedded
+// in 16x16 canvases (128-pixel GEMM tiles are then boxes of the map, so the implicit-GEMM conv applies and no im2col
+// matrix is built): the border must read as the convolution's zero padding again after every layer.
+__global__ void zero_border_nhwc_kernel(__nv_bfloat16* __restrict__ x, int N, int H, int W, int C) {
+  const int c8 = C / 8, ring = 2 * W + 2 * (H - 2);
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(N) * ring * c8) return;
+  const int tc = static_cast<int>(idx % c8);
+  const long long t = idx / c8;
+  const int r = static_cast<int>(t % ring), n = static_cast<int>(t / ring);
+  int y, xx;
+  if (r < W) { y = 0; xx = r; }
+  else if (r < 2 * W) { y = H - 1; xx = r - W; }
+  else { const int k = r - 2 * W; y = 1 + (k >> 1); xx = (k & 1) ? W - 1 : 0; }
+  *reinterpret_cast<uint4*>(x + ((static_cast<size_t>(n) * H + y) * W + xx) * C + tc * 8) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+int zero_border_nhwc(void* x, int N, int H, int W, int C, cudaStream_t stream) {
+  RSP_CHECK_ARG(x && N > 0 && H >= 3 && W >= 3 && C % 8 == 0, "zero_border_nhwc: bad args");
+  const long long total = static_cast<long long>(N) * (2 * W + 2 * (H - 2)) * (C / 8);
+  zero_border_nhwc_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<__nv_bfloat16*>(x), N, H, W, C);
+  RSP_CHECK_LAUNCH();
+  return RSP_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 __global__ void sin_fold_kernel(const float* __restrict__ in, float* __restrict__ out, long long n_out) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;

@@ -30,6 +30,7 @@ int mask_paste_boxes(const float* probs, const float* boxes, unsigned char* out,
                      float thr, int packed, cudaStream_t stream);
 int sigmoid_f32(const float* in, float* out, long long n, cudaStream_t stream);
 int pool2_nhwc(const void* in, void* out, int B, int H, int W, int C, int mode, cudaStream_t stream);
+int zero_border_nhwc(void* x, int N, int H, int W, int C, cudaStream_t stream);
 int sin_fold(const float* in, float* out, long long n_out, cudaStream_t stream);
 
 }  // namespace rsp
