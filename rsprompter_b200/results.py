@@ -78,6 +78,87 @@ class ResultRecord:
         return out
 
 
+# ---- consumer side: COCO run-length encoding of host records -----------------------------------------------------
+# What CocoMetric.process does to every predicted mask before results are collected (coco_metric.py:365 ->
+# mmdet/structures/mask/utils.py:38-53 encode_mask_results -> pycocotools mask_util.encode).  pycocotools is a third-party
+# C extension absent from this image and from /root/reference; the two functions below restate its published format
+# (maskApi.c rleEncode / rleToString / rleFrString: column-major runs starting with a run of zeros; counts written as
+# 5-bit groups + continuation bit, offset 48, with every count from the fourth on stored as the difference to the count
+# two places back).  Host-side numpy on the bit-packed payload - evaluation itself stays outside this package.
+def mask_to_coco_rle(mask) -> dict:
+    """bool / uint8 [H, W] (numpy or CPU tensor) -> {'size': [H, W], 'counts': bytes}."""
+    import numpy as np
+    m = np.asarray(mask.numpy() if isinstance(mask, torch.Tensor) else mask).astype(bool)
+    h, w = m.shape
+    flat = m.T.reshape(-1)                                   # column-major, as the C API walks the mask
+    change = np.flatnonzero(flat[1:] != flat[:-1]) + 1
+    bounds = np.concatenate(([0], change, [flat.size]))
+    counts = np.diff(bounds).tolist()
+    if flat.size and flat[0]:
+        counts = [0] + counts                                # the first run counts zeros
+    out = bytearray()
+    for i, c in enumerate(counts):
+        x = int(c) - (int(counts[i - 2]) if i > 2 else 0)
+        more = True
+        while more:
+            ch = x & 0x1F
+            x >>= 5                                          # arithmetic shift (negative differences)
+            more = (x != -1) if (ch & 0x10) else (x != 0)
+            if more:
+                ch |= 0x20
+            out.append(ch + 48)
+    return dict(size=[int(h), int(w)], counts=bytes(out))
+
+
+def coco_rle_to_mask(rle: dict):
+    """Inverse of mask_to_coco_rle -> numpy bool [H, W]."""
+    import numpy as np
+    h, w = rle["size"]
+    s = rle["counts"]
+    s = s.encode() if isinstance(s, str) else s
+    counts, p = [], 0
+    while p < len(s):
+        x, k, more = 0, 0, True
+        while more:
+            ch = s[p] - 48
+            x |= (ch & 0x1F) << (5 * k)
+            more = bool(ch & 0x20)
+            p += 1
+            k += 1
+            if not more and (ch & 0x10):
+                x |= -1 << (5 * k)
+        if len(counts) > 2:
+            x += counts[-2]
+        counts.append(x)
+    flat = np.zeros(h * w, dtype=bool)
+    pos, val = 0, False
+    for c in counts:
+        if val:
+            flat[pos:pos + c] = True
+        pos += c
+        val = not val
+    return flat.reshape(w, h).T
+
+
+def record_to_coco_results(rec: "ResultRecord", image_ids: list, label_to_cat=None) -> list:
+    """Host record -> the 'segm' result dicts CocoMetric.results2json writes (coco_metric.py:237-262): one dict per
+    valid slot with image_id, bbox (xywh), score, category_id and the RLE-encoded mask."""
+    import numpy as np
+    assert not rec.buf.is_cuda, "copy the record to the host first (ResultRecord.to_host)"
+    H, W = rec.hw
+    out = []
+    bits = rec.mask_bits.numpy()
+    rows = rec.rows.numpy()
+    for b, n in enumerate(rec.counts.tolist()):
+        masks = np.unpackbits(bits[b, :n], axis=-1, bitorder="little")[..., :W].astype(bool)
+        for j in range(n):
+            x1, y1, x2, y2, score, label = rows[b, j].tolist()
+            cat = int(label) if label_to_cat is None else label_to_cat[int(label)]
+            out.append(dict(image_id=image_ids[b], bbox=[x1, y1, x2 - x1, y2 - y1], score=float(score), category_id=cat,
+                            segmentation=mask_to_coco_rle(masks[j])))
+    return out
+
+
 # ---- round-1 helpers kept for callers that only exchange the detection rows -------------------------------------
 def pack_records(bboxes: torch.Tensor, scores: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
     """[B,M,4], [B,M], [B,M] -> fp32 [B, M, 6]."""

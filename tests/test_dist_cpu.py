@@ -71,3 +71,30 @@ def test_record_gather_world2():
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res)
     assert res[0][2] == res[1][2]          # every rank sees the same global counts
+
+
+def test_coco_rle_of_record_masks():
+    """mask_to_coco_rle restates pycocotools' published format (maskApi.c rleEncode + rleToString); hand-derived
+    known answers, the inverse, and the record -> CocoMetric 'segm' result dicts path."""
+    import numpy as np
+    import torch
+    from rsprompter_b200.results import ResultRecord, coco_rle_to_mask, mask_to_coco_rle, record_to_coco_results
+    m = np.array([[0, 1], [1, 1]], dtype=bool)                       # column-major 0,1,1,1 -> runs [1, 3]
+    assert mask_to_coco_rle(m) == dict(size=[2, 2], counts=b"13")
+    assert mask_to_coco_rle(np.ones((4, 5), dtype=bool))["counts"] == b"0d0"     # [0, 20]: 20 = 0x14 -> 'd', '0'
+    assert mask_to_coco_rle(np.zeros((4, 5), dtype=bool))["counts"] == b"d0"
+    g = np.random.default_rng(0)
+    for shape in ((1, 1), (7, 13), (64, 40), (300, 257)):
+        for p in (0.02, 0.5, 0.97):
+            mk = g.random(shape) < p
+            mk[: shape[0] // 3] = mk[:1]                                  # long runs -> negative count differences
+            assert np.array_equal(coco_rle_to_mask(mask_to_coco_rle(mk)), mk)
+    rec = ResultRecord(2, 3, (16, 24))
+    masks = torch.from_numpy(g.random((2, 3, 16, 24)) < 0.4)
+    bits = np.packbits(masks.numpy(), axis=-1, bitorder="little")
+    rec.mask_bits.copy_(torch.from_numpy(bits))
+    rec.rows.copy_(torch.tensor([[[1., 2., 11., 22., 0.9, 4.]] * 3] * 2))
+    rec.counts.copy_(torch.tensor([2, 0], dtype=torch.int32))
+    res = record_to_coco_results(rec, image_ids=[17, 18], label_to_cat={4: 5})
+    assert len(res) == 2 and res[0]["image_id"] == 17 and res[0]["category_id"] == 5 and res[0]["bbox"] == [1., 2., 10., 20.]
+    assert np.array_equal(coco_rle_to_mask(res[1]["segmentation"]), masks[0, 1].numpy())
