@@ -617,6 +617,7 @@ mask_embed_src_mma_kernel(const float* __restrict__ mpp, MaskEmbedW W, const flo
   __shared__ __align__(16) __nv_bfloat16 hid[128][24];      // 16 used + 8 pad: conflict-free fragment reads
   __shared__ __align__(16) __nv_bfloat16 w3s[256][24];
   __shared__ float b3s[256];
+  __shared__ __align__(16) float stage[4][16][72];           // per warp: one 16-row x 64-channel fp32 quarter tile (+8 pad)
   const int n = blockIdx.y;
   const int p0 = blockIdx.x * 128;
   const int HW = h * w;
@@ -692,24 +693,35 @@ mask_embed_src_mma_kernel(const float* __restrict__ mpp, MaskEmbedW W, const flo
     a[1] = *reinterpret_cast<const uint32_t*>(&hid[r0 + g + 8][2 * q]);
     a[2] = *reinterpret_cast<const uint32_t*>(&hid[r0 + g][2 * q + 8]);
     a[3] = *reinterpret_cast<const uint32_t*>(&hid[r0 + g + 8][2 * q + 8]);
-    const size_t pixA = static_cast<size_t>(p0 + r0 + g), pixB = pixA + 8;
-    const float* eA = emb + (static_cast<size_t>(img) * HW + pixA) * 256;
-    const float* eB = emb + (static_cast<size_t>(img) * HW + pixB) * 256;
-    __nv_bfloat16* oA = src + (static_cast<size_t>(n) * HW + pixA) * 256;
-    __nv_bfloat16* oB = src + (static_cast<size_t>(n) * HW + pixB) * 256;
-#pragma unroll 4
-    for (int nt = 0; nt < 32; ++nt) {
-      const int c0 = nt * 8;
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&w3s[c0 + g][2 * q]);        // B(k, n) = w3[c0 + n][k]
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&w3s[c0 + g][2 * q + 8]);
-      float d[4] = {0.f, 0.f, 0.f, 0.f};
-      mma_bf16_16816q(d, a, b0, b1);
-      const int c = c0 + 2 * q;                       // this thread's two output channels
-      const float2 ea = __ldg(reinterpret_cast<const float2*>(eA + c));
-      const float2 eb = __ldg(reinterpret_cast<const float2*>(eB + c));
+    // The accumulator fragments give a lane 2 channels of rows g / g + 8: stored from there, one warp store touches 8
+    // pixel rows x 16 bytes (8 LSU wavefronts per 128 bytes; the kernel ran at 1.4 TB/s, LSU-bound).  Instead the 16 x 64
+    // fp32 quarter tiles go through a per-warp staging buffer and leave as whole rows: lane = 2 channels, one wavefront
+    // per 128-byte bf16 store and two per 256-byte embedding load.  Same arithmetic order ((acc + bias) + embedding).
+    float (*st)[72] = stage[warp];
+#pragma unroll 1
+    for (int qt = 0; qt < 4; ++qt) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int c0 = qt * 64 + nt * 8;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&w3s[c0 + g][2 * q]);        // B(k, n) = w3[c0 + n][k]
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&w3s[c0 + g][2 * q + 8]);
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_bf16_16816q(d, a, b0, b1);
+        *reinterpret_cast<float2*>(&st[g][nt * 8 + 2 * q]) = make_float2(d[0], d[1]);
+        *reinterpret_cast<float2*>(&st[g + 8][nt * 8 + 2 * q]) = make_float2(d[2], d[3]);
+      }
+      __syncwarp();
+      const int c = qt * 64 + 2 * lane;                 // this lane's two output channels
       const float ba = b3s[c], bb = b3s[c + 1];
-      *reinterpret_cast<uint32_t*>(oA + c) = pack_bf16x2(d[0] + ba + ea.x, d[1] + bb + ea.y);
-      *reinterpret_cast<uint32_t*>(oB + c) = pack_bf16x2(d[2] + ba + eb.x, d[3] + bb + eb.y);
+      const float* e0 = emb + (static_cast<size_t>(img) * HW + p0 + r0) * 256 + c;
+      __nv_bfloat16* o0 = src + (static_cast<size_t>(n) * HW + p0 + r0) * 256 + c;
+#pragma unroll 8
+      for (int r = 0; r < 16; ++r) {
+        const float2 v = *reinterpret_cast<const float2*>(&st[r][2 * lane]);
+        const float2 e = __ldg(reinterpret_cast<const float2*>(e0 + static_cast<size_t>(r) * 256));
+        *reinterpret_cast<uint32_t*>(o0 + static_cast<size_t>(r) * 256) = pack_bf16x2(v.x + ba + e.x, v.y + bb + e.y);
+      }
+      __syncwarp();
     }
   }
 }
