@@ -260,11 +260,11 @@ def stock_forward_head(sd: dict, decoder_out, mask_feature, target_size, heads=8
     return cls_pred, mask_pred, am.sigmoid() < 0.5
 
 
-def stock_mask2former_head(sd: dict, feats, levels=3, heads=8, prefix=""):
-    """Mask2FormerHead.forward (mask2former_head.py:382-460) -> the last layer's (cls_pred, mask_pred)."""
+def stock_mask2former_decoder(sd: dict, mask_feature, memories, levels=3, heads=8, prefix=""):
+    """The part of Mask2FormerHead.forward behind the pixel decoder (mask2former_head.py:404-460): level / positional
+    embeddings, the masked-attention decoder layers, _forward_head after each -> the last layer's (cls_pred, mask_pred)."""
     p = prefix
-    B = feats[0].shape[0]
-    mask_feature, memories = pixel_decoder(sd, feats, p + "pixel_decoder.", heads=heads)
+    B = mask_feature.shape[0]
     E = memories[0].shape[1]
     dec_in, dec_pos = [], []
     for i in range(levels):
@@ -288,6 +288,12 @@ def stock_mask2former_head(sd: dict, feats, levels=3, heads=8, prefix=""):
         cls, mp, am = stock_forward_head(sd, qf, mask_feature, memories[(i + 1) % levels].shape[-2:], heads, p)
         i += 1
     return cls, mp
+
+
+def stock_mask2former_head(sd: dict, feats, levels=3, heads=8, prefix=""):
+    """Mask2FormerHead.forward (mask2former_head.py:382-460) -> the last layer's (cls_pred, mask_pred)."""
+    mask_feature, memories = pixel_decoder(sd, feats, prefix + "pixel_decoder.", heads=heads)
+    return stock_mask2former_decoder(sd, mask_feature, memories, levels, heads, prefix)
 
 
 def samseg_mask2former_predict(sd: dict, vision_arch, images: torch.Tensor, num_classes: int, select_layers,
