@@ -309,6 +309,79 @@ def main_state_keys():
     print("wrote", path, {k: len(v) for k, v in out.items()})
 
 
+def main_necks():
+    """tests/golden/reference_necks.pt: inputs, seeded state dicts and outputs of the reference's OWN forward() of
+    RSFeatureAggregator, PseudoFeatureAggregator and RSSimpleFPN (mmdet/rsprompter/models.py), executed with torch only
+    (BaseModule -> nn.Module; RSSimpleFPN's ConvModule / build_norm_layer through the stand-ins documented in
+    main_state_keys: conv -> LN2d, no activation, as ConvModule(norm_cfg=LN2d, act_cfg=None) orders them).  Small
+    channel counts keep the file small; the layer structure is the shipped one."""
+    import einops
+    from torch import nn
+    rel = "mmdet/rsprompter/models.py"
+
+    class BaseModule(nn.Module):
+        def __init__(self, init_cfg=None):
+            super().__init__()
+
+    LayerNorm2d = _exec_class("mmpretrain/models/utils/norm.py", "LayerNorm2d", dict(torch=torch, nn=nn, F=F))
+    ns = dict(torch=torch, nn=nn, F=F, einops=einops, BaseModule=BaseModule, LayerNorm2d=LayerNorm2d, List=list,
+              Tensor=torch.Tensor)
+    LN2d = _exec_class(rel, "LN2d", ns)
+
+    def build_norm_layer(cfg, num_features, postfix=""):
+        return "norm_layer" + str(postfix), LN2d(num_features)
+
+    class ConvModule(nn.Module):
+        def __init__(self, cin, cout, k, padding=0, conv_cfg=None, norm_cfg=None, act_cfg=None, inplace=False):
+            super().__init__()
+            assert norm_cfg is not None and act_cfg is None
+            self.conv = nn.Conv2d(cin, cout, k, padding=padding, bias=False)
+            self.add_module("norm_layer", build_norm_layer(norm_cfg, cout)[1])
+
+        def forward(self, x):
+            return self.norm_layer(self.conv(x))
+
+    ns.update(build_norm_layer=build_norm_layer, ConvModule=ConvModule)
+    g = torch.Generator().manual_seed(777)
+    fx = {}
+
+    def randomise(m):
+        with torch.no_grad():
+            for n, t in m.state_dict().items():
+                if n.endswith("num_batches_tracked"):
+                    continue
+                if n.endswith("running_var"):
+                    t.copy_(1.0 + torch.rand(t.shape, generator=g))
+                elif t.dim() == 1:
+                    t.copy_((1.0 if n.endswith("weight") else 0.0) + 0.2 * torch.randn(t.shape, generator=g))
+                else:
+                    t.copy_(torch.randn(t.shape, generator=g) * (1.5 / (t[0].numel() ** 0.5)))
+        return m.eval()
+
+    sel = range(1, 13, 2)
+    agg = randomise(_exec_class(rel, "RSFeatureAggregator", ns)("sam_vit_base", hidden_channels=8, out_channels=16,
+                                                                select_layers=sel))
+    used = {i: torch.randn(1, 3, 4, 768, generator=g) for i in sel}
+    hidden = [used.get(i, torch.zeros(1, 3, 4, 768)) for i in range(13)]
+    with torch.no_grad():
+        out = agg(hidden)
+    fx["feature_aggregator"] = dict(state_dict={k: v.clone() for k, v in agg.state_dict().items()}, select_layers=list(sel),
+                                    hidden={i: used[i] for i in sel}, out=out)
+    pagg = randomise(_exec_class(rel, "PseudoFeatureAggregator", ns)(24, hidden_channels=16, out_channels=8))
+    x = torch.randn(2, 24, 7, 9, generator=g)
+    with torch.no_grad():
+        out = pagg((x,))
+    fx["pseudo_feature_aggregator"] = dict(state_dict={k: v.clone() for k, v in pagg.state_dict().items()}, x=x, out=out)
+    fpn = randomise(_exec_class(rel, "RSSimpleFPN", ns)(16, [4, 8, 16, 16], 8, 5, norm_cfg=dict(type="LN2d", requires_grad=True)))
+    x = torch.randn(2, 16, 6, 8, generator=g)
+    with torch.no_grad():
+        outs = fpn(x)
+    fx["simple_fpn"] = dict(state_dict={k: v.clone() for k, v in fpn.state_dict().items()}, x=x, outs=list(outs))
+    path = os.path.join(os.path.dirname(OUT), "reference_necks.pt")
+    torch.save(fx, path)
+    print("wrote", path, os.path.getsize(path), {k: list(v.keys()) for k, v in fx.items()})
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("/root/reference not mounted")
@@ -316,5 +389,7 @@ if __name__ == "__main__":
         main_maskrcnn()
     elif "state_keys" in sys.argv[1:]:
         main_state_keys()
+    elif "necks" in sys.argv[1:]:
+        main_necks()
     else:
         main()

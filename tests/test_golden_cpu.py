@@ -218,3 +218,27 @@ def test_head_submodules_take_reference_constructor_state_dicts():
     sh = MODELS.build(ph)
     sh.mask_embed.load_state_dict(_ref_sd("Mask2FormerHead.mask_embed[256,256]"), strict=True)
     sh.cls_embed.load_state_dict(_ref_sd("Mask2FormerHead.cls_embed[256,10]"), strict=True)
+
+
+# ---- necks: the reference's own forward() executed (tests/golden/reference_necks.pt; make_golden.py necks)
+FXN = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_necks.pt"), weights_only=False)
+
+
+def test_feature_aggregator_restatement_matches_reference_forward():
+    f = FXN["feature_aggregator"]
+    hidden = [f["hidden"].get(i, torch.zeros(1, 3, 4, 768)) for i in range(13)]
+    got = ra.feature_aggregator(f["state_dict"], hidden, f["select_layers"])
+    torch.testing.assert_close(got, f["out"], rtol=1e-5, atol=1e-5)
+
+
+def test_pseudo_feature_aggregator_restatement_matches_reference_forward():
+    f = FXN["pseudo_feature_aggregator"]
+    torch.testing.assert_close(ra.pseudo_feature_aggregator(f["state_dict"], f["x"]), f["out"], rtol=1e-5, atol=1e-5)
+
+
+def test_simple_fpn_restatement_matches_reference_forward():
+    f = FXN["simple_fpn"]
+    outs = ra.simple_fpn(f["state_dict"], f["x"], norm_key="norm_layer")
+    assert len(outs) == len(f["outs"]) == 5
+    for a, b in zip(outs, f["outs"]):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5)
