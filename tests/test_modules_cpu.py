@@ -250,3 +250,49 @@ def test_oracle_embed_boxes_matches_hf_prompt_encoder():
         got = restate.embed_boxes(pe.shared_embedding.positional_embedding, pe.point_embed[2].weight,
                                   pe.point_embed[3].weight, boxes, 1024)
     assert torch.allclose(got, ref, atol=1e-5)
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype in include/rsp_b200.h against the ctypes table of _lib: same arity, and every parameter of the
+    same class (pointer / integer / float).  A mismatch here would only show up as garbage arguments on a GPU."""
+    hdr = open(os.path.join(ROOT, "include", "rsp_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = re.findall(r"\b(?:int|const char\s*\*)\s+(rsp_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr)
+    assert len(protos) == len(set(n for n, _ in protos)) == len(_lib.declared_symbols())
+
+    def klass(param: str) -> str:
+        param = param.strip()
+        if "*" in param:
+            return "ptr"
+        base = param.rsplit(" ", 1)[0].replace("const", "").strip()
+        return {"int": "int", "float": "float", "long long": "int", "int64_t": "int", "int32_t": "int", "uint8_t": "int",
+                "size_t": "int"}[base]
+
+    ctype_class = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int: "int", ctypes.c_longlong: "int",
+                   ctypes.c_float: "float", ctypes.c_size_t: "int"}
+    for name, params in protos:
+        params = [p for p in params.split(",") if p.strip() and p.strip() != "void"]
+        argtypes, _ = _lib._SIGNATURES[name]
+        assert len(argtypes) == len(params), f"{name}: header has {len(params)} parameters, ctypes {len(argtypes)}"
+        for k, (p, t) in enumerate(zip(params, argtypes)):
+            assert klass(p) == ctype_class[t], f"{name}: parameter {k} ({p.strip()}) bound as {t.__name__}"
+
+
+def test_detector_meta_helpers():
+    """_metas: None for images at the batch shape with scale 1 (fast batched post-process), otherwise the crop of the
+    resized image (M:1771-1773: int(ori * scale), capped at the batch shape) and the original size; _attach_img_shapes:
+    per-image img_shape tensor only when some image is smaller than the batch, stale attachments are removed."""
+    from rsprompter_b200.detectors import _SamDetectorBase as D
+    from rsprompter_b200.registry import make_data_samples
+    x = torch.zeros(3, 3, 64, 96)
+    ds = make_data_samples(3, (64, 96))
+    ds[1].set_metainfo(dict(ori_shape=(40, 50), img_shape=(51, 64), scale_factor=(1.28, 1.275)))
+    ds[2].set_metainfo(dict(ori_shape=(100, 200), img_shape=(64, 96), scale_factor=(2.0, 2.0)))
+    hw, metas = D._metas(ds, x)
+    assert hw == (64, 96) and metas[0] is None
+    assert metas[1] == dict(ori_hw=(40, 50), crop_hw=(int(40 * 1.275), int(50 * 1.28)), scale_factor=(1.28, 1.275))
+    assert metas[2]["crop_hw"] == (64, 96)                               # capped at the batch shape
+    y = D._attach_img_shapes(ds, x)
+    assert y is x and x.rsp_img_shapes.tolist() == [[64.0, 96.0], [51.0, 64.0], [64.0, 96.0]]
+    D._attach_img_shapes(make_data_samples(3, (64, 96)), x)
+    assert not hasattr(x, "rsp_img_shapes")
